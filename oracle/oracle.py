@@ -1,0 +1,213 @@
+"""
+ctypes front-end of the CPU oracle (``oracle_regrid.c``).
+
+TEST INFRASTRUCTURE ONLY: imported by ``tests/``, ``__graft_entry__.smoke()`` and
+``bench.py``'s CPU-baseline legs.  The product package ``regridding_b200`` never
+imports this module.
+
+The functions mirror the *kernel call sites* of the reference:
+``weights_conservative_2d`` (c2d.py:80-126), ``_coalesce`` (warr.py:44-73),
+``_regrid_from_weights`` (rfw.py:165-182), ``_weights_conservative_1d``
+(c1d.py:60-189) and the 1D ``find_indices`` kernels.
+"""
+
+from __future__ import annotations
+
+import ctypes
+import pathlib
+import subprocess
+
+import numpy as np
+
+_HERE = pathlib.Path(__file__).resolve().parent
+_LIB_PATH = _HERE / "liboracle_regrid.so"
+
+_c_double_p = ctypes.POINTER(ctypes.c_double)
+_c_int64_p = ctypes.POINTER(ctypes.c_int64)
+
+
+def build(force: bool = False) -> pathlib.Path:
+    """Compile the oracle with the recipe in ``oracle/Makefile``."""
+    src = _HERE / "oracle_regrid.c"
+    if force or not _LIB_PATH.exists() or _LIB_PATH.stat().st_mtime < src.stat().st_mtime:
+        subprocess.run(["make", "-C", str(_HERE), "-B"], check=True, capture_output=True)
+    return _LIB_PATH
+
+
+_lib = None
+
+
+def lib() -> ctypes.CDLL:
+    global _lib
+    if _lib is None:
+        if not _LIB_PATH.exists():
+            build()
+        L = ctypes.CDLL(str(_LIB_PATH))
+        L.orc_set_mode.argtypes = [ctypes.c_int]
+        L.orc_get_mode.restype = ctypes.c_int
+        L.orc_num_threads.restype = ctypes.c_int
+        L.orc_free.argtypes = [ctypes.c_void_p]
+        L.orc_point_in_polygon.argtypes = [ctypes.c_double, ctypes.c_double, _c_double_p, _c_double_p, ctypes.c_int64]
+        L.orc_point_in_polygon.restype = ctypes.c_int
+        L.orc_grid_volume.argtypes = [_c_double_p, _c_double_p, ctypes.c_int64, ctypes.c_int64, _c_double_p]
+        for f in (L.orc_index_of_point_secant, L.orc_index_of_point_brute):
+            f.argtypes = [_c_double_p, _c_double_p, ctypes.c_int64, ctypes.c_int64,
+                          ctypes.c_double, ctypes.c_double, _c_int64_p]
+        L.orc_weights_conservative_2d.argtypes = [
+            _c_double_p, _c_double_p, ctypes.c_int64, ctypes.c_int64,
+            _c_double_p, _c_double_p, ctypes.c_int64, ctypes.c_int64,
+            _c_double_p,
+            ctypes.POINTER(_c_int64_p), ctypes.POINTER(_c_int64_p), ctypes.POINTER(_c_double_p),
+        ]
+        L.orc_weights_conservative_2d.restype = ctypes.c_int64
+        L.orc_coalesce.argtypes = [ctypes.c_int64, _c_int64_p, _c_int64_p, _c_double_p,
+                                   _c_int64_p, _c_int64_p, _c_double_p]
+        L.orc_coalesce.restype = ctypes.c_int64
+        L.orc_reduceat_segment.argtypes = [_c_double_p, ctypes.c_int64]
+        L.orc_reduceat_segment.restype = ctypes.c_double
+        L.orc_regrid_from_weights.argtypes = [ctypes.c_int64, _c_int64_p, _c_int64_p, _c_double_p,
+                                              ctypes.c_int64, ctypes.c_int64, ctypes.c_int64,
+                                              _c_double_p, _c_double_p]
+        L.orc_weights_conservative_1d.argtypes = [_c_double_p, ctypes.c_int64, _c_double_p, ctypes.c_int64,
+                                                  _c_double_p, _c_int64_p, _c_int64_p, _c_double_p]
+        L.orc_weights_conservative_1d.restype = ctypes.c_int64
+        L.orc_weights_conservative_1d_batched.argtypes = [
+            ctypes.c_int64, _c_double_p, ctypes.c_int64, _c_double_p, ctypes.c_int64, _c_double_p,
+            _c_int64_p, _c_int64_p, _c_double_p, _c_int64_p]
+        for f in (L.orc_find_indices_brute_1d, L.orc_find_indices_searchsorted_1d):
+            f.argtypes = [ctypes.c_int64, ctypes.c_int64, ctypes.c_int64, _c_double_p, _c_double_p,
+                          ctypes.c_int64, _c_int64_p]
+        _lib = L
+    return _lib
+
+
+def _d(a):
+    return a.ctypes.data_as(_c_double_p)
+
+
+def _i(a):
+    return a.ctypes.data_as(_c_int64_p)
+
+
+def _f64(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def set_mode(mode: str | int) -> None:
+    """``"jit"`` (default; Numba fastmath contraction pattern) or ``"strict"`` (plain IEEE)."""
+    if isinstance(mode, str):
+        mode = {"jit": 1, "strict": 0}[mode]
+    lib().orc_set_mode(int(mode))
+
+
+def num_threads() -> int:
+    return int(lib().orc_num_threads())
+
+
+def point_is_inside_polygon(x, y, vertices_x, vertices_y) -> bool:
+    vx, vy = _f64(vertices_x), _f64(vertices_y)
+    return bool(lib().orc_point_in_polygon(float(x), float(y), _d(vx), _d(vy), vx.size))
+
+
+def grid_volume(x, y) -> np.ndarray:
+    x, y = _f64(x), _f64(y)
+    nx, ny = x.shape
+    out = np.empty((nx - 1, ny - 1))
+    lib().orc_grid_volume(_d(x), _d(y), nx, ny, _d(out))
+    return out
+
+
+def index_of_point(x, y, px, py, method="secant") -> tuple[int, int]:
+    x, y = _f64(x), _f64(y)
+    out = np.empty(2, dtype=np.int64)
+    f = lib().orc_index_of_point_secant if method == "secant" else lib().orc_index_of_point_brute
+    f(_d(x), _d(y), x.shape[0], x.shape[1], float(px), float(py), _i(out))
+    return int(out[0]), int(out[1])
+
+
+def weights_conservative_2d(grid_input, grid_output, weights_input=None):
+    """Raw (uncoalesced) triplets in the reference's emission order (c2d.py:80-126)."""
+    xi, yi = (_f64(a) for a in grid_input)
+    xo, yo = (_f64(a) for a in grid_output)
+    w = None if weights_input is None else _f64(weights_input)
+    pii, pio, pv = _c_int64_p(), _c_int64_p(), _c_double_p()
+    n = lib().orc_weights_conservative_2d(
+        _d(xi), _d(yi), xi.shape[0], xi.shape[1],
+        _d(xo), _d(yo), xo.shape[0], xo.shape[1],
+        _d(w) if w is not None else None,
+        ctypes.byref(pii), ctypes.byref(pio), ctypes.byref(pv),
+    )
+    try:
+        ii = np.ctypeslib.as_array(pii, shape=(max(n, 1),))[:n].copy()
+        io = np.ctypeslib.as_array(pio, shape=(max(n, 1),))[:n].copy()
+        v = np.ctypeslib.as_array(pv, shape=(max(n, 1),))[:n].copy()
+    finally:
+        lib().orc_free(pii)
+        lib().orc_free(pio)
+        lib().orc_free(pv)
+    return ii, io, v
+
+
+def coalesce(indices_input, indices_output, values):
+    """warr.py:44-73."""
+    ii = np.ascontiguousarray(indices_input, dtype=np.int64)
+    io = np.ascontiguousarray(indices_output, dtype=np.int64)
+    v = _f64(values)
+    n = v.size
+    oi, oo, ov = np.empty(n, np.int64), np.empty(n, np.int64), np.empty(n, np.float64)
+    m = lib().orc_coalesce(n, _i(ii), _i(io), _d(v), _i(oi), _i(oo), _d(ov))
+    return oi[:m].copy(), oo[:m].copy(), ov[:m].copy()
+
+
+def reduceat_segment(a) -> float:
+    a = _f64(a)
+    return float(lib().orc_reduceat_segment(_d(a), a.size))
+
+
+def regrid_from_weights(indices_input, indices_output, values, values_input, n_out: int) -> np.ndarray:
+    """rfw.py:165-182 with one set of weights shared by all D slices; ``values_input`` is (D, n_in)."""
+    ii = np.ascontiguousarray(indices_input, dtype=np.int64)
+    io = np.ascontiguousarray(indices_output, dtype=np.int64)
+    v = _f64(values)
+    vin = _f64(values_input)
+    D, n_in = vin.shape
+    out = np.zeros((D, n_out))
+    lib().orc_regrid_from_weights(v.size, _i(ii), _i(io), _d(v), D, n_in, n_out, _d(vin), _d(out))
+    return out
+
+
+def weights_conservative_1d(x_input, x_output, weights_input=None):
+    """c1d.py:60-189 for one spectrum."""
+    xi, xo = _f64(x_input), _f64(x_output)
+    w = None if weights_input is None else _f64(weights_input)
+    cap = xi.size + xo.size
+    ii, io, v = np.empty(cap, np.int64), np.empty(cap, np.int64), np.empty(cap, np.float64)
+    n = lib().orc_weights_conservative_1d(_d(xi), xi.size, _d(xo), xo.size,
+                                          _d(w) if w is not None else None, _i(ii), _i(io), _d(v))
+    return ii[:n].copy(), io[:n].copy(), v[:n].copy()
+
+
+def weights_conservative_1d_batched(x_input, x_output, weights_input=None):
+    """wcons.py:59-106: (S, n) and (S, m) stacks -> list of S triplet tuples."""
+    xi, xo = _f64(x_input), _f64(x_output)
+    S, n = xi.shape
+    m = xo.shape[1]
+    w = None if weights_input is None else _f64(weights_input)
+    cap = n + m
+    ii, io = np.empty((S, cap), np.int64), np.empty((S, cap), np.int64)
+    v = np.empty((S, cap), np.float64)
+    counts = np.empty(S, np.int64)
+    lib().orc_weights_conservative_1d_batched(S, _d(xi), n, _d(xo), m, _d(w) if w is not None else None,
+                                              _i(ii), _i(io), _d(v), _i(counts))
+    return [(ii[s, :c].copy(), io[s, :c].copy(), v[s, :c].copy()) for s, c in enumerate(counts)]
+
+
+def find_indices_1d(x_input, x_output, fill_value: int, method: str = "brute") -> np.ndarray:
+    """fib.py:24-51 / fis.py:24-62 on (D, n) and (D, m) stacks."""
+    xi, xo = _f64(x_input), _f64(x_output)
+    D, n = xi.shape
+    m = xo.shape[1]
+    out = np.empty((D, m), np.int64)
+    f = lib().orc_find_indices_brute_1d if method == "brute" else lib().orc_find_indices_searchsorted_1d
+    f(D, n, m, _d(xi), _d(xo), int(fill_value), _i(out))
+    return out
