@@ -1,0 +1,180 @@
+/*
+ * regrid_b200.h -- C ABI of libregrid_b200.so (CUDA, sm_100a).
+ *
+ * Drop-in boundary for the first-order conservative regridding path of
+ * sun-data/regridding.  The reference has no FFI of its own (it is Python + Numba);
+ * its boundary is the four places where Python hands arrays to a compiled kernel
+ * (SURVEY.md section 8b).  Each entry point below names the reference call site it
+ * replaces (paths relative to the reference root).
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless its name ends in _host;
+ *   - the caller owns every buffer; the library never allocates result memory.
+ *     Variable-length results use  count -> caller allocates -> emit;
+ *     scratch comes from a caller-provided workspace (size-query functions);
+ *   - `stream` is a cudaStream_t passed as void*; work is stream-ordered; functions
+ *     that return a count through a *_host pointer synchronise that stream;
+ *   - `device` is the CUDA device ordinal the pointers live on;
+ *   - return value: 0 = ok, negative = argument error (RG_E_*), positive = cudaError_t.
+ *     rg_last_error_string() describes the last failure on the calling thread;
+ *   - coordinates/values are fp64, public indices int64, internal CSR indices int32;
+ *   - no global mutable state: safe from several host threads on distinct
+ *     streams/workspaces.
+ */
+#ifndef REGRID_B200_H
+#define REGRID_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RG_OK 0
+#define RG_E_ARG (-1)        /* null pointer / non-positive size */
+#define RG_E_TOO_LARGE (-2)  /* a size exceeds the int32 internal index range */
+#define RG_E_WORKSPACE (-3)  /* workspace too small */
+#define RG_E_WALK (-4)       /* a sweep walk did not terminate (degenerate / folded grid) */
+
+const char* rg_last_error_string(void);
+int rg_version(void);
+
+/* ------------------------------------------------------------------------------
+ * 2D conservative weights build (Ramshaw 1985 edge sweep)
+ * replaces: weights_conservative_2d(grid_input, grid_output, weights_input)
+ *           regridding/_weights/_weights_conservative_2d/_weights_conservative_2d.py:80-126
+ *           (called from regridding/_weights/_weights_conservative.py:129-139)
+ *   plus    _coalesce  regridding/_weights/_weights_arrays.py:44-73
+ *
+ * Grids are row-major contiguous fp64 vertex arrays of shape (nx, ny).
+ * Result: the reference's public layout -- unique (input, output) pairs sorted by
+ * (input, output), flat C-order CELL indices, weights summed per pair in NumPy's
+ * np.add.reduceat association over the reference's emission order.
+ *
+ * Protocol (all three calls share one workspace, which must stay untouched between them):
+ *   rg_build2d_workspace_bytes -> caller allocates `workspace`
+ *   rg_build2d_count           -> *n_fragments_host  (raw fragments before merging)
+ *   caller allocates frag_key (uint64[n_fragments]) and frag_val (double[n_fragments])
+ *   rg_build2d_fill            -> *nnz_host
+ *   caller allocates indices_input/indices_output (int64[nnz]), values (double[nnz])
+ *   rg_build2d_emit
+ * cell_lo/cell_hi restrict the build to input cells with flat index in
+ * [cell_lo, cell_hi) (band partition for multi-GPU builds); pass 0 and
+ * (nx_in-1)*(ny_in-1) for a full build.
+ * ------------------------------------------------------------------------------ */
+int rg_build2d_workspace_bytes(int64_t nx_in, int64_t ny_in, int64_t nx_out, int64_t ny_out,
+                               size_t* bytes_host);
+
+int rg_build2d_count(int device, void* stream,
+                     int64_t nx_in, int64_t ny_in, int64_t nx_out, int64_t ny_out,
+                     const double* x_in, const double* y_in,
+                     const double* x_out, const double* y_out,
+                     int64_t cell_lo, int64_t cell_hi,
+                     void* workspace, size_t workspace_bytes,
+                     int64_t* n_fragments_host);
+
+int rg_build2d_fill(int device, void* stream,
+                    int64_t nx_in, int64_t ny_in, int64_t nx_out, int64_t ny_out,
+                    const double* x_in, const double* y_in,
+                    const double* x_out, const double* y_out,
+                    const double* weights_input_or_null,
+                    int64_t cell_lo, int64_t cell_hi,
+                    void* workspace, size_t workspace_bytes,
+                    uint64_t* frag_key, double* frag_val, int64_t n_fragments,
+                    int64_t* nnz_host);
+
+int rg_build2d_emit(int device, void* stream,
+                    int64_t nx_in, int64_t ny_in, int64_t nx_out, int64_t ny_out,
+                    int64_t cell_lo, int64_t cell_hi,
+                    void* workspace, size_t workspace_bytes,
+                    const uint64_t* frag_key, const double* frag_val, int64_t n_fragments,
+                    int64_t* indices_input, int64_t* indices_output, double* values, int64_t nnz);
+
+/* Diagnostics of the last build in `workspace`: stats_host[0] = walk overflow flag,
+ * [1] = segments re-walked by the chain repair, [2] = sweep vertices whose state guess
+ * was unknown, [3] = emission-rank overflow flag; [4..7] reserved. */
+int rg_build2d_stats(int device, void* stream, int64_t nx_in, int64_t ny_in, int64_t nx_out, int64_t ny_out,
+                     void* workspace, int32_t* stats_host);
+
+/* Signed cell areas; replaces grid_volume
+ * regridding/_weights/_weights_conservative_2d/_grids.py:50-140. area: double[(nx-1)*(ny-1)]. */
+int rg_grid_area(int device, void* stream, int64_t nx, int64_t ny,
+                 const double* x, const double* y, double* area);
+
+/* ------------------------------------------------------------------------------
+ * 2D cell location
+ * replaces: index_of_point_brute / index_of_point_secant
+ *           regridding/_weights/_weights_conservative_2d/_grids.py:223-279, 356-463
+ * (the reference's public find_indices is 1D only; this is the 2D extension).
+ * For each of n_points query points: flat index i*(ny-1)+j of the lowest-index cell
+ * whose quad contains the point under point_is_inside_polygon
+ * (regridding/geometry.py:737-829), else `fill`.
+ * ------------------------------------------------------------------------------ */
+int rg_find_indices_2d_workspace_bytes(int64_t nx, int64_t ny, int64_t n_points, size_t* bytes_host);
+
+int rg_find_indices_2d(int device, void* stream, int64_t nx, int64_t ny,
+                       const double* x, const double* y,
+                       int64_t n_points, const double* px, const double* py,
+                       int64_t fill, int64_t* cell_flat,
+                       void* workspace, size_t workspace_bytes);
+
+/* ------------------------------------------------------------------------------
+ * shared-weights apply
+ * replaces: _regrid_from_weights(weights, values_input, values_output)
+ *           regridding/_regrid/_regrid_from_weights.py:165-182
+ *           (called from regridding/_regrid/_regrid_from_weights.py:146-150)
+ *
+ * rg_csr_from_coo turns the public (input, output)-sorted COO into CSR by OUTPUT
+ * row with ascending input index inside each row -- the accumulation order of the
+ * reference's sequential loop -- so that rg_apply_csr is bit-identical to it.
+ * Negative (wrap-around) indices must be normalised by the caller.
+ * ------------------------------------------------------------------------------ */
+int rg_csr_workspace_bytes(int64_t nnz, int64_t n_out, size_t* bytes_host);
+
+int rg_csr_from_coo(int device, void* stream, int64_t nnz, int64_t n_in, int64_t n_out,
+                    const int64_t* indices_input, const int64_t* indices_output, const double* values,
+                    int32_t* row_ptr /* n_out+1 */, int32_t* col /* nnz */, double* val /* nnz */,
+                    void* workspace, size_t workspace_bytes);
+
+/* values_in: (n_frames, n_in) row-major, values_out: (n_frames, n_out) row-major; every
+ * element of values_out is written (rows without weights get +0.0). */
+int rg_apply_csr(int device, void* stream, int64_t n_frames, int64_t n_in, int64_t n_out,
+                 const int32_t* row_ptr, const int32_t* col, const double* val,
+                 const double* values_in, double* values_out);
+
+/* ------------------------------------------------------------------------------
+ * 1D conservative, batched over S independent spectra
+ * replaces: weights_conservative_1d(x_input, x_output, weights_input, weights_output, start, stop)
+ *           regridding/_weights/_weights_conservative_1d/_weights_conservative_1d.py:12-56, 60-189
+ *           (called from regridding/_weights/_weights_conservative.py:89-97)
+ * x_in: (S, n) edges, x_out: (S, m) edges.  Triplets of spectrum s are written at
+ * offset s*(n+m) of the output arrays (capacity n+m each), counts[s] of them, in the
+ * reference's emission order; indices are the reference's (possibly negative,
+ * complemented) indices.
+ * ------------------------------------------------------------------------------ */
+int rg_cons1d_batched(int device, void* stream, int64_t S, int64_t n, int64_t m,
+                      const double* x_in, const double* x_out, const double* weights_input_or_null,
+                      int64_t* indices_input, int64_t* indices_output, double* values,
+                      int64_t* counts);
+
+/* Fused 1D conservative regrid (weights never materialised): values_in (S, n-1) -> values_out (S, m-1),
+ * accumulating in the reference's order (rfw.py:179-182 over c1d.py emission order). */
+int rg_regrid1d_conservative(int device, void* stream, int64_t S, int64_t n, int64_t m,
+                             const double* x_in, const double* x_out, const double* weights_input_or_null,
+                             const double* values_in, double* values_out);
+
+/* ------------------------------------------------------------------------------
+ * 1D cell location
+ * replaces: _find_indices_brute_1d      regridding/_find_indices/_find_indices_brute.py:24-51
+ *           _find_indices_searchsorted_1d regridding/_find_indices/_find_indices_searchsorted.py:24-62
+ *           (called from regridding/_find_indices/_find_indices.py:112-123)
+ * method: 0 = brute, 1 = searchsorted.  x_in (D, n), x_out (D, m) -> out (D, m).
+ * ------------------------------------------------------------------------------ */
+int rg_find_indices_1d(int device, void* stream, int method, int64_t D, int64_t n, int64_t m,
+                       const double* x_in, const double* x_out, int64_t fill, int64_t* out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* REGRID_B200_H */

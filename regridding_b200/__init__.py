@@ -1,0 +1,17 @@
+"""
+regridding_b200 -- B200-native first-order conservative regridding.
+
+Drop-in for the conservative path of sun-data/regridding: ``weights``,
+``regrid_from_weights``, ``regrid`` and ``find_indices`` keep the reference's
+signatures, error behaviour and saved-weights layout; the compiled kernels behind them
+are hand-written CUDA for sm_100a in ``libregrid_b200.so`` (C ABI:
+``include/regrid_b200.h``).  There is no CPU fallback.
+"""
+
+from ._find_indices import find_indices
+from ._regrid import regrid, regrid_from_weights
+from ._weights import weights
+from . import _device as device  # device-resident operators (torch CUDA tensors in / out)
+
+__all__ = ["regrid", "weights", "regrid_from_weights", "find_indices", "device"]
+__version__ = "0.1.0"

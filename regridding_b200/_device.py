@@ -1,0 +1,300 @@
+"""
+Device-level operators: thin, typed wrappers of the C ABI working on
+``torch`` CUDA tensors.  Everything here runs on the GPU; there is no CPU path.
+
+The public, reference-compatible API (``regridding_b200.weights`` etc.) is built on
+these; they are also what ``bench.py`` times for the HBM-resident numbers.
+"""
+
+from __future__ import annotations
+
+import ctypes
+import dataclasses
+
+import numpy as np
+import torch
+
+from . import _lib
+
+F64 = torch.float64
+I64 = torch.int64
+I32 = torch.int32
+
+
+def cuda_device(device=None) -> torch.device:
+    if not torch.cuda.is_available():
+        raise _lib.RegridB200Error("regridding_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
+    if device is None:
+        return torch.device("cuda", torch.cuda.current_device())
+    device = torch.device(device)
+    if device.type != "cuda":
+        raise _lib.RegridB200Error(f"regridding_b200 runs on CUDA devices only, got {device}")
+    if device.index is None:
+        device = torch.device("cuda", torch.cuda.current_device())
+    return device
+
+
+def _stream(device: torch.device) -> int:
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+def to_device(a, device: torch.device, dtype=F64) -> torch.Tensor:
+    """numpy array or tensor -> contiguous tensor on `device`."""
+    if isinstance(a, torch.Tensor):
+        return a.to(device=device, dtype=dtype).contiguous()
+    a = np.ascontiguousarray(a, dtype={F64: np.float64, I64: np.int64, I32: np.int32}[dtype])
+    return torch.from_numpy(a).to(device)
+
+
+def _workspace(nbytes: int, device) -> torch.Tensor:
+    return torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
+
+
+# ---------------------------------------------------------------------------
+# weights container
+# ---------------------------------------------------------------------------
+
+
+@dataclasses.dataclass
+class CSR:
+    row_ptr: torch.Tensor  # int32 [n_out + 1]
+    col: torch.Tensor      # int32 [nnz]
+    val: torch.Tensor      # float64 [nnz]
+    n_in: int
+    n_out: int
+
+
+class DeviceWeights:
+    """One set of weights resident in HBM: the public COO (sorted by (input, output),
+    unique pairs, int64/int64/float64) plus, lazily, the CSR-by-output form the apply uses."""
+
+    def __init__(self, ii: torch.Tensor, io: torch.Tensor, v: torch.Tensor, n_in: int, n_out: int):
+        self.indices_input = ii
+        self.indices_output = io
+        self.values = v
+        self.n_in = int(n_in)
+        self.n_out = int(n_out)
+        self._csr: CSR | None = None
+        self.stats: dict | None = None
+
+    @property
+    def nnz(self) -> int:
+        return int(self.values.numel())
+
+    @property
+    def device(self) -> torch.device:
+        return self.values.device
+
+    def csr(self) -> CSR:
+        if self._csr is None:
+            ii, io = self.indices_input, self.indices_output
+            if self.nnz and (int(ii.min().item()) < 0 or int(io.min().item()) < 0):
+                # negative (wrap-around) indices of descending 1D grids: Numba wraps them (rfw.py:179-182)
+                ii = torch.where(ii < 0, ii + self.n_in, ii)
+                io = torch.where(io < 0, io + self.n_out, io)
+            self._csr = csr_from_coo(ii, io, self.values, self.n_in, self.n_out)
+        return self._csr
+
+    def to_host(self) -> tuple[np.ndarray, np.ndarray, np.ndarray]:
+        """The reference's saved-weights element: ``(indices_input, indices_output, values)``."""
+        return (self.indices_input.cpu().numpy(), self.indices_output.cpu().numpy(), self.values.cpu().numpy())
+
+    @classmethod
+    def from_host(cls, indices_input, indices_output, values, n_in: int, n_out: int, device=None) -> "DeviceWeights":
+        device = cuda_device(device)
+        ii = np.asarray(indices_input).astype(np.int64, copy=True)
+        io = np.asarray(indices_output).astype(np.int64, copy=True)
+        # negative (wrap-around) indices from descending 1D grids: numba wraps them (rfw.py:179-182)
+        if ii.size and ii.min() < 0:
+            ii[ii < 0] += n_in
+        if io.size and io.min() < 0:
+            io[io < 0] += n_out
+        if ii.size and (ii.min() < 0 or ii.max() >= n_in or io.min() < 0 or io.max() >= n_out):
+            raise IndexError("weights index out of range for the given shapes")
+        v = np.ascontiguousarray(np.asarray(values), dtype=np.float64)
+        return cls(to_device(ii, device, I64), to_device(io, device, I64), to_device(v, device, F64), n_in, n_out)
+
+
+# ---------------------------------------------------------------------------
+# 2D conservative build
+# ---------------------------------------------------------------------------
+
+
+def build_weights_2d(x_in, y_in, x_out, y_out, weights_input=None, cell_band: tuple[int, int] | None = None,
+                     device=None) -> DeviceWeights:
+    """weights_conservative_2d + _coalesce on the GPU (see ``rg_build2d_*`` in include/regrid_b200.h).
+
+    All four coordinate arrays are 2D vertex grids; the OUTPUT coordinates must already
+    carry the reference's host-side perturbation if one is wanted.
+    """
+    L = _lib.load()
+    device = cuda_device(device if device is not None else (x_in.device if isinstance(x_in, torch.Tensor) else None))
+    xi, yi = to_device(x_in, device), to_device(y_in, device)
+    xo, yo = to_device(x_out, device), to_device(y_out, device)
+    if xi.ndim != 2 or xi.shape != yi.shape or xo.ndim != 2 or xo.shape != yo.shape:
+        raise ValueError("grids must be 2D arrays with matching x / y shapes")
+    nxi, nyi = xi.shape
+    nxo, nyo = xo.shape
+    n_in, n_out = (nxi - 1) * (nyi - 1), (nxo - 1) * (nyo - 1)
+    w = None
+    if weights_input is not None:
+        w = to_device(weights_input, device)
+        if tuple(w.shape) != (nxi - 1, nyi - 1):
+            raise ValueError(f"weights_input must have the input cell shape {(nxi - 1, nyi - 1)}, got {tuple(w.shape)}")
+    lo, hi = (0, n_in) if cell_band is None else (int(cell_band[0]), int(cell_band[1]))
+
+    with torch.cuda.device(device):
+        st = _stream(device)
+        nbytes = ctypes.c_size_t()
+        _lib.check(L.rg_build2d_workspace_bytes(nxi, nyi, nxo, nyo, ctypes.byref(nbytes)), "rg_build2d_workspace_bytes")
+        ws = _workspace(nbytes.value, device)
+        nfrag = ctypes.c_int64()
+        _lib.check(L.rg_build2d_count(device.index, st, nxi, nyi, nxo, nyo, xi.data_ptr(), yi.data_ptr(),
+                                      xo.data_ptr(), yo.data_ptr(), lo, hi, ws.data_ptr(), ws.numel(),
+                                      ctypes.byref(nfrag)), "rg_build2d_count")
+        nf = nfrag.value
+        fkey = torch.empty(max(nf, 1), dtype=I64, device=device)
+        fval = torch.empty(max(nf, 1), dtype=F64, device=device)
+        nnz_c = ctypes.c_int64()
+        _lib.check(L.rg_build2d_fill(device.index, st, nxi, nyi, nxo, nyo, xi.data_ptr(), yi.data_ptr(),
+                                     xo.data_ptr(), yo.data_ptr(), _lib.ptr(w), lo, hi, ws.data_ptr(), ws.numel(),
+                                     fkey.data_ptr(), fval.data_ptr(), nf, ctypes.byref(nnz_c)), "rg_build2d_fill")
+        nnz = nnz_c.value
+        ii = torch.empty(nnz, dtype=I64, device=device)
+        io = torch.empty(nnz, dtype=I64, device=device)
+        v = torch.empty(nnz, dtype=F64, device=device)
+        _lib.check(L.rg_build2d_emit(device.index, st, nxi, nyi, nxo, nyo, lo, hi, ws.data_ptr(), ws.numel(),
+                                     fkey.data_ptr(), fval.data_ptr(), nf,
+                                     ii.data_ptr(), io.data_ptr(), v.data_ptr(), nnz), "rg_build2d_emit")
+        stats = (ctypes.c_int32 * 8)()
+        _lib.check(L.rg_build2d_stats(device.index, st, nxi, nyi, nxo, nyo, ws.data_ptr(), stats), "rg_build2d_stats")
+    dw = DeviceWeights(ii, io, v, n_in, n_out)
+    dw.stats = {"fragments": nf, "nnz": nnz, "repaired_segments": int(stats[1]), "unknown_guesses": int(stats[2])}
+    return dw
+
+
+def grid_area(x, y, device=None) -> torch.Tensor:
+    L = _lib.load()
+    device = cuda_device(device)
+    xd, yd = to_device(x, device), to_device(y, device)
+    nx, ny = xd.shape
+    out = torch.empty((nx - 1, ny - 1), dtype=F64, device=device)
+    with torch.cuda.device(device):
+        _lib.check(L.rg_grid_area(device.index, _stream(device), nx, ny, xd.data_ptr(), yd.data_ptr(), out.data_ptr()),
+                   "rg_grid_area")
+    return out
+
+
+# ---------------------------------------------------------------------------
+# apply
+# ---------------------------------------------------------------------------
+
+
+def csr_from_coo(ii: torch.Tensor, io: torch.Tensor, v: torch.Tensor, n_in: int, n_out: int) -> CSR:
+    L = _lib.load()
+    device = v.device
+    nnz = int(v.numel())
+    row_ptr = torch.empty(n_out + 1, dtype=I32, device=device)
+    col = torch.empty(max(nnz, 1), dtype=I32, device=device)
+    val = torch.empty(max(nnz, 1), dtype=F64, device=device)
+    with torch.cuda.device(device):
+        nbytes = ctypes.c_size_t()
+        _lib.check(L.rg_csr_workspace_bytes(nnz, n_out, ctypes.byref(nbytes)), "rg_csr_workspace_bytes")
+        ws = _workspace(nbytes.value, device)
+        _lib.check(L.rg_csr_from_coo(device.index, _stream(device), nnz, n_in, n_out,
+                                     ii.data_ptr(), io.data_ptr(), v.data_ptr(),
+                                     row_ptr.data_ptr(), col.data_ptr(), val.data_ptr(),
+                                     ws.data_ptr(), ws.numel()), "rg_csr_from_coo")
+    return CSR(row_ptr, col[:nnz], val[:nnz], int(n_in), int(n_out))
+
+
+def apply_csr(csr: CSR, values_in: torch.Tensor, out: torch.Tensor | None = None) -> torch.Tensor:
+    """values_in (F, n_in) float64 contiguous on the CSR's device -> (F, n_out)."""
+    L = _lib.load()
+    device = csr.val.device
+    if values_in.dtype != F64 or not values_in.is_contiguous() or values_in.device != device:
+        raise ValueError("values_in must be a contiguous float64 tensor on the weights' device")
+    F, n_in = values_in.shape
+    if n_in != csr.n_in:
+        raise ValueError(f"values_in has {n_in} cells per frame, the weights expect {csr.n_in}")
+    if out is None:
+        out = torch.empty((F, csr.n_out), dtype=F64, device=device)
+    elif out.shape != (F, csr.n_out) or out.dtype != F64 or not out.is_contiguous() or out.device != device:
+        raise ValueError("out must be a contiguous float64 (F, n_out) tensor on the weights' device")
+    with torch.cuda.device(device):
+        _lib.check(L.rg_apply_csr(device.index, _stream(device), F, csr.n_in, csr.n_out,
+                                  csr.row_ptr.data_ptr(), csr.col.data_ptr(), csr.val.data_ptr(),
+                                  values_in.data_ptr(), out.data_ptr()), "rg_apply_csr")
+    return out
+
+
+# ---------------------------------------------------------------------------
+# 1D
+# ---------------------------------------------------------------------------
+
+
+def cons1d_batched(x_in: torch.Tensor, x_out: torch.Tensor, weights_input: torch.Tensor | None = None):
+    """(S, n) / (S, m) edge stacks -> (ii, io, v) of shape (S, n + m) and counts (S,), emission order."""
+    L = _lib.load()
+    device = x_in.device
+    S, n = x_in.shape
+    m = x_out.shape[1]
+    cap = n + m
+    ii = torch.empty((S, cap), dtype=I64, device=device)
+    io = torch.empty((S, cap), dtype=I64, device=device)
+    v = torch.empty((S, cap), dtype=F64, device=device)
+    counts = torch.empty(S, dtype=I64, device=device)
+    with torch.cuda.device(device):
+        _lib.check(L.rg_cons1d_batched(device.index, _stream(device), S, n, m, x_in.data_ptr(), x_out.data_ptr(),
+                                       _lib.ptr(weights_input), ii.data_ptr(), io.data_ptr(), v.data_ptr(),
+                                       counts.data_ptr()), "rg_cons1d_batched")
+    return ii, io, v, counts
+
+
+def regrid1d_conservative(x_in: torch.Tensor, x_out: torch.Tensor, values_in: torch.Tensor,
+                          weights_input: torch.Tensor | None = None, out: torch.Tensor | None = None) -> torch.Tensor:
+    """Fused 1D conservative regrid: (S, n), (S, m), (S, n-1) -> (S, m-1)."""
+    L = _lib.load()
+    device = x_in.device
+    S, n = x_in.shape
+    m = x_out.shape[1]
+    if values_in.shape != (S, n - 1):
+        raise ValueError(f"values_in must have shape {(S, n - 1)}, got {tuple(values_in.shape)}")
+    if out is None:
+        out = torch.empty((S, m - 1), dtype=F64, device=device)
+    with torch.cuda.device(device):
+        _lib.check(L.rg_regrid1d_conservative(device.index, _stream(device), S, n, m, x_in.data_ptr(),
+                                              x_out.data_ptr(), _lib.ptr(weights_input), values_in.data_ptr(),
+                                              out.data_ptr()), "rg_regrid1d_conservative")
+    return out
+
+
+def find_indices_1d(x_in: torch.Tensor, x_out: torch.Tensor, fill_value: int, method: str) -> torch.Tensor:
+    L = _lib.load()
+    device = x_in.device
+    D, n = x_in.shape
+    m = x_out.shape[1]
+    out = torch.empty((D, m), dtype=I64, device=device)
+    code = {"brute": 0, "searchsorted": 1}[method]
+    with torch.cuda.device(device):
+        _lib.check(L.rg_find_indices_1d(device.index, _stream(device), code, D, n, m, x_in.data_ptr(),
+                                        x_out.data_ptr(), int(fill_value), out.data_ptr()), "rg_find_indices_1d")
+    return out
+
+
+def find_indices_2d(x: torch.Tensor, y: torch.Tensor, px: torch.Tensor, py: torch.Tensor, fill_value: int) -> torch.Tensor:
+    """Flat cell index i*(ny-1)+j of the lowest-index cell containing each point, else `fill_value`."""
+    L = _lib.load()
+    device = x.device
+    nx, ny = x.shape
+    npts = int(px.numel())
+    out = torch.empty(px.shape, dtype=I64, device=device)
+    with torch.cuda.device(device):
+        nbytes = ctypes.c_size_t()
+        _lib.check(L.rg_find_indices_2d_workspace_bytes(nx, ny, npts, ctypes.byref(nbytes)),
+                   "rg_find_indices_2d_workspace_bytes")
+        ws = _workspace(nbytes.value, device)
+        _lib.check(L.rg_find_indices_2d(device.index, _stream(device), nx, ny, x.data_ptr(), y.data_ptr(), npts,
+                                        px.data_ptr(), py.data_ptr(), int(fill_value), out.data_ptr(),
+                                        ws.data_ptr(), ws.numel()), "rg_find_indices_2d")
+    return out

@@ -1,0 +1,160 @@
+"""
+``regrid_from_weights()`` and ``regrid()``: the reference's public entry points
+(``regridding/_regrid/_regrid_from_weights.py:12-162``, ``regridding/_regrid/_regrid.py:12-149``)
+with the scatter-add kernel (``rfw.py:165-182``) replaced by the CSR apply on the GPU.
+
+NumPy in -> NumPy out (host <-> device copies included); CUDA tensors in -> CUDA tensor
+out with no host round trip.
+"""
+
+from __future__ import annotations
+
+from typing import Literal, Sequence
+
+import numpy as np
+import torch
+
+from . import _cache, _device, _util
+
+__all__ = ["regrid_from_weights", "regrid"]
+
+
+def _orthogonal_shape(shape: tuple[int, ...], axis: tuple[int, ...]) -> tuple[int, ...]:
+    return tuple(shape[a] for a in range(-len(shape), 0) if a not in axis)
+
+
+def _device_weights_of(element, n_in: int, n_out: int, device) -> _device.DeviceWeights:
+    if isinstance(element, _device.DeviceWeights):
+        return element
+    indices_input, indices_output, values = element
+    values = getattr(values, "value", values)  # unit-carrying values (rfw.py:134-141)
+    dw = _cache.lookup(values, device)
+    if dw is None or dw.n_in != n_in or dw.n_out != n_out:
+        dw = _device.DeviceWeights.from_host(indices_input, indices_output, values, n_in, n_out, device)
+        _cache.remember(values, dw)
+    return dw
+
+
+def regrid_from_weights(
+    weights,
+    shape_input: tuple[int, ...],
+    shape_output: tuple[int, ...],
+    values_input,
+    values_output=None,
+    axis_input: None | int | Sequence[int] = None,
+    axis_output: None | int | Sequence[int] = None,
+):
+    """Drop-in for ``regridding.regrid_from_weights``."""
+    on_device = isinstance(values_input, torch.Tensor) and values_input.is_cuda
+    unit = getattr(values_input, "unit", None)
+    if unit is not None:
+        values_input = values_input.value
+
+    # axes are normalised against the WEIGHTS' shapes (rfw.py:64-68)
+    axis_in = _util.normalize_axis(axis_input, len(shape_input))
+    axis_out = _util.normalize_axis(axis_output, len(shape_output))
+
+    orth_in = _orthogonal_shape(tuple(shape_input), axis_in)
+    orth_out = _orthogonal_shape(tuple(shape_output), axis_out)
+    vin_shape = tuple(values_input.shape) if np.ndim(values_input) > 0 else ()
+    orth_val = _orthogonal_shape(vin_shape, axis_in) if vin_shape else ()
+    shape_orth = np.broadcast_shapes(orth_in, orth_out, orth_val)
+
+    axis_in = tuple(sorted(axis_in))
+    axis_out = tuple(sorted(axis_out))
+    full_in = _util._embed(shape_orth, axis_in, {a: shape_input[a] for a in axis_in})
+    full_out = _util._embed(shape_orth, axis_out, {a: shape_output[a] for a in axis_out})
+
+    weights_arr = np.broadcast_to(np.array(weights), shape_orth, subok=True)
+    flat_weights = weights_arr.reshape(-1)
+    unit_weights = getattr(flat_weights[0][2], "unit", None) if flat_weights.size and not isinstance(
+        flat_weights[0], _device.DeviceWeights) else None
+
+    cells_in = tuple(full_in[a] for a in axis_in)
+    cells_out = tuple(full_out[a] for a in axis_out)
+    n_in = int(np.prod(cells_in, dtype=np.int64))
+    n_out = int(np.prod(cells_out, dtype=np.int64))
+    D = int(np.prod(shape_orth, dtype=np.int64))
+    last_in = tuple(range(-len(axis_in), 0))
+    last_out = tuple(range(-len(axis_out), 0))
+
+    if on_device:
+        device = values_input.device
+        vin = torch.broadcast_to(values_input.to(torch.float64), full_in)
+        vin = torch.movedim(vin, axis_in, last_in).reshape(D, n_in).contiguous()
+        if values_output is not None and tuple(values_output.shape) != tuple(full_out):
+            raise ValueError(f"{values_output.shape=} should be equal to {full_out}")
+    else:
+        device = _device.cuda_device()
+        vin_h = np.broadcast_to(np.asarray(values_input, dtype=np.float64), full_in)
+        vin_h = np.ascontiguousarray(np.moveaxis(vin_h, axis_in, last_in).reshape(D, n_in))
+        vin = torch.from_numpy(vin_h).to(device)
+        if values_output is None:
+            values_output = np.zeros(full_out, dtype=float)
+        else:
+            if values_output.shape != full_out:
+                raise ValueError(f"{values_output.shape=} should be equal to {full_out}")
+            values_output.fill(0)
+
+    out = torch.empty((D, n_out), dtype=torch.float64, device=device)
+    # consecutive orthogonal slices that share one weights element are applied in one launch
+    d = 0
+    while d < D:
+        e = d + 1
+        while e < D and flat_weights[e] is flat_weights[d]:
+            e += 1
+        dw = _device_weights_of(flat_weights[d], n_in, n_out, device)
+        _device.apply_csr(dw.csr(), vin[d:e], out[d:e])
+        d = e
+
+    moved_out_shape = tuple(shape_orth) + cells_out
+    if on_device:
+        res = torch.movedim(out.reshape(moved_out_shape), last_out, axis_out)
+        if values_output is not None:
+            values_output.copy_(res)
+            res = values_output
+        return res
+
+    # host: same in-place behaviour as the reference (rfw.py:120-154): the caller's buffer is
+    # updated in place only if its moved/reshaped view is already C-contiguous
+    moved = np.moveaxis(values_output, axis_out, last_out)
+    moved_shape = moved.shape
+    target = np.ascontiguousarray(moved.reshape(D, *cells_out))
+    torch.from_numpy(target.reshape(D, n_out)).copy_(out)  # D2H straight into the result buffer
+    result = np.moveaxis(target.reshape(moved_shape), last_out, axis_out)
+
+    if unit_weights is not None:
+        unit = unit_weights if unit is None else unit * unit_weights
+    if unit is None:
+        return result
+    return result << unit
+
+
+def regrid(
+    coordinates_input,
+    coordinates_output,
+    values_input,
+    values_output=None,
+    axis_input: None | int | Sequence[int] = None,
+    axis_output: None | int | Sequence[int] = None,
+    method: Literal["multilinear", "conservative"] = "multilinear",
+    bounds: Literal["extrapolate", "nan", "raise"] = "extrapolate",
+    perturb: None | bool = None,
+    seed: "None | int | np.random.Generator" = _util.SEED_DEFAULT,
+):
+    """Drop-in for ``regridding.regrid`` (= ``weights`` then ``regrid_from_weights``,
+    regridding/_regrid/_regrid.py:130-149).  For ``method="conservative"`` the weights stay
+    on the GPU between the two steps."""
+    from ._weights import _weights_conservative_device, weights
+
+    if method == "conservative":
+        elements, shape_in, shape_out, shape_orth = _weights_conservative_device(
+            coordinates_input, coordinates_output, axis_input, axis_output, None, perturb, seed)
+        w = np.empty(len(elements), dtype=object)
+        for k, dw in enumerate(elements):
+            w[k] = dw
+        w = w.reshape(shape_orth)
+    else:
+        w, shape_in, shape_out = weights(coordinates_input, coordinates_output, axis_input, axis_output,
+                                         method=method, bounds=bounds, perturb=perturb, seed=seed)
+    return regrid_from_weights(w, shape_in, shape_out, values_input, values_output, axis_input, axis_output)

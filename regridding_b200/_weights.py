@@ -1,0 +1,147 @@
+"""
+``weights()``: the reference's public entry point (``regridding/_weights/_weights.py:13-196``)
+with the compiled kernels replaced by the CUDA library.
+
+Return value (the saved-weights layout, ``_weights.py:31-36``): ``(weights, shape_input,
+shape_output)`` where ``weights`` is an object ndarray of shape ``shape_orthogonal`` whose
+elements are tuples ``(indices_input int64[nnz], indices_output int64[nnz], values
+float64[nnz])`` sorted by (input, output) with unique pairs, and the two shapes are the
+full CELL shapes including orthogonal axes.  It pickles exactly like the reference's.
+
+Every element also stays resident on the GPU (see ``_cache``), so a following
+``regrid_from_weights`` does not upload it again.
+"""
+
+from __future__ import annotations
+
+from typing import Literal, Sequence
+
+import numpy as np
+import torch
+
+from . import _cache, _device, _util
+
+__all__ = ["weights"]
+
+
+def weights(
+    coordinates_input,
+    coordinates_output,
+    axis_input: None | int | Sequence[int] = None,
+    axis_output: None | int | Sequence[int] = None,
+    weights_input=None,
+    method: Literal["multilinear", "conservative"] = "multilinear",
+    bounds: Literal["extrapolate", "nan", "raise"] = "extrapolate",
+    perturb: None | bool = None,
+    seed: "None | int | np.random.Generator" = _util.SEED_DEFAULT,
+) -> tuple[np.ndarray, tuple[int, ...], tuple[int, ...]]:
+    """Drop-in for ``regridding.weights`` (same arguments, same result layout)."""
+    unit_weights = getattr(weights_input, "unit", None)
+    if unit_weights is not None:
+        weights_input = getattr(weights_input, "value")
+
+    if method == "multilinear":
+        from ._multilinear import weights_multilinear
+
+        elements, shape_in, shape_out, shape_orth = weights_multilinear(
+            coordinates_input, coordinates_output, axis_input, axis_output, weights_input, bounds, perturb, seed)
+    elif method == "conservative":
+        elements, shape_in, shape_out, shape_orth = _weights_conservative_device(
+            coordinates_input, coordinates_output, axis_input, axis_output, weights_input, perturb, seed)
+    else:
+        raise ValueError(f"unrecognized method '{method}'")
+
+    result = np.empty(len(elements), dtype=object)
+    for k, dw in enumerate(elements):
+        triple = dw.to_host()
+        if unit_weights is not None:
+            triple = (triple[0], triple[1], triple[2] << unit_weights)
+        else:
+            _cache.remember(triple[2], dw)
+        result[k] = triple
+    return result.reshape(shape_orth), shape_in, shape_out
+
+
+def _weights_conservative_device(
+    coordinates_input,
+    coordinates_output,
+    axis_input,
+    axis_output,
+    weights_input,
+    perturb,
+    seed,
+    device=None,
+) -> tuple[list[_device.DeviceWeights], tuple[int, ...], tuple[int, ...], tuple[int, ...]]:
+    """``_weights_conservative`` (regridding/_weights/_weights_conservative.py:11-146) with
+    the per-slice kernels on the GPU.  Returns one DeviceWeights per orthogonal slice
+    (C order), the cell shapes and the orthogonal shape."""
+    if perturb is None:  # wcons.py:21-25: jitter by default only for >= 2 coordinate arrays
+        perturb = (not isinstance(coordinates_input, np.ndarray)) and len(coordinates_input) > 1
+
+    (coords_in, coords_out, axis_in, axis_out, shape_in, shape_out, shape_orth) = \
+        _util.normalize_input_output_coordinates(coordinates_input, coordinates_output, axis_input, axis_output,
+                                                 perturb=perturb, seed=seed)
+    coords_in = tuple(np.asarray(getattr(c, "value", c), dtype=np.float64) for c in coords_in)
+    coords_out = tuple(np.asarray(getattr(c, "value", c), dtype=np.float64) for c in coords_out)
+
+    shape_cells_in = tuple(s - 1 if (a - len(shape_in)) in axis_in else s for a, s in enumerate(shape_in))
+    shape_cells_out = tuple(s - 1 if (a - len(shape_out)) in axis_out else s for a, s in enumerate(shape_out))
+
+    if weights_input is not None:
+        weights_input = np.broadcast_to(np.asarray(weights_input, dtype=np.float64), shape_cells_in)
+
+    device = _device.cuda_device(device)
+    ndim_resample = len(axis_in)
+    n_slices = int(np.prod(shape_orth, dtype=np.int64))
+
+    def stacked(c, axes):
+        # resampled axes last, in ascending axis order; orthogonal axes flattened in C order
+        src = tuple(sorted(axes))
+        c = np.moveaxis(c, src, tuple(range(-len(src), 0)))
+        return c.reshape((n_slices,) + c.shape[len(c.shape) - len(src):])
+
+    if ndim_resample == 1:
+        x_in, x_out = stacked(coords_in[0], axis_in), stacked(coords_out[0], axis_out)
+        w = None if weights_input is None else stacked(weights_input, axis_in)
+        elements = _conservative_1d(x_in, x_out, w, device)
+    elif ndim_resample == 2:
+        xi, yi = (stacked(c, axis_in) for c in coords_in)
+        xo, yo = (stacked(c, axis_out) for c in coords_out)
+        elements = []
+        for k, index in enumerate(np.ndindex(*shape_orth)):
+            w = None
+            if weights_input is not None:
+                w = weights_input[index]  # wcons.py:125-126: orthogonal axes are assumed to lead
+            elements.append(_device.build_weights_2d(xi[k], yi[k], xo[k], yo[k], w, device=device))
+    else:
+        raise NotImplementedError("Regridding operations greater than 2D are not supported")  # wcons.py:141-144
+    return elements, shape_cells_in, shape_cells_out, tuple(shape_orth)
+
+
+def _conservative_1d(x_in: np.ndarray, x_out: np.ndarray, w, device) -> list[_device.DeviceWeights]:
+    """1D conservative weights of S stacked spectra in the public layout (wcons.py:59-106 +
+    warr.py:44-73).  The walk emits one triplet per overlap; for ascending grids that is
+    already the (input, output)-sorted order, for descending ones the (negative,
+    complemented) indices are re-sorted per spectrum on the device."""
+    S, n = x_in.shape
+    m = x_out.shape[1]
+    xi = _device.to_device(x_in, device)
+    xo = _device.to_device(x_out, device)
+    wd = None if w is None else _device.to_device(w, device)
+    ii, io, v, counts = _device.cons1d_batched(xi, xo, wd)
+    counts_h = counts.cpu().numpy()
+    descending = bool(((xi[:, 0] >= xi[:, -1]) | (xo[:, 0] >= xo[:, -1])).any().item())
+    elements = []
+    for s in range(S):
+        c = int(counts_h[s])
+        a, b, val = ii[s, :c], io[s, :c], v[s, :c]
+        if descending and c > 1:
+            # _coalesce (warr.py:54-59): stable sort on (input - min) * span + (output - min)
+            key = (a - a.min()) * (b.max() - b.min() + 1) + (b - b.min())
+            order = torch.sort(key, stable=True).indices
+            a, b, val = a[order], b[order], val[order]
+        # the saved layout keeps the reference's (possibly negative) indices; the device copy used
+        # by the apply is wrapped to [0, n) like Numba's negative indexing does (rfw.py:179-182)
+        dw = _device.DeviceWeights(a.contiguous(), b.contiguous(), val.contiguous(), n - 1, m - 1)
+        elements.append(dw)
+    return elements

@@ -1,0 +1,239 @@
+// rg_boundary.cuh -- boundary of a static grid: edges in the reference's scan order, two
+// levels of bounding boxes over them, the entry query of _step_outside_static and the
+// exact boundary winding number.  Shared by the 2D build and the 2D cell location.
+#pragma once
+#include "rg_common.cuh"
+#include "rg_geom.cuh"
+
+namespace rg {
+
+struct BBox { double xlo, ylo, xhi, yhi; };
+
+struct Boundary {
+    int n_edges, n_g1, n_g2;
+    int ne_a0;  // ny-1 edges on each axis-0 face (i = 0, i = nx-1)
+    int ne_a1;  // nx-1 edges on each axis-1 face (j = 0, j = ny-1)
+    double *x3, *y3, *x4, *y4;  // endpoints in the reference's scan order (c2d.py:462-483)
+    int32_t* cell;              // flat index of the cell entered through the edge (c2d.py:499-515)
+    BBox* bb1;                  // bbox of 32 consecutive edges
+    BBox* bb2;                  // bbox of 32 consecutive groups
+};
+
+// ---------------------------------------------------------------------------
+// bounding box of a grid (x.min(), y.min(), x.max(), y.max(); c2d.py:179-180)
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ void atomic_min_double(double* addr, double v)
+{
+    unsigned long long* a = (unsigned long long*)addr;
+    unsigned long long old = *a, assumed;
+    do {
+        assumed = old;
+        if (!(v < __longlong_as_double((long long)assumed))) break;
+        old = atomicCAS(a, assumed, (unsigned long long)__double_as_longlong(v));
+    } while (assumed != old);
+}
+__device__ __forceinline__ void atomic_max_double(double* addr, double v)
+{
+    unsigned long long* a = (unsigned long long*)addr;
+    unsigned long long old = *a, assumed;
+    do {
+        assumed = old;
+        if (!(v > __longlong_as_double((long long)assumed))) break;
+        old = atomicCAS(a, assumed, (unsigned long long)__double_as_longlong(v));
+    } while (assumed != old);
+}
+
+static __global__ void k_bbox_init(double* bbox)
+{
+    if (threadIdx.x < 4) bbox[threadIdx.x] = (threadIdx.x < 2) ? INFINITY : -INFINITY;
+}
+
+static __global__ void k_bbox(GridView g, double* __restrict__ bbox /* xlo, ylo, xhi, yhi */)
+{
+    const int64_t n = (int64_t)g.nx * g.ny;
+    double xlo = INFINITY, ylo = INFINITY, xhi = -INFINITY, yhi = -INFINITY;
+    for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < n; q += (int64_t)gridDim.x * blockDim.x) {
+        const double x = g.x[q], y = g.y[q];
+        xlo = fmin(xlo, x); xhi = fmax(xhi, x);
+        ylo = fmin(ylo, y); yhi = fmax(yhi, y);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        xlo = fmin(xlo, __shfl_xor_sync(0xffffffffu, xlo, o));
+        ylo = fmin(ylo, __shfl_xor_sync(0xffffffffu, ylo, o));
+        xhi = fmax(xhi, __shfl_xor_sync(0xffffffffu, xhi, o));
+        yhi = fmax(yhi, __shfl_xor_sync(0xffffffffu, yhi, o));
+    }
+    if ((threadIdx.x & 31) == 0) {
+        atomic_min_double(&bbox[0], xlo);
+        atomic_min_double(&bbox[1], ylo);
+        atomic_max_double(&bbox[2], xhi);
+        atomic_max_double(&bbox[3], yhi);
+    }
+}
+
+// ---------------------------------------------------------------------------
+// K2: boundary edges in the scan order of _step_outside_static (c2d.py:462-483):
+//   axis 0: faces i = 0 then i = nx-1, edge m joins (i_face, m)-(i_face, m+1), enters cell (0 | ncx-1, m)
+//   axis 1: faces j = 0 then j = ny-1, edge m joins (m, j_face)-(m+1, j_face), enters cell (m, 0 | ncy-1)
+// ---------------------------------------------------------------------------
+static __global__ void k_boundary_edges(GridView g, Boundary b)
+{
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= b.n_edges) return;
+    const int ncx = g.nx - 1, ncy = g.ny - 1;
+    int axis, face, m;
+    if (s < 2 * b.ne_a0) {
+        axis = 0; face = s >= b.ne_a0; m = s - face * b.ne_a0;
+    } else {
+        const int r = s - 2 * b.ne_a0;
+        axis = 1; face = r >= b.ne_a1; m = r - face * b.ne_a1;
+    }
+    int64_t v3, v4;
+    int ci, cj;
+    if (axis == 0) {
+        const int i = face ? g.nx - 1 : 0;
+        v3 = (int64_t)i * g.ny + m;
+        v4 = v3 + 1;
+        ci = face ? ncx - 1 : 0;
+        cj = m;
+    } else {
+        const int j = face ? g.ny - 1 : 0;
+        v3 = (int64_t)m * g.ny + j;
+        v4 = v3 + g.ny;
+        ci = m;
+        cj = face ? ncy - 1 : 0;
+    }
+    b.x3[s] = g.x[v3]; b.y3[s] = g.y[v3];
+    b.x4[s] = g.x[v4]; b.y4[s] = g.y[v4];
+    b.cell[s] = ci * ncy + cj;
+}
+
+static __global__ void k_boundary_bb1(Boundary b)
+{
+    const int gi = blockIdx.x * blockDim.x + threadIdx.x;
+    if (gi >= b.n_g1) return;
+    BBox r = { INFINITY, INFINITY, -INFINITY, -INFINITY };
+    const int e1 = min(b.n_edges, (gi + 1) * 32);
+    for (int s = gi * 32; s < e1; s++) {
+        r.xlo = fmin(r.xlo, fmin(b.x3[s], b.x4[s])); r.xhi = fmax(r.xhi, fmax(b.x3[s], b.x4[s]));
+        r.ylo = fmin(r.ylo, fmin(b.y3[s], b.y4[s])); r.yhi = fmax(r.yhi, fmax(b.y3[s], b.y4[s]));
+    }
+    b.bb1[gi] = r;
+}
+
+static __global__ void k_boundary_bb2(Boundary b)
+{
+    const int gi = blockIdx.x * blockDim.x + threadIdx.x;
+    if (gi >= b.n_g2) return;
+    BBox r = { INFINITY, INFINITY, -INFINITY, -INFINITY };
+    const int e1 = min(b.n_g1, (gi + 1) * 32);
+    for (int s = gi * 32; s < e1; s++) {
+        const BBox q = b.bb1[s];
+        r.xlo = fmin(r.xlo, q.xlo); r.xhi = fmax(r.xhi, q.xhi);
+        r.ylo = fmin(r.ylo, q.ylo); r.yhi = fmax(r.yhi, q.yhi);
+    }
+    b.bb2[gi] = r;
+}
+
+__device__ __forceinline__ int edge_local_id(const Boundary& b, int s)
+{
+    // index_flat((face, axis), (2, 2)) = face*2 + axis  (c2d.py:532-535)
+    if (s < b.ne_a0) return 0;
+    if (s < 2 * b.ne_a0) return 2;
+    if (s < 2 * b.ne_a0 + b.ne_a1) return 1;
+    return 3;
+}
+
+// _step_outside_static (c2d.py:401-552): among ALL boundary edges hit by p->q keep the
+// smallest t (strict <: ties keep the first in scan order), skipping the cell just left.
+// The two bbox levels only skip edges whose own bbox test (geometry.py:422-433) fails.
+__device__ inline int boundary_entry(const Boundary& b, double px, double py, double qx, double qy,
+                                     int last_cell, double& t_best)
+{
+    const double sxlo = fmin(px, qx), sxhi = fmax(px, qx);
+    const double sylo = fmin(py, qy), syhi = fmax(py, qy);
+    int best = -1;
+    t_best = INFINITY;
+    for (int g2 = 0; g2 < b.n_g2; g2++) {
+        const BBox B2 = b.bb2[g2];
+        if (!(sxlo <= B2.xhi && B2.xlo <= sxhi && sylo <= B2.yhi && B2.ylo <= syhi)) continue;
+        const int g1e = min(b.n_g1, (g2 + 1) * 32);
+        for (int g1 = g2 * 32; g1 < g1e; g1++) {
+            const BBox B1 = b.bb1[g1];
+            if (!(sxlo <= B1.xhi && B1.xlo <= sxhi && sylo <= B1.yhi && B1.ylo <= syhi)) continue;
+            const int se = min(b.n_edges, (g1 + 1) * 32);
+            for (int s = g1 * 32; s < se; s++) {
+                double t;
+                if (!seg_hit(px, py, qx, qy, b.x3[s], b.y3[s], b.x4[s], b.y4[s], t)) continue;
+                if (!(t < t_best)) continue;
+                if (b.cell[s] == last_cell) continue;
+                t_best = t;
+                best = s;
+            }
+        }
+    }
+    return best;
+}
+
+
+// Extended winding number of the boundary polygon (grid_boundary, _grids.py:167-215, under
+// point_is_inside_polygon, geometry.py:737-829) around (px, py), evaluated only on the
+// edges whose y-range contains py: every other edge contributes exactly 0, and the
+// contributions are multiples of 1/2, so the sum is exact in any order.
+__device__ inline double boundary_winding(const Boundary& b, double px, double py)
+{
+    double w = 0.0;
+    for (int g2 = 0; g2 < b.n_g2; g2++) {
+        const BBox B2 = b.bb2[g2];
+        if (!(B2.ylo <= py && py <= B2.yhi)) continue;
+        const int g1e = min(b.n_g1, (g2 + 1) * 32);
+        for (int g1 = g2 * 32; g1 < g1e; g1++) {
+            const BBox B1 = b.bb1[g1];
+            if (!(B1.ylo <= py && py <= B1.yhi)) continue;
+            const int se = min(b.n_edges, (g1 + 1) * 32);
+            for (int s = g1 * 32; s < se; s++) {
+                const double x0 = dsub(b.x3[s], px), y0 = dsub(b.y3[s], py);
+                const double x1 = dsub(b.x4[s], px), y1 = dsub(b.y4[s], py);
+                // the polygon runs counter-clockwise in index space; the scan-order edges of the
+                // i = 0 face and of the j = ny-1 face run the other way round
+                const bool reversed = (s < b.ne_a0) || (s >= 2 * b.ne_a0 + b.ne_a1);
+                w += reversed ? winding_edge(x1, y1, x0, y0) : winding_edge(x0, y0, x1, y1);
+            }
+        }
+    }
+    return w;
+}
+
+static void carve_boundary(Carver& c, Boundary& b, int64_t nx, int64_t ny)
+{
+    b.ne_a0 = (int)(ny - 1);
+    b.ne_a1 = (int)(nx - 1);
+    b.n_edges = 2 * b.ne_a0 + 2 * b.ne_a1;
+    b.n_g1 = (int)ceil_div(b.n_edges, 32);
+    b.n_g2 = (int)ceil_div(b.n_g1, 32);
+    b.x3 = c.take<double>(b.n_edges);
+    b.y3 = c.take<double>(b.n_edges);
+    b.x4 = c.take<double>(b.n_edges);
+    b.y4 = c.take<double>(b.n_edges);
+    b.cell = c.take<int32_t>(b.n_edges);
+    b.bb1 = c.take<BBox>(b.n_g1);
+    b.bb2 = c.take<BBox>(b.n_g2);
+}
+
+
+// builds the boundary structure and the bbox (xlo, ylo, xhi, yhi) of a grid
+static inline int build_boundary(cudaStream_t st, const GridView& g, const Boundary& b, double* bbox)
+{
+    const int T = 256;
+    k_bbox_init<<<1, 32, 0, st>>>(bbox);
+    k_bbox<<<kNumSM * 2, T, 0, st>>>(g, bbox);
+    RG_LAUNCH_CHECK("k_bbox");
+    k_boundary_edges<<<(unsigned)ceil_div(b.n_edges, T), T, 0, st>>>(g, b);
+    k_boundary_bb1<<<(unsigned)ceil_div(b.n_g1, T), T, 0, st>>>(b);
+    k_boundary_bb2<<<(unsigned)ceil_div(b.n_g2, T), T, 0, st>>>(b);
+    RG_LAUNCH_CHECK("k_boundary");
+    return RG_OK;
+}
+
+}  // namespace rg

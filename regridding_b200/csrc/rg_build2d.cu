@@ -1,0 +1,723 @@
+// rg_build2d.cu -- 2D first-order conservative weights build (Ramshaw 1985 edge sweep).
+//
+// Replaces weights_conservative_2d + _coalesce of the reference
+// (regridding/_weights/_weights_conservative_2d/_weights_conservative_2d.py:80-830,
+//  regridding/_weights/_weights_arrays.py:44-73).
+//
+// The reference walks every sweep line sequentially.  At every sweep VERTEX its state
+// collapses to (inside?, static cell) and the next segment restarts from the exact
+// vertex coordinates (c2d.py:326-327, 386-387), so segments are independent given the
+// state at their first vertex.  This file therefore runs ONE THREAD PER SEGMENT:
+//
+//   K1 k_cell_area        signed input-cell areas (grid_volume, _grids.py:50-140)
+//   K2 k_boundary_*       boundary edges of each static grid in the reference's scan
+//                         order + two levels of bounding boxes (exactly conservative
+//                         w.r.t. the reference's own per-edge bbox pre-check)
+//   K2 k_line_starts      exact start state of every sweep line (bbox test, winding
+//                         number over the whole boundary, cell location; c2d.py:308-322)
+//   K2 k_vertex_guess     Newton cell location of every other sweep vertex: a GUESS of
+//                         the walk state there
+//   K3 k_walk<Count>      walks each segment from its guessed start, records the end
+//                         state and histograms the fragments per input cell
+//   K3 k_repair           warp per line: wherever a segment's end state differs from the
+//                         start state its successor used, the successor is re-walked
+//                         from the true state (sequential propagation), so the chain of
+//                         states is EXACTLY the reference's sequential walk
+//   K3 k_walk<Emit>       re-walks with the verified starts and scatters
+//                         (output cell, emission rank, weight) into per-input-cell buckets
+//   K4 k_bucket_sort      sorts each bucket by (output cell, emission rank): the order the
+//                         reference's stable argsort produces; no atomic decides any order
+//   K4 k_bucket_emit      merges equal pairs in NumPy's reduceat association and writes the
+//                         public (input, output)-sorted arrays
+#include "rg_common.cuh"
+#include "rg_geom.cuh"
+#include "rg_boundary.cuh"
+
+namespace rg {
+
+// ---------------------------------------------------------------------------
+// data structures
+// ---------------------------------------------------------------------------
+
+struct PassParams {
+    GridView sweep, stat;
+    Boundary bnd;  // of the static grid
+    int pass;      // 0..3 = (sweep OUTPUT axis 0, axis 1, sweep INPUT axis 0, axis 1), c2d.py:116,184
+    int axis;
+    int sweep_input;
+    int nlines, nseg;
+    int ncy_in, ncy_out;
+    int ncx_st, ncy_st;
+    const int32_t* guess;       // [sweep vertices] guessed state at each sweep vertex
+    const int32_t* line_start;  // [nlines] exact state at the first vertex of each line
+    int32_t* seg_start;         // [sweep vertices] state each segment starts from
+    int32_t* seg_end;           // [sweep vertices] state each segment ends in
+    int max_iter;
+    int64_t cell_lo, cell_hi;   // input-cell band
+};
+
+constexpr int kStateOutside = -1;
+constexpr int kStateUnknown = -2;
+constexpr int kStateInvalid = -3;
+
+// flags[] slots
+constexpr int kFlagOverflow = 0;   // a verified walk exceeded max_iter
+constexpr int kFlagRepairs = 1;    // number of re-walked segments
+constexpr int kFlagUnknown = 2;    // number of vertices whose guess was "unknown"
+constexpr int kFlagSeqOverflow = 3;  // piece index overflowed the 29-bit rank field
+
+__device__ __forceinline__ int64_t vertex_of(const PassParams& P, int L, int k)
+{
+    return P.axis ? (int64_t)L * P.sweep.ny + k : (int64_t)k * P.sweep.ny + L;
+}
+__device__ __forceinline__ int64_t vertex_step(const PassParams& P) { return P.axis ? 1 : P.sweep.ny; }
+
+// ---------------------------------------------------------------------------
+// K1: cell areas.  grid_volume accumulates, per cell (a, b), first the axis-0 pass
+// then the axis-1 pass, each as "-= area(edge a); += area(edge a+1)":
+//     (((0 - A_a) + A_a+1) - B_b) + B_b+1                      (_grids.py:68-73, 134-140)
+// area = 0.5 * fma(x1, y2, -RN(x2*y1)); the JIT peels the first loop iteration (edge
+// index 0) and there fuses the other product: 0.5 * fma(-x2, y1, RN(x1*y2)).
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ double tri_area(double x1, double y1, double x2, double y2, bool first)
+{
+    if (first) return dmul(0.5, dfma(-x2, y1, dmul(x1, y2)));
+    return dmul(0.5, dfma(x1, y2, -dmul(x2, y1)));
+}
+
+__global__ void k_cell_area(GridView g, double* __restrict__ area)
+{
+    const int ncx = g.nx - 1, ncy = g.ny - 1;
+    const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= (int64_t)ncx * ncy) return;
+    const int a = (int)(c / ncy), b = (int)(c % ncy);
+    const int64_t v = (int64_t)a * g.ny + b;
+    const double x00 = g.x[v], y00 = g.y[v];
+    const double x01 = g.x[v + 1], y01 = g.y[v + 1];
+    const double x10 = g.x[v + g.ny], y10 = g.y[v + g.ny];
+    const double x11 = g.x[v + g.ny + 1], y11 = g.y[v + g.ny + 1];
+    // axis 0: transposed view with x and y swapped; lines i' = b, b+1 ; edge from (a, i') to (a+1, i')
+    const double A0 = tri_area(y00, x00, y10, x10, b == 0);
+    const double A1 = tri_area(y01, x01, y11, x11, false);
+    // axis 1: lines i = a, a+1 ; edge from (i, b) to (i, b+1)
+    const double B0 = tri_area(x00, y00, x01, y01, a == 0);
+    const double B1 = tri_area(x10, y10, x11, y11, false);
+    double r = dsub(0.0, A0);
+    r = dadd(r, A1);
+    r = dsub(r, B0);
+    r = dadd(r, B1);
+    area[c] = r;
+}
+
+// ---------------------------------------------------------------------------
+// the segment walk: state machine of c2d.py:324-387 restricted to one segment
+// ---------------------------------------------------------------------------
+template <class Sink>
+__device__ inline int walk_segment(const PassParams& P, double x1, double y1, double xv, double yv,
+                                   int state, Sink& sink, bool& overflow)
+{
+    const GridView& g = P.stat;
+    int last_edge = -1;   // local edge id just crossed (inside state)
+    int last_cell = -2;   // flat id of the cell just left (outside state)
+    int piece = 0;
+    for (int it = 0; it < P.max_iter; it++) {
+        if (state < 0) {
+            double t;
+            const int s = boundary_entry(P.bnd, x1, y1, xv, yv, last_cell, t);
+            if (s < 0) return kStateOutside;  // c2d.py:539-540: advance to the next sweep vertex
+            seg_point(x1, y1, xv, yv, t, x1, y1);  // c2d.py:526-530, then x1 = x2 at :386
+            state = P.bnd.cell[s];
+            last_edge = edge_local_id(P.bnd, s);
+            last_cell = -2;
+            continue;
+        }
+        // _step_inside_static, c2d.py:561-749
+        const int ci = state / P.ncy_st, cj = state - ci * P.ncy_st;
+        const int64_t a = (int64_t)ci * g.ny + cj;
+        // cell vertices in the order of indices_cell_vertex (_grids.py:153-158)
+        double vx[4], vy[4];
+        vx[0] = g.x[a];            vy[0] = g.y[a];
+        vx[1] = g.x[a + g.ny];     vy[1] = g.y[a + g.ny];
+        vx[2] = g.x[a + g.ny + 1]; vy[2] = g.y[a + g.ny + 1];
+        vx[3] = g.x[a + 1];        vy[3] = g.y[a + 1];
+        int hit_v = -1;
+        double t = 0.0;
+#pragma unroll
+        for (int v = 0; v < 4; v++) {
+            if (hit_v >= 0 || v == last_edge) continue;
+            const int pv = (v + 3) & 3;
+            double tv;
+            if (seg_hit(x1, y1, xv, yv, vx[pv], vy[pv], vx[v], vy[v], tv)) {
+                hit_v = v;
+                t = tv;
+            }
+        }
+        double x2 = xv, y2 = yv;
+        if (hit_v >= 0) seg_point(x1, y1, xv, yv, t, x2, y2);
+        sink.piece(P, x1, y1, x2, y2, ci, cj, piece);  // always (c2d.py:712-725)
+        piece++;
+        if (hit_v < 0) return state;  // reached the sweep vertex inside `state`
+        // cell_normals (_grids.py:143-148)
+        const int ni = ci + (hit_v == 2) - (hit_v == 0);
+        const int nj = cj + (hit_v == 3) - (hit_v == 1);
+        if (ni < 0 || nj < 0 || ni >= P.ncx_st || nj >= P.ncy_st) {
+            last_cell = state;  // c2d.py:727-737
+            state = kStateOutside;
+            last_edge = -1;
+        } else {
+            state = ni * P.ncy_st + nj;
+            last_edge = (hit_v + 2) & 3;
+        }
+        x1 = x2;
+        y1 = y2;
+    }
+    overflow = true;
+    return kStateInvalid;
+}
+
+// _calc_and_save_weights + _index_input_output (c2d.py:757-830, 876-912): which
+// (input cell, output cell) pairs a piece on sweep line L, segment k feeds.
+struct PieceCells {
+    int n;             // number of valid sides
+    int64_t in[2], out[2];
+    int side[2];       // 0 = left (L-1), 1 = right (L)
+};
+
+__device__ __forceinline__ PieceCells piece_cells(const PassParams& P, int L, int k, int ci, int cj)
+{
+    PieceCells r;
+    r.n = 0;
+#pragma unroll
+    for (int side = 0; side < 2; side++) {
+        const int i = side ? L : L - 1;
+        if (side == 0 ? (i < 0) : (i >= P.nlines - 1)) continue;
+        const int si = P.axis ? i : k, sj = P.axis ? k : i;  // axis 0: (line, segment) -> (segment, line)
+        int64_t fin, fout;
+        if (P.sweep_input) { fin = (int64_t)si * P.ncy_in + sj; fout = (int64_t)ci * P.ncy_out + cj; }
+        else               { fin = (int64_t)ci * P.ncy_in + cj; fout = (int64_t)si * P.ncy_out + sj; }
+        if (fin < P.cell_lo || fin >= P.cell_hi) continue;
+        r.in[r.n] = fin; r.out[r.n] = fout; r.side[r.n] = side;
+        r.n++;
+    }
+    return r;
+}
+
+struct CountSink {
+    int32_t* hist;
+    int L, k, delta;
+    __device__ __forceinline__ void piece(const PassParams& P, double, double, double, double, int ci, int cj, int)
+    {
+        const PieceCells pc = piece_cells(P, L, k, ci, cj);
+        for (int q = 0; q < pc.n; q++) atomicAdd(&hist[pc.in[q]], delta);
+    }
+};
+
+struct EmitSink {
+    const int64_t* boff;
+    int32_t* cursor;
+    uint64_t* fkey;
+    double* fval;
+    const double* area_in;
+    const double* w_in;
+    int32_t* flags;
+    int L, k;
+    __device__ __forceinline__ void piece(const PassParams& P, double x1, double y1, double x2, double y2,
+                                          int ci, int cj, int piece_idx)
+    {
+        const PieceCells pc = piece_cells(P, L, k, ci, cj);
+        if (pc.n == 0) return;
+        // area_triangle (geometry.py:993) with the axis sign (c2d.py:783-784); the JIT evaluates the
+        // negated form RN(x2*y1) - x1*y2 (fused) times +-0.5.
+        const double neg2 = dfma(-x1, y2, dmul(x2, y1));
+        const double area = dmul(neg2, P.axis == 0 ? 0.5 : -0.5);
+        if (piece_idx >= (1 << 29)) atomicOr(&flags[kFlagSeqOverflow], 1);
+        for (int q = 0; q < pc.n; q++) {
+            const double a = pc.side[q] ? -area : area;
+            double w;
+            if (w_in) w = ddiv(dmul(a, w_in[pc.in[q]]), area_in[pc.in[q]]);  // fastmath reassociation seen in the JIT
+            else w = ddiv(a, area_in[pc.in[q]]);
+            // emission rank inside one (input, output) pair: pass, then line (the cell right of line L
+            // comes before the cell left of line L+1), then piece order inside the segment.
+            const uint32_t seq = ((uint32_t)P.pass << 30) | (pc.side[q] == 0 ? (1u << 29) : 0u) | (uint32_t)piece_idx;
+            const int64_t slot = boff[pc.in[q]] + atomicAdd(&cursor[pc.in[q]], 1);
+            fkey[slot] = ((uint64_t)pc.out[q] << 32) | seq;
+            fval[slot] = w;
+        }
+    }
+};
+
+// ---------------------------------------------------------------------------
+// K2: exact line-start states (c2d.py:293-322).  One warp per line.
+// ---------------------------------------------------------------------------
+__global__ void k_line_starts(PassParams P, const double* __restrict__ bbox_static, int32_t* __restrict__ out)
+{
+    const int lane = threadIdx.x & 31;
+    const int L = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+    if (L >= P.nlines) return;
+    const int64_t v0 = vertex_of(P, L, 0);
+    const double px = P.sweep.x[v0], py = P.sweep.y[v0];
+    // point_is_inside_box_2d (geometry.py:64-105)
+    const bool in_box = bbox_static[0] <= px && px <= bbox_static[2] && bbox_static[1] <= py && py <= bbox_static[3];
+    int state = kStateOutside;
+    if (in_box) {
+        // point_is_inside_polygon over grid_boundary (_grids.py:167-215): counter-clockwise in index space;
+        // the scan-order edges of the i = 0 face and of the j = ny-1 face run the other way round.
+        const Boundary& b = P.bnd;
+        double w = 0.0;
+        for (int s = lane; s < b.n_edges; s += 32) {
+            double x0 = dsub(b.x3[s], px), y0 = dsub(b.y3[s], py);
+            double x1 = dsub(b.x4[s], px), y1 = dsub(b.y4[s], py);
+            const bool reversed = (s < b.ne_a0) || (s >= 2 * b.ne_a0 + b.ne_a1);
+            w += reversed ? winding_edge(x1, y1, x0, y0) : winding_edge(x0, y0, x1, y1);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) w += __shfl_xor_sync(0xffffffffu, w, o);  // halves: exact in any order
+        if (w != 0.0) {
+            int found = kLocUnknown;
+            if (lane == 0) found = locate_newton(P.stat, px, py, 0.5 * P.stat.nx, 0.5 * P.stat.ny);
+            found = __shfl_sync(0xffffffffu, found, 0);
+            if (found < 0) {
+                // index_of_point_brute (_grids.py:223-279): lowest row-major containing cell
+                const int64_t nc = (int64_t)P.ncx_st * P.ncy_st;
+                int64_t best = INT64_MAX;
+                for (int64_t base = 0; base < nc && best == INT64_MAX; base += 32) {
+                    const int64_t c = base + lane;
+                    bool hit = false;
+                    if (c < nc) hit = cell_contains(P.stat, (int)(c / P.ncy_st), (int)(c % P.ncy_st), px, py);
+                    const unsigned m = __ballot_sync(0xffffffffu, hit);
+                    if (m) best = base + (__ffs(m) - 1);
+                }
+                found = best == INT64_MAX ? kStateOutside : (int)best;
+            }
+            state = found;
+        }
+    }
+    if (lane == 0) out[L] = state;
+}
+
+// K2: guessed state of every sweep vertex
+__global__ void k_vertex_guess(GridView sweep, GridView stat, int32_t* __restrict__ guess, int32_t* flags)
+{
+    const int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= (int64_t)sweep.nx * sweep.ny) return;
+    const int r = locate_newton(stat, sweep.x[v], sweep.y[v], 0.5 * stat.nx, 0.5 * stat.ny);
+    guess[v] = r;
+    if (r == kLocUnknown) atomicAdd(&flags[kFlagUnknown], 1);
+}
+
+// ---------------------------------------------------------------------------
+// K3: walks
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ void segment_of_thread(const PassParams& P, int64_t tid, int& L, int& k)
+{
+    // consecutive lanes take consecutive memory: along the line for axis 1, across lines for axis 0
+    if (P.axis) { L = (int)(tid / P.nseg); k = (int)(tid % P.nseg); }
+    else        { k = (int)(tid / P.nlines); L = (int)(tid % P.nlines); }
+}
+
+__global__ void __launch_bounds__(128) k_walk_count(PassParams P, int32_t* __restrict__ hist)
+{
+    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (tid >= (int64_t)P.nlines * P.nseg) return;
+    int L, k;
+    segment_of_thread(P, tid, L, k);
+    const int64_t v = vertex_of(P, L, k), v2 = v + vertex_step(P);
+    const int start = (k == 0) ? P.line_start[L] : P.guess[v];
+    P.seg_start[v] = start;
+    if (start == kStateUnknown) {
+        P.seg_end[v] = kStateInvalid;
+        return;
+    }
+    CountSink sink{ hist, L, k, 1 };
+    bool overflow = false;
+    P.seg_end[v] = walk_segment(P, P.sweep.x[v], P.sweep.y[v], P.sweep.x[v2], P.sweep.y[v2], start, sink, overflow);
+}
+
+// One warp per line: make the chain of states equal to the sequential walk.
+__global__ void k_repair(PassParams P, int32_t* __restrict__ hist, int32_t* __restrict__ flags)
+{
+    const int lane = threadIdx.x & 31;
+    const int L = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+    if (L >= P.nlines) return;
+    const int64_t step = vertex_step(P);
+    for (int base = 1; base < P.nseg; base += 32) {
+        const int k = base + lane;
+        const int64_t v = vertex_of(P, L, min(k, P.nseg - 1));
+        while (true) {
+            bool bad = false;
+            if (k < P.nseg) bad = ((volatile int32_t*)P.seg_end)[v - step] != ((volatile int32_t*)P.seg_start)[v];
+            const unsigned m = __ballot_sync(0xffffffffu, bad);
+            if (!m) break;
+            if (lane == __ffs(m) - 1) {
+                const int old_start = P.seg_start[v];
+                const int new_start = P.seg_end[v - step];
+                const int64_t v2 = v + step;
+                const double x1 = P.sweep.x[v], y1 = P.sweep.y[v], x2 = P.sweep.x[v2], y2 = P.sweep.y[v2];
+                bool overflow = false;
+                if (old_start != kStateUnknown) {
+                    CountSink undo{ hist, L, k, -1 };
+                    walk_segment(P, x1, y1, x2, y2, old_start, undo, overflow);
+                }
+                CountSink redo{ hist, L, k, 1 };
+                const int e = walk_segment(P, x1, y1, x2, y2, new_start, redo, overflow);
+                P.seg_start[v] = new_start;
+                P.seg_end[v] = e;
+                atomicAdd(&flags[kFlagRepairs], 1);
+                __threadfence();
+            }
+            __syncwarp();
+        }
+        __syncwarp();
+    }
+}
+
+__global__ void __launch_bounds__(128)
+k_walk_emit(PassParams P, const int64_t* __restrict__ boff, int32_t* __restrict__ cursor,
+            uint64_t* __restrict__ fkey, double* __restrict__ fval,
+            const double* __restrict__ area_in, const double* __restrict__ w_in, int32_t* __restrict__ flags)
+{
+    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (tid >= (int64_t)P.nlines * P.nseg) return;
+    int L, k;
+    segment_of_thread(P, tid, L, k);
+    const int64_t v = vertex_of(P, L, k), v2 = v + vertex_step(P);
+    EmitSink sink{ boff, cursor, fkey, fval, area_in, w_in, flags, L, k };
+    bool overflow = false;
+    walk_segment(P, P.sweep.x[v], P.sweep.y[v], P.sweep.x[v2], P.sweep.y[v2], P.seg_start[v], sink, overflow);
+    if (overflow) atomicOr(&flags[kFlagOverflow], 1);
+}
+
+// ---------------------------------------------------------------------------
+// K4: per-input-cell buckets -> public layout
+// ---------------------------------------------------------------------------
+
+// Sort each bucket by key = (output cell << 32 | emission rank).  One lane per bucket
+// (insertion sort; buckets hold ~14 fragments), whole warp (odd-even transposition)
+// for buckets longer than 64.  Also counts the distinct output cells of the bucket.
+__global__ void k_bucket_sort(const int64_t* __restrict__ boff, int64_t n_cells,
+                              uint64_t* __restrict__ fkey, double* __restrict__ fval,
+                              int32_t* __restrict__ nuniq)
+{
+    const int lane = threadIdx.x & 31;
+    const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int64_t beg = 0, end = 0;
+    if (c < n_cells) {
+        beg = boff[c];
+        end = boff[c + 1];
+    }
+    const int64_t len = end - beg;
+    if (len <= 64) {
+        for (int64_t e = beg + 1; e < end; e++) {
+            const uint64_t key = fkey[e];
+            const double val = fval[e];
+            int64_t f = e - 1;
+            while (f >= beg && fkey[f] > key) {
+                fkey[f + 1] = fkey[f];
+                fval[f + 1] = fval[f];
+                f--;
+            }
+            fkey[f + 1] = key;
+            fval[f + 1] = val;
+        }
+    }
+    unsigned longmask = __ballot_sync(0xffffffffu, len > 64);
+    while (longmask) {
+        const int src = __ffs(longmask) - 1;
+        longmask &= longmask - 1;
+        const int64_t b = __shfl_sync(0xffffffffu, beg, src);
+        const int64_t n = __shfl_sync(0xffffffffu, end, src) - b;
+        for (int64_t phase = 0; phase < n; phase++) {
+            for (int64_t p = (phase & 1) + 2 * lane; p + 1 < n; p += 64) {
+                const uint64_t k0 = fkey[b + p], k1 = fkey[b + p + 1];
+                if (k0 > k1) {
+                    fkey[b + p] = k1; fkey[b + p + 1] = k0;
+                    const double t0 = fval[b + p];
+                    fval[b + p] = fval[b + p + 1]; fval[b + p + 1] = t0;
+                }
+            }
+            __syncwarp();
+        }
+    }
+    __syncwarp();
+    if (c < n_cells) {
+        int32_t u = 0;
+        uint32_t prev = 0xffffffffu;
+        for (int64_t e = beg; e < end; e++) {
+            const uint32_t o = (uint32_t)(fkey[e] >> 32);
+            u += (e == beg) || (o != prev);
+            prev = o;
+        }
+        nuniq[c] = u;
+    }
+}
+
+// Merge the runs of equal (input, output) pair: np.add.reduceat association over the
+// emission order (warr.py:59-72) and write the public arrays.
+__global__ void k_bucket_emit(const int64_t* __restrict__ boff, const int64_t* __restrict__ colptr, int64_t n_cells,
+                              const uint64_t* __restrict__ fkey, const double* __restrict__ fval,
+                              int64_t* __restrict__ ii, int64_t* __restrict__ io, double* __restrict__ vv)
+{
+    const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= n_cells) return;
+    const int64_t beg = boff[c], end = boff[c + 1];
+    int64_t w = colptr[c];
+    int64_t s = beg;
+    while (s < end) {
+        const uint32_t o = (uint32_t)(fkey[s] >> 32);
+        int64_t e = s + 1;
+        while (e < end && (uint32_t)(fkey[e] >> 32) == o) e++;
+        ii[w] = c;
+        io[w] = (int64_t)o;
+        vv[w] = np_reduceat_segment(fval + s, e - s);
+        w++;
+        s = e;
+    }
+}
+
+// ---------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------
+struct Layout {
+    // sizes
+    int64_t nxi, nyi, nxo, nyo, Vi, Vo, Ci, Co;
+    // carved pointers
+    double* area_in;
+    double* bbox;  // [2][4]: input grid, output grid
+    Boundary bnd[2];
+    int32_t* guess[2];       // [0]: output vertices located in the input grid, [1]: input vertices in the output grid
+    int32_t* line_start[4];
+    int32_t* seg_start[4];
+    int32_t* seg_end[4];
+    int32_t* hist;
+    int64_t* boff;
+    int32_t* cursor;
+    int32_t* nuniq;
+    int64_t* colptr;
+    int64_t* scan_scratch;
+    int32_t* flags;
+    size_t bytes;
+};
+
+static Layout make_layout(void* ws, int64_t nxi, int64_t nyi, int64_t nxo, int64_t nyo)
+{
+    Layout l;
+    l.nxi = nxi; l.nyi = nyi; l.nxo = nxo; l.nyo = nyo;
+    l.Vi = nxi * nyi; l.Vo = nxo * nyo;
+    l.Ci = (nxi - 1) * (nyi - 1); l.Co = (nxo - 1) * (nyo - 1);
+    Carver c(ws);
+    l.area_in = c.take<double>(l.Ci);
+    l.bbox = c.take<double>(8);
+    carve_boundary(c, l.bnd[0], nxi, nyi);
+    carve_boundary(c, l.bnd[1], nxo, nyo);
+    l.guess[0] = c.take<int32_t>(l.Vo);
+    l.guess[1] = c.take<int32_t>(l.Vi);
+    for (int p = 0; p < 4; p++) {
+        const bool sweep_in = p >= 2;
+        const int64_t nx = sweep_in ? nxi : nxo, ny = sweep_in ? nyi : nyo;
+        const int axis = p & 1;
+        l.line_start[p] = c.take<int32_t>(axis ? nx : ny);
+        l.seg_start[p] = c.take<int32_t>(nx * ny);
+        l.seg_end[p] = c.take<int32_t>(nx * ny);
+    }
+    l.hist = c.take<int32_t>(l.Ci + 1);
+    l.boff = c.take<int64_t>(l.Ci + 1);
+    l.cursor = c.take<int32_t>(l.Ci + 1);
+    l.nuniq = c.take<int32_t>(l.Ci + 1);
+    l.colptr = c.take<int64_t>(l.Ci + 1);
+    l.scan_scratch = c.take<int64_t>(scan_scratch_elems(l.Ci));
+    l.flags = c.take<int32_t>(8);
+    l.bytes = c.total();
+    return l;
+}
+
+static int check_sizes(int64_t nxi, int64_t nyi, int64_t nxo, int64_t nyo)
+{
+    if (nxi < 2 || nyi < 2 || nxo < 2 || nyo < 2) return fail(RG_E_ARG, "rg_build2d: grids need at least 2x2 vertices");
+    if (nxi * nyi >= INT32_MAX || nxo * nyo >= INT32_MAX)
+        return fail(RG_E_TOO_LARGE, "rg_build2d: grid exceeds the int32 cell index range");
+    return RG_OK;
+}
+
+static PassParams make_pass(const Layout& l, int p, const double* xin, const double* yin,
+                            const double* xout, const double* yout, int64_t cell_lo, int64_t cell_hi)
+{
+    PassParams P;
+    const GridView gin{ xin, yin, (int)l.nxi, (int)l.nyi };
+    const GridView gout{ xout, yout, (int)l.nxo, (int)l.nyo };
+    P.pass = p;
+    P.sweep_input = p >= 2;
+    P.axis = p & 1;
+    P.sweep = P.sweep_input ? gin : gout;
+    P.stat = P.sweep_input ? gout : gin;
+    P.bnd = l.bnd[P.sweep_input ? 1 : 0];
+    P.nlines = P.axis ? P.sweep.nx : P.sweep.ny;
+    P.nseg = P.axis ? P.sweep.ny - 1 : P.sweep.nx - 1;
+    P.ncy_in = (int)l.nyi - 1;
+    P.ncy_out = (int)l.nyo - 1;
+    P.ncx_st = P.stat.nx - 1;
+    P.ncy_st = P.stat.ny - 1;
+    P.guess = l.guess[P.sweep_input ? 1 : 0];
+    P.line_start = l.line_start[p];
+    P.seg_start = l.seg_start[p];
+    P.seg_end = l.seg_end[p];
+    P.max_iter = 4 * (P.ncx_st + P.ncy_st) + 64;
+    P.cell_lo = cell_lo;
+    P.cell_hi = cell_hi;
+    return P;
+}
+
+}  // namespace rg
+
+using namespace rg;
+
+extern "C" int rg_build2d_workspace_bytes(int64_t nxi, int64_t nyi, int64_t nxo, int64_t nyo, size_t* bytes_host)
+{
+    if (!bytes_host) return fail(RG_E_ARG, "rg_build2d_workspace_bytes: null output");
+    int rc = check_sizes(nxi, nyi, nxo, nyo);
+    if (rc) return rc;
+    *bytes_host = make_layout(nullptr, nxi, nyi, nxo, nyo).bytes;
+    return RG_OK;
+}
+
+extern "C" int rg_grid_area(int device, void* stream, int64_t nx, int64_t ny,
+                            const double* x, const double* y, double* area)
+{
+    if (nx < 2 || ny < 2 || !x || !y || !area) return fail(RG_E_ARG, "rg_grid_area: bad argument");
+    if (nx * ny >= INT32_MAX) return fail(RG_E_TOO_LARGE, "rg_grid_area: grid too large");
+    RG_CUDA(cudaSetDevice(device));
+    const GridView g{ x, y, (int)nx, (int)ny };
+    const int64_t nc = (nx - 1) * (ny - 1);
+    k_cell_area<<<(unsigned)ceil_div(nc, 256), 256, 0, (cudaStream_t)stream>>>(g, area);
+    RG_LAUNCH_CHECK("k_cell_area");
+    return RG_OK;
+}
+
+extern "C" int rg_build2d_count(int device, void* stream,
+                                int64_t nxi, int64_t nyi, int64_t nxo, int64_t nyo,
+                                const double* xin, const double* yin, const double* xout, const double* yout,
+                                int64_t cell_lo, int64_t cell_hi,
+                                void* workspace, size_t workspace_bytes, int64_t* n_fragments_host)
+{
+    int rc = check_sizes(nxi, nyi, nxo, nyo);
+    if (rc) return rc;
+    if (!xin || !yin || !xout || !yout || !workspace || !n_fragments_host)
+        return fail(RG_E_ARG, "rg_build2d_count: null pointer");
+    Layout l = make_layout(workspace, nxi, nyi, nxo, nyo);
+    if (workspace_bytes < l.bytes) return fail(RG_E_WORKSPACE, "rg_build2d_count: workspace too small");
+    if (cell_lo < 0 || cell_hi > l.Ci || cell_lo > cell_hi) return fail(RG_E_ARG, "rg_build2d_count: bad cell band");
+    RG_CUDA(cudaSetDevice(device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const GridView gin{ xin, yin, (int)nxi, (int)nyi };
+    const GridView gout{ xout, yout, (int)nxo, (int)nyo };
+    const int T = 256;
+
+    RG_CUDA(cudaMemsetAsync(l.flags, 0, sizeof(int32_t) * 8, st));
+    RG_CUDA(cudaMemsetAsync(l.hist, 0, sizeof(int32_t) * (size_t)(l.Ci + 1), st));
+    // K1
+    k_cell_area<<<(unsigned)ceil_div(l.Ci, T), T, 0, st>>>(gin, l.area_in);
+    RG_LAUNCH_CHECK("k_cell_area");
+    // bounding boxes + boundaries of both grids
+    for (int g = 0; g < 2; g++) {
+        const GridView& gv = g ? gout : gin;
+        rc = build_boundary(st, gv, l.bnd[g], l.bbox + 4 * g);
+        if (rc) return rc;
+    }
+    // vertex guesses: output vertices in the input grid, input vertices in the output grid
+    k_vertex_guess<<<(unsigned)ceil_div(l.Vo, T), T, 0, st>>>(gout, gin, l.guess[0], l.flags);
+    k_vertex_guess<<<(unsigned)ceil_div(l.Vi, T), T, 0, st>>>(gin, gout, l.guess[1], l.flags);
+    RG_LAUNCH_CHECK("k_vertex_guess");
+    for (int p = 0; p < 4; p++) {
+        PassParams P = make_pass(l, p, xin, yin, xout, yout, cell_lo, cell_hi);
+        k_line_starts<<<(unsigned)ceil_div((int64_t)P.nlines * 32, T), T, 0, st>>>(
+            P, l.bbox + 4 * (P.sweep_input ? 1 : 0), l.line_start[p]);
+        RG_LAUNCH_CHECK("k_line_starts");
+        const int64_t nthreads = (int64_t)P.nlines * P.nseg;
+        k_walk_count<<<(unsigned)ceil_div(nthreads, 128), 128, 0, st>>>(P, l.hist);
+        RG_LAUNCH_CHECK("k_walk_count");
+        k_repair<<<(unsigned)ceil_div((int64_t)P.nlines * 32, 128), 128, 0, st>>>(P, l.hist, l.flags);
+        RG_LAUNCH_CHECK("k_repair");
+    }
+    rc = exclusive_scan_i32_i64(st, l.hist, l.boff, l.Ci, l.scan_scratch);
+    if (rc) return rc;
+    int64_t total = 0;
+    RG_CUDA(cudaMemcpyAsync(&total, l.boff + l.Ci, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+    RG_CUDA(cudaStreamSynchronize(st));
+    if (total >= INT32_MAX) return fail(RG_E_TOO_LARGE, "rg_build2d_count: more than 2^31 fragments");
+    *n_fragments_host = total;
+    return RG_OK;
+}
+
+extern "C" int rg_build2d_fill(int device, void* stream,
+                               int64_t nxi, int64_t nyi, int64_t nxo, int64_t nyo,
+                               const double* xin, const double* yin, const double* xout, const double* yout,
+                               const double* w_in, int64_t cell_lo, int64_t cell_hi,
+                               void* workspace, size_t workspace_bytes,
+                               uint64_t* frag_key, double* frag_val, int64_t n_fragments, int64_t* nnz_host)
+{
+    int rc = check_sizes(nxi, nyi, nxo, nyo);
+    if (rc) return rc;
+    if (!workspace || !nnz_host || (n_fragments > 0 && (!frag_key || !frag_val)))
+        return fail(RG_E_ARG, "rg_build2d_fill: null pointer");
+    Layout l = make_layout(workspace, nxi, nyi, nxo, nyo);
+    if (workspace_bytes < l.bytes) return fail(RG_E_WORKSPACE, "rg_build2d_fill: workspace too small");
+    RG_CUDA(cudaSetDevice(device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const int T = 256;
+    RG_CUDA(cudaMemsetAsync(l.cursor, 0, sizeof(int32_t) * (size_t)(l.Ci + 1), st));
+    for (int p = 0; p < 4; p++) {
+        PassParams P = make_pass(l, p, xin, yin, xout, yout, cell_lo, cell_hi);
+        const int64_t nthreads = (int64_t)P.nlines * P.nseg;
+        k_walk_emit<<<(unsigned)ceil_div(nthreads, 128), 128, 0, st>>>(P, l.boff, l.cursor, frag_key, frag_val,
+                                                                      l.area_in, w_in, l.flags);
+        RG_LAUNCH_CHECK("k_walk_emit");
+    }
+    k_bucket_sort<<<(unsigned)ceil_div(l.Ci, T), T, 0, st>>>(l.boff, l.Ci, frag_key, frag_val, l.nuniq);
+    RG_LAUNCH_CHECK("k_bucket_sort");
+    rc = exclusive_scan_i32_i64(st, l.nuniq, l.colptr, l.Ci, l.scan_scratch);
+    if (rc) return rc;
+    int64_t nnz = 0;
+    int32_t flags[8];
+    RG_CUDA(cudaMemcpyAsync(&nnz, l.colptr + l.Ci, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+    RG_CUDA(cudaMemcpyAsync(flags, l.flags, sizeof(flags), cudaMemcpyDeviceToHost, st));
+    RG_CUDA(cudaStreamSynchronize(st));
+    if (flags[kFlagOverflow] || flags[kFlagSeqOverflow])
+        return fail(RG_E_WALK, "rg_build2d_fill: a sweep walk did not terminate (degenerate or folded grid)");
+    *nnz_host = nnz;
+    return RG_OK;
+}
+
+extern "C" int rg_build2d_emit(int device, void* stream,
+                               int64_t nxi, int64_t nyi, int64_t nxo, int64_t nyo,
+                               int64_t cell_lo, int64_t cell_hi,
+                               void* workspace, size_t workspace_bytes,
+                               const uint64_t* frag_key, const double* frag_val, int64_t n_fragments,
+                               int64_t* ii, int64_t* io, double* v, int64_t nnz)
+{
+    (void)cell_lo; (void)cell_hi; (void)n_fragments;
+    int rc = check_sizes(nxi, nyi, nxo, nyo);
+    if (rc) return rc;
+    if (!workspace) return fail(RG_E_ARG, "rg_build2d_emit: null workspace");
+    if (nnz > 0 && (!ii || !io || !v || !frag_key || !frag_val)) return fail(RG_E_ARG, "rg_build2d_emit: null pointer");
+    Layout l = make_layout(workspace, nxi, nyi, nxo, nyo);
+    if (workspace_bytes < l.bytes) return fail(RG_E_WORKSPACE, "rg_build2d_emit: workspace too small");
+    RG_CUDA(cudaSetDevice(device));
+    cudaStream_t st = (cudaStream_t)stream;
+    if (nnz > 0) {
+        k_bucket_emit<<<(unsigned)ceil_div(l.Ci, 256), 256, 0, st>>>(l.boff, l.colptr, l.Ci, frag_key, frag_val, ii, io, v);
+        RG_LAUNCH_CHECK("k_bucket_emit");
+    }
+    return RG_OK;
+}
+
+// Debug/diagnostic: copy the 8 status counters of the last build out of the workspace.
+extern "C" int rg_build2d_stats(int device, void* stream, int64_t nxi, int64_t nyi, int64_t nxo, int64_t nyo,
+                                void* workspace, int32_t* stats_host /* 8 */)
+{
+    int rc = check_sizes(nxi, nyi, nxo, nyo);
+    if (rc) return rc;
+    Layout l = make_layout(workspace, nxi, nyi, nxo, nyo);
+    RG_CUDA(cudaSetDevice(device));
+    RG_CUDA(cudaMemcpyAsync(stats_host, l.flags, sizeof(int32_t) * 8, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    RG_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+    return RG_OK;
+}

@@ -1,0 +1,137 @@
+// rg_util.cu -- error strings and the device-wide exclusive scan used by the
+// count -> scan -> emit compaction steps (no atomics decide any output order).
+#include "rg_common.cuh"
+
+namespace rg {
+
+thread_local char g_err[512] = "";
+
+// ---- three-kernel scan: per-tile sums, scan of the tile sums, per-tile scan + offset ----
+
+template <int THREADS, int ITEMS>
+__global__ void k_scan_tile_sums(const int32_t* __restrict__ in, int64_t n, int64_t* __restrict__ tile_sums)
+{
+    __shared__ int64_t warp_sums[THREADS / 32];
+    const int64_t base = (int64_t)blockIdx.x * (THREADS * ITEMS);
+    int64_t acc = 0;
+#pragma unroll
+    for (int q = 0; q < ITEMS; q++) {
+        int64_t idx = base + (int64_t)q * THREADS + threadIdx.x;
+        if (idx < n) acc += in[idx];
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o);
+    if ((threadIdx.x & 31) == 0) warp_sums[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int64_t s = 0;
+        for (int w = 0; w < THREADS / 32; w++) s += warp_sums[w];
+        tile_sums[blockIdx.x] = s;
+    }
+}
+
+// single block: exclusive scan of the tile sums in place; writes the grand total at [ntiles]
+__global__ void k_scan_tile_offsets(int64_t* tile_sums, int64_t ntiles)
+{
+    __shared__ int64_t carry;
+    __shared__ int64_t warp_tot[32];
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    for (int64_t base = 0; base < ntiles; base += blockDim.x) {
+        int64_t idx = base + threadIdx.x;
+        int64_t v = idx < ntiles ? tile_sums[idx] : 0;
+        int64_t inc = v;
+        const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            int64_t t = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += t;
+        }
+        if (lane == 31) warp_tot[wid] = inc;
+        __syncthreads();
+        if (wid == 0) {
+            int64_t w = lane < (int)(blockDim.x >> 5) ? warp_tot[lane] : 0;
+            int64_t winc = w;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                int64_t t = __shfl_up_sync(0xffffffffu, winc, o);
+                if (lane >= o) winc += t;
+            }
+            warp_tot[lane] = winc - w;  // exclusive prefix of warp totals
+        }
+        __syncthreads();
+        int64_t excl = carry + warp_tot[wid] + (inc - v);
+        if (idx < ntiles) tile_sums[idx] = excl;
+        __syncthreads();
+        if (threadIdx.x == blockDim.x - 1) carry = excl + v;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) tile_sums[ntiles] = carry;
+}
+
+template <int THREADS, int ITEMS, class OutT>
+__global__ void k_scan_apply(const int32_t* __restrict__ in, OutT* __restrict__ out, int64_t n,
+                             const int64_t* __restrict__ tile_offsets, int64_t ntiles)
+{
+    // blocked arrangement: thread t owns ITEMS consecutive elements
+    __shared__ int64_t warp_tot[THREADS / 32];
+    const int64_t base = (int64_t)blockIdx.x * (THREADS * ITEMS) + (int64_t)threadIdx.x * ITEMS;
+    int32_t v[ITEMS];
+    int64_t tsum = 0;
+#pragma unroll
+    for (int q = 0; q < ITEMS; q++) {
+        v[q] = (base + q < n) ? in[base + q] : 0;
+        tsum += v[q];
+    }
+    int64_t inc = tsum;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        int64_t t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += t;
+    }
+    if (lane == 31) warp_tot[wid] = inc;
+    __syncthreads();
+    int64_t woff = 0;
+    for (int w = 0; w < wid; w++) woff += warp_tot[w];
+    int64_t run = tile_offsets[blockIdx.x] + woff + (inc - tsum);
+#pragma unroll
+    for (int q = 0; q < ITEMS; q++) {
+        if (base + q < n) out[base + q] = (OutT)run;
+        run += v[q];
+    }
+    if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) out[n] = (OutT)tile_offsets[ntiles];
+}
+
+template <class OutT>
+static int scan_impl(cudaStream_t st, const int32_t* in, OutT* out, int64_t n, int64_t* block_sums)
+{
+    constexpr int THREADS = 256, ITEMS = kScanTile / THREADS;
+    if (n <= 0) {
+        RG_CUDA(cudaMemsetAsync(out, 0, sizeof(OutT), st));
+        return RG_OK;
+    }
+    const int64_t ntiles = ceil_div(n, kScanTile);
+    k_scan_tile_sums<THREADS, ITEMS><<<(unsigned)ntiles, THREADS, 0, st>>>(in, n, block_sums);
+    RG_LAUNCH_CHECK("k_scan_tile_sums");
+    k_scan_tile_offsets<<<1, 1024, 0, st>>>(block_sums, ntiles);
+    RG_LAUNCH_CHECK("k_scan_tile_offsets");
+    k_scan_apply<THREADS, ITEMS, OutT><<<(unsigned)ntiles, THREADS, 0, st>>>(in, out, n, block_sums, ntiles);
+    RG_LAUNCH_CHECK("k_scan_apply");
+    return RG_OK;
+}
+
+int exclusive_scan_i32_i64(cudaStream_t st, const int32_t* in, int64_t* out, int64_t n, int64_t* block_sums)
+{
+    return scan_impl<int64_t>(st, in, out, n, block_sums);
+}
+
+int exclusive_scan_i32_i32(cudaStream_t st, const int32_t* in, int32_t* out, int64_t n, int64_t* block_sums)
+{
+    return scan_impl<int32_t>(st, in, out, n, block_sums);
+}
+
+}  // namespace rg
+
+extern "C" const char* rg_last_error_string(void) { return rg::g_err; }
+extern "C" int rg_version(void) { return 100; }
