@@ -1,0 +1,432 @@
+#!/usr/bin/env python
+"""
+bench.py -- BASELINE.json metric on BASELINE.json config 3 (the largest single-GPU
+configuration the metric is quoted on):
+
+    2D conservative weights build for a 2048x2048-cell distorted curvilinear grid onto a
+    2048x2048-cell rectilinear grid, then regrid_from_weights over 1000 frames sharing the
+    weights.
+
+One "step" = one pass of regrid_from_weights over the F frames resident on this GPU
+(primary metric, regrid_from_weights GB/s, HBM roofline); the weights build (Mcells/s) is
+measured in the same run and reported in the "build" object of the same JSON line.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
+        --master-port P bench.py --gpus N --steps K --warmup W
+
+Multi-GPU: frames are independent units, so every rank applies the shared weights to its
+own F frames with NO data-path collective ("scaling": "weak"); the 2D build is additionally
+timed as an input-row-banded build + NCCL all-gather (strong scaling, "build.banded").
+
+--impl reference: the CPU oracle (a C port of the reference's algorithm, OpenMP over the
+reference's own prange loops) on this box's host cores, same metric / config, bounded sample.
+"""
+
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import pathlib
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = pathlib.Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+METRIC = "regrid_from_weights_GBps"
+UNIT = "GB/s"
+WORKLOAD = ("config3: distorted curvilinear 2049x2049 vertices (2048^2 cells) -> rectilinear 2049x2049, "
+            "weights build + regrid_from_weights over F frames sharing the weights")
+
+
+def grids(n: int):
+    from tests import cases
+
+    gi, go = cases.benchmark_family(n, distorted=True)
+    return gi, go
+
+
+def apply_bytes(F: int, n_in: int, n_out: int, nnz: int) -> int:
+    """ALGORITHMIC bytes of one apply: values read once + written once, weights once."""
+    return 8 * F * (n_in + n_out) + 12 * nnz + 4 * (n_out + 1)
+
+
+def build_bytes(v_in: int, v_out: int, nnz: int) -> int:
+    return 16 * (v_in + v_out) + 24 * nnz
+
+
+def hbm_peak():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        try:
+            return float(json.loads(p.read_text())["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed regions."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index = index
+        self.rows = []
+        self.proc = None
+        self.thread = None
+        self.active = False
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
+        except Exception:
+            self.proc = None
+            return
+        self.thread = threading.Thread(target=self._pump, daemon=True)
+        self.thread.start()
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            if self.active:
+                self.rows.append(line.strip())
+
+    def stop(self):
+        if self.proc is not None:
+            self.proc.terminate()
+
+    def summary(self):
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, val in zip(names, f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------
+# CPU legs (oracle = port of the reference's algorithm; test/bench infrastructure)
+# ---------------------------------------------------------------------------
+
+
+def cpu_apply_sample(ii, io, v, n_in, n_out, frames, reps=3):
+    from oracle import oracle
+
+    vals = np.random.default_rng(0).random((frames, n_in))
+    best = float("inf")
+    for _ in range(reps):
+        t = time.perf_counter()
+        oracle.regrid_from_weights(ii, io, v, vals, n_out)
+        best = min(best, time.perf_counter() - t)
+    return apply_bytes(frames, n_in, n_out, v.size) / best / 1e9, best
+
+
+def cpu_build_sample(n):
+    from oracle import oracle
+    from tests import cases
+
+    gi, go = grids(n)
+    co = cases.perturb_like_reference(go, (-1, -2), 42)
+    t = time.perf_counter()
+    raw = oracle.weights_conservative_2d(gi, co)
+    t_sweep = time.perf_counter() - t
+    t = time.perf_counter()
+    tri = oracle.coalesce(*raw)
+    t_coal = time.perf_counter() - t
+    return tri, t_sweep, t_coal
+
+
+def run_reference(args):
+    """Reference arm: the oracle port on the host cores; rank 0 only."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import oracle
+
+    oracle.build()
+    cores = oracle.num_threads()
+    n = args.n
+    n_in = n_out = (n - 1) ** 2
+    tri, t_sweep, t_coal = cpu_build_sample(n)
+    frames = args.ref_frames
+    vals = np.random.default_rng(0).random((frames, n_in))
+    for _ in range(args.warmup):
+        oracle.regrid_from_weights(*tri, vals, n_out)
+    t = time.perf_counter()
+    for _ in range(args.steps):
+        oracle.regrid_from_weights(*tri, vals, n_out)
+    dt = (time.perf_counter() - t) / args.steps
+    value = apply_bytes(frames, n_in, n_out, tri[2].size) / dt / 1e9
+    sample = f"{frames} of the F frames per step, full 2048^2 weights (nnz {tri[2].size})"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "frames_per_step": frames, "grid_vertices": n},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "build": {"metric": "conservative_2d_weights_build_Mcells_per_s",
+                  "value": n_in / (t_sweep + t_coal) / 1e6, "unit": "Mcells/s",
+                  "sweep_s": t_sweep, "coalesce_s": t_coal, "cores": cores, "kind": "port",
+                  "sample": "full 2048^2-cell build, 1 repetition"},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------
+# GPU arm
+# ---------------------------------------------------------------------------
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    import regridding_b200 as rg
+    from regridding_b200 import _device, _parallel, _util
+    from tests import cases
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device; the product path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def max_over_ranks(x: float) -> float:
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    n = args.n
+    F = args.frames
+    K, W = args.steps, max(args.warmup, 3)
+    n_in = n_out = (n - 1) ** 2
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+
+    # ---- inputs (synthetic, host-generated, seeds fixed) -------------------------------
+    gi, go = grids(n)
+    t0 = time.perf_counter()
+    co = cases.perturb_like_reference(go, (-1, -2), _util.SEED_DEFAULT)  # the reference's host jitter
+    t_perturb = time.perf_counter() - t0
+    xi, yi, xo, yo = (torch.from_numpy(a).to(dev) for a in (*gi, *co))
+
+    # ---- build: device-resident coordinates -> device-resident public triplets -----------
+    def build_once(banded: bool):
+        if banded and world > 1:
+            return _parallel.build_weights_2d_banded(xi, yi, xo, yo, replicate=True, device=dev)
+        return _device.build_weights_2d(xi, yi, xo, yo, device=dev)
+
+    def time_build(banded: bool):
+        for _ in range(W):
+            dw = build_once(banded)
+        barrier()
+        sampler.active = True
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(K):
+            dw = build_once(banded)
+        e1.record()
+        torch.cuda.synchronize(dev)
+        sampler.active = False
+        ms = max_over_ranks(e0.elapsed_time(e1) / K)
+        barrier()
+        return dw, ms
+
+    dw, build_ms = time_build(False)
+    banded_ms = None
+    if world > 1:
+        dw, banded_ms = time_build(True)
+    nnz = dw.nnz
+    csr = dw.csr()
+    torch.cuda.synchronize(dev)
+
+    # ---- apply: F frames resident in HBM ---------------------------------------------
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(1234 + rank)
+    vin = torch.empty((F, n_in), dtype=torch.float64, device=dev)
+    chunk = 50
+    for f in range(0, F, chunk):
+        vin[f:f + chunk].uniform_(0.0, 1.0, generator=gen)
+    vout = torch.empty((F, n_out), dtype=torch.float64, device=dev)
+    for _ in range(W):
+        _device.apply_csr(csr, vin, vout)
+    barrier()
+    sampler.active = True
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(K):
+        _device.apply_csr(csr, vin, vout)
+    e1.record()
+    torch.cuda.synchronize(dev)
+    sampler.active = False
+    apply_ms = max_over_ranks(e0.elapsed_time(e1) / K)
+    barrier()
+    abytes = apply_bytes(F, n_in, n_out, nnz)
+    value = world * abytes / (apply_ms * 1e-3) / 1e9
+    per_gpu = abytes / (apply_ms * 1e-3) / 1e9
+    checksum = float(vout[:2].sum().item())
+    del vin, vout
+    torch.cuda.empty_cache()
+
+    # ---- e2e: reference-facing public API with HOST buffers ------------------------------
+    Fe = min(args.e2e_frames, F)
+    weights_host = np.empty((), dtype=object)
+    weights_host[()] = dw.to_host()
+    from regridding_b200 import _cache
+
+    _cache.remember(weights_host[()][2], dw)
+    shape_in = shape_out = (n - 1, n - 1)
+    pin_in = torch.empty((Fe, n - 1, n - 1), dtype=torch.float64, pin_memory=True)
+    pin_in.uniform_(0.0, 1.0)
+    pin_out = torch.empty((Fe, n - 1, n - 1), dtype=torch.float64, pin_memory=True)
+    host_in, host_out = pin_in.numpy(), pin_out.numpy()
+    for _ in range(2):
+        rg.regrid_from_weights(weights_host, shape_in, shape_out, host_in, values_output=host_out)
+    barrier()
+    t0 = time.perf_counter()
+    Ke = max(2, min(K, 5))
+    for _ in range(Ke):
+        rg.regrid_from_weights(weights_host, shape_in, shape_out, host_in, values_output=host_out)
+    torch.cuda.synchronize(dev)
+    e2e_s = max_over_ranks((time.perf_counter() - t0) / Ke)
+    e2e_value = world * apply_bytes(Fe, n_in, n_out, nnz) / e2e_s / 1e9
+    del pin_in, pin_out
+
+    # e2e build through the public API: host coordinates -> host triplets (perturb + H2D + build + D2H)
+    t0 = time.perf_counter()
+    Wh = rg.weights(gi, go, method="conservative")
+    torch.cuda.synchronize(dev)
+    e2e_build_s = max_over_ranks(time.perf_counter() - t0)
+    assert Wh[0][()][2].size == nnz
+
+    if rank == 0:
+        sampler.stop()
+    peak, peak_src = hbm_peak()
+    clocks = sampler.summary() if rank == 0 else None
+
+    # ---- CPU baseline beside it (rank 0, N = 1 only; bounded sample) ----------------------
+    cpu = None
+    cpu_build = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        from oracle import oracle
+
+        oracle.build()
+        ii_h, io_h, v_h = weights_host[()]
+        frames_cpu = args.cpu_frames
+        cpu_val, cpu_t = cpu_apply_sample(ii_h, io_h, v_h, n_in, n_out, frames_cpu)
+        cpu = {"value": cpu_val, "unit": UNIT, "cores": oracle.num_threads(), "kind": "port",
+               "sample": f"{frames_cpu} frames with the full 2048^2 weights, best of 3 ({cpu_t:.2f} s each)"}
+        nb = args.cpu_build_n
+        _, ts, tc = cpu_build_sample(nb)
+        cpu_build = {"value": (nb - 1) ** 2 / (ts + tc) / 1e6, "unit": "Mcells/s", "cores": oracle.num_threads(),
+                     "kind": "port",
+                     "sample": f"{nb - 1}^2-cell grid of the same family (sweep {ts:.1f} s + coalesce {tc:.1f} s); "
+                               "the CPU algorithm is super-linear in the grid size, so this flatters it"}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    v_in, v_out = n * n, n * n
+    bbytes = build_bytes(v_in, v_out, nnz)
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+        "ms_per_step": apply_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "frames_per_gpu": F, "grid_vertices": n, "nnz": nnz,
+                   "l2": "inputs (33.5 GB in + 33.5 GB out per step at F=1000) are far larger than L2; no flush needed",
+                   "parallelism": f"frames x{world} (no collective)"},
+        "roofline": {"bound": "hbm", "achieved": per_gpu, "peak": peak, "unit": "GB/s", "frac": per_gpu / peak,
+                     "traffic": None, "peak_source": peak_src, "kernel": "rg::k_apply_csr",
+                     "algorithmic_bytes_per_launch": abytes},
+        "e2e": {"value": e2e_value, "unit": UNIT, "frames": Fe,
+                "h2d_bytes_per_step": 8 * Fe * n_in, "d2h_bytes_per_step": 8 * Fe * n_out,
+                "api": "regridding_b200.regrid_from_weights(numpy in pinned host memory -> numpy)"},
+        "gpu_launches": K * _device.LAUNCHES_APPLY,
+        "clocks": clocks,
+        "cpu_baseline": cpu,
+        "build": {
+            "metric": "conservative_2d_weights_build_Mcells_per_s", "unit": "Mcells/s",
+            "value": n_in / (build_ms * 1e-3) / 1e6, "ms": build_ms,
+            "fragments": dw.stats["fragments"] if dw.stats else None,
+            "repaired_segments": dw.stats["repaired_segments"] if dw.stats else None,
+            "scope": "perturbed device-resident coordinates -> device-resident sorted-unique (ii, io, v)",
+            "gpu_launches_per_build": _device.LAUNCHES_BUILD2D,
+            "roofline": {"bound": "hbm", "achieved": bbytes / (build_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                         "frac": bbytes / (build_ms * 1e-3) / 1e9 / peak, "algorithmic_bytes": bbytes,
+                         "note": "the build is fp64-latency / divergence bound, not HBM bound; see DESIGN.md"},
+            "banded": None if banded_ms is None else {
+                "n_gpus": world, "ms": banded_ms, "value": n_in / (banded_ms * 1e-3) / 1e6,
+                "scaling": "strong", "collective": "NCCL all-gather of the band triplets"},
+            "e2e": {"value": n_in / e2e_build_s / 1e6, "unit": "Mcells/s", "seconds": e2e_build_s,
+                    "host_perturb_seconds": t_perturb,
+                    "h2d_bytes": 16 * (v_in + v_out), "d2h_bytes": 24 * nnz,
+                    "api": "regridding_b200.weights(method='conservative') host coords -> host triplets"},
+            "cpu_baseline": cpu_build,
+        },
+        "checksum": checksum,
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--n", type=int, default=2049, help="vertices per axis (config 3: 2049)")
+    ap.add_argument("--frames", type=int, default=1000, help="frames per GPU sharing the weights (config 3: 1000)")
+    ap.add_argument("--e2e-frames", type=int, default=125)
+    ap.add_argument("--cpu-frames", type=int, default=64)
+    ap.add_argument("--cpu-build-n", type=int, default=1025)
+    ap.add_argument("--ref-frames", type=int, default=32)
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

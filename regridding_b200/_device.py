@@ -20,6 +20,11 @@ F64 = torch.float64
 I64 = torch.int64
 I32 = torch.int32
 
+# kernel launches of ours per operator call (checked against the ncu launch list in profiles/)
+LAUNCHES_BUILD2D = 37  # area 1, 2 x (bbox 2 + boundary 3), guess 2, 4 x (starts, count, repair), scans 6, emit 4, sort 1, merge 1
+LAUNCHES_CSR = 6       # hist, scan 3, fill, rank
+LAUNCHES_APPLY = 1     # one k_apply launch per call (up to 65535 frame tiles)
+
 
 def cuda_device(device=None) -> torch.device:
     if not torch.cuda.is_available():

@@ -1,0 +1,400 @@
+"""
+GPU parity tests (``-m gpu``): the CUDA path, called through the C ABI
+(``regridding_b200._device`` = ctypes over ``libregrid_b200.so``) and through the
+reference-compatible public API, against
+
+  * the CPU oracle on the same seeded inputs (bit-exact: indices AND weights, because the
+    kernels reproduce the reference's floating-point contraction pattern),
+  * the committed golden vectors = outputs of the reference itself,
+  * size-independent properties at BASELINE.json's full sizes.
+
+Bars (north_star): triplet index sets bit-exact; weights within 1e-12 relative -- we hold
+them to bit equality; resampled sums within 1e-10 relative -- also held to bit equality.
+"""
+
+import pickle
+
+import numpy as np
+import pytest
+
+from tests import cases
+
+pytestmark = pytest.mark.gpu
+
+torch = pytest.importorskip("torch")
+
+
+@pytest.fixture(scope="module")
+def dev():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    return torch.device("cuda", 0)
+
+
+@pytest.fixture(scope="module")
+def rg():
+    import regridding_b200
+
+    return regridding_b200
+
+
+def T(a, dev):
+    return torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+
+
+# ---------------------------------------------------------------------------
+# 2D conservative build + apply
+# ---------------------------------------------------------------------------
+
+
+@pytest.mark.parametrize("name", cases.CASES_2D)
+def test_build2d_bit_exact_vs_oracle_and_reference(rg, dev, oracle, golden, name):
+    gi, go, w = cases.case_2d(name)
+    co = cases.perturb_like_reference(go, (-1, -2), 42)
+    dw = rg.device.build_weights_2d(gi[0], gi[1], co[0], co[1], w, device=dev)
+    ii, io, v = dw.to_host()
+    oi, oo, ov = oracle.coalesce(*oracle.weights_conservative_2d(gi, co, w))
+    assert np.array_equal(ii, oi) and np.array_equal(io, oo)
+    assert np.array_equal(v, ov), f"max rel {np.max(np.abs(v - ov) / np.abs(ov))}"
+    assert dw.stats["fragments"] == int(golden[f"c2d/{name}/raw_n"])
+    # the reference itself
+    assert cases.sha(ii, io, v) == str(golden[f"c2d/{name}/final_sha"])
+    # apply: three frames sharing the weights
+    shape_in, shape_out = tuple(golden[f"c2d/{name}/shape_in"]), tuple(golden[f"c2d/{name}/shape_out"])
+    vals = np.random.default_rng(0).random((3, *shape_in))
+    out = rg.device.apply_csr(dw.csr(), T(vals.reshape(3, -1), dev)).cpu().numpy()
+    ref = oracle.regrid_from_weights(oi, oo, ov, vals.reshape(3, -1), dw.n_out)
+    assert np.array_equal(out, ref)
+    assert cases.sha(out.reshape(3, *shape_out)) == str(golden[f"c2d/{name}/apply_sha"])
+
+
+def test_grid_area_bit_exact(rg, dev, oracle, golden):
+    for name in ("fam40", "coarsen", "flipx"):
+        g, _, _ = cases.case_2d(name)
+        a = rg.device.grid_area(*g, device=dev).cpu().numpy()
+        assert np.array_equal(a, golden[f"prim/volume_{name}"])
+        assert np.array_equal(a, oracle.grid_volume(*g))
+
+
+@pytest.mark.parametrize("n,mx,my", [(301, 280, 333), (513, 513, 513)])
+def test_build2d_vs_oracle_benchmark_family(rg, dev, oracle, n, mx, my):
+    """benchmarks/regrid.py family (libm sin/cos inputs, so oracle only -- no golden)."""
+    gi, go = cases.benchmark_family(n, mx, my, distorted=True)
+    co = cases.perturb_like_reference(go, (-1, -2), 42)
+    dw = rg.device.build_weights_2d(gi[0], gi[1], co[0], co[1], device=dev)
+    oi, oo, ov = oracle.coalesce(*oracle.weights_conservative_2d(gi, co))
+    ii, io, v = dw.to_host()
+    assert np.array_equal(ii, oi) and np.array_equal(io, oo) and np.array_equal(v, ov)
+
+
+def test_build2d_band_partition_concatenates(rg, dev):
+    """Input-cell bands (the multi-GPU partition) concatenate to the full build, bit for bit."""
+    gi, go, _ = cases.case_2d("dist129")
+    co = cases.perturb_like_reference(go, (-1, -2), 42)
+    full = rg.device.build_weights_2d(gi[0], gi[1], co[0], co[1], device=dev).to_host()
+    ncx, ncy = gi[0].shape[0] - 1, gi[0].shape[1] - 1
+    parts = []
+    rows = [0, 17, 64, 65, ncx]
+    for a, b in zip(rows[:-1], rows[1:]):
+        parts.append(rg.device.build_weights_2d(gi[0], gi[1], co[0], co[1], cell_band=(a * ncy, b * ncy),
+                                                device=dev).to_host())
+    for k in range(3):
+        assert np.array_equal(np.concatenate([p[k] for p in parts]), full[k])
+
+
+def test_build2d_disjoint_and_tiny_grids(rg, dev, oracle):
+    # no overlap at all -> empty weights
+    gi = cases.curvilinear(9, 7)
+    go = cases.rectilinear_over(gi[0] + 10.0, gi[1], 5, 6)
+    dw = rg.device.build_weights_2d(gi[0], gi[1], go[0], go[1], device=dev)
+    assert dw.nnz == 0
+    out = rg.device.apply_csr(dw.csr(), torch.ones((2, dw.n_in), dtype=torch.float64, device=dev))
+    assert out.shape == (2, dw.n_out) and float(out.abs().sum()) == 0.0
+    # single cell onto single cell (first case of _weights_conservative_2d_test.py:27-44)
+    bx, by = np.meshgrid(np.linspace(-1, 1, 2), np.linspace(-1, 1, 2), indexing="ij")
+    dw = rg.device.build_weights_2d(bx, by, 2 * bx + 1e-6, 2 * by + 1e-6, device=dev)
+    oi, oo, ov = oracle.coalesce(*oracle.weights_conservative_2d((bx, by), (2 * bx + 1e-6, 2 * by + 1e-6)))
+    ii, io, v = dw.to_host()
+    assert np.array_equal(ii, oi) and np.array_equal(io, oo) and np.array_equal(v, ov)
+    assert np.allclose(v.sum(), 1.0, rtol=1e-3)
+
+
+def test_config3_full_size_properties(rg, dev):
+    """2048x2048 cells -> 2048x2048 cells (BASELINE.json config 3): structure and conservation."""
+    n = 2049
+    gi, go = cases.benchmark_family(n, distorted=True)
+    co = cases.perturb_like_reference(go, (-1, -2), 42)
+    dw = rg.device.build_weights_2d(gi[0], gi[1], co[0], co[1], device=dev)
+    ii, io, v = dw.indices_input, dw.indices_output, dw.values
+    assert dw.stats["repaired_segments"] >= 0
+    # sorted by (input, output), pairs unique
+    key = ii * dw.n_out + io
+    assert bool((key[1:] > key[:-1]).all())
+    assert int(ii.min()) >= 0 and int(ii.max()) < dw.n_in and int(io.min()) >= 0 and int(io.max()) < dw.n_out
+    # the output grid covers the input grid, so every input cell is fully redistributed:
+    # the weights of each input cell sum to 1 (up to eps * (r/h)^2)
+    colsum = torch.zeros(dw.n_in, dtype=torch.float64, device=dev).index_add_(0, ii, v)
+    assert float((colsum - 1).abs().max()) < 1e-8
+    # apply: constant field in -> area-weighted constant out wherever the output cell is covered;
+    # linearity: A(a x + b y) = a A(x) + b A(y) up to rounding
+    F = 4
+    x = torch.rand((F, dw.n_in), dtype=torch.float64, device=dev)
+    y = torch.rand((F, dw.n_in), dtype=torch.float64, device=dev)
+    csr = dw.csr()
+    ax, ay = rg.device.apply_csr(csr, x), rg.device.apply_csr(csr, y)
+    axy = rg.device.apply_csr(csr, (2.0 * x + 0.5 * y).contiguous())
+    assert float((axy - (2.0 * ax + 0.5 * ay)).abs().max()) < 1e-9
+    # CSR apply == straightforward COO scatter-add of the public triplets (different summation order)
+    ref = torch.zeros((F, dw.n_out), dtype=torch.float64, device=dev)
+    ref.index_add_(1, io, x[:, ii] * v)
+    assert float((ax - ref).abs().max() / ref.abs().max()) < 1e-12
+    # total mass: sum_out = sum_in of (value * column sum)
+    assert abs(float(ax.sum()) - float((x * colsum).sum())) / float(ax.sum()) < 1e-10
+
+
+# ---------------------------------------------------------------------------
+# public API (reference signatures)
+# ---------------------------------------------------------------------------
+
+
+def test_api_weights_layout_and_roundtrip(rg, golden):
+    """regridding/_regrid/_tests/test_regrid_from_weights.py:38-117."""
+    gi, go, _ = cases.case_2d("fam40")
+    W = rg.weights(gi, go, method="conservative")
+    weights, shape_in, shape_out = W
+    assert weights.dtype == object and weights.shape == ()
+    ii, io, v = weights[()]
+    assert ii.ndim == 1 and ii.shape == io.shape == v.shape
+    assert ii.dtype == np.int64 and io.dtype == np.int64 and v.dtype == np.float64
+    assert shape_in == tuple(golden["c2d/fam40/shape_in"]) and shape_out == tuple(golden["c2d/fam40/shape_out"])
+    assert np.array_equal(ii, golden["c2d/fam40/ii"]) and np.array_equal(io, golden["c2d/fam40/io"])
+    assert np.array_equal(v, golden["c2d/fam40/v"])
+    key = ii * (io.max() + 1) + io
+    assert np.unique(key).size == key.size
+    vals = np.random.default_rng(0).random((3, *shape_in))
+    res = rg.regrid_from_weights(*W, vals)
+    assert res.dtype == np.float64 and np.array_equal(res, golden["c2d/fam40/apply"])
+    # pickle round trip gives bitwise-equal regrids
+    res2 = rg.regrid_from_weights(*pickle.loads(pickle.dumps(W)), vals)
+    assert np.array_equal(res, res2)
+    # regrid == weights + regrid_from_weights, bitwise
+    res3 = rg.regrid(gi, go, vals, method="conservative")
+    assert np.array_equal(res, res3)
+    # values_output supplied: filled in place
+    buf = np.full_like(res, 7.0)
+    res4 = rg.regrid_from_weights(*W, vals, values_output=buf)
+    assert np.array_equal(buf, res) and np.shares_memory(res4, buf)
+    with pytest.raises(ValueError):
+        rg.regrid_from_weights(*W, vals, values_output=np.zeros((2, 2)))
+
+
+def test_api_weights_input(rg, golden):
+    gi, go, w = cases.case_2d("winput")
+    W = rg.weights(gi, go, weights_input=w, method="conservative")
+    assert cases.sha(*W[0][()]) == str(golden["c2d/winput/final_sha"])
+    vals = np.random.default_rng(0).random((3, *W[1]))
+    assert np.array_equal(rg.regrid_from_weights(*W, vals), golden["c2d/winput/apply"])
+
+
+def test_api_batched_frames_and_seeds(rg, golden):
+    """Per-slice grids (orthogonal axis 0) + the perturbation stream order and seeding rules
+    (regridding/_weights/_weights_test.py:39-103)."""
+    gi, go = cases.case_2d_batched()
+    kw = dict(axis_input=(1, 2), axis_output=(1, 2), method="conservative")
+    W, shape_in, shape_out = rg.weights(gi, go, **kw)
+    assert W.shape == (3,) and shape_in == tuple(golden["c2d_batched/shape_in"])
+    for f in range(3):
+        assert np.array_equal(W[f][0], golden[f"c2d_batched/{f}/ii"])
+        assert np.array_equal(W[f][1], golden[f"c2d_batched/{f}/io"])
+        assert np.array_equal(W[f][2], golden[f"c2d_batched/{f}/v"])
+    vals = np.random.default_rng(0).random(shape_in)
+    res = rg.regrid_from_weights(W, shape_in, shape_out, vals, axis_input=(1, 2), axis_output=(1, 2))
+    assert np.array_equal(res, golden["c2d_batched/apply"])
+    assert np.array_equal(rg.regrid(gi, go, vals, **kw), golden["c2d_batched/apply"])
+    # seeds
+    W7, *_ = rg.weights(gi, go, seed=7, **kw)
+    assert np.array_equal(W7[0][2], golden["c2d_batched/seed7_v0"])
+    Wg, *_ = rg.weights(gi, go, seed=np.random.default_rng(7), **kw)
+    assert np.array_equal(Wg[0][2], W7[0][2])
+    Wn, *_ = rg.weights(gi, go, perturb=False, seed=123, **kw)
+    assert np.array_equal(Wn[0][2], golden["c2d_batched/noperturb_v0"])
+    assert np.array_equal(Wn[0][0], golden["c2d_batched/noperturb_ii0"])
+    Wr1, *_ = rg.weights(gi, go, seed=None, **kw)
+    Wr2, *_ = rg.weights(gi, go, seed=None, **kw)
+    assert not (Wr1[0][2].shape == Wr2[0][2].shape and np.array_equal(Wr1[0][2], Wr2[0][2]))
+
+
+def test_api_shared_weights_over_frames_and_device_tensors(rg, dev, golden):
+    """2D weights applied to (F, H, W) values: F is an orthogonal axis sharing the weights (rfw.py:108)."""
+    gi, go, _ = cases.case_2d("fam40")
+    W = rg.weights(gi, go, method="conservative")
+    vals = np.random.default_rng(0).random((3, *W[1]))
+    res = rg.regrid_from_weights(*W, vals)
+    assert res.shape == (3, *W[2])
+    one = np.stack([rg.regrid_from_weights(*W, vals[f]) for f in range(3)])
+    assert np.array_equal(res, one)
+    # trailing batch axis with explicit axes is a broadcast error, like the reference (rfw.py:109)
+    with pytest.raises(ValueError):
+        rg.regrid_from_weights(*W, np.moveaxis(vals, 0, -1), axis_input=(0, 1), axis_output=(0, 1))
+    # scalar values
+    s = rg.regrid_from_weights(*W, np.float64(2.0))
+    assert s.shape == W[2]
+    # device tensors in -> device tensor out, same bits
+    rd = rg.regrid_from_weights(*W, torch.from_numpy(vals).to(dev))
+    assert isinstance(rd, torch.Tensor) and rd.is_cuda and np.array_equal(rd.cpu().numpy(), res)
+
+
+ANALYTIC_2D = "regridding/_weights/_weights_conservative_2d/_weights_conservative_2d_test.py:16-301"
+
+
+def _analytic_cases():
+    box_x = np.linspace(-1, 1, num=2)[..., np.newaxis]
+    box_y = np.linspace(-1, 1, num=2)
+    x = np.linspace(-1, 1, num=6)[..., np.newaxis]
+    y = np.linspace(-1, 1, num=6)
+    x2 = np.linspace(-1, 1, num=11)[..., np.newaxis]
+    y2 = np.linspace(-1, 1, num=11)
+    c90, s90 = 0.0, 1.0
+    ones5 = np.ones((5, 5))
+    A = np.random.RandomState(42).uniform(0, 10, size=(5, 5))
+    out = [
+        ((box_x, box_y), (2 * box_x, 2 * box_y), np.array([[1]]), None, np.array([[1]])),
+        ((-box_x, -box_y), (2 * box_x, 2 * box_y), np.array([[1]]), None, np.array([[1]])),
+        ((2 * box_x, 2 * box_y), (box_x, box_y), np.array([[1]]), None, np.array([[0.25]])),
+        ((x, y), (x, y), A, None, A),
+        ((x, y), (x2, y2), ones5, None, 0.25 * np.ones((10, 10))),
+        ((x2, y2), (x, y), np.ones((10, 10)), None, 4 * ones5),
+        ((x, y), (x * c90 - y * s90, x * s90 + y * c90), A, None,
+         np.rot90(A, -1)),
+        ((x, y), (x, y), ones5, 2 * ones5, 2 * ones5),
+        ((x, y), (-x, -y), A, None, A[::-1, ::-1]),
+        ((x * c90 - y * s90, x * s90 + y * c90), (x, y), A, None, np.rot90(A)),
+    ]
+    return out
+
+
+@pytest.mark.parametrize("k", range(10))
+def test_api_analytic_cases_like_reference_tests(rg, oracle, k):
+    """Analytic expectations in the style of the reference's own 2D test module
+    (output shifted by 1e-6, perturb=False, rtol=1e-3); cross-checked against the oracle."""
+    ci, co, vals, w, expected = _analytic_cases()[k]
+    co = (co[0] + 1e-6, co[1] + 1e-6)
+    W = rg.weights(ci, co, weights_input=w, method="conservative", perturb=False)
+    res = rg.regrid_from_weights(*W, vals)
+    assert np.allclose(res, expected, rtol=1e-3)
+    gi = tuple(np.ascontiguousarray(np.broadcast_to(c, np.broadcast(*ci).shape), dtype=float) for c in ci)
+    go = tuple(np.ascontiguousarray(np.broadcast_to(c, np.broadcast(*co).shape), dtype=float) for c in co)
+    wi = None if w is None else np.ascontiguousarray(w, dtype=float)
+    oi, oo, ov = oracle.coalesce(*oracle.weights_conservative_2d(gi, go, wi))
+    ii, io, v = W[0][()]
+    assert np.array_equal(ii, oi) and np.array_equal(io, oo) and np.array_equal(v, ov)
+
+
+# ---------------------------------------------------------------------------
+# 1D conservative
+# ---------------------------------------------------------------------------
+
+
+@pytest.mark.parametrize("name", list(cases.cases_1d()))
+def test_conservative_1d_vs_reference(rg, dev, oracle, golden, name):
+    xin, xout, w = cases.cases_1d()[name]
+    W = rg.weights((xin,), (xout,), axis_input=-1, axis_output=-1, weights_input=w, method="conservative")
+    flat = W[0].reshape(-1)
+    assert [e[2].size for e in flat] == list(golden[f"c1d/{name}/counts"])
+    assert np.array_equal(np.concatenate([e[0] for e in flat]), golden[f"c1d/{name}/ii"])
+    assert np.array_equal(np.concatenate([e[1] for e in flat]), golden[f"c1d/{name}/io"])
+    assert np.array_equal(np.concatenate([e[2] for e in flat]), golden[f"c1d/{name}/v"])
+    vals = np.random.default_rng(0).random(W[1])
+    res = rg.regrid_from_weights(*W, vals, axis_input=-1, axis_output=-1)
+    assert np.array_equal(res, golden[f"c1d/{name}/apply"])
+    # raw emission order of the kernel call site == oracle walk
+    ii, io, v, counts = rg.device.cons1d_batched(T(xin, dev), T(xout, dev), None if w is None else T(w, dev))
+    raw = oracle.weights_conservative_1d_batched(xin, xout, w)
+    for s, (ri, ro, rv) in enumerate(raw):
+        c = int(counts[s])
+        assert c == rv.size
+        assert np.array_equal(ii[s, :c].cpu().numpy(), ri) and np.array_equal(io[s, :c].cpu().numpy(), ro)
+        assert np.array_equal(v[s, :c].cpu().numpy(), rv)
+    # fused regrid (weights never materialised) gives the same bits
+    fused = rg.device.regrid1d_conservative(T(xin, dev), T(xout, dev), T(vals, dev), None if w is None else T(w, dev))
+    assert np.array_equal(fused.cpu().numpy(), golden[f"c1d/{name}/apply"])
+    # and so does regrid()
+    if w is None:
+        assert np.array_equal(rg.regrid((xin,), (xout,), vals, axis_input=-1, axis_output=-1, method="conservative"),
+                              golden[f"c1d/{name}/apply"])
+
+
+def test_conservative_1d_config2_shape_properties(rg, dev, oracle):
+    """BASELINE.json config 2 at reduced S: 4096 bins, per-spectrum grids; fused == oracle; flux conserved."""
+    rng = np.random.default_rng(0)
+    S, n = 64, 4097
+    base = np.linspace(4000.0, 7000.0, n)
+    xin = base * (1 + 1e-4 * rng.standard_normal((S, 1))) + 0.3 * np.sin(base / 500 + rng.random((S, 1)))
+    xout = np.linspace(4001.0, 6999.0, n) + 0.05 * rng.random((S, 1))
+    vals = rng.random((S, n - 1))
+    fused = rg.device.regrid1d_conservative(T(xin, dev), T(xout, dev), T(vals, dev)).cpu().numpy()
+    for s in (0, 17, 63):
+        tri = oracle.coalesce(*oracle.weights_conservative_1d(xin[s], xout[s]))
+        ref = oracle.regrid_from_weights(*tri, vals[s:s + 1], n - 1)[0]
+        assert np.array_equal(fused[s], ref)
+        assert tri[2].size == 8189 or abs(tri[2].size - 8189) < 8
+
+
+# ---------------------------------------------------------------------------
+# find_indices
+# ---------------------------------------------------------------------------
+
+
+@pytest.mark.parametrize("method", ["brute", "searchsorted"])
+def test_find_indices_1d(rg, golden, method):
+    xin, xout = cases.cases_find_indices()
+    (r,) = rg.find_indices((xin,), (xout,), axis_input=-1, axis_output=-1, method=method)
+    assert r.dtype == np.int64 and np.array_equal(r, golden[f"find/{method}"])
+    (r,) = rg.find_indices((xin,), (xout,), axis_input=-1, axis_output=-1, method=method, fill_value=-1)
+    assert np.array_equal(r, golden[f"find/{method}_fillm1"])
+    # regridding/_find_indices/_tests/test_find_indices.py:54-91: sentinel regression
+    x = np.linspace(0, 1, 5)
+    p = np.array([-0.5, 0.0, 0.1, 0.9, 1.0, 1.5])
+    (r,) = rg.find_indices((x,), (p,), method=method)
+    big = np.iinfo(np.int64).max
+    assert list(r) == [big, 0, 0, 3, 3, big]
+
+
+def test_find_indices_2d_matches_reference_locators(rg, dev, oracle, golden):
+    gi, _, _ = cases.case_2d("fam40")
+    pts = golden["prim/points"]
+    ri, rj = rg.find_indices(gi, (pts[:, 0].reshape(20, 20), pts[:, 1].reshape(20, 20)))
+    assert np.array_equal(ri.reshape(-1), golden["prim/locate_brute"][:, 0])
+    assert np.array_equal(rj.reshape(-1), golden["prim/locate_brute"][:, 1])
+    assert np.array_equal(ri.reshape(-1), golden["prim/locate_secant"][:, 0])
+    # larger random set against the oracle's brute locator, incl. points outside
+    g = cases.curvilinear(70, 55, distort=0.01)
+    rng = np.random.default_rng(9)
+    P = 3000
+    px = rng.uniform(g[0].min() - 0.1, g[0].max() + 0.1, P)
+    py = rng.uniform(g[1].min() - 0.1, g[1].max() + 0.1, P)
+    flat = rg.device.find_indices_2d(T(g[0], dev), T(g[1], dev), T(px, dev), T(py, dev), -1).cpu().numpy()
+    big = np.iinfo(np.int64).max
+    n_out = 0
+    for k in range(P):
+        i, j = oracle.index_of_point(g[0], g[1], px[k], py[k], "brute")
+        want = -1 if i == big else i * (g[0].shape[1] - 1) + j
+        assert flat[k] == want, (k, flat[k], want)
+        n_out += want < 0
+    assert 0 < n_out < P
+
+
+def test_multilinear_1d(rg):
+    """regridding/_weights/_weights_multilinear_test.py: linear functions are reproduced exactly."""
+    x = np.linspace(0, 1, 11)
+    p = np.linspace(0.05, 0.95, 7)
+    vals = 3 * x + 1
+    res = rg.regrid((x,), (p,), vals)
+    assert np.allclose(res, 3 * p + 1)
+    W = rg.weights((x,), (np.array([-0.2, 0.5, 1.3]),), bounds="nan")
+    out = rg.regrid_from_weights(*W, vals)
+    assert np.isnan(out[0]) and np.isnan(out[2]) and np.isclose(out[1], 2.5)
+    with pytest.raises(ValueError):
+        rg.weights((x,), (np.array([-0.2, 0.5]),), bounds="raise")
+    ext = rg.regrid((x,), (np.array([-0.2, 1.3]),), vals)
+    assert np.allclose(ext, 3 * np.array([-0.2, 1.3]) + 1)

@@ -1,0 +1,107 @@
+"""CPU tests of the host-side logic that mirrors the reference's Python layer (no GPU needed)."""
+
+import numpy as np
+import pytest
+
+from regridding_b200 import _cache, _parallel, _util
+from tests import cases
+
+
+def test_perturbation_matches_reference_stream(golden):
+    """The seeded 1e-9 jitter (regridding/_util.py:121-129) -- golden SHA of the reference's output."""
+    for name in cases.CASES_2D:
+        gi, go, _ = cases.case_2d(name)
+        _, co, axis_in, axis_out, *_ = _util.normalize_input_output_coordinates(gi, go, perturb=True, seed=42)
+        assert axis_in == (-1, -2) and axis_out == (-1, -2)
+        assert cases.sha(*(np.ascontiguousarray(c) for c in co)) == str(golden[f"c2d/{name}/perturbed_sha"])
+
+
+def test_perturbation_stream_order_batched():
+    """x for ALL orthogonal slices first, then y; per-slice spread."""
+    gi, go = cases.case_2d_batched()
+    _, co, *_ = _util.normalize_input_output_coordinates(gi, go, axis_input=(1, 2), axis_output=(1, 2),
+                                                         perturb=True, seed=42)
+    ref = cases.perturb_like_reference(go, (-1, -2), 42)
+    assert np.array_equal(co[0], ref[0]) and np.array_equal(co[1], ref[1])
+    rng = np.random.default_rng(42)
+    zx = rng.standard_normal(go[0].shape)
+    spread = np.ptp(go[0], axis=(-1, -2), keepdims=True)
+    assert np.array_equal(co[0], go[0] + (spread * 1e-9) * zx)
+    # a slice built alone gets a different jitter than inside the batch
+    _, alone, *_ = _util.normalize_input_output_coordinates((gi[0][1], gi[1][1]), (go[0][1], go[1][1]),
+                                                            perturb=True, seed=42)
+    assert not np.array_equal(alone[0], co[0][1])
+
+
+def test_normalize_shapes_and_axes():
+    x = np.zeros((7, 5, 6))
+    y = np.zeros((7, 5, 6))
+    xo = np.zeros((1, 4, 3))
+    r = _util.normalize_input_output_coordinates((x, y), (xo, xo), axis_input=(1, 2), axis_output=(-2, -1))
+    ci, co, ai, ao, si, so, orth = r
+    assert ai == (-1, -2) and ao == (-1, -2) and orth == (7,)
+    assert ci[0].shape == (7, 5, 6) and co[0].shape == (7, 4, 3)
+    # resampled axis in the middle
+    r = _util.normalize_input_output_coordinates((np.zeros((3, 9, 2)),), (np.zeros((3, 4, 2)),), axis_input=1,
+                                                 axis_output=1)
+    assert r[2] == (-2,) and r[6] == (3, 2) and r[0][0].shape == (3, 9, 2) and r[1][0].shape == (3, 4, 2)
+    # bare arrays are wrapped
+    r = _util.normalize_input_output_coordinates(np.zeros(5), np.zeros(3))
+    assert r[2] == (-1,) and r[6] == ()
+    assert _util.normalize_axis(None, 3) == (-3, -2, -1)
+    assert _util.normalize_axis((0, -1), 3) == (-3, -1)
+    assert _util._embed((7, 2), (-1, -3), {-1: 5, -3: 9}) == (7, 9, 2, 5)
+
+
+def test_argument_errors_like_reference():
+    """regridding/_util.py:68-84 and _weights.py:184 / _find_indices.py:125 -- raised before any GPU work."""
+    x = np.zeros((4, 4))
+    with pytest.raises(ValueError, match="number of axes"):
+        _util.normalize_input_output_coordinates((x, x), (x, x), axis_input=(0, 1), axis_output=(0,))
+    with pytest.raises(ValueError, match="coordinates_input"):
+        _util.normalize_input_output_coordinates((x,), (x,), axis_input=(0, 1), axis_output=(0, 1))
+    with pytest.raises(ValueError, match="coordinates_output"):
+        _util.normalize_input_output_coordinates((x,), (x, x), axis_input=(0,), axis_output=(0,))
+    import regridding_b200 as rg
+
+    with pytest.raises(ValueError, match="unrecognized method"):
+        rg.weights((x, x), (x, x), method="bogus")
+    with pytest.raises(ValueError, match="not recognized"):
+        rg.find_indices((np.zeros(3),), (np.zeros(3),), method="bogus")
+    with pytest.raises(ValueError, match="bounds"):
+        rg.weights((np.zeros(3),), (np.zeros(3),), bounds="bogus")
+
+
+def test_no_cpu_fallback_without_cuda():
+    import torch
+
+    import regridding_b200 as rg
+
+    if torch.cuda.is_available():
+        pytest.skip("CUDA present")
+    x = np.linspace(0, 1, 5)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        rg.weights((x,), (x,), method="conservative")
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        rg.find_indices((x,), (x,))
+
+
+def test_cache_is_identity_keyed():
+    v = np.arange(3.0)
+    token = object()
+    _cache.remember(v, token)
+    assert _cache.lookup(v) is token
+    assert _cache.lookup(v.copy()) is None
+    del v
+    assert all(ref() is not None for ref, _ in _cache._entries.values())
+
+
+def test_shard_ranges_cover_exactly():
+    for n in (0, 1, 7, 64, 1000, 2048):
+        for w in (1, 2, 3, 8):
+            parts = [_parallel.shard_range(n, r, w) for r in range(w)]
+            assert parts[0][0] == 0 and parts[-1][1] == n
+            assert all(a[1] == b[0] for a, b in zip(parts[:-1], parts[1:]))
+            sizes = [b - a for a, b in parts]
+            assert max(sizes) - min(sizes) <= 1
+    assert _parallel.band_cells(2048, 2048, 3, 8) == (3 * 256 * 2048, 4 * 256 * 2048)

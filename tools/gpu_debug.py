@@ -88,8 +88,8 @@ for method in ("brute", "searchsorted"):
     print("find fill", method, cmp("idx", r, G[f"find/{method}_fillm1"]))
 gi, _, _ = cases.case_2d("fam40")
 pts = G["prim/points"]
-ri, rj = rg.find_indices(gi, (pts[:, 0], pts[:, 1]))
-print("find2d", cmp("i", ri, G["prim/locate_brute"][:, 0]), cmp("j", rj, G["prim/locate_brute"][:, 1]))
+ri, rj = rg.find_indices(gi, (pts[:, 0].reshape(20, 20), pts[:, 1].reshape(20, 20)))
+print("find2d", cmp("i", ri.reshape(-1), G["prim/locate_brute"][:, 0]), cmp("j", rj.reshape(-1), G["prim/locate_brute"][:, 1]))
 
 # timing at scale
 for n in (513, 1025, 2049):
