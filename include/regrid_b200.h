@@ -143,6 +143,30 @@ int rg_apply_csr(int device, void* stream, int64_t n_frames, int64_t n_in, int64
                  const int32_t* row_ptr, const int32_t* col, const double* val,
                  const double* values_in, double* values_out);
 
+/* Planned (shared-memory staged) apply for weights between 2D cell grids
+ * (h_in, w_in) -> (h_out, w_out): the same arithmetic and bits as rg_apply_csr, organised
+ * for HBM bandwidth.  rg_apply_plan_build analyses a CSR once (per output tile: the
+ * footprint of input cells it references, tile-local u16 indices); rg_apply_planned then
+ * streams any number of frames through it.  Tiles whose footprint does not fit on chip are
+ * counted in *n_generic_tiles_host and served by the generic per-cell kernel.
+ * Buffers (caller-allocated, sizes from rg_apply_plan_sizes): tile_info int32[tile_info_ints],
+ * tile_rows int32[tile_rows_ints], lidx uint16[nnz]. */
+int rg_apply_plan_sizes(int64_t h_out, int64_t w_out, int64_t* n_tiles_host,
+                        int64_t* tile_info_ints_host, int64_t* tile_rows_ints_host);
+
+int rg_apply_plan_build(int device, void* stream, int64_t nnz,
+                        int64_t h_in, int64_t w_in, int64_t h_out, int64_t w_out,
+                        const int32_t* row_ptr, const int32_t* col,
+                        int32_t* tile_info, int32_t* tile_rows, uint16_t* lidx,
+                        int64_t* n_generic_tiles_host);
+
+int rg_apply_planned(int device, void* stream, int64_t n_frames,
+                     int64_t h_in, int64_t w_in, int64_t h_out, int64_t w_out,
+                     const int32_t* row_ptr, const int32_t* col, const double* val,
+                     const int32_t* tile_info, const int32_t* tile_rows, const uint16_t* lidx,
+                     int64_t n_generic_tiles,
+                     const double* values_in, double* values_out);
+
 /* ------------------------------------------------------------------------------
  * 1D conservative, batched over S independent spectra
  * replaces: weights_conservative_1d(x_input, x_output, weights_input, weights_output, start, stop)

@@ -69,6 +69,20 @@ class CSR:
     n_out: int
 
 
+@dataclasses.dataclass
+class ApplyPlan:
+    """Per-tile footprints + tile-local indices of one CSR between 2D cell grids (rg_apply_plan_build)."""
+
+    csr: CSR
+    shape_in: tuple[int, int]
+    shape_out: tuple[int, int]
+    tile_info: torch.Tensor
+    tile_rows: torch.Tensor
+    lidx: torch.Tensor
+    n_tiles: int
+    n_generic_tiles: int
+
+
 class DeviceWeights:
     """One set of weights resident in HBM: the public COO (sorted by (input, output),
     unique pairs, int64/int64/float64) plus, lazily, the CSR-by-output form the apply uses."""
@@ -80,6 +94,7 @@ class DeviceWeights:
         self.n_in = int(n_in)
         self.n_out = int(n_out)
         self._csr: CSR | None = None
+        self._plans: dict = {}
         self.stats: dict | None = None
 
     @property
@@ -99,6 +114,12 @@ class DeviceWeights:
                 io = torch.where(io < 0, io + self.n_out, io)
             self._csr = csr_from_coo(ii, io, self.values, self.n_in, self.n_out)
         return self._csr
+
+    def plan(self, shape_in: tuple[int, int], shape_out: tuple[int, int]) -> ApplyPlan:
+        key = (tuple(shape_in), tuple(shape_out))
+        if key not in self._plans:
+            self._plans[key] = build_apply_plan(self.csr(), key[0], key[1])
+        return self._plans[key]
 
     def to_host(self) -> tuple[np.ndarray, np.ndarray, np.ndarray]:
         """The reference's saved-weights element: ``(indices_input, indices_output, values)``."""
@@ -230,6 +251,51 @@ def apply_csr(csr: CSR, values_in: torch.Tensor, out: torch.Tensor | None = None
         _lib.check(L.rg_apply_csr(device.index, _stream(device), F, csr.n_in, csr.n_out,
                                   csr.row_ptr.data_ptr(), csr.col.data_ptr(), csr.val.data_ptr(),
                                   values_in.data_ptr(), out.data_ptr()), "rg_apply_csr")
+    return out
+
+
+def build_apply_plan(csr: CSR, shape_in: tuple[int, int], shape_out: tuple[int, int]) -> ApplyPlan:
+    L = _lib.load()
+    device = csr.val.device
+    (h_in, w_in), (h_out, w_out) = (int(s) for s in shape_in), (int(s) for s in shape_out)
+    if h_in * w_in != csr.n_in or h_out * w_out != csr.n_out:
+        raise ValueError("plan shapes do not match the weights")
+    nt, ni, nr = ctypes.c_int64(), ctypes.c_int64(), ctypes.c_int64()
+    _lib.check(L.rg_apply_plan_sizes(h_out, w_out, ctypes.byref(nt), ctypes.byref(ni), ctypes.byref(nr)),
+               "rg_apply_plan_sizes")
+    tile_info = torch.empty(ni.value, dtype=I32, device=device)
+    tile_rows = torch.empty(nr.value, dtype=I32, device=device)
+    nnz = int(csr.val.numel())
+    lidx = torch.empty(max(nnz, 1), dtype=torch.int16, device=device)
+    ng = ctypes.c_int64()
+    with torch.cuda.device(device):
+        _lib.check(L.rg_apply_plan_build(device.index, _stream(device), nnz, h_in, w_in, h_out, w_out,
+                                         csr.row_ptr.data_ptr(), csr.col.data_ptr(), tile_info.data_ptr(),
+                                         tile_rows.data_ptr(), lidx.data_ptr(), ctypes.byref(ng)),
+                   "rg_apply_plan_build")
+    return ApplyPlan(csr, (h_in, w_in), (h_out, w_out), tile_info, tile_rows, lidx, nt.value, ng.value)
+
+
+def apply_planned(plan: ApplyPlan, values_in: torch.Tensor, out: torch.Tensor | None = None) -> torch.Tensor:
+    """Shared-memory staged apply: values_in (F, n_in) -> (F, n_out); same bits as ``apply_csr``."""
+    L = _lib.load()
+    csr = plan.csr
+    device = csr.val.device
+    if values_in.dtype != F64 or not values_in.is_contiguous() or values_in.device != device:
+        raise ValueError("values_in must be a contiguous float64 tensor on the weights' device")
+    F, n_in = values_in.shape
+    if n_in != csr.n_in:
+        raise ValueError(f"values_in has {n_in} cells per frame, the weights expect {csr.n_in}")
+    if out is None:
+        out = torch.empty((F, csr.n_out), dtype=F64, device=device)
+    elif out.shape != (F, csr.n_out) or out.dtype != F64 or not out.is_contiguous() or out.device != device:
+        raise ValueError("out must be a contiguous float64 (F, n_out) tensor on the weights' device")
+    with torch.cuda.device(device):
+        _lib.check(L.rg_apply_planned(device.index, _stream(device), F, plan.shape_in[0], plan.shape_in[1],
+                                      plan.shape_out[0], plan.shape_out[1], csr.row_ptr.data_ptr(),
+                                      csr.col.data_ptr(), csr.val.data_ptr(), plan.tile_info.data_ptr(),
+                                      plan.tile_rows.data_ptr(), plan.lidx.data_ptr(), plan.n_generic_tiles,
+                                      values_in.data_ptr(), out.data_ptr()), "rg_apply_planned")
     return out
 
 

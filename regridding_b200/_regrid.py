@@ -104,7 +104,10 @@ def regrid_from_weights(
         while e < D and flat_weights[e] is flat_weights[d]:
             e += 1
         dw = _device_weights_of(flat_weights[d], n_in, n_out, device)
-        _device.apply_csr(dw.csr(), vin[d:e], out[d:e])
+        if len(cells_in) == 2 and len(cells_out) == 2:
+            _device.apply_planned(dw.plan(cells_in, cells_out), vin[d:e], out[d:e])
+        else:
+            _device.apply_csr(dw.csr(), vin[d:e], out[d:e])
         d = e
 
     moved_out_shape = tuple(shape_orth) + cells_out

@@ -66,6 +66,13 @@ def test_build2d_bit_exact_vs_oracle_and_reference(rg, dev, oracle, golden, name
     ref = oracle.regrid_from_weights(oi, oo, ov, vals.reshape(3, -1), dw.n_out)
     assert np.array_equal(out, ref)
     assert cases.sha(out.reshape(3, *shape_out)) == str(golden[f"c2d/{name}/apply_sha"])
+    # the shared-memory staged (planned) apply gives the same bits, incl. frame counts that do not fill a sub-block
+    plan = dw.plan(shape_in, shape_out)
+    for F in (3, 16, 37):
+        vals_f = np.random.default_rng(F).random((F, dw.n_in))
+        a = rg.device.apply_csr(dw.csr(), T(vals_f, dev))
+        b = rg.device.apply_planned(plan, T(vals_f, dev))
+        assert torch.equal(a, b), (name, F, plan.n_generic_tiles, plan.n_tiles)
 
 
 def test_grid_area_bit_exact(rg, dev, oracle, golden):
@@ -144,6 +151,9 @@ def test_config3_full_size_properties(rg, dev):
     ax, ay = rg.device.apply_csr(csr, x), rg.device.apply_csr(csr, y)
     axy = rg.device.apply_csr(csr, (2.0 * x + 0.5 * y).contiguous())
     assert float((axy - (2.0 * ax + 0.5 * ay)).abs().max()) < 1e-9
+    plan = dw.plan((n - 1, n - 1), (n - 1, n - 1))
+    assert plan.n_generic_tiles == 0
+    assert torch.equal(rg.device.apply_planned(plan, x), ax)
     # CSR apply == straightforward COO scatter-add of the public triplets (different summation order)
     ref = torch.zeros((F, dw.n_out), dtype=torch.float64, device=dev)
     ref.index_add_(1, io, x[:, ii] * v)

@@ -111,3 +111,15 @@ for n in (513, 1025, 2049):
         torch.cuda.synchronize(); dt = time.time() - t
     byt = 8 * F * (dw.n_in + dw.n_out) + 12 * dw.nnz + 4 * (dw.n_out + 1)
     print(f"apply {n} F={F}: {dt*1e3:.2f} ms  {byt/dt/1e9:.0f} GB/s")
+    plan = dw.plan((n - 1, n - 1), (n - 1, n - 1))
+    out2 = torch.empty_like(out)
+    for F2 in (64, 256):
+        vin2 = torch.rand((F2, dw.n_in), dtype=torch.float64, device=dev)
+        out2 = torch.empty((F2, dw.n_out), dtype=torch.float64, device=dev)
+        for rep in range(3):
+            torch.cuda.synchronize(); t = time.time()
+            _device.apply_planned(plan, vin2, out2)
+            torch.cuda.synchronize(); dt = time.time() - t
+        byt = 8 * F2 * (dw.n_in + dw.n_out) + 12 * dw.nnz + 4 * (dw.n_out + 1)
+        ref2 = _device.apply_csr(csr, vin2)
+        print(f"planned {n} F={F2}: {dt*1e3:.2f} ms  {byt/dt/1e9:.0f} GB/s  generic tiles {plan.n_generic_tiles}/{plan.n_tiles} equal {torch.equal(ref2, out2)}")
