@@ -29,30 +29,33 @@ namespace rg {
 constexpr int kTH = 8;           // tile height (output rows)
 constexpr int kTW = 32;          // tile width  (output cols) = one full coalesced row of 256 B
 constexpr int kTileCells = kTH * kTW;
+constexpr int kQuads = kTileCells / 4;  // a quad = 4 consecutive output cells = the 4 quarter-warps of a warp
 constexpr int kT = 16;           // frames per sub-block: 8 lanes x 2 frames per lane
 constexpr int kFB = 256;         // frames per CTA (the tile-local CSR is reread every kFB frames)
 constexpr int kRMAX = 64;        // max input rows in a footprint
-constexpr int kCP = 770;         // staged cells per frame (capacity); kCP/2 odd => the 8 frame lanes of a
-                                 // quarter-warp hit 8 distinct 16-byte bank groups
-constexpr int kCellsMax = kCP;
+constexpr int kCP = 770;         // doubles per staged frame; kCP/2 odd => the 8 frame lanes of a quarter-warp
+                                 // hit 8 distinct 16-byte bank groups.  Slot kCP-1 of every frame holds 0.0.
+constexpr int kCellsMax = kCP - 2;
+constexpr int kZeroSlot = kCP - 1;
 constexpr int kNnzMax = 2560;    // max CSR entries per tile
-constexpr int kOutStride = kTileCells + 2;  // doubles per staged output frame (= 2 mod 16)
+constexpr int kPadMax = 3072;    // max entries after padding the 4 rows of every quad to a common length
+constexpr int kOutStride = kCP;  // staged output frame t lives in slots [0, 256) of staged input frame t
 constexpr int kStagedThreads = 1024;
+constexpr int kPairsPerLane = (kCP / 2 + 63) / 64;  // 16-byte pairs of one frame a lane copies per sub-block
 constexpr int kPatch = 12;       // tiles are issued in 12 x 12 patches (~ one wave of 148 CTAs) so that
                                  // footprint halos are shared through L2
 static_assert((kCP / 2) % 2 == 1 && kCP % 2 == 0, "kCP/2 must be odd");
-static_assert(kT * kOutStride <= kT * kCP, "output staging aliases one input buffer");
 
 constexpr int kTileInfoInts = 4;  // r0, nrows, cells, nnz (nnz < 0: tile handled by the generic kernel)
 
 struct StagedSmem {
-    double in_s[2][kT * kCP];     // [buffer][frame][cell]; the consumed buffer doubles as out_s[frame][kOutStride]
-    double val[kNnzMax];
-    uint16_t lidx[kNnzMax];       // BYTE offset of the referenced cell inside a staged frame
+    double in_s[2][kT * kCP];     // [buffer][frame][cell]; after compute, frame t's slots [0,256) hold its outputs
+    double val[kPadMax];          // padded tile-local CSR, interleaved per quad: entry (quad, w, q)
+    uint16_t lidx[kPadMax];       // BYTE offset of the referenced cell inside a staged frame
+    uint16_t quad_beg[kQuads + 1];
     uint16_t rowptr[kTileCells + 2];
     int32_t row_src[kRMAX];       // per footprint row: offset of its span inside one input frame (doubles)
-    int32_t row_off[kRMAX];       //                    offset of its span inside one staged frame
-    int32_t row_len[kRMAX];       //                    span length
+    int32_t row_off[kRMAX + 1];   //                    offset of its span inside one staged frame
     alignas(8) uint64_t full[2];  // mbarriers: "buffer filled"
 };
 
@@ -92,13 +95,13 @@ k_plan_tiles(int64_t h_in, int64_t w_in, int64_t h_out, int64_t w_out, int tiles
              int32_t* __restrict__ tile_info, int32_t* __restrict__ tile_rows, uint16_t* __restrict__ lidx,
              int32_t* __restrict__ n_generic)
 {
-    __shared__ int s_rmin, s_rmax, s_nnz;
+    __shared__ int s_rmin, s_rmax, s_nnz, s_pad;
     __shared__ int s_clo[kRMAX], s_chi[kRMAX], s_off[kRMAX + 1];
     const int tile = blockIdx.x;
     const int ty = tile / tiles_x, tx = tile % tiles_x;
     const int th = (int)min((int64_t)kTH, h_out - (int64_t)ty * kTH);
     const int tw = (int)min((int64_t)kTW, w_out - (int64_t)tx * kTW);
-    if (threadIdx.x == 0) { s_rmin = INT32_MAX; s_rmax = -1; s_nnz = 0; }
+    if (threadIdx.x == 0) { s_rmin = INT32_MAX; s_rmax = -1; s_nnz = 0; s_pad = 0; }
     for (int r = threadIdx.x; r < kRMAX; r += blockDim.x) { s_clo[r] = INT32_MAX; s_chi[r] = -1; }
     __syncthreads();
     // pass 1: input row range and entry count
@@ -117,7 +120,18 @@ k_plan_tiles(int64_t h_in, int64_t w_in, int64_t h_out, int64_t w_out, int tiles
     __syncthreads();
     const int rmin = s_rmin, nnz = s_nnz;
     const int nrows = nnz ? s_rmax - rmin + 1 : 0;
-    bool generic = nrows > kRMAX || nnz > kNnzMax;
+    // entries after padding the 4 rows of every quad (4 consecutive cells of a tile row) to a common length
+    for (int qd = threadIdx.x; qd < kQuads; qd += blockDim.x) {
+        const int tr = (4 * qd) / kTW, c0 = (4 * qd) % kTW;
+        int m = 0;
+        if (tr < th) {
+            const int64_t o0 = ((int64_t)ty * kTH + tr) * w_out + (int64_t)tx * kTW;
+            for (int c = c0; c < c0 + 4 && c < tw; c++) m = max(m, row_ptr[o0 + c + 1] - row_ptr[o0 + c]);
+        }
+        if (m) atomicAdd(&s_pad, 4 * m);
+    }
+    __syncthreads();
+    bool generic = nrows > kRMAX || nnz > kNnzMax || s_pad > kPadMax || !pad_even;
     if (!generic && nnz) {
         // pass 2: column span of every input row
         for (int tr = 0; tr < th; tr++) {
@@ -136,10 +150,8 @@ k_plan_tiles(int64_t h_in, int64_t w_in, int64_t h_out, int64_t w_out, int tiles
             for (int r = 0; r < nrows; r++) {
                 s_off[r] = off;
                 if (s_chi[r] >= s_clo[r]) {
-                    if (pad_even) {  // spans start on even columns and have even length: 16-byte copies
-                        s_clo[r] &= ~1;
-                        s_chi[r] |= 1;
-                    }
+                    s_clo[r] &= ~1;  // spans start on even columns and have even length: 16-byte copies
+                    s_chi[r] |= 1;
                     off += s_chi[r] - s_clo[r] + 1;
                 } else {
                     s_clo[r] = 0;
@@ -182,23 +194,18 @@ k_plan_tiles(int64_t h_in, int64_t w_in, int64_t h_out, int64_t w_out, int tiles
 // ---------------------------------------------------------------------------
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
 
-template <int BYTES>
-__device__ __forceinline__ void cp_async(void* smem_dst, const void* gmem_src)
+__device__ __forceinline__ void cp_async_16(unsigned smem_dst, const void* gmem_src)
 {
-    asm volatile("cp.async.ca.shared.global [%0], [%1], %2;\n" ::"r"(smem_u32(smem_dst)), "l"(gmem_src), "n"(BYTES));
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(smem_dst), "l"(gmem_src));
 }
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
-
-// mbarrier + bulk (TMA engine) copies: one instruction moves a whole footprint row span
 __device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned count)
 {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(count));
 }
-__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, unsigned bytes)
+// the mbarrier receives one arrival from this thread once all its earlier cp.async have landed
+__device__ __forceinline__ void cp_async_mbar_arrive(uint64_t* bar)
 {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];\n" ::"r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity)
 {
@@ -212,17 +219,9 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity)
         "DONE_%=:\n"
         "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
 }
-__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, unsigned bytes, uint64_t* bar)
-{
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(smem_u32(smem_dst)),
-                 "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
-                 : "memory");
-}
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory"); }
 
-// WIDE: spans are even-aligned and the frame pitch is even, so every span is a 16-byte aligned,
-// 16-byte multiple run and moves as ONE bulk copy; otherwise 8-byte cp.async per element.
-template <bool WIDE>
+// Requires even w_in / n_in and a 16-byte aligned values_in (the plan pads every footprint span to an even
+// start and even length), so the footprint moves in 16-byte pieces.
 __global__ void __launch_bounds__(kStagedThreads, 1)
 k_apply_staged(int64_t n_frames, int64_t w_in, int64_t n_in, int64_t h_out, int64_t w_out, int tiles_x, int tiles_y,
                const int32_t* __restrict__ row_ptr, const double* __restrict__ val,
@@ -259,114 +258,138 @@ k_apply_staged(int64_t n_frames, int64_t w_in, int64_t n_in, int64_t h_out, int6
         return;
     }
 
-    // ---- tile-local CSR and footprint table: loaded once, reused for every frame of this CTA ----
+    // ---- once per CTA: footprint table, tile-local CSR (padded per quad), zero slots, barriers ----
     {
         int base = 0;
         for (int tr = 0; tr < kTH; tr++) {
+            int32_t b = 0, e = 0;
             if (tr < th) {
                 const int64_t o0 = out_base + (int64_t)tr * w_out;
-                const int32_t b = row_ptr[o0], e = row_ptr[o0 + tw];
-                if (threadIdx.x < kTW)
-                    S.rowptr[tr * kTW + threadIdx.x] = (uint16_t)(base + (row_ptr[o0 + min((int)threadIdx.x, tw)] - b));
-                for (int32_t w = b + threadIdx.x; w < e; w += kStagedThreads) {
-                    S.val[base + (w - b)] = val[w];
-                    S.lidx[base + (w - b)] = (uint16_t)(lidx[w] * 8u);  // byte offset inside a staged frame
-                }
-                base += e - b;
+                b = row_ptr[o0];
+                e = row_ptr[o0 + tw];
+                if (threadIdx.x < kTW) S.rowptr[tr * kTW + threadIdx.x] = (uint16_t)(base + (row_ptr[o0 + min((int)threadIdx.x, tw)] - b));
             } else if (threadIdx.x < kTW) {
                 S.rowptr[tr * kTW + threadIdx.x] = (uint16_t)base;
             }
+            base += e - b;
         }
         if (threadIdx.x == 0) S.rowptr[kTileCells] = (uint16_t)base;
         for (int r = threadIdx.x; r < nrows; r += kStagedThreads) {
-            const int clo = tile_rows[((int64_t)tile * kRMAX + r) * 2 + 0];
-            const int off = tile_rows[((int64_t)tile * kRMAX + r) * 2 + 1];
-            const int end = (r + 1 < nrows) ? tile_rows[((int64_t)tile * kRMAX + r + 1) * 2 + 1] : cells;
-            S.row_src[r] = (int32_t)((int64_t)(r0 + r) * w_in + clo);
-            S.row_off[r] = off;
-            S.row_len[r] = end - off;
+            S.row_src[r] = (int32_t)((int64_t)(r0 + r) * w_in + tile_rows[((int64_t)tile * kRMAX + r) * 2 + 0]);
+            S.row_off[r] = tile_rows[((int64_t)tile * kRMAX + r) * 2 + 1];
         }
         if (threadIdx.x == 0) {
-            mbar_init(&S.full[0], kT);
-            mbar_init(&S.full[1], kT);
+            S.row_off[nrows] = cells;
+            mbar_init(&S.full[0], kStagedThreads);
+            mbar_init(&S.full[1], kStagedThreads);
             asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+        }
+        if (threadIdx.x < 2 * kT) S.in_s[threadIdx.x / kT][(threadIdx.x % kT) * kCP + kZeroSlot] = 0.0;
+    }
+    __syncthreads();
+    {
+        // quad q4 holds cells 4*q4 .. 4*q4+3; all four rows are padded to the longest with (zero slot, 0.0)
+        if (threadIdx.x == 0) {
+            int acc = 0;
+            for (int qd = 0; qd < kQuads; qd++) {
+                S.quad_beg[qd] = (uint16_t)acc;
+                int m = 0;
+                for (int c = 0; c < 4; c++) m = max(m, (int)S.rowptr[4 * qd + c + 1] - (int)S.rowptr[4 * qd + c]);
+                acc += 4 * m;
+            }
+            S.quad_beg[kQuads] = (uint16_t)acc;
+        }
+    }
+    __syncthreads();
+    if (S.quad_beg[kQuads] > kPadMax) __trap();  // cannot happen: the plan routes such tiles to the generic kernel
+    {
+        // source position of local CSR entry j of cell c: the tile's rows are contiguous runs of the global CSR
+        for (int qd = warp; qd < kQuads; qd += NW) {
+            const int qb = S.quad_beg[qd], qn = (S.quad_beg[qd + 1] - qb) >> 2;
+            const int c = lane & 3;  // cell of the quad
+            const int cell = 4 * qd + c;
+            const int tr = cell / kTW;
+            const int lb = S.rowptr[cell], ln = (int)S.rowptr[cell + 1] - lb;
+            const int64_t o0 = out_base + (int64_t)tr * w_out;
+            const int32_t gb = (tr < th) ? row_ptr[o0] - (int32_t)S.rowptr[tr * kTW] : 0;  // global = gb + local
+            for (int w = lane >> 2; w < qn; w += 8) {
+                double v = 0.0;
+                unsigned lo = kZeroSlot * 8u;
+                if (w < ln) {
+                    v = val[gb + lb + w];
+                    lo = (unsigned)lidx[gb + lb + w] * 8u;
+                }
+                S.val[qb + 4 * w + c] = v;
+                S.lidx[qb + 4 * w + c] = (uint16_t)lo;
+            }
         }
     }
     __syncthreads();
 
-    // ---- footprint copy of one 16-frame sub-block: warp w (< 16) moves frame w, lane r moves input row r ----
-    auto prefetch = [&](int64_t f0, int buf) {
-        if (warp >= kT) return;
-        const int64_t f = f0 + warp;
-        double* dst = S.in_s[buf] + warp * kCP;
-        if (WIDE) {
-            const bool valid = f < f_end;
-            if (lane == 0) mbar_arrive_expect_tx(&S.full[buf], valid ? (unsigned)cells * 8u : 0u);
-            __syncwarp();
-            if (valid) {
-                const double* src = vin + f * n_in;
-                for (int r = lane; r < nrows; r += 32) {
-                    const int len = S.row_len[r];
-                    if (len > 0) bulk_g2s(dst + S.row_off[r], src + S.row_src[r], (unsigned)len * 8u, &S.full[buf]);
+    // ---- footprint copy: thread -> frame (warp & 15), 16-byte pairs (warp >> 4) * 32 + lane + 64 j ----
+    const int tt_p = warp & (kT - 1);
+    int32_t pair_off[kPairsPerLane];  // source offset (doubles, inside a frame) of each of this lane's pairs; -1: none
+    {
+        const int npairs = cells >> 1;
+#pragma unroll
+        for (int j = 0; j < kPairsPerLane; j++) {
+            const int p = (warp >> 4) * 32 + lane + 64 * j;
+            int32_t off = -1;
+            if (p < npairs) {
+                // row of staged cell 2p: last r with row_off[r] <= 2p
+                int lo = 0, hi = nrows - 1;
+                while (lo < hi) {
+                    const int mid = (lo + hi + 1) >> 1;
+                    if (S.row_off[mid] <= 2 * p) lo = mid; else hi = mid - 1;
                 }
+                off = S.row_src[lo] + (2 * p - S.row_off[lo]);
             }
-        } else {
-            if (f < f_end) {
-                const double* src = vin + f * n_in;
-                for (int r = 0; r < nrows; r++) {
-                    const double* rs = src + S.row_src[r];
-                    double* rd = dst + S.row_off[r];
-                    for (int c = lane; c < S.row_len[r]; c += 32) cp_async<8>(rd + c, rs + c);
-                }
-            }
+            pair_off[j] = off;
         }
+    }
+    const unsigned dst_lane = (unsigned)((tt_p * kCP + 2 * ((warp >> 4) * 32 + lane)) * 8);
+    auto prefetch = [&](int64_t f0, int buf) {
+        const int64_t f = f0 + tt_p;
+        if (f < f_end) {
+            const double* src = vin + f * n_in;
+            const unsigned dst = smem_u32(S.in_s[buf]) + dst_lane;
+#pragma unroll
+            for (int j = 0; j < kPairsPerLane; j++)
+                if (pair_off[j] >= 0) cp_async_16(dst + j * 64 * 16, src + pair_off[j]);
+        }
+        cp_async_mbar_arrive(&S.full[buf]);
     };
 
     const int nsub = (int)((f_end - f_begin + kT - 1) / kT);
     prefetch(f_begin, 0);
-    if (!WIDE) cp_async_commit();
     if (nsub > 1) prefetch(f_begin + kT, 1);
-    if (!WIDE) cp_async_commit();
     const int q = lane >> 3, t = lane & 7;  // quarter-warp = one output cell; lane owns frames t and t + 8
     for (int s = 0; s < nsub; s++) {
         const int64_t f0 = f_begin + (int64_t)s * kT;
         const int buf = s & 1;
-        if (WIDE) {
-            mbar_wait(&S.full[buf], (unsigned)((s >> 1) & 1));
-        } else {
-            cp_async_wait<1>();
-            __syncthreads();
-        }
+        mbar_wait(&S.full[buf], (unsigned)((s >> 1) & 1));
         double* in = S.in_s[buf];
         const char* in0 = reinterpret_cast<const char*>(in + t * kCP);
-        // ---- compute: quarter-warp per output cell; the trip count is made warp-uniform ----
+        // ---- compute: quarter-warp per output cell, rows of a quad share one (padded) trip count ----
         double acc[2][2];
 #pragma unroll
         for (int k = 0; k < 2; k++) {
-            const int o_local = 4 * (warp + k * NW) + q;
-            const int beg = S.rowptr[o_local], n = (int)S.rowptr[o_local + 1] - beg;
-            int nmax = n;
-            nmax = max(nmax, __shfl_xor_sync(0xffffffffu, nmax, 8));
-            nmax = max(nmax, __shfl_xor_sync(0xffffffffu, nmax, 16));
-            const int last = max(beg + n - 1, 0);
+            const int qd = warp + k * NW;
+            const int qb = S.quad_beg[qd], qe = S.quad_beg[qd + 1];
             double a0 = 0.0, a1 = 0.0;
-#pragma unroll 2
-            for (int w = 0; w < nmax; w++) {
-                const int wi = min(beg + w, last);
-                const unsigned lo = S.lidx[wi];
-                const double v = S.val[wi];
+#pragma unroll 4
+            for (int e = qb + q; e < qe; e += 4) {
+                const unsigned lo = S.lidx[e];
+                const double v = S.val[e];
                 const double x0 = *reinterpret_cast<const double*>(in0 + lo);
                 const double x1 = *reinterpret_cast<const double*>(in0 + lo + 8 * kCP * 8);
-                const double p0 = dmul(v, x0), p1 = dmul(v, x1);
-                if (w < n) {
-                    a0 = dadd(a0, p0);
-                    a1 = dadd(a1, p1);
-                }
+                a0 = dadd(a0, dmul(v, x0));
+                a1 = dadd(a1, dmul(v, x1));
             }
             acc[k][0] = a0;
             acc[k][1] = a1;
         }
-        __syncthreads();  // everyone is done reading in_s[buf]: reuse it as out_s[frame][cell]
+        __syncthreads();  // everyone is done reading in_s[buf]: frame t's slots [0,256) now take its outputs
 #pragma unroll
         for (int k = 0; k < 2; k++) {
             const int o_local = 4 * (warp + k * NW) + q;
@@ -376,22 +399,16 @@ k_apply_staged(int64_t n_frames, int64_t w_in, int64_t n_in, int64_t h_out, int6
         __syncthreads();
         // ---- write-out: warp w stores frame (w & 15), tile rows (w >> 4), +2, ...; 256 B per instruction ----
         {
-            const int tt = warp & (kT - 1);
-            const int64_t f = f0 + tt;
+            const int64_t f = f0 + tt_p;
             if (f < f_end && lane < tw) {
                 double* o = vout + f * n_out + out_base + lane;
-                const double* si = in + tt * kOutStride + lane;
+                const double* si = in + tt_p * kOutStride + lane;
                 for (int tr = warp >> 4; tr < th; tr += 2) o[(int64_t)tr * w_out] = si[tr * kTW];
             }
         }
-        __syncthreads();  // out_s consumed: the buffer may be refilled
-        if (s + 2 < nsub) {
-            if (WIDE) fence_proxy_async();  // order our generic-proxy accesses before the async-proxy refill
-            prefetch(f0 + 2 * kT, buf);
-        }
-        if (!WIDE) cp_async_commit();
+        __syncthreads();  // outputs consumed: the buffer may be refilled
+        if (s + 2 < nsub) prefetch(f0 + 2 * kT, buf);
     }
-    if (!WIDE) cp_async_wait<0>();
 }
 
 // generic per-cell kernel restricted to the tiles the plan flagged
@@ -495,16 +512,19 @@ extern "C" int rg_apply_planned(int device, void* stream, int64_t n_frames,
     const int64_t n_tiles = tiles_of(h_out, w_out, &tiles_x);
     const int64_t n_in = h_in * w_in, n_out = h_out * w_out;
     static_assert(sizeof(StagedSmem) <= 227 * 1024, "staged tile does not fit in shared memory");
-    const bool wide = (w_in % 2 == 0) && (n_in % 2 == 0) && ((uintptr_t)values_in % 16 == 0);
+    const bool aligned = ((uintptr_t)values_in % 16 == 0);
     const int tiles_y = (int)(n_tiles / tiles_x);
-    auto kern = wide ? k_apply_staged<true> : k_apply_staged<false>;
-    RG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(StagedSmem)));
+    if (!aligned) {
+        // the staged kernel moves 16-byte pieces; a misaligned values pointer takes the generic kernel
+        return rg_apply_csr(device, stream, n_frames, n_in, n_out, row_ptr, col, val, values_in, values_out);
+    }
+    RG_CUDA(cudaFuncSetAttribute(k_apply_staged, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(StagedSmem)));
     if (n_generic_tiles < n_tiles) {
         const int64_t chunk = 65535LL * kFB;
         for (int64_t f = 0; f < n_frames; f += chunk) {
             const int64_t nf = n_frames - f < chunk ? n_frames - f : chunk;
             dim3 grid((unsigned)n_tiles, (unsigned)ceil_div(nf, kFB));
-            kern<<<grid, kStagedThreads, sizeof(StagedSmem), st>>>(
+            k_apply_staged<<<grid, kStagedThreads, sizeof(StagedSmem), st>>>(
                 nf, w_in, n_in, h_out, w_out, tiles_x, tiles_y, row_ptr, val, tile_info, tile_rows, lidx,
                 values_in + f * n_in, values_out + f * n_out);
             RG_LAUNCH_CHECK("k_apply_staged");
