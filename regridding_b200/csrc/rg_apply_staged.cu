@@ -26,22 +26,22 @@
 
 namespace rg {
 
-constexpr int kTH = 8;           // tile height (output rows)
+constexpr int kTH = 4;           // tile height (output rows)
 constexpr int kTW = 32;          // tile width  (output cols) = one full coalesced row of 256 B
 constexpr int kTileCells = kTH * kTW;
 constexpr int kQuads = kTileCells / 4;  // a quad = 4 consecutive output cells = the 4 quarter-warps of a warp
 constexpr int kT = 16;           // frames per sub-block: 8 lanes x 2 frames per lane
 constexpr int kFB = 256;         // frames per CTA (the tile-local CSR is reread every kFB frames)
 constexpr int kRMAX = 64;        // max input rows in a footprint
-constexpr int kCP = 770;         // doubles per staged frame; kCP/2 odd => the 8 frame lanes of a quarter-warp
+constexpr int kCP = 386;         // doubles per staged frame; kCP/2 odd => the 8 frame lanes of a quarter-warp
                                  // hit 8 distinct 16-byte bank groups.  Slot kCP-1 of every frame holds 0.0.
 constexpr int kCellsMax = kCP - 2;
 constexpr int kZeroSlot = kCP - 1;
-constexpr int kNnzMax = 2560;    // max CSR entries per tile
-constexpr int kPadMax = 3072;    // max entries after padding the 4 rows of every quad to a common length
-constexpr int kOutStride = kCP;  // staged output frame t lives in slots [0, 256) of staged input frame t
-constexpr int kStagedThreads = 1024;
-constexpr int kPairsPerLane = (kCP / 2 + 63) / 64;  // 16-byte pairs of one frame a lane copies per sub-block
+constexpr int kNnzMax = 1280;    // max CSR entries per tile
+constexpr int kPadMax = 1536;    // max entries after padding the 4 rows of every quad to a common length
+constexpr int kOutStride = kCP;  // staged output frame t lives in slots [0, 128) of staged input frame t
+constexpr int kStagedThreads = 512;   // 2 CTAs per SM: their load / compute / store phases overlap
+constexpr int kPairsPerLane = (kCP / 2 + 31) / 32;  // 16-byte pairs of one frame a lane copies per sub-block
 constexpr int kPatch = 12;       // tiles are issued in 12 x 12 patches (~ one wave of 148 CTAs) so that
                                  // footprint halos are shared through L2
 static_assert((kCP / 2) % 2 == 1 && kCP % 2 == 0, "kCP/2 must be odd");
@@ -222,7 +222,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity)
 
 // Requires even w_in / n_in and a 16-byte aligned values_in (the plan pads every footprint span to an even
 // start and even length), so the footprint moves in 16-byte pieces.
-__global__ void __launch_bounds__(kStagedThreads, 1)
+__global__ void __launch_bounds__(kStagedThreads, 2)
 k_apply_staged(int64_t n_frames, int64_t w_in, int64_t n_in, int64_t h_out, int64_t w_out, int tiles_x, int tiles_y,
                const int32_t* __restrict__ row_ptr, const double* __restrict__ val,
                const int32_t* __restrict__ tile_info, const int32_t* __restrict__ tile_rows,
@@ -326,14 +326,15 @@ k_apply_staged(int64_t n_frames, int64_t w_in, int64_t n_in, int64_t h_out, int6
     }
     __syncthreads();
 
-    // ---- footprint copy: thread -> frame (warp & 15), 16-byte pairs (warp >> 4) * 32 + lane + 64 j ----
-    const int tt_p = warp & (kT - 1);
+    // ---- footprint copy: warp -> frame, lane -> 16-byte pairs lane + 32 j ----
+    static_assert(kStagedThreads / 32 == kT, "one warp per frame of a sub-block");
+    const int tt_p = warp;
     int32_t pair_off[kPairsPerLane];  // source offset (doubles, inside a frame) of each of this lane's pairs; -1: none
     {
         const int npairs = cells >> 1;
 #pragma unroll
         for (int j = 0; j < kPairsPerLane; j++) {
-            const int p = (warp >> 4) * 32 + lane + 64 * j;
+            const int p = lane + 32 * j;
             int32_t off = -1;
             if (p < npairs) {
                 // row of staged cell 2p: last r with row_off[r] <= 2p
@@ -347,7 +348,7 @@ k_apply_staged(int64_t n_frames, int64_t w_in, int64_t n_in, int64_t h_out, int6
             pair_off[j] = off;
         }
     }
-    const unsigned dst_lane = (unsigned)((tt_p * kCP + 2 * ((warp >> 4) * 32 + lane)) * 8);
+    const unsigned dst_lane = (unsigned)((tt_p * kCP + 2 * lane) * 8);
     auto prefetch = [&](int64_t f0, int buf) {
         const int64_t f = f0 + tt_p;
         if (f < f_end) {
@@ -355,7 +356,7 @@ k_apply_staged(int64_t n_frames, int64_t w_in, int64_t n_in, int64_t h_out, int6
             const unsigned dst = smem_u32(S.in_s[buf]) + dst_lane;
 #pragma unroll
             for (int j = 0; j < kPairsPerLane; j++)
-                if (pair_off[j] >= 0) cp_async_16(dst + j * 64 * 16, src + pair_off[j]);
+                if (pair_off[j] >= 0) cp_async_16(dst + j * 32 * 16, src + pair_off[j]);
         }
         cp_async_mbar_arrive(&S.full[buf]);
     };
@@ -397,13 +398,13 @@ k_apply_staged(int64_t n_frames, int64_t w_in, int64_t n_in, int64_t h_out, int6
             in[(t + 8) * kOutStride + o_local] = acc[k][1];
         }
         __syncthreads();
-        // ---- write-out: warp w stores frame (w & 15), tile rows (w >> 4), +2, ...; 256 B per instruction ----
+        // ---- write-out: warp w stores frame w, all tile rows; 256 B per instruction ----
         {
             const int64_t f = f0 + tt_p;
             if (f < f_end && lane < tw) {
                 double* o = vout + f * n_out + out_base + lane;
                 const double* si = in + tt_p * kOutStride + lane;
-                for (int tr = warp >> 4; tr < th; tr += 2) o[(int64_t)tr * w_out] = si[tr * kTW];
+                for (int tr = 0; tr < th; tr++) o[(int64_t)tr * w_out] = si[tr * kTW];
             }
         }
         __syncthreads();  // outputs consumed: the buffer may be refilled
