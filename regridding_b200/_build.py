@@ -39,10 +39,14 @@ def needs_build() -> bool:
     return any(p.stat().st_mtime > t for p in deps)
 
 
-def build(force: bool = False, verbose: bool = False) -> pathlib.Path:
-    if not force and not needs_build():
+def build(force: bool = False, verbose: bool = False, defines: list[str] | None = None,
+          out: pathlib.Path | None = None) -> pathlib.Path:
+    """``defines``/``out`` build a tuning variant next to the product library (development only)."""
+    if out is None and not force and not needs_build():
         return LIB
-    cmd = [nvcc(), *NVCC_FLAGS, "-ccbin", "/usr/bin/g++", "-o", str(LIB), *[str(CSRC / s) for s in SOURCES]]
+    out = out or LIB
+    cmd = [nvcc(), *NVCC_FLAGS, *[f"-D{d}" for d in (defines or [])], "-ccbin", "/usr/bin/g++", "-o", str(out),
+           *[str(CSRC / s) for s in SOURCES]]
     if verbose:
         cmd.insert(1, "-Xptxas")
         cmd.insert(2, "-v")
@@ -52,7 +56,7 @@ def build(force: bool = False, verbose: bool = False) -> pathlib.Path:
         raise RuntimeError("nvcc failed building libregrid_b200.so")
     if verbose:
         sys.stderr.write(res.stdout + res.stderr)
-    return LIB
+    return out
 
 
 if __name__ == "__main__":

@@ -57,12 +57,16 @@ def load() -> ctypes.CDLL:
     """Load the CUDA library; fail loudly if it has not been built."""
     global _lib
     if _lib is None:
-        if not LIB_PATH.exists():
+        import os
+
+        override = os.environ.get("REGRID_B200_LIB")  # development: load an alternative build of the same ABI
+        path = pathlib.Path(override) if override else LIB_PATH
+        if not path.exists():
             raise RegridB200Error(
-                f"{LIB_PATH} is missing: build it with `python -m regridding_b200._build` "
+                f"{path} is missing: build it with `python -m regridding_b200._build` "
                 "(there is no CPU fallback)"
             )
-        L = ctypes.CDLL(str(LIB_PATH))
+        L = ctypes.CDLL(str(path))
         for name, argtypes in SIGNATURES.items():
             f = getattr(L, name)
             f.argtypes = argtypes

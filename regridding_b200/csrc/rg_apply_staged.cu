@@ -24,6 +24,34 @@
 // flagged by the plan and handled by the generic per-cell kernel.
 #include "rg_common.cuh"
 
+#ifndef RG_QUAD_INTERLEAVE
+#define RG_QUAD_INTERLEAVE 0
+#endif
+#ifndef RG_PATCH_ROWS
+#define RG_PATCH_ROWS 24
+#endif
+#ifndef RG_SKIP_COMPUTE
+#define RG_SKIP_COMPUTE 0
+#endif
+#ifndef RG_SKIP_LOAD
+#define RG_SKIP_LOAD 0
+#endif
+#ifndef RG_SKIP_STORE
+#define RG_SKIP_STORE 0
+#endif
+#ifndef RG_L2_AHEAD
+#define RG_L2_AHEAD 0
+#endif
+#ifndef RG_BULK_FILL
+#define RG_BULK_FILL 0
+#endif
+#ifndef RG_PACKED_ENTRIES
+#define RG_PACKED_ENTRIES 0
+#endif
+#ifndef RG_FB
+#define RG_FB 512
+#endif
+
 namespace rg {
 
 constexpr int kTH = 4;           // tile height (output rows)
@@ -31,27 +59,40 @@ constexpr int kTW = 32;          // tile width  (output cols) = one full coalesc
 constexpr int kTileCells = kTH * kTW;
 constexpr int kQuads = kTileCells / 4;  // a quad = 4 consecutive output cells = the 4 quarter-warps of a warp
 constexpr int kT = 16;           // frames per sub-block: 8 lanes x 2 frames per lane
-constexpr int kFB = 256;         // frames per CTA (the tile-local CSR is reread every kFB frames)
+constexpr int kFB = RG_FB;         // frames per CTA (the tile-local CSR is reread every kFB frames)
 constexpr int kRMAX = 64;        // max input rows in a footprint
-constexpr int kCP = 386;         // doubles per staged frame; kCP/2 odd => the 8 frame lanes of a quarter-warp
+#if RG_PACKED_ENTRIES
+constexpr int kCP = 370;
+constexpr int kPadMax = 1216;
+#else
+constexpr int kCP = 386;
+constexpr int kPadMax = 1536;
+#endif
+                                 // kCP = doubles per staged frame; kCP/2 odd => the 8 frame lanes of a quarter-warp
                                  // hit 8 distinct 16-byte bank groups.  Slot kCP-1 of every frame holds 0.0.
 constexpr int kCellsMax = kCP - 2;
 constexpr int kZeroSlot = kCP - 1;
 constexpr int kNnzMax = 1280;    // max CSR entries per tile
-constexpr int kPadMax = 1536;    // max entries after padding the 4 rows of every quad to a common length
+// kPadMax: max entries after padding the 4 rows of every quad to a common length
 constexpr int kOutStride = kCP;  // staged output frame t lives in slots [0, 128) of staged input frame t
 constexpr int kStagedThreads = 512;   // 2 CTAs per SM: their load / compute / store phases overlap
 constexpr int kPairsPerLane = (kCP / 2 + 31) / 32;  // 16-byte pairs of one frame a lane copies per sub-block
-constexpr int kPatch = 12;       // tiles are issued in 12 x 12 patches (~ one wave of 148 CTAs) so that
-                                 // footprint halos are shared through L2
+constexpr int kPatch = 12;       // tiles are issued in patches of kPatchRows x kPatch tiles (~ one wave of 2 x 148
+constexpr int kPatchRows = RG_PATCH_ROWS;   // CTAs) so that footprint halos are shared through L2
 static_assert((kCP / 2) % 2 == 1 && kCP % 2 == 0, "kCP/2 must be odd");
 
 constexpr int kTileInfoInts = 4;  // r0, nrows, cells, nnz (nnz < 0: tile handled by the generic kernel)
 
 struct StagedSmem {
     double in_s[2][kT * kCP];     // [buffer][frame][cell]; after compute, frame t's slots [0,256) hold its outputs
+#if RG_PACKED_ENTRIES
+    struct alignas(16) Entry { double v; unsigned lo; unsigned pad; };
+    Entry ent[kPadMax];           // padded tile-local CSR, interleaved per quad: entry (quad, w, q);
+                                  // lo = BYTE offset of the referenced cell inside a staged frame
+#else
     double val[kPadMax];          // padded tile-local CSR, interleaved per quad: entry (quad, w, q)
     uint16_t lidx[kPadMax];       // BYTE offset of the referenced cell inside a staged frame
+#endif
     uint16_t quad_beg[kQuads + 1];
     uint16_t rowptr[kTileCells + 2];
     int32_t row_src[kRMAX];       // per footprint row: offset of its span inside one input frame (doubles)
@@ -61,28 +102,27 @@ struct StagedSmem {
 
 __host__ __device__ inline void tile_of_block(int64_t b, int tiles_x, int tiles_y, int& ty, int& tx)
 {
-    // patch-major order; patches and the tiles inside a patch are row-major
+    // patch-major order; patches (kPatchRows x kPatch tiles) and the tiles inside a patch are row-major
     const int px_count = (tiles_x + kPatch - 1) / kPatch;
-    const int64_t full_rows = tiles_y / kPatch;                       // complete patch rows
-    const int64_t per_patch_row = (int64_t)kPatch * tiles_x;           // tiles in a complete patch row
+    const int64_t full_rows = tiles_y / kPatchRows;                    // complete patch rows
+    const int64_t per_patch_row = (int64_t)kPatchRows * tiles_x;       // tiles in a complete patch row
     int prow, ph;
     int64_t rem;
     if (b < full_rows * per_patch_row) {
         prow = (int)(b / per_patch_row);
         rem = b - (int64_t)prow * per_patch_row;
-        ph = kPatch;
+        ph = kPatchRows;
     } else {
         prow = (int)full_rows;
         rem = b - full_rows * per_patch_row;
-        ph = tiles_y - prow * kPatch;
+        ph = tiles_y - prow * kPatchRows;
     }
-    // inside a patch row: patches of width kPatch (last one narrower), each ph x pw tiles
     const int64_t per_full_patch = (int64_t)ph * kPatch;
     int pcol = (int)(rem / per_full_patch);
     if (pcol >= px_count) pcol = px_count - 1;
     const int64_t rem2 = rem - (int64_t)pcol * per_full_patch;
     const int pw = min(kPatch, tiles_x - pcol * kPatch);
-    ty = prow * kPatch + (int)(rem2 / pw);
+    ty = prow * kPatchRows + (int)(rem2 / pw);
     tx = pcol * kPatch + (int)(rem2 % pw);
 }
 
@@ -220,6 +260,26 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity)
         "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
 }
 
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory"); }
+__device__ __forceinline__ void bulk_s2g(void* gmem_dst, const void* smem_src, unsigned bytes)
+{
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;\n" ::"l"(gmem_dst), "r"(smem_u32(smem_src)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;\n" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory"); }
+
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, unsigned bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, unsigned bytes, uint64_t* bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(smem_u32(smem_dst)),
+                 "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
 // Requires even w_in / n_in and a 16-byte aligned values_in (the plan pads every footprint span to an even
 // start and even length), so the footprint moves in 16-byte pieces.
 __global__ void __launch_bounds__(kStagedThreads, 2)
@@ -280,8 +340,8 @@ k_apply_staged(int64_t n_frames, int64_t w_in, int64_t n_in, int64_t h_out, int6
         }
         if (threadIdx.x == 0) {
             S.row_off[nrows] = cells;
-            mbar_init(&S.full[0], kStagedThreads);
-            mbar_init(&S.full[1], kStagedThreads);
+            mbar_init(&S.full[0], RG_BULK_FILL ? kT : kStagedThreads);
+            mbar_init(&S.full[1], RG_BULK_FILL ? kT : kStagedThreads);
             asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
         }
         if (threadIdx.x < 2 * kT) S.in_s[threadIdx.x / kT][(threadIdx.x % kT) * kCP + kZeroSlot] = 0.0;
@@ -319,8 +379,13 @@ k_apply_staged(int64_t n_frames, int64_t w_in, int64_t n_in, int64_t h_out, int6
                     v = val[gb + lb + w];
                     lo = (unsigned)lidx[gb + lb + w] * 8u;
                 }
+#if RG_PACKED_ENTRIES
+                S.ent[qb + 4 * w + c].v = v;
+                S.ent[qb + 4 * w + c].lo = lo;
+#else
                 S.val[qb + 4 * w + c] = v;
                 S.lidx[qb + 4 * w + c] = (uint16_t)lo;
+#endif
             }
         }
     }
@@ -329,6 +394,7 @@ k_apply_staged(int64_t n_frames, int64_t w_in, int64_t n_in, int64_t h_out, int6
     // ---- footprint copy: warp -> frame, lane -> 16-byte pairs lane + 32 j ----
     static_assert(kStagedThreads / 32 == kT, "one warp per frame of a sub-block");
     const int tt_p = warp;
+    unsigned pf_mask = 0;
     int32_t pair_off[kPairsPerLane];  // source offset (doubles, inside a frame) of each of this lane's pairs; -1: none
     {
         const int npairs = cells >> 1;
@@ -336,6 +402,7 @@ k_apply_staged(int64_t n_frames, int64_t w_in, int64_t n_in, int64_t h_out, int6
         for (int j = 0; j < kPairsPerLane; j++) {
             const int p = lane + 32 * j;
             int32_t off = -1;
+            bool first_of_row = false;
             if (p < npairs) {
                 // row of staged cell 2p: last r with row_off[r] <= 2p
                 int lo = 0, hi = nrows - 1;
@@ -344,26 +411,57 @@ k_apply_staged(int64_t n_frames, int64_t w_in, int64_t n_in, int64_t h_out, int6
                     if (S.row_off[mid] <= 2 * p) lo = mid; else hi = mid - 1;
                 }
                 off = S.row_src[lo] + (2 * p - S.row_off[lo]);
+                first_of_row = (2 * p == S.row_off[lo]);
             }
             pair_off[j] = off;
+            // this lane touches L2 for the pair if it starts a 128-byte line or a footprint row
+            if (off >= 0 && ((off & 15) == 0 || first_of_row)) pf_mask |= 1u << j;
         }
     }
     const unsigned dst_lane = (unsigned)((tt_p * kCP + 2 * lane) * 8);
     auto prefetch = [&](int64_t f0, int buf) {
         const int64_t f = f0 + tt_p;
+#if RG_BULK_FILL
+        // one bulk (TMA engine) copy per footprint row of this warp's frame: no LSU / MIO traffic
+        const bool valid = f < f_end && !RG_SKIP_LOAD;
+        if (lane == 0) mbar_arrive_expect_tx(&S.full[buf], valid ? (unsigned)cells * 8u : 0u);
+        __syncwarp();
+        if (valid) {
+            const double* src = vin + f * n_in;
+            double* dst = S.in_s[buf] + tt_p * kCP;
+            for (int r = lane; r < nrows; r += 32) {
+                const int off = S.row_off[r], len = S.row_off[r + 1] - off;
+                if (len > 0) bulk_g2s(dst + off, src + S.row_src[r], (unsigned)len * 8u, &S.full[buf]);
+            }
+        }
+#else
         if (f < f_end) {
             const double* src = vin + f * n_in;
             const unsigned dst = smem_u32(S.in_s[buf]) + dst_lane;
 #pragma unroll
             for (int j = 0; j < kPairsPerLane; j++)
-                if (pair_off[j] >= 0) cp_async_16(dst + j * 32 * 16, src + pair_off[j]);
+                if (pair_off[j] >= 0 && !RG_SKIP_LOAD) cp_async_16(dst + j * 32 * 16, src + pair_off[j]);
         }
         cp_async_mbar_arrive(&S.full[buf]);
+#endif
+    };
+
+    // HBM -> L2 a few sub-blocks ahead of the shared-memory copy: the copy then sees L2 latency, and DRAM
+    // requests are spread over the whole iteration instead of arriving in bursts
+    auto l2_prefetch = [&](int64_t f0) {
+        const int64_t f = f0 + tt_p;
+        if (RG_L2_AHEAD > 0 && f < f_end) {
+            const double* src = vin + f * n_in;
+#pragma unroll
+            for (int j = 0; j < kPairsPerLane; j++)
+                if (pf_mask & (1u << j)) asm volatile("prefetch.global.L2 [%0];\n" ::"l"(src + pair_off[j]));
+        }
     };
 
     const int nsub = (int)((f_end - f_begin + kT - 1) / kT);
     prefetch(f_begin, 0);
     if (nsub > 1) prefetch(f_begin + kT, 1);
+    for (int a = 2; a < 2 + RG_L2_AHEAD; a++) l2_prefetch(f_begin + (int64_t)a * kT);
     const int q = lane >> 3, t = lane & 7;  // quarter-warp = one output cell; lane owns frames t and t + 8
     for (int s = 0; s < nsub; s++) {
         const int64_t f0 = f_begin + (int64_t)s * kT;
@@ -373,15 +471,58 @@ k_apply_staged(int64_t n_frames, int64_t w_in, int64_t n_in, int64_t h_out, int6
         const char* in0 = reinterpret_cast<const char*>(in + t * kCP);
         // ---- compute: quarter-warp per output cell, rows of a quad share one (padded) trip count ----
         double acc[2][2];
+#if RG_QUAD_INTERLEAVE
+        {
+            // the warp's two quads are walked together: two independent dependency chains per lane
+            const int qbA = S.quad_beg[warp], qeA = S.quad_beg[warp + 1];
+            const int qbB = S.quad_beg[warp + NW], qeB = S.quad_beg[warp + NW + 1];
+            const int nA = (qeA - qbA) >> 2, nB = (qeB - qbB) >> 2;
+            const int nmin = min(nA, nB);
+            double a0 = 0.0, a1 = 0.0, b0 = 0.0, b1 = 0.0;
+            int eA = qbA + q, eB = qbB + q;
+#pragma unroll 2
+            for (int w = 0; w < nmin; w++, eA += 4, eB += 4) {
+                const unsigned loA = S.lidx[eA], loB = S.lidx[eB];
+                const double vA = S.val[eA], vB = S.val[eB];
+                const double xA0 = *reinterpret_cast<const double*>(in0 + loA);
+                const double xA1 = *reinterpret_cast<const double*>(in0 + loA + 8 * kCP * 8);
+                const double xB0 = *reinterpret_cast<const double*>(in0 + loB);
+                const double xB1 = *reinterpret_cast<const double*>(in0 + loB + 8 * kCP * 8);
+                a0 = dadd(a0, dmul(vA, xA0));
+                a1 = dadd(a1, dmul(vA, xA1));
+                b0 = dadd(b0, dmul(vB, xB0));
+                b1 = dadd(b1, dmul(vB, xB1));
+            }
+            for (int w = nmin; w < nA; w++, eA += 4) {
+                const unsigned lo = S.lidx[eA];
+                const double v = S.val[eA];
+                a0 = dadd(a0, dmul(v, *reinterpret_cast<const double*>(in0 + lo)));
+                a1 = dadd(a1, dmul(v, *reinterpret_cast<const double*>(in0 + lo + 8 * kCP * 8)));
+            }
+            for (int w = nmin; w < nB; w++, eB += 4) {
+                const unsigned lo = S.lidx[eB];
+                const double v = S.val[eB];
+                b0 = dadd(b0, dmul(v, *reinterpret_cast<const double*>(in0 + lo)));
+                b1 = dadd(b1, dmul(v, *reinterpret_cast<const double*>(in0 + lo + 8 * kCP * 8)));
+            }
+            acc[0][0] = a0; acc[0][1] = a1; acc[1][0] = b0; acc[1][1] = b1;
+        }
+#else
 #pragma unroll
         for (int k = 0; k < 2; k++) {
             const int qd = warp + k * NW;
             const int qb = S.quad_beg[qd], qe = S.quad_beg[qd + 1];
             double a0 = 0.0, a1 = 0.0;
 #pragma unroll 4
-            for (int e = qb + q; e < qe; e += 4) {
+            for (int e = qb + q; e < (RG_SKIP_COMPUTE ? qb : qe); e += 4) {
+#if RG_PACKED_ENTRIES
+                const int4 raw = *reinterpret_cast<const int4*>(&S.ent[e]);  // one 16-byte shared load per entry
+                const double v = __hiloint2double(raw.y, raw.x);
+                const unsigned lo = (unsigned)raw.z;
+#else
                 const unsigned lo = S.lidx[e];
                 const double v = S.val[e];
+#endif
                 const double x0 = *reinterpret_cast<const double*>(in0 + lo);
                 const double x1 = *reinterpret_cast<const double*>(in0 + lo + 8 * kCP * 8);
                 a0 = dadd(a0, dmul(v, x0));
@@ -390,6 +531,7 @@ k_apply_staged(int64_t n_frames, int64_t w_in, int64_t n_in, int64_t h_out, int6
             acc[k][0] = a0;
             acc[k][1] = a1;
         }
+#endif
         __syncthreads();  // everyone is done reading in_s[buf]: frame t's slots [0,256) now take its outputs
 #pragma unroll
         for (int k = 0; k < 2; k++) {
@@ -404,11 +546,15 @@ k_apply_staged(int64_t n_frames, int64_t w_in, int64_t n_in, int64_t h_out, int6
             if (f < f_end && lane < tw) {
                 double* o = vout + f * n_out + out_base + lane;
                 const double* si = in + tt_p * kOutStride + lane;
-                for (int tr = 0; tr < th; tr++) o[(int64_t)tr * w_out] = si[tr * kTW];
+                for (int tr = 0; tr < (RG_SKIP_STORE ? 0 : th); tr++) o[(int64_t)tr * w_out] = si[tr * kTW];
             }
         }
         __syncthreads();  // outputs consumed: the buffer may be refilled
-        if (s + 2 < nsub) prefetch(f0 + 2 * kT, buf);
+        if (s + 2 < nsub) {
+            if (RG_BULK_FILL) fence_proxy_async();  // our generic-proxy accesses of the buffer precede the async refill
+            prefetch(f0 + 2 * kT, buf);
+        }
+        l2_prefetch(f0 + (int64_t)(2 + RG_L2_AHEAD) * kT);
     }
 }
 
