@@ -35,6 +35,62 @@ def _device_weights_of(element, n_in: int, n_out: int, device) -> _device.Device
     return dw
 
 
+_CHUNK_BYTES = 256 << 20  # host <-> device pipeline granularity
+_RING = 3
+
+
+def _host_pipeline(groups, apply, vin_h: np.ndarray, out_h: np.ndarray, device) -> None:
+    """values on the HOST -> result on the HOST, as a 3-stage pipeline over chunks of orthogonal
+    slices: H2D copy, apply and D2H copy run on three streams with a ring of device buffers, so the
+    PCIe link carries input and output at the same time (full duplex) while the kernels run.
+    Device memory use is bounded by the ring, not by the number of slices.  Every output cell
+    is written by the apply (cells no weight reaches get +0.0), so no zero fill is needed."""
+    import warnings
+
+    D, n_in = vin_h.shape
+    n_out = out_h.shape[1]
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore", UserWarning)  # read-only views of broadcast inputs are only read
+        src_t = torch.from_numpy(vin_h)
+    dst_t = torch.from_numpy(out_h)
+    per = max(1, min(D, _CHUNK_BYTES // (8 * max(n_in, n_out, 1))))
+    items = []
+    for d, e, dw in groups:
+        for a in range(d, e, per):
+            items.append((a, min(e, a + per), dw))
+    if not items:
+        return
+    ring = min(_RING, len(items))
+    main = torch.cuda.current_stream(device)
+    s_in, s_out = torch.cuda.Stream(device), torch.cuda.Stream(device)
+    buf_in = [torch.empty((per, n_in), dtype=torch.float64, device=device) for _ in range(ring)]
+    buf_out = [torch.empty((per, n_out), dtype=torch.float64, device=device) for _ in range(ring)]
+    applied = [None] * ring   # apply of the chunk that last used slot k finished (input buffer reusable)
+    drained = [None] * ring   # D2H of the chunk that last used slot k finished (output buffer reusable)
+    s_in.wait_stream(main)
+    s_out.wait_stream(main)
+    for k, (a, b, dw) in enumerate(items):
+        slot = k % ring
+        n = b - a
+        with torch.cuda.stream(s_in):
+            if applied[slot] is not None:
+                s_in.wait_event(applied[slot])
+            buf_in[slot][:n].copy_(src_t[a:b], non_blocking=True)
+            loaded = s_in.record_event()
+        main.wait_event(loaded)
+        if drained[slot] is not None:
+            main.wait_event(drained[slot])
+        apply(dw, buf_in[slot][:n], buf_out[slot][:n])
+        applied[slot] = main.record_event()
+        with torch.cuda.stream(s_out):
+            s_out.wait_event(applied[slot])
+            dst_t[a:b].copy_(buf_out[slot][:n], non_blocking=True)
+            drained[slot] = s_out.record_event()
+    main.wait_stream(s_out)
+    main.wait_stream(s_in)
+    torch.cuda.synchronize(device)  # the ring buffers are idle from here on; results are on the host
+
+
 def regrid_from_weights(
     weights,
     shape_input: tuple[int, ...],
@@ -88,30 +144,32 @@ def regrid_from_weights(
         device = _device.cuda_device()
         vin_h = np.broadcast_to(np.asarray(values_input, dtype=np.float64), full_in)
         vin_h = np.ascontiguousarray(np.moveaxis(vin_h, axis_in, last_in).reshape(D, n_in))
-        vin = torch.from_numpy(vin_h).to(device)
         if values_output is None:
             values_output = np.zeros(full_out, dtype=float)
-        else:
-            if values_output.shape != full_out:
-                raise ValueError(f"{values_output.shape=} should be equal to {full_out}")
-            values_output.fill(0)
+        elif values_output.shape != full_out:
+            raise ValueError(f"{values_output.shape=} should be equal to {full_out}")
 
-    out = torch.empty((D, n_out), dtype=torch.float64, device=device)
     # consecutive orthogonal slices that share one weights element are applied in one launch
-    d = 0
-    while d < D:
-        e = d + 1
-        while e < D and flat_weights[e] is flat_weights[d]:
-            e += 1
-        dw = _device_weights_of(flat_weights[d], n_in, n_out, device)
+    def groups():
+        d = 0
+        while d < D:
+            e = d + 1
+            while e < D and flat_weights[e] is flat_weights[d]:
+                e += 1
+            yield d, e, _device_weights_of(flat_weights[d], n_in, n_out, device)
+            d = e
+
+    def apply(dw, src, dst):
         if len(cells_in) == 2 and len(cells_out) == 2:
-            _device.apply_planned(dw.plan(cells_in, cells_out), vin[d:e], out[d:e])
+            _device.apply_planned(dw.plan(cells_in, cells_out), src, dst)
         else:
-            _device.apply_csr(dw.csr(), vin[d:e], out[d:e])
-        d = e
+            _device.apply_csr(dw.csr(), src, dst)
 
     moved_out_shape = tuple(shape_orth) + cells_out
     if on_device:
+        out = torch.empty((D, n_out), dtype=torch.float64, device=device)
+        for d, e, dw in groups():
+            apply(dw, vin[d:e], out[d:e])
         res = torch.movedim(out.reshape(moved_out_shape), last_out, axis_out)
         if values_output is not None:
             values_output.copy_(res)
@@ -119,11 +177,16 @@ def regrid_from_weights(
         return res
 
     # host: same in-place behaviour as the reference (rfw.py:120-154): the caller's buffer is
-    # updated in place only if its moved/reshaped view is already C-contiguous
+    # updated in place only if its moved/reshaped view is already C-contiguous; otherwise it is
+    # left zeroed and the result is a fresh array
     moved = np.moveaxis(values_output, axis_out, last_out)
     moved_shape = moved.shape
-    target = np.ascontiguousarray(moved.reshape(D, *cells_out))
-    torch.from_numpy(target.reshape(D, n_out)).copy_(out)  # D2H straight into the result buffer
+    if moved.flags.c_contiguous:
+        target = moved.reshape(D, *cells_out)
+    else:
+        values_output.fill(0)
+        target = np.empty((D, *cells_out), dtype=float)
+    _host_pipeline(groups(), apply, vin_h, target.reshape(D, n_out), device)
     result = np.moveaxis(target.reshape(moved_shape), last_out, axis_out)
 
     if unit_weights is not None:
