@@ -145,12 +145,20 @@ int rg_apply_csr(int device, void* stream, int64_t n_frames, int64_t n_in, int64
 
 /* Planned (shared-memory staged) apply for weights between 2D cell grids
  * (h_in, w_in) -> (h_out, w_out): the same arithmetic and bits as rg_apply_csr, organised
- * for HBM bandwidth.  rg_apply_plan_build analyses a CSR once (per output tile: the
- * footprint of input cells it references, tile-local u16 indices); rg_apply_planned then
- * streams any number of frames through it.  Tiles whose footprint does not fit on chip are
- * counted in *n_generic_tiles_host and served by the generic per-cell kernel.
- * Buffers (caller-allocated, sizes from rg_apply_plan_sizes): tile_info int32[tile_info_ints],
- * tile_rows int32[tile_rows_ints], lidx uint16[nnz]. */
+ * for HBM bandwidth.  The plan analyses a CSR once and rg_apply_planned then streams any
+ * number of frames through it:
+ *   rg_apply_plan_build  per 4x32 output tile: the footprint of input cells it references,
+ *                        tile-local u16 indices, and the SLOT layout of its entries (the two
+ *                        output cells that share a half-warp are aligned so that their
+ *                        shared-memory gathers fall into different banks); returns the number
+ *                        of slot entries in *n_slots_host;
+ *   rg_apply_plan_slots  fills the caller-allocated slot arrays (weights + byte offsets in
+ *                        the order the kernel consumes them).
+ * Tiles whose footprint does not fit on chip are counted in *n_generic_tiles_host and
+ * served by the generic per-cell kernel.
+ * Buffers (caller-allocated; sizes from rg_apply_plan_sizes): tile_info int32[tile_info_ints]
+ * (8-byte aligned), tile_rows int32[tile_rows_ints], lidx uint16[nnz]; slot_val
+ * double[n_slots], slot_lidx uint16[n_slots] (both 16-byte aligned). */
 int rg_apply_plan_sizes(int64_t h_out, int64_t w_out, int64_t* n_tiles_host,
                         int64_t* tile_info_ints_host, int64_t* tile_rows_ints_host);
 
@@ -158,12 +166,18 @@ int rg_apply_plan_build(int device, void* stream, int64_t nnz,
                         int64_t h_in, int64_t w_in, int64_t h_out, int64_t w_out,
                         const int32_t* row_ptr, const int32_t* col,
                         int32_t* tile_info, int32_t* tile_rows, uint16_t* lidx,
-                        int64_t* n_generic_tiles_host);
+                        int64_t* n_generic_tiles_host, int64_t* n_slots_host);
+
+int rg_apply_plan_slots(int device, void* stream, int64_t h_out, int64_t w_out,
+                        const int32_t* row_ptr, const double* val,
+                        const int32_t* tile_info, const uint16_t* lidx,
+                        int64_t n_slots, double* slot_val, uint16_t* slot_lidx);
 
 int rg_apply_planned(int device, void* stream, int64_t n_frames,
                      int64_t h_in, int64_t w_in, int64_t h_out, int64_t w_out,
                      const int32_t* row_ptr, const int32_t* col, const double* val,
-                     const int32_t* tile_info, const int32_t* tile_rows, const uint16_t* lidx,
+                     const int32_t* tile_info, const int32_t* tile_rows,
+                     const double* slot_val, const uint16_t* slot_lidx,
                      int64_t n_generic_tiles,
                      const double* values_in, double* values_out);
 

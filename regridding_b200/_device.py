@@ -78,7 +78,8 @@ class ApplyPlan:
     shape_out: tuple[int, int]
     tile_info: torch.Tensor
     tile_rows: torch.Tensor
-    lidx: torch.Tensor
+    slot_val: torch.Tensor   # float64 [n_slots]: weights in the order the staged kernel consumes them
+    slot_lidx: torch.Tensor  # int16 (uint16 bits) [n_slots]: byte offset of the referenced cell in a staged frame
     n_tiles: int
     n_generic_tiles: int
 
@@ -266,14 +267,20 @@ def build_apply_plan(csr: CSR, shape_in: tuple[int, int], shape_out: tuple[int, 
     tile_info = torch.empty(ni.value, dtype=I32, device=device)
     tile_rows = torch.empty(nr.value, dtype=I32, device=device)
     nnz = int(csr.val.numel())
-    lidx = torch.empty(max(nnz, 1), dtype=torch.int16, device=device)
-    ng = ctypes.c_int64()
+    lidx = torch.empty(max(nnz, 1), dtype=torch.int16, device=device)  # scratch: tile-local index of every entry
+    ng, ns = ctypes.c_int64(), ctypes.c_int64()
     with torch.cuda.device(device):
         _lib.check(L.rg_apply_plan_build(device.index, _stream(device), nnz, h_in, w_in, h_out, w_out,
                                          csr.row_ptr.data_ptr(), csr.col.data_ptr(), tile_info.data_ptr(),
-                                         tile_rows.data_ptr(), lidx.data_ptr(), ctypes.byref(ng)),
+                                         tile_rows.data_ptr(), lidx.data_ptr(), ctypes.byref(ng), ctypes.byref(ns)),
                    "rg_apply_plan_build")
-    return ApplyPlan(csr, (h_in, w_in), (h_out, w_out), tile_info, tile_rows, lidx, nt.value, ng.value)
+        slot_val = torch.empty(max(ns.value, 8), dtype=F64, device=device)
+        slot_lidx = torch.empty(max(ns.value, 8), dtype=torch.int16, device=device)
+        _lib.check(L.rg_apply_plan_slots(device.index, _stream(device), h_out, w_out, csr.row_ptr.data_ptr(),
+                                         csr.val.data_ptr(), tile_info.data_ptr(), lidx.data_ptr(), ns.value,
+                                         slot_val.data_ptr(), slot_lidx.data_ptr()), "rg_apply_plan_slots")
+        torch.cuda.current_stream(device).synchronize()  # lidx (scratch) is released on return
+    return ApplyPlan(csr, (h_in, w_in), (h_out, w_out), tile_info, tile_rows, slot_val, slot_lidx, nt.value, ng.value)
 
 
 def apply_planned(plan: ApplyPlan, values_in: torch.Tensor, out: torch.Tensor | None = None) -> torch.Tensor:
@@ -294,7 +301,8 @@ def apply_planned(plan: ApplyPlan, values_in: torch.Tensor, out: torch.Tensor | 
         _lib.check(L.rg_apply_planned(device.index, _stream(device), F, plan.shape_in[0], plan.shape_in[1],
                                       plan.shape_out[0], plan.shape_out[1], csr.row_ptr.data_ptr(),
                                       csr.col.data_ptr(), csr.val.data_ptr(), plan.tile_info.data_ptr(),
-                                      plan.tile_rows.data_ptr(), plan.lidx.data_ptr(), plan.n_generic_tiles,
+                                      plan.tile_rows.data_ptr(), plan.slot_val.data_ptr(), plan.slot_lidx.data_ptr(),
+                                      plan.n_generic_tiles,
                                       values_in.data_ptr(), out.data_ptr()), "rg_apply_planned")
     return out
 

@@ -38,8 +38,9 @@ SIGNATURES: dict[str, list] = {
     "rg_csr_from_coo": [_int, _vp, _i64, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz],
     "rg_apply_csr": [_int, _vp, _i64, _i64, _i64, _vp, _vp, _vp, _vp, _vp],
     "rg_apply_plan_sizes": [_i64, _i64, _p_i64, _p_i64, _p_i64],
-    "rg_apply_plan_build": [_int, _vp, _i64, _i64, _i64, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _p_i64],
-    "rg_apply_planned": [_int, _vp, _i64, _i64, _i64, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp],
+    "rg_apply_plan_build": [_int, _vp, _i64, _i64, _i64, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _p_i64, _p_i64],
+    "rg_apply_plan_slots": [_int, _vp, _i64, _i64, _vp, _vp, _vp, _vp, _i64, _vp, _vp],
+    "rg_apply_planned": [_int, _vp, _i64, _i64, _i64, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp],
     "rg_cons1d_batched": [_int, _vp, _i64, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
     "rg_regrid1d_conservative": [_int, _vp, _i64, _i64, _i64, _vp, _vp, _vp, _vp, _vp],
     "rg_find_indices_1d": [_int, _vp, _int, _i64, _i64, _i64, _vp, _vp, _i64, _vp],

@@ -24,9 +24,7 @@
 // flagged by the plan and handled by the generic per-cell kernel.
 #include "rg_common.cuh"
 
-#ifndef RG_QUAD_INTERLEAVE
-#define RG_QUAD_INTERLEAVE 0
-#endif
+// development switches (ablations for profiles/r1_apply_tuning.md); all 0 in the product build
 #ifndef RG_PATCH_ROWS
 #define RG_PATCH_ROWS 24
 #endif
@@ -39,14 +37,8 @@
 #ifndef RG_SKIP_STORE
 #define RG_SKIP_STORE 0
 #endif
-#ifndef RG_L2_AHEAD
-#define RG_L2_AHEAD 0
-#endif
-#ifndef RG_BULK_FILL
-#define RG_BULK_FILL 0
-#endif
-#ifndef RG_PACKED_ENTRIES
-#define RG_PACKED_ENTRIES 0
+#ifndef RG_NO_ALIGN
+#define RG_NO_ALIGN 0
 #endif
 #ifndef RG_FB
 #define RG_FB 512
@@ -58,43 +50,37 @@ constexpr int kTH = 4;           // tile height (output rows)
 constexpr int kTW = 32;          // tile width  (output cols) = one full coalesced row of 256 B
 constexpr int kTileCells = kTH * kTW;
 constexpr int kQuads = kTileCells / 4;  // a quad = 4 consecutive output cells = the 4 quarter-warps of a warp
+constexpr int kPairs = kTileCells / 2;  // a pair = 2 consecutive output cells = the 2 quarter-warps of a half-warp
 constexpr int kT = 16;           // frames per sub-block: 8 lanes x 2 frames per lane
-constexpr int kFB = RG_FB;         // frames per CTA (the tile-local CSR is reread every kFB frames)
+constexpr int kFB = RG_FB;       // frames per CTA (the tile-local CSR is rebuilt every kFB frames)
 constexpr int kRMAX = 64;        // max input rows in a footprint
-#if RG_PACKED_ENTRIES
-constexpr int kCP = 370;
-constexpr int kPadMax = 1216;
-#else
-constexpr int kCP = 386;
-constexpr int kPadMax = 1536;
-#endif
-                                 // kCP = doubles per staged frame; kCP/2 odd => the 8 frame lanes of a quarter-warp
-                                 // hit 8 distinct 16-byte bank groups.  Slot kCP-1 of every frame holds 0.0.
+constexpr int kCP = 386;         // doubles per staged frame; kCP/2 odd => the 8 frame lanes of a quarter-warp
+                                 // hit 8 distinct 16-byte bank groups
 constexpr int kCellsMax = kCP - 2;
-constexpr int kZeroSlot = kCP - 1;
+constexpr int kZeroEven = kCP - 2;   // slots kCP-2 (even) and kCP-1 (odd) of every staged frame hold 0.0:
+constexpr int kZeroOdd = kCP - 1;    // the targets of padding entries, one per bank parity
 constexpr int kNnzMax = 1280;    // max CSR entries per tile
-// kPadMax: max entries after padding the 4 rows of every quad to a common length
+constexpr int kPadMax = 1536;    // max SLOT entries per tile (4 cells x padded, aligned slots of every quad)
+constexpr int kAlignMax = 16;    // rows up to this length take part in the bank-parity alignment
 constexpr int kOutStride = kCP;  // staged output frame t lives in slots [0, 128) of staged input frame t
 constexpr int kStagedThreads = 512;   // 2 CTAs per SM: their load / compute / store phases overlap
-constexpr int kPairsPerLane = (kCP / 2 + 31) / 32;  // 16-byte pairs of one frame a lane copies per sub-block
+constexpr int kPairsPerLane = (kCellsMax / 2 + 31) / 32;  // 16-byte pairs of one frame a lane copies per sub-block
 constexpr int kPatch = 12;       // tiles are issued in patches of kPatchRows x kPatch tiles (~ one wave of 2 x 148
 constexpr int kPatchRows = RG_PATCH_ROWS;   // CTAs) so that footprint halos are shared through L2
 static_assert((kCP / 2) % 2 == 1 && kCP % 2 == 0, "kCP/2 must be odd");
+static_assert(kPairs <= kStagedThreads, "one thread per pair in the setup");
 
-constexpr int kTileInfoInts = 4;  // r0, nrows, cells, nnz (nnz < 0: tile handled by the generic kernel)
+// per-tile plan record (int32): r0, nrows, cells, nnz (nnz < 0: tile handled by the generic kernel), plain layout?,
+// slot entries, slot base (int64 in two words), then quad_beg[kQuads + 1] as uint16
+constexpr int kTileInfoInts = 8 + (kQuads + 2) / 2;
 
+// Slot layout of a quad (4 cells c, L slots w, L even):  entry(w, c) = qb + (w >> 1) * 8 + c * 2 + (w & 1),
+// so the two values (16 B) and the two offsets (4 B) of slots (w, w+1) of a cell are one shared-memory load each.
 struct StagedSmem {
-    double in_s[2][kT * kCP];     // [buffer][frame][cell]; after compute, frame t's slots [0,256) hold its outputs
-#if RG_PACKED_ENTRIES
-    struct alignas(16) Entry { double v; unsigned lo; unsigned pad; };
-    Entry ent[kPadMax];           // padded tile-local CSR, interleaved per quad: entry (quad, w, q);
-                                  // lo = BYTE offset of the referenced cell inside a staged frame
-#else
-    double val[kPadMax];          // padded tile-local CSR, interleaved per quad: entry (quad, w, q)
-    uint16_t lidx[kPadMax];       // BYTE offset of the referenced cell inside a staged frame
-#endif
-    uint16_t quad_beg[kQuads + 1];
-    uint16_t rowptr[kTileCells + 2];
+    double in_s[2][kT * kCP];     // [buffer][frame][cell]; after compute, frame t's slots [0,128) hold its outputs
+    alignas(16) double val[kPadMax];
+    alignas(16) uint16_t lidx[kPadMax];   // BYTE offset of the referenced cell inside a staged frame
+    uint16_t quad_beg[kQuads + 2];
     int32_t row_src[kRMAX];       // per footprint row: offset of its span inside one input frame (doubles)
     int32_t row_off[kRMAX + 1];   //                    offset of its span inside one staged frame
     alignas(8) uint64_t full[2];  // mbarriers: "buffer filled"
@@ -126,6 +112,85 @@ __host__ __device__ inline void tile_of_block(int64_t b, int tiles_x, int tiles_
     tx = pcol * kPatch + (int)(rem2 % pw);
 }
 
+// Bank-parity alignment of the entry lists of two cells that share a half-warp.
+//
+// In the compute loop a half-warp reads, per slot, entry w of cell A (8 lanes = 8 frames) and entry w of cell B.
+// With the frame-major staging (frame stride 16 B-odd) the 8 frame lanes of one cell cover all eight 16-byte
+// bank groups at the 8-byte half selected by the PARITY of the staged cell index, so the two cells collide
+// (2 wavefronts instead of 1) exactly when their indices have equal parity and differ.  Padding entries
+// (weight 0.0 at an always-zero slot) may be inserted anywhere in a cell's list without changing its sum
+// (acc + 0.0 * 0.0 == acc bit for bit; acc is never -0.0), so the two lists are aligned like an LCS:
+// minimise 3 * slots + 2 * conflicts.  ops: 2 bits per slot, bit 0 = A advances, bit 1 = B advances.
+__device__ void align_pair(const uint16_t* la, int a, const uint16_t* lb, int b, uint64_t& ops, int& L)
+{
+    uint8_t ch[kAlignMax + 1][kAlignMax + 1];
+    int prev[kAlignMax + 1], cur[kAlignMax + 1];
+    prev[0] = 0;
+    for (int j = 1; j <= b; j++) { prev[j] = prev[j - 1] + 3; ch[0][j] = 2; }
+    for (int i = 1; i <= a; i++) {
+        cur[0] = prev[0] + 3;
+        ch[i][0] = 1;
+        const unsigned x = la[i - 1];
+        for (int j = 1; j <= b; j++) {
+            const unsigned y = lb[j - 1];
+            const int conflict = (((x ^ y) & 1u) == 0u && x != y) ? 2 : 0;
+            int best = prev[j - 1] + 3 + conflict, c = 3;
+            if (prev[j] + 3 < best) { best = prev[j] + 3; c = 1; }
+            if (cur[j - 1] + 3 < best) { best = cur[j - 1] + 3; c = 2; }
+            cur[j] = best;
+            ch[i][j] = (uint8_t)c;
+        }
+        for (int j = 0; j <= b; j++) prev[j] = cur[j];
+    }
+    int i = a, j = b, n = 0;
+    uint64_t r = 0;
+    while (i > 0 || j > 0) {   // walks from the last slot to the first: slot 0 ends up in the lowest bits
+        const unsigned c = ch[i][j];
+        r = (r << 2) | c;
+        n++;
+        i -= (int)(c & 1u);
+        j -= (int)(c >> 1);
+    }
+    ops = r;
+    L = n;
+}
+
+// Entry lists of the pair of cells (2p, 2p+1) of a tile and their slot layout.
+struct PairLayout {
+    int a, b;          // row lengths
+    int32_t gA, gB;    // global CSR position of their first entries
+    uint64_t ops;      // aligned: 2 bits per slot (bit 0: A advances, bit 1: B advances)
+    int L;             // slots
+    bool aligned;
+};
+
+__device__ PairLayout pair_layout(int p, int th, int tw, int64_t out_base, int64_t w_out,
+                                  const int32_t* __restrict__ row_ptr, const uint16_t* __restrict__ lidx, bool align)
+{
+    PairLayout P;
+    P.a = P.b = 0;
+    P.gA = P.gB = 0;
+    P.ops = 0;
+    P.aligned = false;
+    const int cA = 2 * p, tr = cA / kTW, col = cA % kTW;
+    if (tr < th && col < tw) {
+        const int64_t o = out_base + (int64_t)tr * w_out + col;
+        P.gA = row_ptr[o];
+        P.gB = row_ptr[o + 1];
+        P.a = P.gB - P.gA;
+        if (col + 1 < tw) P.b = row_ptr[o + 2] - P.gB;
+    }
+    P.L = max(P.a, P.b);
+    if (align && P.a > 0 && P.b > 0 && P.a <= kAlignMax && P.b <= kAlignMax) {
+        uint16_t la[kAlignMax], lb[kAlignMax];
+        for (int k = 0; k < P.a; k++) la[k] = lidx[P.gA + k];
+        for (int k = 0; k < P.b; k++) lb[k] = lidx[P.gB + k];
+        align_pair(la, P.a, lb, P.b, P.ops, P.L);
+        P.aligned = true;
+    }
+    return P;
+}
+
 // ---------------------------------------------------------------------------
 // plan: footprint of every tile + tile-local indices
 // ---------------------------------------------------------------------------
@@ -133,9 +198,10 @@ __global__ void __launch_bounds__(128)
 k_plan_tiles(int64_t h_in, int64_t w_in, int64_t h_out, int64_t w_out, int tiles_x, int pad_even,
              const int32_t* __restrict__ row_ptr, const int32_t* __restrict__ col,
              int32_t* __restrict__ tile_info, int32_t* __restrict__ tile_rows, uint16_t* __restrict__ lidx,
-             int32_t* __restrict__ n_generic)
+             int32_t* __restrict__ n_generic, int32_t* __restrict__ tile_slots)
 {
-    __shared__ int s_rmin, s_rmax, s_nnz, s_pad;
+    __shared__ int s_rmin, s_rmax, s_nnz, s_pad, s_plain;
+    __shared__ uint16_t s_pair_len[kPairs], s_quad_beg[kQuads + 2];
     __shared__ int s_clo[kRMAX], s_chi[kRMAX], s_off[kRMAX + 1];
     const int tile = blockIdx.x;
     const int ty = tile / tiles_x, tx = tile % tiles_x;
@@ -160,7 +226,8 @@ k_plan_tiles(int64_t h_in, int64_t w_in, int64_t h_out, int64_t w_out, int tiles
     __syncthreads();
     const int rmin = s_rmin, nnz = s_nnz;
     const int nrows = nnz ? s_rmax - rmin + 1 : 0;
-    // entries after padding the 4 rows of every quad (4 consecutive cells of a tile row) to a common length
+    // slot entries of the UNALIGNED layout (the apply kernel's fall-back): the 4 rows of every quad padded to
+    // their longest, rounded up to even
     for (int qd = threadIdx.x; qd < kQuads; qd += blockDim.x) {
         const int tr = (4 * qd) / kTW, c0 = (4 * qd) % kTW;
         int m = 0;
@@ -168,7 +235,7 @@ k_plan_tiles(int64_t h_in, int64_t w_in, int64_t h_out, int64_t w_out, int tiles
             const int64_t o0 = ((int64_t)ty * kTH + tr) * w_out + (int64_t)tx * kTW;
             for (int c = c0; c < c0 + 4 && c < tw; c++) m = max(m, row_ptr[o0 + c + 1] - row_ptr[o0 + c]);
         }
-        if (m) atomicAdd(&s_pad, 4 * m);
+        if (m) atomicAdd(&s_pad, 4 * ((m + 1) & ~1));
     }
     __syncthreads();
     bool generic = nrows > kRMAX || nnz > kNnzMax || s_pad > kPadMax || !pad_even;
@@ -218,15 +285,109 @@ k_plan_tiles(int64_t h_in, int64_t w_in, int64_t h_out, int64_t w_out, int tiles
             tile_rows[((int64_t)tile * kRMAX + r) * 2 + 1] = s_off[r];
         }
     }
+    // slot layout: the two cells of a half-warp are aligned for bank parity (align_pair); the two pairs of a quad
+    // share one even slot count.  If the aligned layout is too long for the tile, fall back to the unaligned one.
+    int slots = 0, plain = RG_NO_ALIGN;
+    if (!generic && nnz) {
+        __syncthreads();  // lidx of this tile is complete
+        const int64_t out_base = ((int64_t)ty * kTH) * w_out + (int64_t)tx * kTW;
+        if (threadIdx.x < kPairs) {
+            const PairLayout P = pair_layout(threadIdx.x, th, tw, out_base, w_out, row_ptr, lidx, !RG_NO_ALIGN);
+            s_pair_len[threadIdx.x] = (uint16_t)min(P.L, 65535);
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            int acc = 0;
+            for (int qd = 0; qd < kQuads; qd++) acc += 4 * ((max((int)s_pair_len[2 * qd], (int)s_pair_len[2 * qd + 1]) + 1) & ~1);
+            s_plain = (acc > kPadMax) ? 1 : RG_NO_ALIGN;
+        }
+        __syncthreads();
+        plain = s_plain;
+        if (plain && threadIdx.x < kPairs) {
+            const PairLayout P = pair_layout(threadIdx.x, th, tw, out_base, w_out, row_ptr, lidx, false);
+            s_pair_len[threadIdx.x] = (uint16_t)min(P.L, 65535);
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            int acc = 0;
+            for (int qd = 0; qd < kQuads; qd++) {
+                s_quad_beg[qd] = (uint16_t)acc;
+                acc += 4 * ((max((int)s_pair_len[2 * qd], (int)s_pair_len[2 * qd + 1]) + 1) & ~1);
+            }
+            s_quad_beg[kQuads] = (uint16_t)acc;
+            s_quad_beg[kQuads + 1] = 0;
+            s_pad = acc;  // <= kPadMax: the unaligned layout was checked above
+        }
+        __syncthreads();
+        slots = s_pad;
+        uint16_t* qdst = reinterpret_cast<uint16_t*>(tile_info + (int64_t)tile * kTileInfoInts + 8);
+        for (int k = threadIdx.x; k < kQuads + 2; k += blockDim.x) qdst[k] = s_quad_beg[k];
+    }
     if (threadIdx.x == 0) {
         int32_t* info = tile_info + (int64_t)tile * kTileInfoInts;
         info[0] = nnz ? rmin : 0;
         info[1] = generic ? 0 : nrows;
         info[2] = (generic || !nnz) ? 0 : s_off[nrows];
         info[3] = generic ? -1 : nnz;
+        info[4] = plain;
+        info[5] = slots;
+        info[6] = info[7] = 0;  // slot base: k_plan_base
+        tile_slots[tile] = slots;
         if (generic) atomicAdd(n_generic, 1);
     }
     (void)h_in;
+}
+
+__global__ void k_plan_base(int64_t n_tiles, const int64_t* __restrict__ base, int32_t* __restrict__ tile_info)
+{
+    const int64_t tile = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (tile >= n_tiles) return;
+    memcpy(tile_info + tile * kTileInfoInts + 6, base + tile, sizeof(int64_t));
+}
+
+// slot arrays of every staged tile: entry(w, c) of quad qd at base + quad_beg[qd] + (w >> 1) * 8 + c * 2 + (w & 1)
+__global__ void __launch_bounds__(kPairs)
+k_plan_slots(int64_t h_out, int64_t w_out, int tiles_x, const int32_t* __restrict__ row_ptr, const double* __restrict__ val,
+             const int32_t* __restrict__ tile_info, const uint16_t* __restrict__ lidx,
+             double* __restrict__ slot_val, uint16_t* __restrict__ slot_lidx)
+{
+    const int tile = blockIdx.x;
+    const int32_t* info = tile_info + (int64_t)tile * kTileInfoInts;
+    if (info[3] <= 0) return;
+    const int ty = tile / tiles_x, tx = tile % tiles_x;
+    const int th = (int)min((int64_t)kTH, h_out - (int64_t)ty * kTH);
+    const int tw = (int)min((int64_t)kTW, w_out - (int64_t)tx * kTW);
+    const int64_t out_base = ((int64_t)ty * kTH) * w_out + (int64_t)tx * kTW;
+    int64_t base;
+    memcpy(&base, info + 6, sizeof(int64_t));
+    const uint16_t* quad_beg = reinterpret_cast<const uint16_t*>(info + 8);
+    const PairLayout P = pair_layout(threadIdx.x, th, tw, out_base, w_out, row_ptr, lidx, info[4] == 0);
+    const int qd = (int)threadIdx.x >> 1, cA = (2 * (int)threadIdx.x) & 3;  // my cells are cA, cA + 1 of quad qd
+    const int qb = quad_beg[qd], Lq = ((int)quad_beg[qd + 1] - qb) >> 2;
+    int ia = 0, ib = 0;
+    for (int w = 0; w < Lq; w++) {
+        bool hasA, hasB;
+        if (!P.aligned) {
+            hasA = w < P.a;
+            hasB = w < P.b;
+        } else {
+            const unsigned op = (w < P.L) ? (unsigned)((P.ops >> (2 * w)) & 3u) : 0u;
+            hasA = op & 1u;
+            hasB = op & 2u;
+        }
+        double vA = 0.0, vB = 0.0;
+        unsigned lA = 0, lB = 0;
+        if (hasA) { vA = val[P.gA + ia]; lA = lidx[P.gA + ia]; ia++; }
+        if (hasB) { vB = val[P.gB + ib]; lB = lidx[P.gB + ib]; ib++; }
+        // a padding entry reads the always-zero slot of the bank parity its partner does NOT use
+        if (!hasA) lA = (hasB && (lB & 1u)) ? kZeroEven : kZeroOdd;
+        if (!hasB) lB = (lA & 1u) ? kZeroEven : kZeroOdd;
+        const int64_t e = base + qb + (w >> 1) * 8 + cA * 2 + (w & 1);
+        slot_val[e] = vA;
+        slot_val[e + 2] = vB;
+        slot_lidx[e] = (uint16_t)(lA * 8u);
+        slot_lidx[e + 2] = (uint16_t)(lB * 8u);
+    }
 }
 
 // ---------------------------------------------------------------------------
@@ -260,33 +421,12 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity)
         "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
 }
 
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory"); }
-__device__ __forceinline__ void bulk_s2g(void* gmem_dst, const void* smem_src, unsigned bytes)
-{
-    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;\n" ::"l"(gmem_dst), "r"(smem_u32(smem_src)), "r"(bytes)
-                 : "memory");
-}
-__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;\n" ::: "memory"); }
-__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory"); }
-
-__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, unsigned bytes)
-{
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, unsigned bytes, uint64_t* bar)
-{
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(smem_u32(smem_dst)),
-                 "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
-                 : "memory");
-}
-
 // Requires even w_in / n_in and a 16-byte aligned values_in (the plan pads every footprint span to an even
 // start and even length), so the footprint moves in 16-byte pieces.
 __global__ void __launch_bounds__(kStagedThreads, 2)
 k_apply_staged(int64_t n_frames, int64_t w_in, int64_t n_in, int64_t h_out, int64_t w_out, int tiles_x, int tiles_y,
-               const int32_t* __restrict__ row_ptr, const double* __restrict__ val,
                const int32_t* __restrict__ tile_info, const int32_t* __restrict__ tile_rows,
-               const uint16_t* __restrict__ lidx,
+               const double* __restrict__ slot_val, const uint16_t* __restrict__ slot_lidx,
                const double* __restrict__ vin, double* __restrict__ vout)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -318,75 +458,33 @@ k_apply_staged(int64_t n_frames, int64_t w_in, int64_t n_in, int64_t h_out, int6
         return;
     }
 
-    // ---- once per CTA: footprint table, tile-local CSR (padded per quad), zero slots, barriers ----
+    // ---- once per CTA: footprint table, the tile's slot arrays (built by the plan), zero slots, barriers ----
     {
-        int base = 0;
-        for (int tr = 0; tr < kTH; tr++) {
-            int32_t b = 0, e = 0;
-            if (tr < th) {
-                const int64_t o0 = out_base + (int64_t)tr * w_out;
-                b = row_ptr[o0];
-                e = row_ptr[o0 + tw];
-                if (threadIdx.x < kTW) S.rowptr[tr * kTW + threadIdx.x] = (uint16_t)(base + (row_ptr[o0 + min((int)threadIdx.x, tw)] - b));
-            } else if (threadIdx.x < kTW) {
-                S.rowptr[tr * kTW + threadIdx.x] = (uint16_t)base;
-            }
-            base += e - b;
-        }
-        if (threadIdx.x == 0) S.rowptr[kTileCells] = (uint16_t)base;
+        const int nslots = info[5];
+        int64_t base;
+        memcpy(&base, info + 6, sizeof(int64_t));
+        const uint16_t* qsrc = reinterpret_cast<const uint16_t*>(info + 8);
+        if (threadIdx.x < kQuads + 2) S.quad_beg[threadIdx.x] = qsrc[threadIdx.x];
+        // slot base and count are multiples of 8 entries: 16-byte pieces
+        const int4* sv = reinterpret_cast<const int4*>(slot_val + base);
+        int4* dv = reinterpret_cast<int4*>(S.val);
+        for (int k = threadIdx.x; k < nslots / 2; k += kStagedThreads) dv[k] = sv[k];
+        const int4* sl = reinterpret_cast<const int4*>(slot_lidx + base);
+        int4* dl = reinterpret_cast<int4*>(S.lidx);
+        for (int k = threadIdx.x; k < nslots / 8; k += kStagedThreads) dl[k] = sl[k];
         for (int r = threadIdx.x; r < nrows; r += kStagedThreads) {
             S.row_src[r] = (int32_t)((int64_t)(r0 + r) * w_in + tile_rows[((int64_t)tile * kRMAX + r) * 2 + 0]);
             S.row_off[r] = tile_rows[((int64_t)tile * kRMAX + r) * 2 + 1];
         }
         if (threadIdx.x == 0) {
             S.row_off[nrows] = cells;
-            mbar_init(&S.full[0], RG_BULK_FILL ? kT : kStagedThreads);
-            mbar_init(&S.full[1], RG_BULK_FILL ? kT : kStagedThreads);
+            mbar_init(&S.full[0], kStagedThreads);
+            mbar_init(&S.full[1], kStagedThreads);
             asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
         }
-        if (threadIdx.x < 2 * kT) S.in_s[threadIdx.x / kT][(threadIdx.x % kT) * kCP + kZeroSlot] = 0.0;
-    }
-    __syncthreads();
-    {
-        // quad q4 holds cells 4*q4 .. 4*q4+3; all four rows are padded to the longest with (zero slot, 0.0)
-        if (threadIdx.x == 0) {
-            int acc = 0;
-            for (int qd = 0; qd < kQuads; qd++) {
-                S.quad_beg[qd] = (uint16_t)acc;
-                int m = 0;
-                for (int c = 0; c < 4; c++) m = max(m, (int)S.rowptr[4 * qd + c + 1] - (int)S.rowptr[4 * qd + c]);
-                acc += 4 * m;
-            }
-            S.quad_beg[kQuads] = (uint16_t)acc;
-        }
-    }
-    __syncthreads();
-    if (S.quad_beg[kQuads] > kPadMax) __trap();  // cannot happen: the plan routes such tiles to the generic kernel
-    {
-        // source position of local CSR entry j of cell c: the tile's rows are contiguous runs of the global CSR
-        for (int qd = warp; qd < kQuads; qd += NW) {
-            const int qb = S.quad_beg[qd], qn = (S.quad_beg[qd + 1] - qb) >> 2;
-            const int c = lane & 3;  // cell of the quad
-            const int cell = 4 * qd + c;
-            const int tr = cell / kTW;
-            const int lb = S.rowptr[cell], ln = (int)S.rowptr[cell + 1] - lb;
-            const int64_t o0 = out_base + (int64_t)tr * w_out;
-            const int32_t gb = (tr < th) ? row_ptr[o0] - (int32_t)S.rowptr[tr * kTW] : 0;  // global = gb + local
-            for (int w = lane >> 2; w < qn; w += 8) {
-                double v = 0.0;
-                unsigned lo = kZeroSlot * 8u;
-                if (w < ln) {
-                    v = val[gb + lb + w];
-                    lo = (unsigned)lidx[gb + lb + w] * 8u;
-                }
-#if RG_PACKED_ENTRIES
-                S.ent[qb + 4 * w + c].v = v;
-                S.ent[qb + 4 * w + c].lo = lo;
-#else
-                S.val[qb + 4 * w + c] = v;
-                S.lidx[qb + 4 * w + c] = (uint16_t)lo;
-#endif
-            }
+        if (threadIdx.x < 4 * kT) {
+            const int b = threadIdx.x / (2 * kT), t = (threadIdx.x / 2) % kT;
+            S.in_s[b][t * kCP + kZeroEven + (threadIdx.x & 1)] = 0.0;
         }
     }
     __syncthreads();
@@ -394,15 +492,13 @@ k_apply_staged(int64_t n_frames, int64_t w_in, int64_t n_in, int64_t h_out, int6
     // ---- footprint copy: warp -> frame, lane -> 16-byte pairs lane + 32 j ----
     static_assert(kStagedThreads / 32 == kT, "one warp per frame of a sub-block");
     const int tt_p = warp;
-    unsigned pf_mask = 0;
     int32_t pair_off[kPairsPerLane];  // source offset (doubles, inside a frame) of each of this lane's pairs; -1: none
+    const int npairs = cells >> 1;
     {
-        const int npairs = cells >> 1;
 #pragma unroll
         for (int j = 0; j < kPairsPerLane; j++) {
             const int p = lane + 32 * j;
             int32_t off = -1;
-            bool first_of_row = false;
             if (p < npairs) {
                 // row of staged cell 2p: last r with row_off[r] <= 2p
                 int lo = 0, hi = nrows - 1;
@@ -411,128 +507,65 @@ k_apply_staged(int64_t n_frames, int64_t w_in, int64_t n_in, int64_t h_out, int6
                     if (S.row_off[mid] <= 2 * p) lo = mid; else hi = mid - 1;
                 }
                 off = S.row_src[lo] + (2 * p - S.row_off[lo]);
-                first_of_row = (2 * p == S.row_off[lo]);
             }
             pair_off[j] = off;
-            // this lane touches L2 for the pair if it starts a 128-byte line or a footprint row
-            if (off >= 0 && ((off & 15) == 0 || first_of_row)) pf_mask |= 1u << j;
         }
     }
     const unsigned dst_lane = (unsigned)((tt_p * kCP + 2 * lane) * 8);
     auto prefetch = [&](int64_t f0, int buf) {
         const int64_t f = f0 + tt_p;
-#if RG_BULK_FILL
-        // one bulk (TMA engine) copy per footprint row of this warp's frame: no LSU / MIO traffic
-        const bool valid = f < f_end && !RG_SKIP_LOAD;
-        if (lane == 0) mbar_arrive_expect_tx(&S.full[buf], valid ? (unsigned)cells * 8u : 0u);
-        __syncwarp();
-        if (valid) {
-            const double* src = vin + f * n_in;
-            double* dst = S.in_s[buf] + tt_p * kCP;
-            for (int r = lane; r < nrows; r += 32) {
-                const int off = S.row_off[r], len = S.row_off[r + 1] - off;
-                if (len > 0) bulk_g2s(dst + off, src + S.row_src[r], (unsigned)len * 8u, &S.full[buf]);
-            }
-        }
-#else
         if (f < f_end) {
             const double* src = vin + f * n_in;
             const unsigned dst = smem_u32(S.in_s[buf]) + dst_lane;
 #pragma unroll
-            for (int j = 0; j < kPairsPerLane; j++)
+            for (int j = 0; j < kPairsPerLane; j++) {
+                if (32 * j >= npairs) break;  // uniform: no copy instruction is issued beyond the footprint
                 if (pair_off[j] >= 0 && !RG_SKIP_LOAD) cp_async_16(dst + j * 32 * 16, src + pair_off[j]);
+            }
         }
         cp_async_mbar_arrive(&S.full[buf]);
-#endif
-    };
-
-    // HBM -> L2 a few sub-blocks ahead of the shared-memory copy: the copy then sees L2 latency, and DRAM
-    // requests are spread over the whole iteration instead of arriving in bursts
-    auto l2_prefetch = [&](int64_t f0) {
-        const int64_t f = f0 + tt_p;
-        if (RG_L2_AHEAD > 0 && f < f_end) {
-            const double* src = vin + f * n_in;
-#pragma unroll
-            for (int j = 0; j < kPairsPerLane; j++)
-                if (pf_mask & (1u << j)) asm volatile("prefetch.global.L2 [%0];\n" ::"l"(src + pair_off[j]));
-        }
     };
 
     const int nsub = (int)((f_end - f_begin + kT - 1) / kT);
     prefetch(f_begin, 0);
     if (nsub > 1) prefetch(f_begin + kT, 1);
-    for (int a = 2; a < 2 + RG_L2_AHEAD; a++) l2_prefetch(f_begin + (int64_t)a * kT);
     const int q = lane >> 3, t = lane & 7;  // quarter-warp = one output cell; lane owns frames t and t + 8
+    // full-width tiles of 16-byte aligned output rows are written with 16-byte stores
+    const bool vec_store = tw == kTW && (w_out & 1) == 0 && ((uintptr_t)vout & 15) == 0;
     for (int s = 0; s < nsub; s++) {
         const int64_t f0 = f_begin + (int64_t)s * kT;
         const int buf = s & 1;
         mbar_wait(&S.full[buf], (unsigned)((s >> 1) & 1));
         double* in = S.in_s[buf];
         const char* in0 = reinterpret_cast<const char*>(in + t * kCP);
-        // ---- compute: quarter-warp per output cell, rows of a quad share one (padded) trip count ----
+        // ---- compute: quarter-warp per output cell, all cells of a quad share one slot count ----
         double acc[2][2];
-#if RG_QUAD_INTERLEAVE
-        {
-            // the warp's two quads are walked together: two independent dependency chains per lane
-            const int qbA = S.quad_beg[warp], qeA = S.quad_beg[warp + 1];
-            const int qbB = S.quad_beg[warp + NW], qeB = S.quad_beg[warp + NW + 1];
-            const int nA = (qeA - qbA) >> 2, nB = (qeB - qbB) >> 2;
-            const int nmin = min(nA, nB);
-            double a0 = 0.0, a1 = 0.0, b0 = 0.0, b1 = 0.0;
-            int eA = qbA + q, eB = qbB + q;
-#pragma unroll 2
-            for (int w = 0; w < nmin; w++, eA += 4, eB += 4) {
-                const unsigned loA = S.lidx[eA], loB = S.lidx[eB];
-                const double vA = S.val[eA], vB = S.val[eB];
-                const double xA0 = *reinterpret_cast<const double*>(in0 + loA);
-                const double xA1 = *reinterpret_cast<const double*>(in0 + loA + 8 * kCP * 8);
-                const double xB0 = *reinterpret_cast<const double*>(in0 + loB);
-                const double xB1 = *reinterpret_cast<const double*>(in0 + loB + 8 * kCP * 8);
-                a0 = dadd(a0, dmul(vA, xA0));
-                a1 = dadd(a1, dmul(vA, xA1));
-                b0 = dadd(b0, dmul(vB, xB0));
-                b1 = dadd(b1, dmul(vB, xB1));
-            }
-            for (int w = nmin; w < nA; w++, eA += 4) {
-                const unsigned lo = S.lidx[eA];
-                const double v = S.val[eA];
-                a0 = dadd(a0, dmul(v, *reinterpret_cast<const double*>(in0 + lo)));
-                a1 = dadd(a1, dmul(v, *reinterpret_cast<const double*>(in0 + lo + 8 * kCP * 8)));
-            }
-            for (int w = nmin; w < nB; w++, eB += 4) {
-                const unsigned lo = S.lidx[eB];
-                const double v = S.val[eB];
-                b0 = dadd(b0, dmul(v, *reinterpret_cast<const double*>(in0 + lo)));
-                b1 = dadd(b1, dmul(v, *reinterpret_cast<const double*>(in0 + lo + 8 * kCP * 8)));
-            }
-            acc[0][0] = a0; acc[0][1] = a1; acc[1][0] = b0; acc[1][1] = b1;
-        }
-#else
 #pragma unroll
         for (int k = 0; k < 2; k++) {
             const int qd = warp + k * NW;
             const int qb = S.quad_beg[qd], qe = S.quad_beg[qd + 1];
+            const double2* vp = reinterpret_cast<const double2*>(S.val + qb) + q;
+            const uint32_t* lp = reinterpret_cast<const uint32_t*>(S.lidx + qb) + q;
+            const int n2 = RG_SKIP_COMPUTE ? 0 : (qe - qb) >> 3;  // slot pairs
             double a0 = 0.0, a1 = 0.0;
-#pragma unroll 4
-            for (int e = qb + q; e < (RG_SKIP_COMPUTE ? qb : qe); e += 4) {
-#if RG_PACKED_ENTRIES
-                const int4 raw = *reinterpret_cast<const int4*>(&S.ent[e]);  // one 16-byte shared load per entry
-                const double v = __hiloint2double(raw.y, raw.x);
-                const unsigned lo = (unsigned)raw.z;
-#else
-                const unsigned lo = S.lidx[e];
-                const double v = S.val[e];
-#endif
-                const double x0 = *reinterpret_cast<const double*>(in0 + lo);
-                const double x1 = *reinterpret_cast<const double*>(in0 + lo + 8 * kCP * 8);
-                a0 = dadd(a0, dmul(v, x0));
-                a1 = dadd(a1, dmul(v, x1));
+#pragma unroll 2
+            for (int j = 0; j < n2; j++) {
+                const uint32_t l2 = lp[4 * j];   // offsets of slots 2j, 2j+1: one 4-byte load
+                const double2 v2 = vp[4 * j];    // weights of slots 2j, 2j+1: one 16-byte load
+                const unsigned lo0 = l2 & 0xffffu, lo1 = l2 >> 16;
+                const double x00 = *reinterpret_cast<const double*>(in0 + lo0);
+                const double x01 = *reinterpret_cast<const double*>(in0 + lo0 + 8 * kCP * 8);
+                const double x10 = *reinterpret_cast<const double*>(in0 + lo1);
+                const double x11 = *reinterpret_cast<const double*>(in0 + lo1 + 8 * kCP * 8);
+                a0 = dadd(a0, dmul(v2.x, x00));
+                a1 = dadd(a1, dmul(v2.x, x01));
+                a0 = dadd(a0, dmul(v2.y, x10));
+                a1 = dadd(a1, dmul(v2.y, x11));
             }
             acc[k][0] = a0;
             acc[k][1] = a1;
         }
-#endif
-        __syncthreads();  // everyone is done reading in_s[buf]: frame t's slots [0,256) now take its outputs
+        __syncthreads();  // everyone is done reading in_s[buf]: frame t's slots [0,128) now take its outputs
 #pragma unroll
         for (int k = 0; k < 2; k++) {
             const int o_local = 4 * (warp + k * NW) + q;
@@ -540,21 +573,26 @@ k_apply_staged(int64_t n_frames, int64_t w_in, int64_t n_in, int64_t h_out, int6
             in[(t + 8) * kOutStride + o_local] = acc[k][1];
         }
         __syncthreads();
-        // ---- write-out: warp w stores frame w, all tile rows; 256 B per instruction ----
+        // ---- write-out: warp w stores frame w; 16 B per lane, two tile rows (2 x 256 B) per instruction ----
         {
             const int64_t f = f0 + tt_p;
-            if (f < f_end && lane < tw) {
-                double* o = vout + f * n_out + out_base + lane;
-                const double* si = in + tt_p * kOutStride + lane;
-                for (int tr = 0; tr < (RG_SKIP_STORE ? 0 : th); tr++) o[(int64_t)tr * w_out] = si[tr * kTW];
+            if (f < f_end && !RG_SKIP_STORE) {
+                if (vec_store) {
+                    const int hr = lane >> 4, c2 = (lane & 15) * 2;  // half-warp -> tile row, lane -> 2 cells
+                    double* o = vout + f * n_out + out_base + c2;
+                    const double* si = in + tt_p * kOutStride + c2;
+#pragma unroll
+                    for (int tr = hr; tr < kTH; tr += 2)
+                        if (tr < th) *reinterpret_cast<double2*>(o + (int64_t)tr * w_out) = *reinterpret_cast<const double2*>(si + tr * kTW);
+                } else if (lane < tw) {
+                    double* o = vout + f * n_out + out_base + lane;
+                    const double* si = in + tt_p * kOutStride + lane;
+                    for (int tr = 0; tr < th; tr++) o[(int64_t)tr * w_out] = si[tr * kTW];
+                }
             }
         }
         __syncthreads();  // outputs consumed: the buffer may be refilled
-        if (s + 2 < nsub) {
-            if (RG_BULK_FILL) fence_proxy_async();  // our generic-proxy accesses of the buffer precede the async refill
-            prefetch(f0 + 2 * kT, buf);
-        }
-        l2_prefetch(f0 + (int64_t)(2 + RG_L2_AHEAD) * kT);
+        if (s + 2 < nsub) prefetch(f0 + 2 * kT, buf);
     }
 }
 
@@ -603,6 +641,23 @@ static int64_t tiles_of(int64_t h_out, int64_t w_out, int* tiles_x)
     return tx * ty;
 }
 
+// layout of the caller's tile_info buffer: [n_tiles records][4 counters][n_tiles slot counts]
+// [n_tiles + 1 slot bases (int64)][scan scratch (int64)]
+struct PlanLayout {
+    int64_t n_tiles, counter, counts, base, scratch, total_ints;
+};
+static PlanLayout plan_layout(int64_t n_tiles)
+{
+    PlanLayout L;
+    L.n_tiles = n_tiles;
+    L.counter = n_tiles * kTileInfoInts;
+    L.counts = L.counter + 4;
+    L.base = (L.counts + n_tiles + 1) / 2 * 2;  // int64-aligned (the buffer itself is >= 8-byte aligned)
+    L.scratch = L.base + 2 * (n_tiles + 1);
+    L.total_ints = L.scratch + 2 * (int64_t)scan_scratch_elems(n_tiles);
+    return L;
+}
+
 extern "C" int rg_apply_plan_sizes(int64_t h_out, int64_t w_out, int64_t* n_tiles_host,
                                    int64_t* tile_info_ints_host, int64_t* tile_rows_ints_host)
 {
@@ -610,7 +665,7 @@ extern "C" int rg_apply_plan_sizes(int64_t h_out, int64_t w_out, int64_t* n_tile
         return fail(RG_E_ARG, "rg_apply_plan_sizes: bad argument");
     const int64_t n = tiles_of(h_out, w_out, nullptr);
     *n_tiles_host = n;
-    *tile_info_ints_host = n * kTileInfoInts + 4;  // + counter
+    *tile_info_ints_host = plan_layout(n).total_ints;
     *tile_rows_ints_host = n * kRMAX * 2;
     return RG_OK;
 }
@@ -619,33 +674,67 @@ extern "C" int rg_apply_plan_build(int device, void* stream, int64_t nnz,
                                    int64_t h_in, int64_t w_in, int64_t h_out, int64_t w_out,
                                    const int32_t* row_ptr, const int32_t* col,
                                    int32_t* tile_info, int32_t* tile_rows, uint16_t* lidx,
-                                   int64_t* n_generic_tiles_host)
+                                   int64_t* n_generic_tiles_host, int64_t* n_slots_host)
 {
-    if (h_in <= 0 || w_in <= 0 || h_out <= 0 || w_out <= 0 || !row_ptr || !tile_info || !tile_rows || !n_generic_tiles_host)
+    if (h_in <= 0 || w_in <= 0 || h_out <= 0 || w_out <= 0 || !row_ptr || !tile_info || !tile_rows || !n_generic_tiles_host ||
+        !n_slots_host)
         return fail(RG_E_ARG, "rg_apply_plan_build: bad argument");
     if (nnz > 0 && (!col || !lidx)) return fail(RG_E_ARG, "rg_apply_plan_build: null pointer");
     if (h_in * w_in >= INT32_MAX || h_out * w_out >= INT32_MAX) return fail(RG_E_TOO_LARGE, "rg_apply_plan_build: too large");
+    if ((uintptr_t)tile_info % 8 != 0) return fail(RG_E_ARG, "rg_apply_plan_build: tile_info must be 8-byte aligned");
     RG_CUDA(cudaSetDevice(device));
     cudaStream_t st = (cudaStream_t)stream;
     int tiles_x;
     const int64_t n_tiles = tiles_of(h_out, w_out, &tiles_x);
-    int32_t* counter = tile_info + n_tiles * kTileInfoInts;
+    const PlanLayout L = plan_layout(n_tiles);
+    int32_t* counter = tile_info + L.counter;
+    int32_t* counts = tile_info + L.counts;
+    int64_t* base = reinterpret_cast<int64_t*>(tile_info + L.base);
+    int64_t* scratch = reinterpret_cast<int64_t*>(tile_info + L.scratch);
     RG_CUDA(cudaMemsetAsync(counter, 0, sizeof(int32_t) * 4, st));
     const int pad_even = (w_in % 2 == 0) && ((h_in * w_in) % 2 == 0);
     k_plan_tiles<<<(unsigned)n_tiles, 128, 0, st>>>(h_in, w_in, h_out, w_out, tiles_x, pad_even, row_ptr, col,
-                                                    tile_info, tile_rows, lidx, counter);
+                                                    tile_info, tile_rows, lidx, counter, counts);
     RG_LAUNCH_CHECK("k_plan_tiles");
+    const int rc = exclusive_scan_i32_i64(st, counts, base, n_tiles, scratch);
+    if (rc != RG_OK) return rc;
+    k_plan_base<<<(unsigned)ceil_div(n_tiles, 256), 256, 0, st>>>(n_tiles, base, tile_info);
+    RG_LAUNCH_CHECK("k_plan_base");
     int32_t n_generic = 0;
+    int64_t n_slots = 0;
     RG_CUDA(cudaMemcpyAsync(&n_generic, counter, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    RG_CUDA(cudaMemcpyAsync(&n_slots, base + n_tiles, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
     RG_CUDA(cudaStreamSynchronize(st));
     *n_generic_tiles_host = n_generic;
+    *n_slots_host = n_slots;
+    return RG_OK;
+}
+
+extern "C" int rg_apply_plan_slots(int device, void* stream, int64_t h_out, int64_t w_out,
+                                   const int32_t* row_ptr, const double* val,
+                                   const int32_t* tile_info, const uint16_t* lidx,
+                                   int64_t n_slots, double* slot_val, uint16_t* slot_lidx)
+{
+    if (h_out <= 0 || w_out <= 0 || n_slots < 0 || !row_ptr || !tile_info)
+        return fail(RG_E_ARG, "rg_apply_plan_slots: bad argument");
+    if (n_slots == 0) return RG_OK;
+    if (!val || !lidx || !slot_val || !slot_lidx) return fail(RG_E_ARG, "rg_apply_plan_slots: null pointer");
+    if ((uintptr_t)slot_val % 16 != 0 || (uintptr_t)slot_lidx % 16 != 0)
+        return fail(RG_E_ARG, "rg_apply_plan_slots: slot arrays must be 16-byte aligned");
+    RG_CUDA(cudaSetDevice(device));
+    cudaStream_t st = (cudaStream_t)stream;
+    int tiles_x;
+    const int64_t n_tiles = tiles_of(h_out, w_out, &tiles_x);
+    k_plan_slots<<<(unsigned)n_tiles, kPairs, 0, st>>>(h_out, w_out, tiles_x, row_ptr, val, tile_info, lidx, slot_val, slot_lidx);
+    RG_LAUNCH_CHECK("k_plan_slots");
     return RG_OK;
 }
 
 extern "C" int rg_apply_planned(int device, void* stream, int64_t n_frames,
                                 int64_t h_in, int64_t w_in, int64_t h_out, int64_t w_out,
                                 const int32_t* row_ptr, const int32_t* col, const double* val,
-                                const int32_t* tile_info, const int32_t* tile_rows, const uint16_t* lidx,
+                                const int32_t* tile_info, const int32_t* tile_rows,
+                                const double* slot_val, const uint16_t* slot_lidx,
                                 int64_t n_generic_tiles,
                                 const double* values_in, double* values_out)
 {
@@ -658,7 +747,7 @@ extern "C" int rg_apply_planned(int device, void* stream, int64_t n_frames,
     int tiles_x;
     const int64_t n_tiles = tiles_of(h_out, w_out, &tiles_x);
     const int64_t n_in = h_in * w_in, n_out = h_out * w_out;
-    static_assert(sizeof(StagedSmem) <= 227 * 1024, "staged tile does not fit in shared memory");
+    static_assert(sizeof(StagedSmem) <= 113 * 1024, "two staged CTAs must fit in one SM's shared memory");
     const bool aligned = ((uintptr_t)values_in % 16 == 0);
     const int tiles_y = (int)(n_tiles / tiles_x);
     if (!aligned) {
@@ -672,7 +761,7 @@ extern "C" int rg_apply_planned(int device, void* stream, int64_t n_frames,
             const int64_t nf = n_frames - f < chunk ? n_frames - f : chunk;
             dim3 grid((unsigned)n_tiles, (unsigned)ceil_div(nf, kFB));
             k_apply_staged<<<grid, kStagedThreads, sizeof(StagedSmem), st>>>(
-                nf, w_in, n_in, h_out, w_out, tiles_x, tiles_y, row_ptr, val, tile_info, tile_rows, lidx,
+                nf, w_in, n_in, h_out, w_out, tiles_x, tiles_y, tile_info, tile_rows, slot_val, slot_lidx,
                 values_in + f * n_in, values_out + f * n_out);
             RG_LAUNCH_CHECK("k_apply_staged");
         }
