@@ -64,15 +64,19 @@ constexpr int kPadMax = 1536;    // max SLOT entries per tile (4 cells x padded,
 constexpr int kAlignMax = 16;    // rows up to this length take part in the bank-parity alignment
 constexpr int kOutStride = kCP;  // staged output frame t lives in slots [0, 128) of staged input frame t
 constexpr int kStagedThreads = 512;   // 2 CTAs per SM: their load / compute / store phases overlap
-constexpr int kPairsPerLane = (kCellsMax / 2 + 31) / 32;  // 16-byte pairs of one frame a lane copies per sub-block
+constexpr int kCopyPairs = kCellsMax / 2;            // 16-byte pieces of one staged frame
+constexpr int kPairsPerLane = (kCopyPairs + 31) / 32;  // ... of which a lane copies up to this many per sub-block
 constexpr int kPatch = 12;       // tiles are issued in patches of kPatchRows x kPatch tiles (~ one wave of 2 x 148
 constexpr int kPatchRows = RG_PATCH_ROWS;   // CTAs) so that footprint halos are shared through L2
 static_assert((kCP / 2) % 2 == 1 && kCP % 2 == 0, "kCP/2 must be odd");
-static_assert(kPairs <= kStagedThreads, "one thread per pair in the setup");
+
 
 // per-tile plan record (int32): r0, nrows, cells, nnz (nnz < 0: tile handled by the generic kernel), plain layout?,
-// slot entries, slot base (int64 in two words), then quad_beg[kQuads + 1] as uint16
-constexpr int kTileInfoInts = 8 + (kQuads + 2) / 2;
+// slot entries, slot base (int64 in two words), then quad_beg[kQuads + 1] as uint16, then pair_of[kPairs] as uint8:
+// quad g is made of the pairs pair_of[2g], pair_of[2g+1] (pairs sorted by slot count, so that the two pairs of a
+// quad -- which share one trip count -- have nearly equal lengths)
+constexpr int kQuadWords = (kQuads + 2) / 2;
+constexpr int kTileInfoInts = 8 + kQuadWords + kPairs / 4;
 
 // Slot layout of a quad (4 cells c, L slots w, L even):  entry(w, c) = qb + (w >> 1) * 8 + c * 2 + (w & 1),
 // so the two values (16 B) and the two offsets (4 B) of slots (w, w+1) of a cell are one shared-memory load each.
@@ -81,8 +85,7 @@ struct StagedSmem {
     alignas(16) double val[kPadMax];
     alignas(16) uint16_t lidx[kPadMax];   // BYTE offset of the referenced cell inside a staged frame
     uint16_t quad_beg[kQuads + 2];
-    int32_t row_src[kRMAX];       // per footprint row: offset of its span inside one input frame (doubles)
-    int32_t row_off[kRMAX + 1];   //                    offset of its span inside one staged frame
+    uint8_t pair_of[kPairs];      // pair (2 consecutive output cells) handled by each half-warp slot of the tile
     alignas(8) uint64_t full[2];  // mbarriers: "buffer filled"
 };
 
@@ -202,6 +205,7 @@ k_plan_tiles(int64_t h_in, int64_t w_in, int64_t h_out, int64_t w_out, int tiles
 {
     __shared__ int s_rmin, s_rmax, s_nnz, s_pad, s_plain;
     __shared__ uint16_t s_pair_len[kPairs], s_quad_beg[kQuads + 2];
+    __shared__ uint8_t s_pair_of[kPairs];  // rank -> pair
     __shared__ int s_clo[kRMAX], s_chi[kRMAX], s_off[kRMAX + 1];
     const int tile = blockIdx.x;
     const int ty = tile / tiles_x, tx = tile % tiles_x;
@@ -280,9 +284,19 @@ k_plan_tiles(int64_t h_in, int64_t w_in, int64_t h_out, int64_t w_out, int tiles
                 lidx[w] = (uint16_t)(s_off[ci - rmin] + cj - s_clo[ci - rmin]);
             }
         }
-        for (int r = threadIdx.x; r < nrows; r += blockDim.x) {
-            tile_rows[((int64_t)tile * kRMAX + r) * 2 + 0] = s_clo[r];
-            tile_rows[((int64_t)tile * kRMAX + r) * 2 + 1] = s_off[r];
+        // copy table: source offset (doubles, inside one input frame) of every 16-byte piece of the staged frame
+        const int npairs = s_off[nrows] >> 1;
+        for (int p = threadIdx.x; p < kCopyPairs; p += blockDim.x) {
+            int32_t off = -1;
+            if (p < npairs) {
+                int lo = 0, hi = nrows - 1;  // row of staged cell 2p: last r with s_off[r] <= 2p
+                while (lo < hi) {
+                    const int mid = (lo + hi + 1) >> 1;
+                    if (s_off[mid] <= 2 * p) lo = mid; else hi = mid - 1;
+                }
+                off = (int32_t)((int64_t)(rmin + lo) * w_in + s_clo[lo] + (2 * p - s_off[lo]));
+            }
+            tile_rows[(int64_t)tile * kCopyPairs + p] = off;
         }
     }
     // slot layout: the two cells of a half-warp are aligned for bank parity (align_pair); the two pairs of a quad
@@ -296,32 +310,55 @@ k_plan_tiles(int64_t h_in, int64_t w_in, int64_t h_out, int64_t w_out, int tiles
             s_pair_len[threadIdx.x] = (uint16_t)min(P.L, 65535);
         }
         __syncthreads();
+        // pairs sorted by slot count (stable): rank -> pair.  Quad g = ranks 2g, 2g+1.
+        auto rank_pairs = [&]() {
+            if (threadIdx.x < kPairs) {
+                const int me = s_pair_len[threadIdx.x];
+                int r = 0;
+                for (int k = 0; k < kPairs; k++) {
+                    const int o = s_pair_len[k];
+                    r += (o < me) || (o == me && k < (int)threadIdx.x);
+                }
+                s_pair_of[r] = (uint8_t)threadIdx.x;
+            }
+            __syncthreads();
+        };
+        auto quad_len = [&](int qd) { return (max((int)s_pair_len[s_pair_of[2 * qd]], (int)s_pair_len[s_pair_of[2 * qd + 1]]) + 1) & ~1; };
+        rank_pairs();
         if (threadIdx.x == 0) {
             int acc = 0;
-            for (int qd = 0; qd < kQuads; qd++) acc += 4 * ((max((int)s_pair_len[2 * qd], (int)s_pair_len[2 * qd + 1]) + 1) & ~1);
+            for (int qd = 0; qd < kQuads; qd++) acc += 4 * quad_len(qd);
             s_plain = (acc > kPadMax) ? 1 : RG_NO_ALIGN;
         }
         __syncthreads();
         plain = s_plain;
-        if (plain && threadIdx.x < kPairs) {
-            const PairLayout P = pair_layout(threadIdx.x, th, tw, out_base, w_out, row_ptr, lidx, false);
-            s_pair_len[threadIdx.x] = (uint16_t)min(P.L, 65535);
+        if (plain) {
+            if (threadIdx.x < kPairs) {
+                const PairLayout P = pair_layout(threadIdx.x, th, tw, out_base, w_out, row_ptr, lidx, false);
+                s_pair_len[threadIdx.x] = (uint16_t)min(P.L, 65535);
+            }
+            __syncthreads();
+            rank_pairs();
         }
-        __syncthreads();
         if (threadIdx.x == 0) {
             int acc = 0;
             for (int qd = 0; qd < kQuads; qd++) {
-                s_quad_beg[qd] = (uint16_t)acc;
-                acc += 4 * ((max((int)s_pair_len[2 * qd], (int)s_pair_len[2 * qd + 1]) + 1) & ~1);
+                // offsets are multiples of 8: bit 0 flags an odd slot count (the last, padding slot is not processed)
+                const int odd = max((int)s_pair_len[s_pair_of[2 * qd]], (int)s_pair_len[s_pair_of[2 * qd + 1]]) & 1;
+                s_quad_beg[qd] = (uint16_t)(min(acc, 65528) | odd);
+                acc += 4 * quad_len(qd);
             }
-            s_quad_beg[kQuads] = (uint16_t)acc;
+            s_quad_beg[kQuads] = (uint16_t)min(acc, 65535);
             s_quad_beg[kQuads + 1] = 0;
-            s_pad = acc;  // <= kPadMax: the unaligned layout was checked above
+            s_pad = acc;
         }
         __syncthreads();
-        slots = s_pad;
+        if (s_pad > kPadMax) generic = true;  // (sorted quads never need more slots than the positional ones checked above)
+        slots = generic ? 0 : s_pad;
         uint16_t* qdst = reinterpret_cast<uint16_t*>(tile_info + (int64_t)tile * kTileInfoInts + 8);
         for (int k = threadIdx.x; k < kQuads + 2; k += blockDim.x) qdst[k] = s_quad_beg[k];
+        uint8_t* pdst = reinterpret_cast<uint8_t*>(tile_info + (int64_t)tile * kTileInfoInts + 8 + kQuadWords);
+        for (int k = threadIdx.x; k < kPairs; k += blockDim.x) pdst[k] = s_pair_of[k];
     }
     if (threadIdx.x == 0) {
         int32_t* info = tile_info + (int64_t)tile * kTileInfoInts;
@@ -362,8 +399,12 @@ k_plan_slots(int64_t h_out, int64_t w_out, int tiles_x, const int32_t* __restric
     memcpy(&base, info + 6, sizeof(int64_t));
     const uint16_t* quad_beg = reinterpret_cast<const uint16_t*>(info + 8);
     const PairLayout P = pair_layout(threadIdx.x, th, tw, out_base, w_out, row_ptr, lidx, info[4] == 0);
-    const int qd = (int)threadIdx.x >> 1, cA = (2 * (int)threadIdx.x) & 3;  // my cells are cA, cA + 1 of quad qd
-    const int qb = quad_beg[qd], Lq = ((int)quad_beg[qd + 1] - qb) >> 2;
+    const uint8_t* pair_of = reinterpret_cast<const uint8_t*>(info + 8 + kQuadWords);
+    int rank = 0;
+    for (int k = 0; k < kPairs; k++)
+        if (pair_of[k] == threadIdx.x) rank = k;
+    const int qd = rank >> 1, cA = (rank & 1) * 2;  // my cells are cells cA, cA + 1 of quad qd
+    const int qb = quad_beg[qd] & ~7, Lq = (((int)quad_beg[qd + 1] & ~7) - qb) >> 2;
     int ia = 0, ib = 0;
     for (int w = 0; w < Lq; w++) {
         bool hasA, hasB;
@@ -437,7 +478,7 @@ k_apply_staged(int64_t n_frames, int64_t w_in, int64_t n_in, int64_t h_out, int6
     const int32_t* info = tile_info + (int64_t)tile * kTileInfoInts;
     const int tile_nnz = info[3];
     if (tile_nnz < 0) return;  // handled by the generic kernel
-    const int r0 = info[0], nrows = info[1], cells = info[2];
+    const int cells = info[2];
     const int th = (int)min((int64_t)kTH, h_out - (int64_t)ty * kTH);
     const int tw = (int)min((int64_t)kTW, w_out - (int64_t)tx * kTW);
     const int64_t n_out = h_out * w_out;
@@ -449,7 +490,16 @@ k_apply_staged(int64_t n_frames, int64_t w_in, int64_t n_in, int64_t h_out, int6
 
     if (tile_nnz == 0) {
         // no weights reach this tile: the reference leaves zeros (rfw.py:111-118)
-        if (lane < tw) {
+        if (tw == kTW && th == kTH && (w_out & 1) == 0 && ((uintptr_t)vout & 15) == 0) {
+            const int hr = lane >> 4, c2 = (lane & 15) * 2;
+            double2* o = reinterpret_cast<double2*>(vout + (f_begin + warp) * n_out + out_base + (int64_t)hr * w_out + c2);
+            const int64_t frame_step = NW * (n_out >> 1), row_step = w_out;  // in double2
+            const double2 z = make_double2(0.0, 0.0);
+            for (int64_t f = f_begin + warp; f < f_end; f += NW, o += frame_step) {
+                o[0] = z;
+                o[row_step] = z;
+            }
+        } else if (lane < tw) {
             for (int64_t f = f_begin + warp; f < f_end; f += NW) {
                 double* o = vout + f * n_out + out_base + lane;
                 for (int tr = 0; tr < th; tr++) o[(int64_t)tr * w_out] = 0.0;
@@ -465,6 +515,8 @@ k_apply_staged(int64_t n_frames, int64_t w_in, int64_t n_in, int64_t h_out, int6
         memcpy(&base, info + 6, sizeof(int64_t));
         const uint16_t* qsrc = reinterpret_cast<const uint16_t*>(info + 8);
         if (threadIdx.x < kQuads + 2) S.quad_beg[threadIdx.x] = qsrc[threadIdx.x];
+        if (threadIdx.x < kPairs / 4)
+            reinterpret_cast<int32_t*>(S.pair_of)[threadIdx.x] = info[8 + kQuadWords + threadIdx.x];
         // slot base and count are multiples of 8 entries: 16-byte pieces
         const int4* sv = reinterpret_cast<const int4*>(slot_val + base);
         int4* dv = reinterpret_cast<int4*>(S.val);
@@ -472,12 +524,7 @@ k_apply_staged(int64_t n_frames, int64_t w_in, int64_t n_in, int64_t h_out, int6
         const int4* sl = reinterpret_cast<const int4*>(slot_lidx + base);
         int4* dl = reinterpret_cast<int4*>(S.lidx);
         for (int k = threadIdx.x; k < nslots / 8; k += kStagedThreads) dl[k] = sl[k];
-        for (int r = threadIdx.x; r < nrows; r += kStagedThreads) {
-            S.row_src[r] = (int32_t)((int64_t)(r0 + r) * w_in + tile_rows[((int64_t)tile * kRMAX + r) * 2 + 0]);
-            S.row_off[r] = tile_rows[((int64_t)tile * kRMAX + r) * 2 + 1];
-        }
         if (threadIdx.x == 0) {
-            S.row_off[nrows] = cells;
             mbar_init(&S.full[0], kStagedThreads);
             mbar_init(&S.full[1], kStagedThreads);
             asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
@@ -489,38 +536,32 @@ k_apply_staged(int64_t n_frames, int64_t w_in, int64_t n_in, int64_t h_out, int6
     }
     __syncthreads();
 
-    // ---- footprint copy: warp -> frame, lane -> 16-byte pairs lane + 32 j ----
+    // ---- footprint copy: warp -> frame, lane -> 16-byte pieces lane + 32 j (source offsets from the plan) ----
     static_assert(kStagedThreads / 32 == kT, "one warp per frame of a sub-block");
     const int tt_p = warp;
-    int32_t pair_off[kPairsPerLane];  // source offset (doubles, inside a frame) of each of this lane's pairs; -1: none
     const int npairs = cells >> 1;
-    {
+    const int nops = (npairs + 31) >> 5;
+    int32_t pair_off[kPairsPerLane];  // source offset (doubles, inside a frame) of each of this lane's pieces; -1: none
 #pragma unroll
-        for (int j = 0; j < kPairsPerLane; j++) {
-            const int p = lane + 32 * j;
-            int32_t off = -1;
-            if (p < npairs) {
-                // row of staged cell 2p: last r with row_off[r] <= 2p
-                int lo = 0, hi = nrows - 1;
-                while (lo < hi) {
-                    const int mid = (lo + hi + 1) >> 1;
-                    if (S.row_off[mid] <= 2 * p) lo = mid; else hi = mid - 1;
-                }
-                off = S.row_src[lo] + (2 * p - S.row_off[lo]);
-            }
-            pair_off[j] = off;
-        }
+    for (int j = 0; j < kPairsPerLane; j++) {
+        const int p = lane + 32 * j;
+        pair_off[j] = (p < npairs) ? tile_rows[(int64_t)tile * kCopyPairs + p] : -1;
     }
     const unsigned dst_lane = (unsigned)((tt_p * kCP + 2 * lane) * 8);
     auto prefetch = [&](int64_t f0, int buf) {
         const int64_t f = f0 + tt_p;
-        if (f < f_end) {
-            const double* src = vin + f * n_in;
+        if (f < f_end && !RG_SKIP_LOAD) {
+            const unsigned long long src = (unsigned long long)(vin + f * n_in);
             const unsigned dst = smem_u32(S.in_s[buf]) + dst_lane;
 #pragma unroll
             for (int j = 0; j < kPairsPerLane; j++) {
-                if (32 * j >= npairs) break;  // uniform: no copy instruction is issued beyond the footprint
-                if (pair_off[j] >= 0 && !RG_SKIP_LOAD) cp_async_16(dst + j * 32 * 16, src + pair_off[j]);
+                if (j < nops)  // uniform: no copy instruction is issued beyond the footprint
+                    asm volatile(
+                        "{\n.reg .pred p;\n.reg .u64 a;\n"
+                        "setp.ge.s32 p, %2, 0;\n"
+                        "mad.wide.u32 a, %2, 8, %1;\n"
+                        "@p cp.async.cg.shared.global [%0], [a], 16;\n}\n" ::"r"(dst + j * 32 * 16),
+                        "l"(src), "r"(pair_off[j]));
             }
         }
         cp_async_mbar_arrive(&S.full[buf]);
@@ -530,47 +571,73 @@ k_apply_staged(int64_t n_frames, int64_t w_in, int64_t n_in, int64_t h_out, int6
     prefetch(f_begin, 0);
     if (nsub > 1) prefetch(f_begin + kT, 1);
     const int q = lane >> 3, t = lane & 7;  // quarter-warp = one output cell; lane owns frames t and t + 8
+    // output cell (index in the tile) of this quarter-warp in its two quads: half-warp h of quad g owns pair pair_of[2g+h]
+    int o_local[2];
+#pragma unroll
+    for (int k = 0; k < 2; k++) o_local[k] = 2 * (int)S.pair_of[2 * (2 * warp + k) + (q >> 1)] + (q & 1);
     // full-width tiles of 16-byte aligned output rows are written with 16-byte stores
-    const bool vec_store = tw == kTW && (w_out & 1) == 0 && ((uintptr_t)vout & 15) == 0;
+    const bool vec_store = tw == kTW && th >= 2 && (w_out & 1) == 0 && ((uintptr_t)vout & 15) == 0;
     for (int s = 0; s < nsub; s++) {
         const int64_t f0 = f_begin + (int64_t)s * kT;
         const int buf = s & 1;
         mbar_wait(&S.full[buf], (unsigned)((s >> 1) & 1));
         double* in = S.in_s[buf];
         const char* in0 = reinterpret_cast<const char*>(in + t * kCP);
-        // ---- compute: quarter-warp per output cell, all cells of a quad share one slot count ----
+        // ---- compute: quarter-warp per output cell, all cells of a quad share one slot count.  The warp's two
+        // quads (neighbours in the length-sorted order) are walked together: two independent chains per lane ----
         double acc[2][2];
-#pragma unroll
-        for (int k = 0; k < 2; k++) {
-            const int qd = warp + k * NW;
-            const int qb = S.quad_beg[qd], qe = S.quad_beg[qd + 1];
-            const double2* vp = reinterpret_cast<const double2*>(S.val + qb) + q;
-            const uint32_t* lp = reinterpret_cast<const uint32_t*>(S.lidx + qb) + q;
-            const int n2 = RG_SKIP_COMPUTE ? 0 : (qe - qb) >> 3;  // slot pairs
-            double a0 = 0.0, a1 = 0.0;
-#pragma unroll 2
-            for (int j = 0; j < n2; j++) {
-                const uint32_t l2 = lp[4 * j];   // offsets of slots 2j, 2j+1: one 4-byte load
-                const double2 v2 = vp[4 * j];    // weights of slots 2j, 2j+1: one 16-byte load
+        {
+            const int qvA = S.quad_beg[2 * warp], qvB = S.quad_beg[2 * warp + 1], qvC = S.quad_beg[2 * warp + 2];
+            const int qbA = qvA & ~7, qbB = qvB & ~7, qeB = qvC & ~7;
+            const double2* vpA = reinterpret_cast<const double2*>(S.val + qbA) + q;
+            const uint32_t* lpA = reinterpret_cast<const uint32_t*>(S.lidx + qbA) + q;
+            const double2* vpB = reinterpret_cast<const double2*>(S.val + qbB) + q;
+            const uint32_t* lpB = reinterpret_cast<const uint32_t*>(S.lidx + qbB) + q;
+            const int oddA = qvA & 1, oddB = qvB & 1;
+            const int nA = RG_SKIP_COMPUTE ? 0 : ((qbB - qbA) >> 3) - oddA;  // complete slot pairs
+            const int nB = RG_SKIP_COMPUTE ? 0 : ((qeB - qbB) >> 3) - oddB;
+            const int nmin = min(nA, nB);
+            double a0 = 0.0, a1 = 0.0, b0 = 0.0, b1 = 0.0;
+            auto two_slots = [&](const uint32_t* lp, const double2* vp, double& c0, double& c1) {
+                const uint32_t l2 = *lp;   // offsets of slots 2j, 2j+1: one 4-byte load
+                const double2 v2 = *vp;    // weights of slots 2j, 2j+1: one 16-byte load
                 const unsigned lo0 = l2 & 0xffffu, lo1 = l2 >> 16;
                 const double x00 = *reinterpret_cast<const double*>(in0 + lo0);
                 const double x01 = *reinterpret_cast<const double*>(in0 + lo0 + 8 * kCP * 8);
                 const double x10 = *reinterpret_cast<const double*>(in0 + lo1);
                 const double x11 = *reinterpret_cast<const double*>(in0 + lo1 + 8 * kCP * 8);
-                a0 = dadd(a0, dmul(v2.x, x00));
-                a1 = dadd(a1, dmul(v2.x, x01));
-                a0 = dadd(a0, dmul(v2.y, x10));
-                a1 = dadd(a1, dmul(v2.y, x11));
+                c0 = dadd(c0, dmul(v2.x, x00));
+                c1 = dadd(c1, dmul(v2.x, x01));
+                c0 = dadd(c0, dmul(v2.y, x10));
+                c1 = dadd(c1, dmul(v2.y, x11));
+            };
+            auto one_slot = [&](const uint32_t* lp, const double2* vp, double& c0, double& c1) {
+                const unsigned lo0 = *reinterpret_cast<const uint16_t*>(lp);
+                const double v = *reinterpret_cast<const double*>(vp);
+                c0 = dadd(c0, dmul(v, *reinterpret_cast<const double*>(in0 + lo0)));
+                c1 = dadd(c1, dmul(v, *reinterpret_cast<const double*>(in0 + lo0 + 8 * kCP * 8)));
+            };
+            int j = 0;
+#pragma unroll 1
+            for (; j < nmin; j++) {
+                two_slots(lpA + 4 * j, vpA + 4 * j, a0, a1);
+                two_slots(lpB + 4 * j, vpB + 4 * j, b0, b1);
             }
-            acc[k][0] = a0;
-            acc[k][1] = a1;
+#pragma unroll 1
+            for (int i = j; i < nA; i++) two_slots(lpA + 4 * i, vpA + 4 * i, a0, a1);
+#pragma unroll 1
+            for (int i = j; i < nB; i++) two_slots(lpB + 4 * i, vpB + 4 * i, b0, b1);
+            if (!RG_SKIP_COMPUTE) {
+                if (oddA) one_slot(lpA + 4 * nA, vpA + 4 * nA, a0, a1);  // odd slot count: the last slot on its own
+                if (oddB) one_slot(lpB + 4 * nB, vpB + 4 * nB, b0, b1);
+            }
+            acc[0][0] = a0; acc[0][1] = a1; acc[1][0] = b0; acc[1][1] = b1;
         }
         __syncthreads();  // everyone is done reading in_s[buf]: frame t's slots [0,128) now take its outputs
 #pragma unroll
         for (int k = 0; k < 2; k++) {
-            const int o_local = 4 * (warp + k * NW) + q;
-            in[t * kOutStride + o_local] = acc[k][0];
-            in[(t + 8) * kOutStride + o_local] = acc[k][1];
+            in[t * kOutStride + o_local[k]] = acc[k][0];
+            in[(t + 8) * kOutStride + o_local[k]] = acc[k][1];
         }
         __syncthreads();
         // ---- write-out: warp w stores frame w; 16 B per lane, two tile rows (2 x 256 B) per instruction ----
@@ -579,11 +646,12 @@ k_apply_staged(int64_t n_frames, int64_t w_in, int64_t n_in, int64_t h_out, int6
             if (f < f_end && !RG_SKIP_STORE) {
                 if (vec_store) {
                     const int hr = lane >> 4, c2 = (lane & 15) * 2;  // half-warp -> tile row, lane -> 2 cells
-                    double* o = vout + f * n_out + out_base + c2;
-                    const double* si = in + tt_p * kOutStride + c2;
-#pragma unroll
-                    for (int tr = hr; tr < kTH; tr += 2)
-                        if (tr < th) *reinterpret_cast<double2*>(o + (int64_t)tr * w_out) = *reinterpret_cast<const double2*>(si + tr * kTW);
+                    double* o = vout + f * n_out + out_base + (int64_t)hr * w_out + c2;
+                    const double* si = in + tt_p * kOutStride + hr * kTW + c2;
+                    const double2 r0 = *reinterpret_cast<const double2*>(si);
+                    const double2 r1 = *reinterpret_cast<const double2*>(si + 2 * kTW);
+                    *reinterpret_cast<double2*>(o) = r0;
+                    if (hr + 2 < th) *reinterpret_cast<double2*>(o + 2 * w_out) = r1;
                 } else if (lane < tw) {
                     double* o = vout + f * n_out + out_base + lane;
                     const double* si = in + tt_p * kOutStride + lane;
@@ -666,7 +734,7 @@ extern "C" int rg_apply_plan_sizes(int64_t h_out, int64_t w_out, int64_t* n_tile
     const int64_t n = tiles_of(h_out, w_out, nullptr);
     *n_tiles_host = n;
     *tile_info_ints_host = plan_layout(n).total_ints;
-    *tile_rows_ints_host = n * kRMAX * 2;
+    *tile_rows_ints_host = n * kCopyPairs;
     return RG_OK;
 }
 

@@ -20,7 +20,7 @@ for _ in range(10): _device.apply_planned(plan, vin, out)
 e1.record(); torch.cuda.synchronize()
 ms = e0.elapsed_time(e1) / 10
 byt = 8*F*2*(n-1)**2 + 12*dw.nnz + 4*((n-1)**2+1)
-print("%%s: %%.3f ms  %%.0f GB/s" %% (sys.argv[1], ms, byt/ms/1e6))
+print("%%s: %%.3f ms  %%.0f GB/s  slots/nnz %%.3f" %% (sys.argv[1], ms, byt/ms/1e6, plan.slot_val.numel()/dw.nnz))
 ''' % ROOT
 for lib in sorted((ROOT / "regridding_b200" / "variants").glob("lib_*.so")):
     env = dict(os.environ, REGRID_B200_LIB=str(lib))
