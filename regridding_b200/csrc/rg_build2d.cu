@@ -391,21 +391,74 @@ k_walk_emit(PassParams P, const int64_t* __restrict__ boff, int32_t* __restrict_
 // K4: per-input-cell buckets -> public layout
 // ---------------------------------------------------------------------------
 
-// Sort each bucket by key = (output cell << 32 | emission rank).  One lane per bucket
-// (insertion sort; buckets hold ~14 fragments), whole warp (odd-even transposition)
-// for buckets longer than 64.  Also counts the distinct output cells of the bucket.
-__global__ void k_bucket_sort(const int64_t* __restrict__ boff, int64_t n_cells,
-                              uint64_t* __restrict__ fkey, double* __restrict__ fval,
-                              int32_t* __restrict__ nuniq)
+// Sort each bucket by key = (output cell << 32 | emission rank) and count its distinct output cells.
+// A CTA owns kSortCells consecutive buckets = one contiguous range of fragments: the range is staged in shared
+// memory with coalesced loads, every thread insertion-sorts its own bucket there (buckets hold ~14 fragments),
+// and the range is written back coalesced.  CTAs whose range does not fit (or that hold a bucket longer than 64)
+// sort in global memory: one lane per bucket, the whole warp (odd-even transposition) for the long ones.
+constexpr int kSortCells = 128;
+constexpr int kSortCap = 3040;  // fragments staged per CTA (just under the 48 KB of static shared memory)
+
+__global__ void __launch_bounds__(kSortCells)
+k_bucket_sort(const int64_t* __restrict__ boff, int64_t n_cells,
+              uint64_t* __restrict__ fkey, double* __restrict__ fval,
+              int32_t* __restrict__ nuniq)
 {
+    __shared__ uint64_t s_key[kSortCap];
+    __shared__ double s_val[kSortCap];
+    __shared__ int s_long;
     const int lane = threadIdx.x & 31;
-    const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t c0 = (int64_t)blockIdx.x * kSortCells;
+    const int64_t c = c0 + threadIdx.x;
     int64_t beg = 0, end = 0;
     if (c < n_cells) {
         beg = boff[c];
         end = boff[c + 1];
     }
     const int64_t len = end - beg;
+    const int64_t lo = boff[c0], hi = boff[min(c0 + (int64_t)kSortCells, n_cells)];
+    if (threadIdx.x == 0) s_long = 0;
+    __syncthreads();
+    if (len > 64) s_long = 1;
+    __syncthreads();
+    if (hi - lo <= kSortCap && !s_long) {
+        const int n = (int)(hi - lo);
+        for (int e = threadIdx.x; e < n; e += kSortCells) {
+            s_key[e] = fkey[lo + e];
+            s_val[e] = fval[lo + e];
+        }
+        __syncthreads();
+        const int b = (int)(beg - lo), n_mine = (int)len;
+        for (int e = b + 1; e < b + n_mine; e++) {
+            const uint64_t key = s_key[e];
+            const double val = s_val[e];
+            int f = e - 1;
+            while (f >= b && s_key[f] > key) {
+                s_key[f + 1] = s_key[f];
+                s_val[f + 1] = s_val[f];
+                f--;
+            }
+            s_key[f + 1] = key;
+            s_val[f + 1] = val;
+        }
+        if (c < n_cells) {
+            int32_t u = 0;
+            uint32_t prev = 0xffffffffu;
+            for (int e = b; e < b + n_mine; e++) {
+                const uint32_t o = (uint32_t)(s_key[e] >> 32);
+                u += (e == b) || (o != prev);
+                prev = o;
+            }
+            nuniq[c] = u;
+        }
+        __syncthreads();
+        for (int e = threadIdx.x; e < n; e += kSortCells) {
+            fkey[lo + e] = s_key[e];
+            fval[lo + e] = s_val[e];
+        }
+        return;
+    }
+    // ---- global-memory path ----
     if (len <= 64) {
         for (int64_t e = beg + 1; e < end; e++) {
             const uint64_t key = fkey[e];
@@ -671,7 +724,7 @@ extern "C" int rg_build2d_fill(int device, void* stream,
                                                                       l.area_in, w_in, l.flags);
         RG_LAUNCH_CHECK("k_walk_emit");
     }
-    k_bucket_sort<<<(unsigned)ceil_div(l.Ci, T), T, 0, st>>>(l.boff, l.Ci, frag_key, frag_val, l.nuniq);
+    k_bucket_sort<<<(unsigned)ceil_div(l.Ci, kSortCells), kSortCells, 0, st>>>(l.boff, l.Ci, frag_key, frag_val, l.nuniq);
     RG_LAUNCH_CHECK("k_bucket_sort");
     rc = exclusive_scan_i32_i64(st, l.nuniq, l.colptr, l.Ci, l.scan_scratch);
     if (rc) return rc;
