@@ -43,6 +43,12 @@
 #ifndef RG_FB
 #define RG_FB 512
 #endif
+#ifndef RG_NBUF
+#define RG_NBUF 2   // footprint buffers per CTA (experiment: 1 buffer, 3 CTAs per SM)
+#endif
+#ifndef RG_CTAS
+#define RG_CTAS 2
+#endif
 
 namespace rg {
 
@@ -81,7 +87,7 @@ constexpr int kTileInfoInts = 8 + kQuadWords + kPairs / 4;
 // Slot layout of a quad (4 cells c, L slots w, L even):  entry(w, c) = qb + (w >> 1) * 8 + c * 2 + (w & 1),
 // so the two values (16 B) and the two offsets (4 B) of slots (w, w+1) of a cell are one shared-memory load each.
 struct StagedSmem {
-    double in_s[2][kT * kCP];     // [buffer][frame][cell]; after compute, frame t's slots [0,128) hold its outputs
+    double in_s[RG_NBUF][kT * kCP];     // [buffer][frame][cell]; after compute, frame t's slots [0,128) hold its outputs
     alignas(16) double val[kPadMax];
     alignas(16) uint16_t lidx[kPadMax];   // BYTE offset of the referenced cell inside a staged frame
     uint16_t quad_beg[kQuads + 2];
@@ -464,7 +470,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity)
 
 // Requires even w_in / n_in and a 16-byte aligned values_in (the plan pads every footprint span to an even
 // start and even length), so the footprint moves in 16-byte pieces.
-__global__ void __launch_bounds__(kStagedThreads, 2)
+__global__ void __launch_bounds__(kStagedThreads, RG_CTAS)
 k_apply_staged(int64_t n_frames, int64_t w_in, int64_t n_in, int64_t h_out, int64_t w_out, int tiles_x, int tiles_y,
                const int32_t* __restrict__ tile_info, const int32_t* __restrict__ tile_rows,
                const double* __restrict__ slot_val, const uint16_t* __restrict__ slot_lidx,
@@ -529,7 +535,7 @@ k_apply_staged(int64_t n_frames, int64_t w_in, int64_t n_in, int64_t h_out, int6
             mbar_init(&S.full[1], kStagedThreads);
             asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
         }
-        if (threadIdx.x < 4 * kT) {
+        if (threadIdx.x < 2 * RG_NBUF * kT) {
             const int b = threadIdx.x / (2 * kT), t = (threadIdx.x / 2) % kT;
             S.in_s[b][t * kCP + kZeroEven + (threadIdx.x & 1)] = 0.0;
         }
@@ -569,7 +575,7 @@ k_apply_staged(int64_t n_frames, int64_t w_in, int64_t n_in, int64_t h_out, int6
 
     const int nsub = (int)((f_end - f_begin + kT - 1) / kT);
     prefetch(f_begin, 0);
-    if (nsub > 1) prefetch(f_begin + kT, 1);
+    if (RG_NBUF > 1 && nsub > 1) prefetch(f_begin + kT, 1);
     const int q = lane >> 3, t = lane & 7;  // quarter-warp = one output cell; lane owns frames t and t + 8
     // output cell (index in the tile) of this quarter-warp in its two quads: half-warp h of quad g owns pair pair_of[2g+h]
     int o_local[2];
@@ -579,8 +585,8 @@ k_apply_staged(int64_t n_frames, int64_t w_in, int64_t n_in, int64_t h_out, int6
     const bool vec_store = tw == kTW && th >= 2 && (w_out & 1) == 0 && ((uintptr_t)vout & 15) == 0;
     for (int s = 0; s < nsub; s++) {
         const int64_t f0 = f_begin + (int64_t)s * kT;
-        const int buf = s & 1;
-        mbar_wait(&S.full[buf], (unsigned)((s >> 1) & 1));
+        const int buf = (RG_NBUF > 1) ? (s & 1) : 0;
+        mbar_wait(&S.full[buf], (unsigned)((RG_NBUF > 1 ? (s >> 1) : s) & 1));
         double* in = S.in_s[buf];
         const char* in0 = reinterpret_cast<const char*>(in + t * kCP);
         // ---- compute: quarter-warp per output cell, all cells of a quad share one slot count.  The warp's two
@@ -660,7 +666,7 @@ k_apply_staged(int64_t n_frames, int64_t w_in, int64_t n_in, int64_t h_out, int6
             }
         }
         __syncthreads();  // outputs consumed: the buffer may be refilled
-        if (s + 2 < nsub) prefetch(f0 + 2 * kT, buf);
+        if (s + RG_NBUF < nsub) prefetch(f0 + RG_NBUF * kT, buf);
     }
 }
 
@@ -815,7 +821,7 @@ extern "C" int rg_apply_planned(int device, void* stream, int64_t n_frames,
     int tiles_x;
     const int64_t n_tiles = tiles_of(h_out, w_out, &tiles_x);
     const int64_t n_in = h_in * w_in, n_out = h_out * w_out;
-    static_assert(sizeof(StagedSmem) <= 113 * 1024, "two staged CTAs must fit in one SM's shared memory");
+    static_assert(sizeof(StagedSmem) <= (228 / RG_CTAS - 1) * 1024, "the staged CTAs must fit in one SM's shared memory");
     const bool aligned = ((uintptr_t)values_in % 16 == 0);
     const int tiles_y = (int)(n_tiles / tiles_x);
     if (!aligned) {

@@ -715,7 +715,6 @@ extern "C" int rg_build2d_fill(int device, void* stream,
     if (workspace_bytes < l.bytes) return fail(RG_E_WORKSPACE, "rg_build2d_fill: workspace too small");
     RG_CUDA(cudaSetDevice(device));
     cudaStream_t st = (cudaStream_t)stream;
-    const int T = 256;
     RG_CUDA(cudaMemsetAsync(l.cursor, 0, sizeof(int32_t) * (size_t)(l.Ci + 1), st));
     for (int p = 0; p < 4; p++) {
         PassParams P = make_pass(l, p, xin, yin, xout, yout, cell_lo, cell_hi);

@@ -387,6 +387,30 @@ def test_conservative_1d_config2_shape_properties(rg, dev, oracle):
         assert tri[2].size == 8189 or abs(tri[2].size - 8189) < 8
 
 
+def test_conservative_1d_fused_paths_agree(rg, dev, oracle):
+    """The fused 1D regrid has a shared-memory staged kernel (one spectrum on chip, bracketed searches) and a
+    generic one for spectra too long for that; both must give the oracle's bits, also for non-uniform grids
+    (bracket fall-back), descending grids and weights."""
+    rng = np.random.default_rng(5)
+    for n, m in ((700, 333), (9001, 8800)):  # staged / generic (n + m + n-1 doubles > 200 KB)
+        S = 3
+        xin = np.sort(rng.uniform(0.0, 100.0, (S, n)), axis=1)
+        xin[1] = xin[1, ::-1]                       # one descending input grid
+        xin[2] = np.linspace(0, 100, n) ** 1.0      # one uniform
+        xout = np.sort(rng.uniform(-5.0, 105.0, (S, m)), axis=1)
+        xout[2] = xout[2, ::-1]                     # one descending output grid
+        vals = rng.random((S, n - 1))
+        w = rng.random((S, n - 1))
+        for ww in (None, w):
+            fused = rg.device.regrid1d_conservative(T(xin, dev), T(xout, dev), T(vals, dev),
+                                                    None if ww is None else T(ww, dev)).cpu().numpy()
+            for s_ in range(S):
+                tri = oracle.coalesce(*oracle.weights_conservative_1d(xin[s_], xout[s_], None if ww is None else ww[s_]))
+                ii_, io_ = tri[0] % (n - 1), tri[1] % (m - 1)
+                ref = oracle.regrid_from_weights(ii_, io_, tri[2], vals[s_:s_ + 1], m - 1)[0]
+                assert np.array_equal(fused[s_], ref), (n, m, s_, ww is None)
+
+
 # ---------------------------------------------------------------------------
 # find_indices
 # ---------------------------------------------------------------------------
