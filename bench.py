@@ -318,7 +318,7 @@ def run_ours(args):
     weights_host[()] = dw.to_host()
     from regridding_b200 import _cache
 
-    _cache.remember(weights_host[()][2], dw)
+    _cache.remember(weights_host[()], dw)
     shape_in = shape_out = (n - 1, n - 1)
     pin_in = torch.empty((Fe, n - 1, n - 1), dtype=torch.float64, pin_memory=True)
     pin_in.uniform_(0.0, 1.0)

@@ -182,6 +182,25 @@ int rg_apply_planned(int device, void* stream, int64_t n_frames,
                      const double* values_in, double* values_out);
 
 /* ------------------------------------------------------------------------------
+ * transposed weights
+ * replaces the per-element arithmetic of transpose_weights_conservative
+ *           regridding/_weights/_weights_transposed/_weights_transposed.py:236-249
+ *           and its cell volumes (_cell_volume_1d :306-322 = cell_length, c1d/_grids.py:10-35;
+ *           _cell_volume_2d :325-340 = rg_grid_area)
+ * values_transposed[e] = values[e] [/ w[ii[e]]^2] * volume_input[ii[e]] / volume_output[io[e]]
+ * in NumPy's evaluation order; negative indices wrap.  The index arrays themselves are
+ * only swapped by the caller (transpose_weights, :13-52).
+ * ------------------------------------------------------------------------------ */
+int rg_cell_length_1d(int device, void* stream, int64_t S, int64_t n, const double* x /* (S, n) */,
+                      double* length /* (S, n-1) */);
+
+int rg_transpose_conservative(int device, void* stream, int64_t nnz, int64_t n_in, int64_t n_out,
+                              const int64_t* indices_input, const int64_t* indices_output,
+                              const double* values, const double* volume_input /* n_in */,
+                              const double* volume_output /* n_out */, const double* weights_input /* n_in | NULL */,
+                              double* values_transposed);
+
+/* ------------------------------------------------------------------------------
  * 1D conservative, batched over S independent spectra
  * replaces: weights_conservative_1d(x_input, x_output, weights_input, weights_output, start, stop)
  *           regridding/_weights/_weights_conservative_1d/_weights_conservative_1d.py:12-56, 60-189

@@ -211,3 +211,13 @@ def find_indices_1d(x_input, x_output, fill_value: int, method: str = "brute") -
     f = lib().orc_find_indices_brute_1d if method == "brute" else lib().orc_find_indices_searchsorted_1d
     f(D, n, m, _d(xi), _d(xo), int(fill_value), _i(out))
     return out
+
+
+def transpose_weights_conservative_values(indices_input, indices_output, values, volume_input, volume_output,
+                                          weights_input=None) -> np.ndarray:
+    """wT.py:236-249 for one element: NumPy's own evaluation order (the reference IS NumPy here);
+    volumes from ``grid_volume`` (2D) or ``np.diff`` (= cell_length, c1d/_grids.py:10-35)."""
+    v = np.array(values, dtype=np.float64)
+    if weights_input is not None:
+        v = v / np.square(weights_input[indices_input])
+    return v * volume_input[indices_input] / volume_output[indices_output]

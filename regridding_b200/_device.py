@@ -212,6 +212,33 @@ def grid_area(x, y, device=None) -> torch.Tensor:
     return out
 
 
+def cell_length_1d(x: torch.Tensor) -> torch.Tensor:
+    """(S, n) edge stacks -> (S, n-1) cell lengths x[i+1] - x[i]."""
+    L = _lib.load()
+    device = x.device
+    S, n = x.shape
+    out = torch.empty((S, n - 1), dtype=F64, device=device)
+    with torch.cuda.device(device):
+        _lib.check(L.rg_cell_length_1d(device.index, _stream(device), S, n, x.data_ptr(), out.data_ptr()),
+                   "rg_cell_length_1d")
+    return out
+
+
+def transpose_conservative(dw: "DeviceWeights", volume_input: torch.Tensor, volume_output: torch.Tensor,
+                           weights_input: torch.Tensor | None = None) -> torch.Tensor:
+    """Values of the conservatively transposed weights (same order as ``dw``'s triplets)."""
+    L = _lib.load()
+    device = dw.device
+    out = torch.empty(dw.nnz, dtype=F64, device=device)
+    with torch.cuda.device(device):
+        _lib.check(L.rg_transpose_conservative(device.index, _stream(device), dw.nnz, dw.n_in, dw.n_out,
+                                               dw.indices_input.data_ptr(), dw.indices_output.data_ptr(),
+                                               dw.values.data_ptr(), volume_input.data_ptr(), volume_output.data_ptr(),
+                                               _lib.ptr(weights_input), out.data_ptr()),
+                   "rg_transpose_conservative")
+    return out
+
+
 # ---------------------------------------------------------------------------
 # apply
 # ---------------------------------------------------------------------------

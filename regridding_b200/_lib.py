@@ -44,6 +44,8 @@ SIGNATURES: dict[str, list] = {
     "rg_cons1d_batched": [_int, _vp, _i64, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
     "rg_regrid1d_conservative": [_int, _vp, _i64, _i64, _i64, _vp, _vp, _vp, _vp, _vp],
     "rg_find_indices_1d": [_int, _vp, _int, _i64, _i64, _i64, _vp, _vp, _i64, _vp],
+    "rg_cell_length_1d": [_int, _vp, _i64, _i64, _vp, _vp],
+    "rg_transpose_conservative": [_int, _vp, _i64, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp],
 }
 OTHER_SYMBOLS = ["rg_last_error_string", "rg_version"]
 

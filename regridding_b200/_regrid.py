@@ -28,10 +28,11 @@ def _device_weights_of(element, n_in: int, n_out: int, device) -> _device.Device
         return element
     indices_input, indices_output, values = element
     values = getattr(values, "value", values)  # unit-carrying values (rfw.py:134-141)
-    dw = _cache.lookup(values, device)
+    key = (indices_input, indices_output, values)
+    dw = _cache.lookup(key, device)
     if dw is None or dw.n_in != n_in or dw.n_out != n_out:
         dw = _device.DeviceWeights.from_host(indices_input, indices_output, values, n_in, n_out, device)
-        _cache.remember(values, dw)
+        _cache.remember(key, dw)
     return dw
 
 

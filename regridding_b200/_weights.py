@@ -57,7 +57,7 @@ def weights(
         if unit_weights is not None:
             triple = (triple[0], triple[1], triple[2] << unit_weights)
         else:
-            _cache.remember(triple[2], dw)
+            _cache.remember(triple, dw)
         result[k] = triple
     return result.reshape(shape_orth), shape_in, shape_out
 

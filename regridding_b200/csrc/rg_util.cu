@@ -131,7 +131,69 @@ int exclusive_scan_i32_i32(cudaStream_t st, const int32_t* in, int32_t* out, int
     return scan_impl<int32_t>(st, in, out, n, block_sums);
 }
 
+// ---------------------------------------------------------------------------
+// transposed weights (regridding/_weights/_weights_transposed/_weights_transposed.py)
+// ---------------------------------------------------------------------------
+
+// cell_length (c1d/_grids.py:10-35) of S stacked edge arrays: out[s, i] = x[s, i+1] - x[s, i]
+__global__ void k_cell_length(int64_t S, int64_t n, const double* __restrict__ x, double* __restrict__ out)
+{
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= S * (n - 1)) return;
+    const int64_t s = e / (n - 1), i = e - s * (n - 1);
+    out[e] = dsub(x[s * n + i + 1], x[s * n + i]);
+}
+
+// wT.py:236-249: values / square(w[ii]) (only with weights), then * vol_in[ii] / vol_out[io], NumPy's evaluation
+// order (no fastmath); negative indices wrap like NumPy fancy indexing
+__global__ void k_transpose_conservative(int64_t nnz, int64_t n_in, int64_t n_out,
+                                         const int64_t* __restrict__ ii, const int64_t* __restrict__ io,
+                                         const double* __restrict__ v, const double* __restrict__ vol_in,
+                                         const double* __restrict__ vol_out, const double* __restrict__ w_in,
+                                         double* __restrict__ out)
+{
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= nnz) return;
+    int64_t a = ii[e], b = io[e];
+    if (a < 0) a += n_in;
+    if (b < 0) b += n_out;
+    double x = v[e];
+    if (w_in) {
+        const double w = w_in[a];
+        x = ddiv(x, dmul(w, w));
+    }
+    out[e] = ddiv(dmul(x, vol_in[a]), vol_out[b]);
+}
+
 }  // namespace rg
+
+extern "C" int rg_cell_length_1d(int device, void* stream, int64_t S, int64_t n, const double* x, double* length)
+{
+    if (S < 0 || n < 2 || !x || !length) return rg::fail(RG_E_ARG, "rg_cell_length_1d: bad argument");
+    if (S == 0) return RG_OK;
+    RG_CUDA(cudaSetDevice(device));
+    rg::k_cell_length<<<(unsigned)rg::ceil_div(S * (n - 1), 256), 256, 0, (cudaStream_t)stream>>>(S, n, x, length);
+    RG_LAUNCH_CHECK("k_cell_length");
+    return RG_OK;
+}
+
+extern "C" int rg_transpose_conservative(int device, void* stream, int64_t nnz, int64_t n_in, int64_t n_out,
+                                         const int64_t* indices_input, const int64_t* indices_output,
+                                         const double* values, const double* volume_input,
+                                         const double* volume_output, const double* weights_input,
+                                         double* values_transposed)
+{
+    if (nnz < 0 || n_in <= 0 || n_out <= 0) return rg::fail(RG_E_ARG, "rg_transpose_conservative: bad sizes");
+    if (nnz == 0) return RG_OK;
+    if (!indices_input || !indices_output || !values || !volume_input || !volume_output || !values_transposed)
+        return rg::fail(RG_E_ARG, "rg_transpose_conservative: null pointer");
+    RG_CUDA(cudaSetDevice(device));
+    rg::k_transpose_conservative<<<(unsigned)rg::ceil_div(nnz, 256), 256, 0, (cudaStream_t)stream>>>(
+        nnz, n_in, n_out, indices_input, indices_output, values, volume_input, volume_output, weights_input,
+        values_transposed);
+    RG_LAUNCH_CHECK("k_transpose_conservative");
+    return RG_OK;
+}
 
 extern "C" const char* rg_last_error_string(void) { return rg::g_err; }
 extern "C" int rg_version(void) { return 100; }

@@ -16,8 +16,11 @@ def pytest_configure(config):
 @pytest.fixture(scope="session")
 def golden():
     """Outputs of the reference itself (tests/golden/make_golden.py)."""
-    with np.load(ROOT / "tests" / "golden" / "golden_v1.npz") as z:
-        return {k: z[k] for k in z.files}
+    out = {}
+    for name in ("golden_v1.npz", "golden_v2.npz"):  # v2: transposed weights (make_golden_v2.py)
+        with np.load(ROOT / "tests" / "golden" / name) as z:
+            out.update({k: z[k] for k in z.files})
+    return out
 
 
 @pytest.fixture(scope="session")

@@ -469,3 +469,58 @@ def test_multilinear_1d(rg):
         rg.weights((x,), (np.array([-0.2, 0.5]),), bounds="raise")
     ext = rg.regrid((x,), (np.array([-0.2, 1.3]),), vals)
     assert np.allclose(ext, 3 * np.array([-0.2, 1.3]) + 1)
+
+
+# ---------------------------------------------------------------------------
+# transposed weights (regridding/_weights/_weights_transposed)
+# ---------------------------------------------------------------------------
+
+
+@pytest.mark.parametrize("name", ["fam40", "winput", "coarsen"])
+def test_transposed_weights_2d_vs_reference(rg, oracle, golden, name):
+    gi, go, w = cases.case_2d(name)
+    W = rg.weights(gi, go, weights_input=w, method="conservative")
+    vals = np.random.default_rng(0).random((3, *W[1]))
+    fwd = rg.regrid_from_weights(*W, vals)
+    # plain transpose: index arrays swapped, values shared; the apply must NOT pick up the forward matrix
+    Wt = rg.transpose_weights(W)
+    assert Wt[1] == W[2] and Wt[2] == W[1] and Wt[0][()][2] is W[0][()][2] and Wt[0][()][0] is W[0][()][1]
+    assert cases.sha(*Wt[0][()]) == str(golden[f"t2d/{name}/plain_sha"])
+    assert np.array_equal(rg.regrid_from_weights(*Wt, fwd), golden[f"t2d/{name}/plain_apply"])
+    # conservative transpose: the reference's values, bit for bit
+    Wc = rg.transpose_weights_conservative(W, gi, go, weights_input=w)
+    ii, io, v = Wc[0][()]
+    assert np.array_equal(ii, golden[f"t2d/{name}/cons_ii"]) and np.array_equal(io, golden[f"t2d/{name}/cons_io"])
+    assert np.array_equal(v, golden[f"t2d/{name}/cons_v"])
+    assert [*Wc[1], *Wc[2]] == list(golden[f"t2d/{name}/cons_shapes"])
+    assert np.array_equal(rg.regrid_from_weights(*Wc, fwd), golden[f"t2d/{name}/cons_apply"])
+    # oracle restatement (NumPy arithmetic + the C grid_volume)
+    fi, fo, fv = W[0][()]
+    ref = oracle.transpose_weights_conservative_values(fi, fo, fv, oracle.grid_volume(*gi).reshape(-1),
+                                                       oracle.grid_volume(*go).reshape(-1),
+                                                       None if w is None else np.asarray(w, dtype=float).reshape(-1))
+    assert np.array_equal(v, ref)
+
+
+def test_transposed_weights_batched_and_1d_vs_reference(rg, golden):
+    gi, go = cases.case_2d_batched()
+    kw = dict(axis_input=(1, 2), axis_output=(1, 2))
+    W = rg.weights(gi, go, method="conservative", **kw)
+    Wc = rg.transpose_weights_conservative(W, gi, go, **kw)
+    for f in range(3):
+        assert np.array_equal(Wc[0][f][2], golden[f"t2d_batched/{f}/v"])
+        assert cases.sha(*Wc[0][f]) == str(golden[f"t2d_batched/{f}/sha"])
+    vals = np.random.default_rng(0).random(W[1])
+    fwd = rg.regrid_from_weights(*W, vals, **kw)
+    assert np.array_equal(rg.regrid_from_weights(*Wc, fwd, **kw), golden["t2d_batched/apply"])
+    for name in ("spectra", "spectra_w", "descending_nonuniform", "descending_both"):
+        xin, xout, w = cases.cases_1d()[name]
+        k1 = dict(axis_input=-1, axis_output=-1)
+        W1 = rg.weights((xin,), (xout,), weights_input=w, method="conservative", **k1)
+        W1c = rg.transpose_weights_conservative(W1, (xin,), (xout,), weights_input=w, **k1)
+        flat = W1c[0].reshape(-1)
+        assert np.array_equal(np.concatenate([e[2] for e in flat]), golden[f"t1d/{name}/v"]), name
+        assert np.array_equal(np.concatenate([e[0] for e in flat]), golden[f"t1d/{name}/ii"])
+        vals1 = np.random.default_rng(0).random(W1[1])
+        fwd1 = rg.regrid_from_weights(*W1, vals1, **k1)
+        assert np.array_equal(rg.regrid_from_weights(*W1c, fwd1, **k1), golden[f"t1d/{name}/apply"], equal_nan=True), name

@@ -87,13 +87,20 @@ def test_no_cpu_fallback_without_cuda():
 
 
 def test_cache_is_identity_keyed():
-    v = np.arange(3.0)
+    ii, io, v = np.arange(3), np.arange(3) + 1, np.arange(3.0)
     token = object()
-    _cache.remember(v, token)
-    assert _cache.lookup(v) is token
-    assert _cache.lookup(v.copy()) is None
+    _cache.remember((ii, io, v), token)
+    assert _cache.lookup((ii, io, v)) is token
+    assert _cache.lookup((ii, io, v.copy())) is None
+    # transpose_weights re-uses the values array with the index arrays swapped: must not hit the forward matrix
+    assert _cache.lookup((io, ii, v)) is None
+    assert _cache.lookup((ii.copy(), io, v)) is None
+    n = len(_cache._entries)
     del v
-    assert all(ref() is not None for ref, _ in _cache._entries.values())
+    import gc
+
+    gc.collect()
+    assert len(_cache._entries) == n - 1
 
 
 def test_shard_ranges_cover_exactly():
