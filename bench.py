@@ -403,6 +403,10 @@ def run_ours(args):
             "roofline": {"bound": "hbm", "achieved": bbytes / (build_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
                          "frac": bbytes / (build_ms * 1e-3) / 1e9 / peak, "algorithmic_bytes": bbytes,
                          "note": "the build is fp64-latency / divergence bound, not HBM bound; see DESIGN.md"},
+            # config 4 (every orthogonal slice carries its own grid): slices shard across ranks with no collective,
+            # every rank runs full builds of its own slices -> aggregate = ranks x the per-rank rate (max over ranks)
+            "per_slice_sharded": {"n_gpus": world, "value": world * n_in / (build_ms * 1e-3) / 1e6, "unit": "Mcells/s",
+                                  "scaling": "weak", "collective": None},
             "banded": None if banded_ms is None else {
                 "n_gpus": world, "ms": banded_ms, "value": n_in / (banded_ms * 1e-3) / 1e6,
                 "scaling": "strong", "collective": "NCCL all-gather of the band triplets"},

@@ -9,6 +9,9 @@ The path shards without any data-path collective:
     per-rank results concatenate in rank order with no re-sort.
 The only collective is the optional all-gather of the band triplets when the caller
 wants the full matrix replicated on every rank (e.g. before a frame-sharded apply).
+A banded build still verifies every sweep line end to end (that is what keeps it
+bit-identical to the full build), but the emit walk, the bucket sort and the merge only
+touch the segments / fragments of the rank's own band.
 """
 
 from __future__ import annotations
@@ -38,22 +41,42 @@ def band_cells(ncx: int, ncy: int, rank: int, world_size: int) -> tuple[int, int
     return r0 * ncy, r1 * ncy
 
 
-def allgather_concat(t: torch.Tensor, group=None) -> torch.Tensor:
-    """Variable-length all-gather along dim 0: every rank gets cat([t_0, ..., t_{W-1}]).
-    Equal-size padded ``all_gather_into_tensor`` (NCCL-friendly); works under gloo on CPU too."""
+def allgather_concat(tensors, group=None):
+    """Variable-length all-gather along dim 0 of one tensor or of a list of tensors that share their
+    dim-0 length: every rank gets ``cat([t_0, ..., t_{W-1}])`` of each.  One small collective for the
+    lengths, then point-to-point copies of every band straight into its place in the result (one
+    NCCL group, no padding, no concatenation pass); works under gloo on CPU too."""
+    single = isinstance(tensors, torch.Tensor)
+    ts = [tensors] if single else list(tensors)
     rank, W = world(group)
     if W == 1:
-        return t
-    n = torch.tensor([t.shape[0]], dtype=torch.int64, device=t.device)
-    counts = torch.empty(W, dtype=torch.int64, device=t.device)
+        return tensors
+    dev = ts[0].device
+    n = torch.tensor([ts[0].shape[0]], dtype=torch.int64, device=dev)
+    counts = torch.empty(W, dtype=torch.int64, device=dev)
     dist.all_gather_into_tensor(counts, n, group=group)
     counts_h = counts.cpu().tolist()
-    m = max(counts_h)
-    padded = torch.zeros((m,) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
-    padded[: t.shape[0]] = t
-    gathered = torch.empty((W * m,) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
-    dist.all_gather_into_tensor(gathered, padded, group=group)
-    return torch.cat([gathered[r * m: r * m + c] for r, c in enumerate(counts_h)], dim=0)
+    offs = [0]
+    for c in counts_h:
+        offs.append(offs[-1] + c)
+    outs, ops = [], []
+    for t in ts:
+        t = t.contiguous()
+        out = torch.empty((offs[-1],) + tuple(t.shape[1:]), dtype=t.dtype, device=dev)
+        out[offs[rank]:offs[rank + 1]] = t
+        for r in range(W):
+            if r == rank:
+                continue
+            peer = r if group is None else dist.get_global_rank(group, r)
+            if counts_h[rank]:
+                ops.append(dist.P2POp(dist.isend, t, peer, group=group))
+            if counts_h[r]:
+                ops.append(dist.P2POp(dist.irecv, out[offs[r]:offs[r + 1]], peer, group=group))
+        outs.append(out)
+    if ops:
+        for req in dist.batch_isend_irecv(ops):
+            req.wait()
+    return outs[0] if single else outs
 
 
 def build_weights_2d_banded(x_in, y_in, x_out, y_out, weights_input=None, replicate: bool = True,
@@ -67,9 +90,7 @@ def build_weights_2d_banded(x_in, y_in, x_out, y_out, weights_input=None, replic
     dw = _device.build_weights_2d(x_in, y_in, x_out, y_out, weights_input, cell_band=band, device=device)
     if not replicate or W == 1:
         return dw
-    ii = allgather_concat(dw.indices_input, group)
-    io = allgather_concat(dw.indices_output, group)
-    v = allgather_concat(dw.values, group)
+    ii, io, v = allgather_concat([dw.indices_input, dw.indices_output, dw.values], group)
     out = _device.DeviceWeights(ii, io, v, dw.n_in, dw.n_out)
     out.stats = dw.stats
     return out

@@ -54,6 +54,8 @@ struct PassParams {
     int32_t* seg_end;           // [sweep vertices] state each segment ends in
     int max_iter;
     int64_t cell_lo, cell_hi;   // input-cell band
+    uint8_t* seg_hit;           // [sweep vertices] banded builds: does the segment emit anything inside the band?
+    int banded;
 };
 
 constexpr int kStateOutside = -1;
@@ -205,10 +207,12 @@ __device__ __forceinline__ PieceCells piece_cells(const PassParams& P, int L, in
 struct CountSink {
     int32_t* hist;
     int L, k, delta;
+    int total;  // fragments of this segment that fall inside the band
     __device__ __forceinline__ void piece(const PassParams& P, double, double, double, double, int ci, int cj, int)
     {
         const PieceCells pc = piece_cells(P, L, k, ci, cj);
         for (int q = 0; q < pc.n; q++) atomicAdd(&hist[pc.in[q]], delta);
+        total += pc.n;
     }
 };
 
@@ -326,11 +330,13 @@ __global__ void __launch_bounds__(128) k_walk_count(PassParams P, int32_t* __res
     P.seg_start[v] = start;
     if (start == kStateUnknown) {
         P.seg_end[v] = kStateInvalid;
+        if (P.banded) P.seg_hit[v] = 1;  // decided by the repair pass
         return;
     }
-    CountSink sink{ hist, L, k, 1 };
+    CountSink sink{ hist, L, k, 1, 0 };
     bool overflow = false;
     P.seg_end[v] = walk_segment(P, P.sweep.x[v], P.sweep.y[v], P.sweep.x[v2], P.sweep.y[v2], start, sink, overflow);
+    if (P.banded) P.seg_hit[v] = sink.total > 0;
 }
 
 // One warp per line: make the chain of states equal to the sequential walk.
@@ -355,13 +361,14 @@ __global__ void k_repair(PassParams P, int32_t* __restrict__ hist, int32_t* __re
                 const double x1 = P.sweep.x[v], y1 = P.sweep.y[v], x2 = P.sweep.x[v2], y2 = P.sweep.y[v2];
                 bool overflow = false;
                 if (old_start != kStateUnknown) {
-                    CountSink undo{ hist, L, k, -1 };
+                    CountSink undo{ hist, L, k, -1, 0 };
                     walk_segment(P, x1, y1, x2, y2, old_start, undo, overflow);
                 }
-                CountSink redo{ hist, L, k, 1 };
+                CountSink redo{ hist, L, k, 1, 0 };
                 const int e = walk_segment(P, x1, y1, x2, y2, new_start, redo, overflow);
                 P.seg_start[v] = new_start;
                 P.seg_end[v] = e;
+                if (P.banded) P.seg_hit[v] = redo.total > 0;
                 atomicAdd(&flags[kFlagRepairs], 1);
                 __threadfence();
             }
@@ -381,6 +388,7 @@ k_walk_emit(PassParams P, const int64_t* __restrict__ boff, int32_t* __restrict_
     int L, k;
     segment_of_thread(P, tid, L, k);
     const int64_t v = vertex_of(P, L, k), v2 = v + vertex_step(P);
+    if (P.banded && !P.seg_hit[v]) return;  // the count walk saw nothing of this segment inside the band
     EmitSink sink{ boff, cursor, fkey, fval, area_in, w_in, flags, L, k };
     bool overflow = false;
     walk_segment(P, P.sweep.x[v], P.sweep.y[v], P.sweep.x[v2], P.sweep.y[v2], P.seg_start[v], sink, overflow);
@@ -541,6 +549,7 @@ struct Layout {
     int32_t* line_start[4];
     int32_t* seg_start[4];
     int32_t* seg_end[4];
+    uint8_t* seg_hit[4];
     int32_t* hist;
     int64_t* boff;
     int32_t* cursor;
@@ -571,6 +580,7 @@ static Layout make_layout(void* ws, int64_t nxi, int64_t nyi, int64_t nxo, int64
         l.line_start[p] = c.take<int32_t>(axis ? nx : ny);
         l.seg_start[p] = c.take<int32_t>(nx * ny);
         l.seg_end[p] = c.take<int32_t>(nx * ny);
+        l.seg_hit[p] = c.take<uint8_t>(nx * ny);
     }
     l.hist = c.take<int32_t>(l.Ci + 1);
     l.boff = c.take<int64_t>(l.Ci + 1);
@@ -616,6 +626,8 @@ static PassParams make_pass(const Layout& l, int p, const double* xin, const dou
     P.max_iter = 4 * (P.ncx_st + P.ncy_st) + 64;
     P.cell_lo = cell_lo;
     P.cell_hi = cell_hi;
+    P.seg_hit = l.seg_hit[p];
+    P.banded = (cell_lo > 0 || cell_hi < l.Ci) ? 1 : 0;
     return P;
 }
 

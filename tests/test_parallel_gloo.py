@@ -34,6 +34,9 @@ def _worker(rank, world, port, ret):
         sel = (ii >= lo) & (ii < hi)
         parts = [_parallel.allgather_concat(torch.from_numpy(a[sel])) for a in (ii, io, v)]
         ok = all(np.array_equal(p.numpy(), a) for p, a in zip(parts, (ii, io, v)))
+        # the list form gathers all three arrays of a band in one batch
+        both = _parallel.allgather_concat([torch.from_numpy(a[sel]) for a in (ii, io, v)])
+        ok = ok and all(np.array_equal(p.numpy(), a) for p, a in zip(both, (ii, io, v)))
         # frame sharding covers every frame exactly once
         f_lo, f_hi = _parallel.shard_range(11, rank, world)
         mine = torch.zeros(11, dtype=torch.int64)
