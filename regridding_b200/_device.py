@@ -10,6 +10,7 @@ from __future__ import annotations
 
 import ctypes
 import dataclasses
+import warnings
 
 import numpy as np
 import torch
@@ -48,7 +49,9 @@ def to_device(a, device: torch.device, dtype=F64) -> torch.Tensor:
     if isinstance(a, torch.Tensor):
         return a.to(device=device, dtype=dtype).contiguous()
     a = np.ascontiguousarray(a, dtype={F64: np.float64, I64: np.int64, I32: np.int32}[dtype])
-    return torch.from_numpy(a).to(device)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore", UserWarning)  # read-only (broadcast) inputs are only read
+        return torch.from_numpy(a).to(device)
 
 
 def _workspace(nbytes: int, device) -> torch.Tensor:

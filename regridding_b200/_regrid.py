@@ -214,6 +214,11 @@ def regrid(
     on the GPU between the two steps."""
     from ._weights import _weights_conservative_device, weights
 
+    n_coordinates = 1 if isinstance(coordinates_input, np.ndarray) else len(coordinates_input)
+    if method == "conservative" and n_coordinates == 1 and not (
+            isinstance(values_input, torch.Tensor) and values_input.is_cuda):
+        return _regrid_conservative_1d_fused(coordinates_input, coordinates_output, values_input, values_output,
+                                             axis_input, axis_output, perturb, seed)
     if method == "conservative":
         elements, shape_in, shape_out, shape_orth = _weights_conservative_device(
             coordinates_input, coordinates_output, axis_input, axis_output, None, perturb, seed)
@@ -225,3 +230,69 @@ def regrid(
         w, shape_in, shape_out = weights(coordinates_input, coordinates_output, axis_input, axis_output,
                                          method=method, bounds=bounds, perturb=perturb, seed=seed)
     return regrid_from_weights(w, shape_in, shape_out, values_input, values_output, axis_input, axis_output)
+
+
+_FUSED_1D_CHUNK_BYTES = 1 << 30
+
+
+def _regrid_conservative_1d_fused(coordinates_input, coordinates_output, values_input, values_output,
+                                  axis_input, axis_output, perturb, seed):
+    """``regrid(method="conservative")`` along ONE axis without materialising weights: every
+    orthogonal slice (spectrum) goes through the fused kernel ``rg_regrid1d_conservative``,
+    which accumulates exactly like ``weights`` + ``regrid_from_weights`` would (same bits).
+    This is the BASELINE.json config-2 path (1M spectra x 4096 bins with per-spectrum grids):
+    the reference layout would need one Python tuple of three arrays per spectrum."""
+    unit = getattr(values_input, "unit", None)
+    if unit is not None:
+        values_input = values_input.value
+    if perturb is None:
+        perturb = False  # wcons.py:21-25: jitter by default only for >= 2 coordinate arrays
+    (coords_in, coords_out, axis_in, axis_out, shape_in, shape_out, orth_coords) = \
+        _util.normalize_input_output_coordinates(coordinates_input, coordinates_output, axis_input, axis_output,
+                                                 perturb=perturb, seed=seed)
+    (a_in,), (a_out,) = axis_in, axis_out
+    x_in = np.asarray(getattr(coords_in[0], "value", coords_in[0]), dtype=np.float64)
+    x_out = np.asarray(getattr(coords_out[0], "value", coords_out[0]), dtype=np.float64)
+    n, m = x_in.shape[a_in], x_out.shape[a_out]
+    values_input = np.asarray(values_input, dtype=np.float64)
+    orth_val = _orthogonal_shape(tuple(values_input.shape), (a_in,)) if values_input.ndim else ()
+    shape_orth = np.broadcast_shapes(orth_coords, orth_val)
+    full_in = _util._embed(shape_orth, (a_in,), {a_in: n - 1})
+    full_out = _util._embed(shape_orth, (a_out,), {a_out: m - 1})
+    D = int(np.prod(shape_orth, dtype=np.int64))
+
+    def stacked(c, axis, size):
+        c = np.broadcast_to(c, _util._embed(shape_orth, (axis,), {axis: size}))
+        return np.moveaxis(c, axis, -1).reshape(D, size)
+
+    xi_h, xo_h = stacked(x_in, a_in, n), stacked(x_out, a_out, m)
+    vi_h = stacked(values_input, a_in, n - 1)
+    if values_output is not None and values_output.shape != full_out:
+        raise ValueError(f"{values_output.shape=} should be equal to {full_out}")
+
+    device = _device.cuda_device()
+    out_h = np.empty((D, m - 1), dtype=float)
+    per = max(1, min(D, _FUSED_1D_CHUNK_BYTES // (8 * (2 * n + 2 * m))))
+    for d in range(0, D, per):
+        e = min(D, d + per)
+        xi = _device.to_device(xi_h[d:e], device)
+        xo = _device.to_device(xo_h[d:e], device)
+        vi = _device.to_device(vi_h[d:e], device)
+        res = _device.regrid1d_conservative(xi, xo, vi)
+        torch.from_numpy(out_h[d:e]).copy_(res)
+
+    last = (-1,)
+    if values_output is None:
+        result = np.moveaxis(out_h.reshape(tuple(shape_orth) + (m - 1,)), last, (a_out,))
+    else:
+        # the reference's in-place rule (rfw.py:120-154), see regrid_from_weights
+        moved = np.moveaxis(values_output, (a_out,), last)
+        if moved.flags.c_contiguous:
+            moved.reshape(D, m - 1)[...] = out_h
+            result = values_output
+        else:
+            values_output.fill(0)
+            result = np.moveaxis(out_h.reshape(moved.shape), last, (a_out,))
+    if unit is None:
+        return result
+    return result << unit

@@ -411,6 +411,34 @@ def test_conservative_1d_fused_paths_agree(rg, dev, oracle):
                 assert np.array_equal(fused[s_], ref), (n, m, s_, ww is None)
 
 
+def test_regrid_1d_fused_fast_path_equals_weights_path(rg):
+    """regrid(method="conservative") along one axis takes the fused kernel (no weights materialised);
+    it must return what weights() + regrid_from_weights() return, for any axis position, broadcast
+    coordinates and a caller-supplied output buffer."""
+    rng = np.random.default_rng(3)
+    n, m = 41, 29
+    xin = np.sort(rng.uniform(0, 10, (3, n, 2)), axis=1)
+    xout = np.sort(rng.uniform(-1, 11, (1, m, 2)), axis=1)          # broadcast along the first orthogonal axis
+    vals = rng.random((3, n - 1, 2))
+    kw = dict(axis_input=1, axis_output=1, method="conservative")
+    W = rg.weights((xin,), (xout,), **kw)
+    ref = rg.regrid_from_weights(*W, vals, axis_input=1, axis_output=1)
+    got = rg.regrid((xin,), (xout,), vals, **kw)
+    assert got.shape == (3, m - 1, 2) and np.array_equal(got, ref)
+    # resampled axis last + output buffer: filled in place
+    xin2, xout2, vals2 = (np.ascontiguousarray(np.moveaxis(a, 1, -1)) for a in (xin, np.broadcast_to(xout, (3, m, 2)), vals))
+    buf = np.full((3, 2, m - 1), 9.0)
+    got2 = rg.regrid((xin2,), (xout2,), vals2, values_output=buf, axis_input=-1, axis_output=-1, method="conservative")
+    assert np.shares_memory(got2, buf) and np.array_equal(np.moveaxis(buf, -1, 1), ref)
+    # resampled axis first + output buffer: the reference leaves the buffer zeroed and returns a fresh array
+    buf3 = np.full((m - 1, 3, 2), 9.0)
+    got3 = rg.regrid((np.moveaxis(xin, 1, 0),), (np.moveaxis(np.broadcast_to(xout, (3, m, 2)), 1, 0),),
+                     np.moveaxis(vals, 1, 0), values_output=buf3, axis_input=0, axis_output=0, method="conservative")
+    assert not buf3.any() and np.array_equal(np.moveaxis(got3, 0, 1), ref)
+    with pytest.raises(ValueError):
+        rg.regrid((xin,), (xout,), vals, values_output=np.zeros((2, 2)), **kw)
+
+
 # ---------------------------------------------------------------------------
 # find_indices
 # ---------------------------------------------------------------------------
