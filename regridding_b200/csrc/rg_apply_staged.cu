@@ -50,6 +50,7 @@
 #define RG_CTAS 2
 #endif
 
+
 namespace rg {
 
 constexpr int kTH = 4;           // tile height (output rows)
