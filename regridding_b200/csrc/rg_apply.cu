@@ -177,9 +177,9 @@ extern "C" int rg_apply_csr(int device, void* stream, int64_t n_frames, int64_t 
                             const int32_t* row_ptr, const int32_t* col, const double* val,
                             const double* values_in, double* values_out)
 {
+    if (n_frames == 0) return RG_OK;  // nothing to do (empty tensors have null data pointers)
     if (n_frames < 0 || n_in <= 0 || n_out <= 0 || !row_ptr || !values_in || !values_out)
         return fail(RG_E_ARG, "rg_apply_csr: bad argument");
-    if (n_frames == 0) return RG_OK;
     RG_CUDA(cudaSetDevice(device));
     cudaStream_t st = (cudaStream_t)stream;
     constexpr int FT = 8;

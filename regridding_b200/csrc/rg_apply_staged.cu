@@ -813,10 +813,10 @@ extern "C" int rg_apply_planned(int device, void* stream, int64_t n_frames,
                                 int64_t n_generic_tiles,
                                 const double* values_in, double* values_out)
 {
+    if (n_frames == 0) return RG_OK;  // nothing to do (empty tensors have null data pointers)
     if (n_frames < 0 || h_in <= 0 || w_in <= 0 || h_out <= 0 || w_out <= 0 || !row_ptr || !tile_info || !tile_rows ||
         !values_in || !values_out)
         return fail(RG_E_ARG, "rg_apply_planned: bad argument");
-    if (n_frames == 0) return RG_OK;
     RG_CUDA(cudaSetDevice(device));
     cudaStream_t st = (cudaStream_t)stream;
     int tiles_x;

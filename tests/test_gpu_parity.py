@@ -552,3 +552,50 @@ def test_transposed_weights_batched_and_1d_vs_reference(rg, golden):
         vals1 = np.random.default_rng(0).random(W1[1])
         fwd1 = rg.regrid_from_weights(*W1, vals1, **k1)
         assert np.array_equal(rg.regrid_from_weights(*W1c, fwd1, **k1), golden[f"t1d/{name}/apply"], equal_nan=True), name
+
+
+def test_find_indices_2d_config5_shape_properties(rg, dev):
+    """BASELINE.json config 5 at reduced size (1024^2 vertices, 2048^2 points over the full bounding box):
+    every located point lies inside the cell it was assigned to, and every point reported outside lies
+    outside the grid (its winding number around the boundary polygon is 0)."""
+    n, m = 1024, 2048
+    gi, _ = cases.benchmark_family(n, distorted=True)
+    X, Y = gi
+    px = np.broadcast_to(np.linspace(X.min(), X.max(), m)[:, None], (m, m)).copy()
+    py = np.broadcast_to(np.linspace(Y.min(), Y.max(), m)[None, :], (m, m)).copy()
+    flat = rg.device.find_indices_2d(T(X, dev), T(Y, dev), T(px, dev), T(py, dev), -1).cpu().numpy()
+    inside = flat >= 0
+    assert 0.5 < inside.mean() < 0.65  # the rotated grid covers ~58 % of its bounding box
+    ci, cj = flat[inside] // (n - 1), flat[inside] % (n - 1)
+    qx, qy = px[inside], py[inside]
+    # counter-clockwise (in index space) corners of the assigned cells
+    cx = np.stack([X[ci, cj], X[ci + 1, cj], X[ci + 1, cj + 1], X[ci, cj + 1]])
+    cy = np.stack([Y[ci, cj], Y[ci + 1, cj], Y[ci + 1, cj + 1], Y[ci, cj + 1]])
+    cross = [(cx[(k + 1) % 4] - cx[k]) * (qy - cy[k]) - (cy[(k + 1) % 4] - cy[k]) * (qx - cx[k]) for k in range(4)]
+    cross = np.stack(cross)
+    sign = np.sign(cross.sum(axis=0))  # orientation of the cell
+    assert np.all(cross * sign >= -1e-12), "a point was assigned to a cell that does not contain it"
+    # outside points: winding number around the boundary polygon
+    bx = np.concatenate([X[:-1, 0], X[-1, :-1], X[:0:-1, -1], X[0, :0:-1]])
+    by = np.concatenate([Y[:-1, 0], Y[-1, :-1], Y[:0:-1, -1], Y[0, :0:-1]])
+    ox, oy = px[~inside][::97], py[~inside][::97]
+    ang = np.zeros(ox.shape)
+    for k in range(bx.size):
+        x0, y0 = bx[k] - ox, by[k] - oy
+        x1, y1 = bx[(k + 1) % bx.size] - ox, by[(k + 1) % bx.size] - oy
+        ang += np.arctan2(x0 * y1 - x1 * y0, x0 * x1 + y0 * y1)
+    assert np.all(np.abs(ang) < 1.0), "a point inside the grid was reported as outside"
+
+
+def test_apply_degenerate_sizes(rg, dev):
+    """Zero frames and odd (not 16-byte friendly) grid widths take the generic paths and stay correct."""
+    gi = cases.curvilinear(12, 10)                     # 11 x 9 cells: odd input width
+    go = cases.rectilinear_over(gi[0], gi[1], 8, 8)    # 7 x 7 cells: odd output width
+    dw = rg.device.build_weights_2d(gi[0], gi[1], go[0], go[1], device=dev)
+    plan = dw.plan((11, 9), (7, 7))
+    assert plan.n_generic_tiles == plan.n_tiles  # odd widths cannot be moved in 16-byte pieces
+    x = torch.rand((5, dw.n_in), dtype=torch.float64, device=dev)
+    assert torch.equal(rg.device.apply_planned(plan, x), rg.device.apply_csr(dw.csr(), x))
+    empty = torch.empty((0, dw.n_in), dtype=torch.float64, device=dev)
+    assert rg.device.apply_planned(plan, empty).shape == (0, dw.n_out)
+    assert rg.device.apply_csr(dw.csr(), empty).shape == (0, dw.n_out)
