@@ -97,6 +97,56 @@ int rg_build2d_emit(int device, void* stream,
 int rg_build2d_stats(int device, void* stream, int64_t nx_in, int64_t ny_in, int64_t nx_out, int64_t ny_out,
                      void* workspace, int32_t* stats_host);
 
+/* ------------------------------------------------------------------------------
+ * Line-sharded 2D build (strong scaling of ONE large build over W ranks).
+ * replaces the same reference code as rg_build2d_* (the reference parallelises the sweep lines with
+ * numba.prange, _weights_conservative_2d.py:286; here the lines are dealt out across GPUs).
+ *
+ * Rank r of W walks the sweep lines of every W-th block of 32 lines of all four passes
+ * (rg_build2d_part_count / _part_fill, same workspace as rg_build2d_*).  Its fragments come out
+ * bucketed by input cell, so the fragments of every input-row band are one contiguous range:
+ * frag_offsets_host[b] = first fragment of input cell cell_bounds_host[b] (n_bounds bounds, ascending).
+ * The per-input-cell fragment counts (int32[(nx_in-1)*(ny_in-1)]) live in the workspace at byte
+ * offset *counts_offset_host.  The caller exchanges counts and fragment ranges (all-to-all; NCCL in
+ * regridding_b200/_parallel.py) so that every band owner holds, per source rank s, counts[s][c] and the
+ * chunks concatenated in source order; rg_build2d_merge gathers the chunks cell by cell, sorts every
+ * bucket by (output cell, emission rank) and counts the distinct pairs; rg_build2d_merge_emit writes
+ * the band's public triplets (indices_input = cell_offset + band cell).  The emission rank does not
+ * depend on which rank walked a segment: the concatenated bands equal the single-GPU result bit for bit.
+ * ------------------------------------------------------------------------------ */
+int rg_build2d_part_count(int device, void* stream,
+                          int64_t nx_in, int64_t ny_in, int64_t nx_out, int64_t ny_out,
+                          const double* x_in, const double* y_in,
+                          const double* x_out, const double* y_out,
+                          int part_rank, int part_world,
+                          void* workspace, size_t workspace_bytes,
+                          int64_t* n_fragments_host,
+                          int n_bounds, const int64_t* cell_bounds_host, int64_t* frag_offsets_host,
+                          size_t* counts_offset_host);
+
+int rg_build2d_part_fill(int device, void* stream,
+                         int64_t nx_in, int64_t ny_in, int64_t nx_out, int64_t ny_out,
+                         const double* x_in, const double* y_in,
+                         const double* x_out, const double* y_out,
+                         const double* weights_input_or_null,
+                         int part_rank, int part_world,
+                         void* workspace, size_t workspace_bytes,
+                         uint64_t* frag_key, double* frag_val, int64_t n_fragments);
+
+int rg_build2d_merge_workspace_bytes(int64_t n_cells, int n_src, size_t* bytes_host);
+
+int rg_build2d_merge(int device, void* stream, int64_t n_cells, int n_src,
+                     const int32_t* counts /* [n_src][n_cells] */,
+                     const uint64_t* recv_key, const double* recv_val, int64_t n_recv,
+                     void* workspace, size_t workspace_bytes,
+                     uint64_t* frag_key /* [n_recv] */, double* frag_val /* [n_recv] */,
+                     int64_t* nnz_host);
+
+int rg_build2d_merge_emit(int device, void* stream, int64_t n_cells, int n_src, int64_t cell_offset,
+                          void* workspace, size_t workspace_bytes,
+                          const uint64_t* frag_key, const double* frag_val,
+                          int64_t* indices_input, int64_t* indices_output, double* values, int64_t nnz);
+
 /* Signed cell areas; replaces grid_volume
  * regridding/_weights/_weights_conservative_2d/_grids.py:50-140. area: double[(nx-1)*(ny-1)]. */
 int rg_grid_area(int device, void* stream, int64_t nx, int64_t ny,

@@ -23,6 +23,8 @@ I32 = torch.int32
 
 # kernel launches of ours per operator call (checked against the ncu launch list in profiles/)
 LAUNCHES_BUILD2D = 37  # area 1, 2 x (bbox 2 + boundary 3), guess 2, 4 x (starts, count, repair), scans 6, emit 4, sort 1, merge 1
+# line-sharded build per rank: area 1, boundaries 10, 4 x (guess, starts, count, repair), scan 3, emit 4, merge: transpose 1, scans 9, sort 1, emit 1
+LAUNCHES_BUILD2D_SHARDED = 46
 LAUNCHES_CSR = 6       # hist, scan 3, fill, rank
 LAUNCHES_APPLY = 1     # one k_apply launch per call (up to 65535 frame tiles)
 
@@ -200,6 +202,111 @@ def build_weights_2d(x_in, y_in, x_out, y_out, weights_input=None, cell_band: tu
         _lib.check(L.rg_build2d_stats(device.index, st, nxi, nyi, nxo, nyo, ws.data_ptr(), stats), "rg_build2d_stats")
     dw = DeviceWeights(ii, io, v, n_in, n_out)
     dw.stats = {"fragments": nf, "nnz": nnz, "repaired_segments": int(stats[1]), "unknown_guesses": int(stats[2])}
+    return dw
+
+
+@dataclasses.dataclass
+class PartFragments:
+    """Fragments one rank produced by walking its share of the sweep lines (line-sharded build):
+    bucketed by input cell, so every input-row band is the contiguous range
+    ``[band_offsets[b], band_offsets[b + 1])`` of ``frag_key`` / ``frag_val``."""
+
+    counts: torch.Tensor        # int32 [n_in]: fragments per input cell (view into the workspace)
+    frag_key: torch.Tensor      # int64 [n_fragments]: output cell << 32 | emission rank
+    frag_val: torch.Tensor      # float64 [n_fragments]
+    band_offsets: list[int]     # host: first fragment of every band bound
+    n_in: int
+    n_out: int
+    workspace: torch.Tensor
+    shape: tuple[int, int, int, int]
+
+    def check(self) -> dict:
+        """Synchronises; raises if a walk of this rank did not terminate."""
+        L = _lib.load()
+        device = self.frag_key.device
+        stats = (ctypes.c_int32 * 8)()
+        with torch.cuda.device(device):
+            _lib.check(L.rg_build2d_stats(device.index, _stream(device), *self.shape, self.workspace.data_ptr(), stats),
+                       "rg_build2d_stats")
+        if stats[0] or stats[3]:
+            raise _lib.RegridB200Error("rg_build2d_part_fill: a sweep walk did not terminate (degenerate or folded grid)")
+        return {"fragments_walked": int(self.frag_key.numel()), "repaired_segments": int(stats[1]),
+                "unknown_guesses": int(stats[2])}
+
+
+def build2d_part_walk(x_in, y_in, x_out, y_out, weights_input, part_rank: int, part_world: int,
+                      cell_bounds: list[int], device=None) -> PartFragments:
+    """Rank ``part_rank`` of ``part_world``: walk every ``part_world``-th block of 32 sweep lines of all four
+    passes (``rg_build2d_part_count`` / ``rg_build2d_part_fill``)."""
+    L = _lib.load()
+    device = cuda_device(device if device is not None else (x_in.device if isinstance(x_in, torch.Tensor) else None))
+    xi, yi = to_device(x_in, device), to_device(y_in, device)
+    xo, yo = to_device(x_out, device), to_device(y_out, device)
+    if xi.ndim != 2 or xi.shape != yi.shape or xo.ndim != 2 or xo.shape != yo.shape:
+        raise ValueError("grids must be 2D arrays with matching x / y shapes")
+    nxi, nyi = xi.shape
+    nxo, nyo = xo.shape
+    n_in, n_out = (nxi - 1) * (nyi - 1), (nxo - 1) * (nyo - 1)
+    w = None
+    if weights_input is not None:
+        w = to_device(weights_input, device)
+        if tuple(w.shape) != (nxi - 1, nyi - 1):
+            raise ValueError(f"weights_input must have the input cell shape {(nxi - 1, nyi - 1)}, got {tuple(w.shape)}")
+    nb = len(cell_bounds)
+    bounds = (ctypes.c_int64 * nb)(*[int(b) for b in cell_bounds])
+    offsets = (ctypes.c_int64 * nb)()
+    with torch.cuda.device(device):
+        st = _stream(device)
+        nbytes = ctypes.c_size_t()
+        _lib.check(L.rg_build2d_workspace_bytes(nxi, nyi, nxo, nyo, ctypes.byref(nbytes)), "rg_build2d_workspace_bytes")
+        ws = _workspace(nbytes.value, device)
+        nfrag = ctypes.c_int64()
+        coff = ctypes.c_size_t()
+        _lib.check(L.rg_build2d_part_count(device.index, st, nxi, nyi, nxo, nyo, xi.data_ptr(), yi.data_ptr(),
+                                           xo.data_ptr(), yo.data_ptr(), part_rank, part_world,
+                                           ws.data_ptr(), ws.numel(), ctypes.byref(nfrag),
+                                           nb, bounds, offsets, ctypes.byref(coff)), "rg_build2d_part_count")
+        nf = nfrag.value
+        fkey = torch.empty(max(nf, 1), dtype=I64, device=device)[:nf]
+        fval = torch.empty(max(nf, 1), dtype=F64, device=device)[:nf]
+        _lib.check(L.rg_build2d_part_fill(device.index, st, nxi, nyi, nxo, nyo, xi.data_ptr(), yi.data_ptr(),
+                                          xo.data_ptr(), yo.data_ptr(), _lib.ptr(w), part_rank, part_world,
+                                          ws.data_ptr(), ws.numel(), fkey.data_ptr(), fval.data_ptr(), nf),
+                   "rg_build2d_part_fill")
+    counts = ws[coff.value:coff.value + 4 * n_in].view(I32)
+    return PartFragments(counts, fkey, fval, [int(o) for o in offsets], n_in, n_out, ws, (nxi, nyi, nxo, nyo))
+
+
+def build2d_merge(counts: torch.Tensor, recv_key: torch.Tensor, recv_val: torch.Tensor, cell_offset: int,
+                  n_in: int, n_out: int) -> DeviceWeights:
+    """Band owner: ``counts`` int32 ``[n_src, n_band_cells]``, the chunks of all sources concatenated in source
+    order -> the band's public triplets (``rg_build2d_merge`` / ``rg_build2d_merge_emit``)."""
+    L = _lib.load()
+    device = recv_key.device
+    n_src, n_cells = int(counts.shape[0]), int(counts.shape[1])
+    counts = counts.contiguous()
+    n_recv = int(recv_key.numel())
+    with torch.cuda.device(device):
+        st = _stream(device)
+        nbytes = ctypes.c_size_t()
+        _lib.check(L.rg_build2d_merge_workspace_bytes(n_cells, n_src, ctypes.byref(nbytes)),
+                   "rg_build2d_merge_workspace_bytes")
+        ws = _workspace(nbytes.value, device)
+        fkey = torch.empty(max(n_recv, 1), dtype=I64, device=device)
+        fval = torch.empty(max(n_recv, 1), dtype=F64, device=device)
+        nnz_c = ctypes.c_int64()
+        _lib.check(L.rg_build2d_merge(device.index, st, n_cells, n_src, counts.data_ptr(),
+                                      recv_key.data_ptr(), recv_val.data_ptr(), n_recv, ws.data_ptr(), ws.numel(),
+                                      fkey.data_ptr(), fval.data_ptr(), ctypes.byref(nnz_c)), "rg_build2d_merge")
+        nnz = nnz_c.value
+        ii = torch.empty(nnz, dtype=I64, device=device)
+        io = torch.empty(nnz, dtype=I64, device=device)
+        v = torch.empty(nnz, dtype=F64, device=device)
+        _lib.check(L.rg_build2d_merge_emit(device.index, st, n_cells, n_src, int(cell_offset), ws.data_ptr(), ws.numel(),
+                                           fkey.data_ptr(), fval.data_ptr(), ii.data_ptr(), io.data_ptr(),
+                                           v.data_ptr(), nnz), "rg_build2d_merge_emit")
+    dw = DeviceWeights(ii, io, v, n_in, n_out)
+    dw.stats = {"fragments": n_recv, "nnz": nnz}
     return dw
 
 

@@ -12,6 +12,11 @@ wants the full matrix replicated on every rank (e.g. before a frame-sharded appl
 A banded build still verifies every sweep line end to end (that is what keeps it
 bit-identical to the full build), but the emit walk, the bucket sort and the merge only
 touch the segments / fragments of the rank's own band.
+
+``build_weights_2d_sharded`` is the strong-scaling build: the sweep LINES are dealt out across
+the ranks (every rank walks 1/W of all four passes), the fragments travel to the owner of their
+input-row band in one all-to-all over NVLink, and the owner sorts and merges its band.  Nothing
+is walked twice, and the result is still bit-identical to the single-GPU build.
 """
 
 from __future__ import annotations
@@ -93,4 +98,81 @@ def build_weights_2d_banded(x_in, y_in, x_out, y_out, weights_input=None, replic
     ii, io, v = allgather_concat([dw.indices_input, dw.indices_output, dw.values], group)
     out = _device.DeviceWeights(ii, io, v, dw.n_in, dw.n_out)
     out.stats = dw.stats
+    return out
+
+
+def band_bounds(ncx: int, ncy: int, world_size: int) -> list[int]:
+    """Flat input-cell bounds of the W input-row bands: ``[lo_0, lo_1, ..., lo_{W-1}, n_in]``."""
+    return [band_cells(ncx, ncy, r, world_size)[0] for r in range(world_size)] + [ncx * ncy]
+
+
+def _merge_band(rank: int, bounds: list[int], counts_by_src: torch.Tensor, recv_key, recv_val, n_in, n_out):
+    return _device.build2d_merge(counts_by_src, recv_key, recv_val, bounds[rank], n_in, n_out)
+
+
+def build_weights_2d_sharded(x_in, y_in, x_out, y_out, weights_input=None, replicate: bool = False,
+                             group=None, device=None) -> _device.DeviceWeights:
+    """Strong-scaling build of ONE large grid pair over the ranks of ``group``.
+
+    Every rank holds the full coordinate arrays (134 MB at 2049^2) and walks every W-th block of 32 sweep
+    lines of all four passes; its fragments come out bucketed by input cell, so the share of every
+    input-row band is one contiguous range.  Two all-to-alls follow (the per-cell fragment counts, fixed
+    size; then the fragments themselves, ~1 GB / W^2 per pair of ranks at 2048^2), and each rank merges its
+    band (``rg_build2d_merge``).  Returns this rank's band of the public triplets; with ``replicate`` the
+    bands are all-gathered so that every rank holds the full matrix (equal to the single-GPU build bit
+    for bit)."""
+    rank, W = world(group)
+    if W == 1:
+        return _device.build_weights_2d(x_in, y_in, x_out, y_out, weights_input, device=device)
+    nxi, nyi = x_in.shape
+    bounds = band_bounds(nxi - 1, nyi - 1, W)
+    part = _device.build2d_part_walk(x_in, y_in, x_out, y_out, weights_input, rank, W, bounds, device=device)
+    dev = part.frag_key.device
+    band_sizes = [bounds[r + 1] - bounds[r] for r in range(W)]
+    cb = band_sizes[rank]
+    # 1. counts: my counts of band d -> rank d; I receive [W, cb]
+    counts_by_src = torch.empty(W * cb, dtype=torch.int32, device=dev)
+    dist.all_to_all_single(counts_by_src, part.counts, output_split_sizes=[cb] * W,
+                           input_split_sizes=band_sizes, group=group)
+    counts_by_src = counts_by_src.view(W, cb)
+    recv_sizes = counts_by_src.sum(dim=1, dtype=torch.int64).cpu().tolist()  # the one host sync of the exchange
+    send_sizes = [part.band_offsets[r + 1] - part.band_offsets[r] for r in range(W)]
+    # 2. fragments
+    n_recv = int(sum(recv_sizes))
+    recv_key = torch.empty(n_recv, dtype=torch.int64, device=dev)
+    recv_val = torch.empty(n_recv, dtype=torch.float64, device=dev)
+    dist.all_to_all_single(recv_key, part.frag_key, output_split_sizes=recv_sizes, input_split_sizes=send_sizes,
+                           group=group)
+    dist.all_to_all_single(recv_val, part.frag_val, output_split_sizes=recv_sizes, input_split_sizes=send_sizes,
+                           group=group)
+    dw = _merge_band(rank, bounds, counts_by_src, recv_key, recv_val, part.n_in, part.n_out)
+    dw.stats.update(part.check())
+    if not replicate:
+        return dw
+    ii, io, v = allgather_concat([dw.indices_input, dw.indices_output, dw.values], group)
+    out = _device.DeviceWeights(ii, io, v, dw.n_in, dw.n_out)
+    out.stats = dw.stats
+    return out
+
+
+def build_weights_2d_sharded_local(x_in, y_in, x_out, y_out, weights_input=None, world_size: int = 2,
+                                   device=None) -> list[_device.DeviceWeights]:
+    """The line-sharded build with all ``world_size`` ranks played one after the other on ONE GPU and the
+    all-to-all replaced by slicing: the same kernels and the same merge as ``build_weights_2d_sharded``,
+    used to validate the partition on a single device (tests) and to time the per-rank share."""
+    W = int(world_size)
+    nxi, nyi = x_in.shape
+    bounds = band_bounds(nxi - 1, nyi - 1, W)
+    parts = [_device.build2d_part_walk(x_in, y_in, x_out, y_out, weights_input, r, W, bounds, device=device)
+             for r in range(W)]
+    out = []
+    for d in range(W):
+        lo, hi = bounds[d], bounds[d + 1]
+        counts_by_src = torch.stack([p.counts[lo:hi] for p in parts])
+        recv_key = torch.cat([p.frag_key[p.band_offsets[d]:p.band_offsets[d + 1]] for p in parts])
+        recv_val = torch.cat([p.frag_val[p.band_offsets[d]:p.band_offsets[d + 1]] for p in parts])
+        dw = _merge_band(d, bounds, counts_by_src, recv_key, recv_val, parts[0].n_in, parts[0].n_out)
+        out.append(dw)
+    for d, p in enumerate(parts):
+        out[d].stats.update(p.check())
     return out

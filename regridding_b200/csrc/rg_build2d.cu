@@ -56,6 +56,9 @@ struct PassParams {
     int64_t cell_lo, cell_hi;   // input-cell band
     uint8_t* seg_hit;           // [sweep vertices] banded builds: does the segment emit anything inside the band?
     int banded;
+    // line-sharded builds: this rank walks the sweep lines of every part_world-th block of 32 lines
+    int part_rank, part_world;
+    int nl_slots;               // line slots of this rank (== nlines when part_world == 1)
 };
 
 constexpr int kStateOutside = -1;
@@ -73,6 +76,15 @@ __device__ __forceinline__ int64_t vertex_of(const PassParams& P, int L, int k)
     return P.axis ? (int64_t)L * P.sweep.ny + k : (int64_t)k * P.sweep.ny + L;
 }
 __device__ __forceinline__ int64_t vertex_step(const PassParams& P) { return P.axis ? 1 : P.sweep.ny; }
+
+// Line-sharded builds deal the sweep lines out block-cyclically in blocks of 32 (a warp's worth of
+// consecutive lines keeps the axis-0 loads coalesced; the cyclic deal balances lines that cross
+// little of the static grid against lines that cross all of it).
+__device__ __forceinline__ int line_of_slot(const PassParams& P, int s)
+{
+    if (P.part_world == 1) return s;
+    return ((((s >> 5) * P.part_world) + P.part_rank) << 5) | (s & 31);
+}
 
 // ---------------------------------------------------------------------------
 // K1: cell areas.  grid_volume accumulates, per cell (a, b), first the axis-0 pass
@@ -256,7 +268,9 @@ struct EmitSink {
 __global__ void k_line_starts(PassParams P, const double* __restrict__ bbox_static, int32_t* __restrict__ out)
 {
     const int lane = threadIdx.x & 31;
-    const int L = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+    const int slot = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+    if (slot >= P.nl_slots) return;
+    const int L = line_of_slot(P, slot);
     if (L >= P.nlines) return;
     const int64_t v0 = vertex_of(P, L, 0);
     const double px = P.sweep.x[v0], py = P.sweep.y[v0];
@@ -312,19 +326,35 @@ __global__ void k_vertex_guess(GridView sweep, GridView stat, int32_t* __restric
 // ---------------------------------------------------------------------------
 // K3: walks
 // ---------------------------------------------------------------------------
-__device__ __forceinline__ void segment_of_thread(const PassParams& P, int64_t tid, int& L, int& k)
+__device__ __forceinline__ bool segment_of_thread(const PassParams& P, int64_t tid, int& L, int& k)
 {
+    if (tid >= (int64_t)P.nl_slots * P.nseg) return false;
     // consecutive lanes take consecutive memory: along the line for axis 1, across lines for axis 0
-    if (P.axis) { L = (int)(tid / P.nseg); k = (int)(tid % P.nseg); }
-    else        { k = (int)(tid / P.nlines); L = (int)(tid % P.nlines); }
+    int slot;
+    if (P.axis) { slot = (int)(tid / P.nseg); k = (int)(tid % P.nseg); }
+    else        { k = (int)(tid / P.nl_slots); slot = (int)(tid % P.nl_slots); }
+    L = line_of_slot(P, slot);
+    return L < P.nlines;
+}
+
+// K2 (line-sharded builds): guessed state at the first vertex of every segment this rank walks
+__global__ void k_vertex_guess_part(PassParams P, int32_t* __restrict__ guess, int32_t* flags)
+{
+    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int L, k;
+    if (!segment_of_thread(P, tid, L, k)) return;
+    if (k == 0) return;  // the line start is located exactly by k_line_starts
+    const int64_t v = vertex_of(P, L, k);
+    const int r = locate_newton(P.stat, P.sweep.x[v], P.sweep.y[v], 0.5 * P.stat.nx, 0.5 * P.stat.ny);
+    guess[v] = r;
+    if (r == kLocUnknown) atomicAdd(&flags[kFlagUnknown], 1);
 }
 
 __global__ void __launch_bounds__(128) k_walk_count(PassParams P, int32_t* __restrict__ hist)
 {
     const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (tid >= (int64_t)P.nlines * P.nseg) return;
     int L, k;
-    segment_of_thread(P, tid, L, k);
+    if (!segment_of_thread(P, tid, L, k)) return;
     const int64_t v = vertex_of(P, L, k), v2 = v + vertex_step(P);
     const int start = (k == 0) ? P.line_start[L] : P.guess[v];
     P.seg_start[v] = start;
@@ -343,7 +373,9 @@ __global__ void __launch_bounds__(128) k_walk_count(PassParams P, int32_t* __res
 __global__ void k_repair(PassParams P, int32_t* __restrict__ hist, int32_t* __restrict__ flags)
 {
     const int lane = threadIdx.x & 31;
-    const int L = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+    const int slot = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+    if (slot >= P.nl_slots) return;
+    const int L = line_of_slot(P, slot);
     if (L >= P.nlines) return;
     const int64_t step = vertex_step(P);
     for (int base = 1; base < P.nseg; base += 32) {
@@ -384,9 +416,8 @@ k_walk_emit(PassParams P, const int64_t* __restrict__ boff, int32_t* __restrict_
             const double* __restrict__ area_in, const double* __restrict__ w_in, int32_t* __restrict__ flags)
 {
     const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (tid >= (int64_t)P.nlines * P.nseg) return;
     int L, k;
-    segment_of_thread(P, tid, L, k);
+    if (!segment_of_thread(P, tid, L, k)) return;
     const int64_t v = vertex_of(P, L, k), v2 = v + vertex_step(P);
     if (P.banded && !P.seg_hit[v]) return;  // the count walk saw nothing of this segment inside the band
     EmitSink sink{ boff, cursor, fkey, fval, area_in, w_in, flags, L, k };
@@ -407,10 +438,25 @@ k_walk_emit(PassParams P, const int64_t* __restrict__ boff, int32_t* __restrict_
 constexpr int kSortCells = 128;
 constexpr int kSortCap = 3040;  // fragments staged per CTA (just under the 48 KB of static shared memory)
 
+// Line-sharded builds: the fragments of a band arrive as one chunk per source rank, each chunk bucketed by
+// input cell.  cntT[c * W + s] = fragments of band cell c in the chunk of source s; src_off = exclusive scan of
+// the counts in [s][c] order (position in the concatenated chunks), dst_off = exclusive scan in [c][s] order
+// (position in the merged bucket array).  The sort kernel then gathers instead of staging a contiguous range.
+struct GatherSrc {
+    const int32_t* cntT;
+    const int64_t* src_off;
+    const int64_t* dst_off;
+    const uint64_t* rkey;
+    const double* rval;
+    int W;
+    int64_t Cb;
+};
+
+template <bool kGather>
 __global__ void __launch_bounds__(kSortCells)
 k_bucket_sort(const int64_t* __restrict__ boff, int64_t n_cells,
               uint64_t* __restrict__ fkey, double* __restrict__ fval,
-              int32_t* __restrict__ nuniq)
+              int32_t* __restrict__ nuniq, GatherSrc G)
 {
     __shared__ uint64_t s_key[kSortCap];
     __shared__ double s_val[kSortCap];
@@ -418,25 +464,41 @@ k_bucket_sort(const int64_t* __restrict__ boff, int64_t n_cells,
     const int lane = threadIdx.x & 31;
     const int64_t c0 = (int64_t)blockIdx.x * kSortCells;
     const int64_t c = c0 + threadIdx.x;
+    const int64_t bstride = kGather ? G.W : 1;  // boff == dst_off in gather mode
     int64_t beg = 0, end = 0;
     if (c < n_cells) {
-        beg = boff[c];
-        end = boff[c + 1];
+        beg = boff[c * bstride];
+        end = boff[(c + 1) * bstride];
     }
     const int64_t len = end - beg;
-    const int64_t lo = boff[c0], hi = boff[min(c0 + (int64_t)kSortCells, n_cells)];
+    const int64_t lo = boff[c0 * bstride], hi = boff[min(c0 + (int64_t)kSortCells, n_cells) * bstride];
     if (threadIdx.x == 0) s_long = 0;
     __syncthreads();
     if (len > 64) s_long = 1;
     __syncthreads();
     if (hi - lo <= kSortCap && !s_long) {
         const int n = (int)(hi - lo);
-        for (int e = threadIdx.x; e < n; e += kSortCells) {
-            s_key[e] = fkey[lo + e];
-            s_val[e] = fval[lo + e];
-        }
-        __syncthreads();
         const int b = (int)(beg - lo), n_mine = (int)len;
+        if (kGather) {
+            if (c < n_cells) {
+                int w = b;
+                for (int s = 0; s < G.W; s++) {
+                    const int ns = G.cntT[c * G.W + s];
+                    const int64_t src = G.src_off[(int64_t)s * G.Cb + c];
+                    for (int e = 0; e < ns; e++) {
+                        s_key[w] = G.rkey[src + e];
+                        s_val[w] = G.rval[src + e];
+                        w++;
+                    }
+                }
+            }
+        } else {
+            for (int e = threadIdx.x; e < n; e += kSortCells) {
+                s_key[e] = fkey[lo + e];
+                s_val[e] = fval[lo + e];
+            }
+            __syncthreads();
+        }
         for (int e = b + 1; e < b + n_mine; e++) {
             const uint64_t key = s_key[e];
             const double val = s_val[e];
@@ -467,6 +529,21 @@ k_bucket_sort(const int64_t* __restrict__ boff, int64_t n_cells,
         return;
     }
     // ---- global-memory path ----
+    if (kGather) {
+        if (c < n_cells) {
+            int64_t w = beg;
+            for (int s = 0; s < G.W; s++) {
+                const int ns = G.cntT[c * G.W + s];
+                const int64_t src = G.src_off[(int64_t)s * G.Cb + c];
+                for (int e = 0; e < ns; e++) {
+                    fkey[w] = G.rkey[src + e];
+                    fval[w] = G.rval[src + e];
+                    w++;
+                }
+            }
+        }
+        __syncwarp();
+    }
     if (len <= 64) {
         for (int64_t e = beg + 1; e < end; e++) {
             const uint64_t key = fkey[e];
@@ -514,20 +591,21 @@ k_bucket_sort(const int64_t* __restrict__ boff, int64_t n_cells,
 
 // Merge the runs of equal (input, output) pair: np.add.reduceat association over the
 // emission order (warr.py:59-72) and write the public arrays.
-__global__ void k_bucket_emit(const int64_t* __restrict__ boff, const int64_t* __restrict__ colptr, int64_t n_cells,
+__global__ void k_bucket_emit(const int64_t* __restrict__ boff, int64_t bstride, int64_t cell_offset,
+                              const int64_t* __restrict__ colptr, int64_t n_cells,
                               const uint64_t* __restrict__ fkey, const double* __restrict__ fval,
                               int64_t* __restrict__ ii, int64_t* __restrict__ io, double* __restrict__ vv)
 {
     const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= n_cells) return;
-    const int64_t beg = boff[c], end = boff[c + 1];
+    const int64_t beg = boff[c * bstride], end = boff[(c + 1) * bstride];
     int64_t w = colptr[c];
     int64_t s = beg;
     while (s < end) {
         const uint32_t o = (uint32_t)(fkey[s] >> 32);
         int64_t e = s + 1;
         while (e < end && (uint32_t)(fkey[e] >> 32) == o) e++;
-        ii[w] = c;
+        ii[w] = c + cell_offset;
         io[w] = (int64_t)o;
         vv[w] = np_reduceat_segment(fval + s, e - s);
         w++;
@@ -602,7 +680,8 @@ static int check_sizes(int64_t nxi, int64_t nyi, int64_t nxo, int64_t nyo)
 }
 
 static PassParams make_pass(const Layout& l, int p, const double* xin, const double* yin,
-                            const double* xout, const double* yout, int64_t cell_lo, int64_t cell_hi)
+                            const double* xout, const double* yout, int64_t cell_lo, int64_t cell_hi,
+                            int part_rank = 0, int part_world = 1)
 {
     PassParams P;
     const GridView gin{ xin, yin, (int)l.nxi, (int)l.nyi };
@@ -628,6 +707,15 @@ static PassParams make_pass(const Layout& l, int p, const double* xin, const dou
     P.cell_hi = cell_hi;
     P.seg_hit = l.seg_hit[p];
     P.banded = (cell_lo > 0 || cell_hi < l.Ci) ? 1 : 0;
+    P.part_rank = part_rank;
+    P.part_world = part_world;
+    if (part_world == 1) {
+        P.nl_slots = P.nlines;
+    } else {
+        const int nblocks = (P.nlines + 31) / 32;
+        const int mine = nblocks > part_rank ? (nblocks - part_rank + part_world - 1) / part_world : 0;
+        P.nl_slots = mine * 32;
+    }
     return P;
 }
 
@@ -657,11 +745,12 @@ extern "C" int rg_grid_area(int device, void* stream, int64_t nx, int64_t ny,
     return RG_OK;
 }
 
-extern "C" int rg_build2d_count(int device, void* stream,
-                                int64_t nxi, int64_t nyi, int64_t nxo, int64_t nyo,
-                                const double* xin, const double* yin, const double* xout, const double* yout,
-                                int64_t cell_lo, int64_t cell_hi,
-                                void* workspace, size_t workspace_bytes, int64_t* n_fragments_host)
+static int count_impl(int device, void* stream,
+                      int64_t nxi, int64_t nyi, int64_t nxo, int64_t nyo,
+                      const double* xin, const double* yin, const double* xout, const double* yout,
+                      int64_t cell_lo, int64_t cell_hi, int part_rank, int part_world,
+                      void* workspace, size_t workspace_bytes, int64_t* n_fragments_host,
+                      int n_bounds, const int64_t* cell_bounds_host, int64_t* frag_offsets_host)
 {
     int rc = check_sizes(nxi, nyi, nxo, nyo);
     if (rc) return rc;
@@ -670,6 +759,13 @@ extern "C" int rg_build2d_count(int device, void* stream,
     Layout l = make_layout(workspace, nxi, nyi, nxo, nyo);
     if (workspace_bytes < l.bytes) return fail(RG_E_WORKSPACE, "rg_build2d_count: workspace too small");
     if (cell_lo < 0 || cell_hi > l.Ci || cell_lo > cell_hi) return fail(RG_E_ARG, "rg_build2d_count: bad cell band");
+    if (part_world < 1 || part_rank < 0 || part_rank >= part_world)
+        return fail(RG_E_ARG, "rg_build2d_count: bad line partition");
+    if (n_bounds < 0 || n_bounds > 1024 || (n_bounds > 0 && (!cell_bounds_host || !frag_offsets_host)))
+        return fail(RG_E_ARG, "rg_build2d_count: bad band bounds");
+    for (int b = 0; b < n_bounds; b++)
+        if (cell_bounds_host[b] < 0 || cell_bounds_host[b] > l.Ci)
+            return fail(RG_E_ARG, "rg_build2d_count: band bound outside the input cells");
     RG_CUDA(cudaSetDevice(device));
     cudaStream_t st = (cudaStream_t)stream;
     const GridView gin{ xin, yin, (int)nxi, (int)nyi };
@@ -687,29 +783,50 @@ extern "C" int rg_build2d_count(int device, void* stream,
         rc = build_boundary(st, gv, l.bnd[g], l.bbox + 4 * g);
         if (rc) return rc;
     }
-    // vertex guesses: output vertices in the input grid, input vertices in the output grid
-    k_vertex_guess<<<(unsigned)ceil_div(l.Vo, T), T, 0, st>>>(gout, gin, l.guess[0], l.flags);
-    k_vertex_guess<<<(unsigned)ceil_div(l.Vi, T), T, 0, st>>>(gin, gout, l.guess[1], l.flags);
-    RG_LAUNCH_CHECK("k_vertex_guess");
+    if (part_world == 1) {
+        // vertex guesses: output vertices in the input grid, input vertices in the output grid
+        k_vertex_guess<<<(unsigned)ceil_div(l.Vo, T), T, 0, st>>>(gout, gin, l.guess[0], l.flags);
+        k_vertex_guess<<<(unsigned)ceil_div(l.Vi, T), T, 0, st>>>(gin, gout, l.guess[1], l.flags);
+        RG_LAUNCH_CHECK("k_vertex_guess");
+    }
     for (int p = 0; p < 4; p++) {
-        PassParams P = make_pass(l, p, xin, yin, xout, yout, cell_lo, cell_hi);
-        k_line_starts<<<(unsigned)ceil_div((int64_t)P.nlines * 32, T), T, 0, st>>>(
+        PassParams P = make_pass(l, p, xin, yin, xout, yout, cell_lo, cell_hi, part_rank, part_world);
+        if (P.nl_slots == 0) continue;
+        const int64_t nthreads = (int64_t)P.nl_slots * P.nseg;
+        if (part_world > 1) {
+            // only the vertices on this rank's lines (the two axis passes of a grid use different lines)
+            k_vertex_guess_part<<<(unsigned)ceil_div(nthreads, T), T, 0, st>>>(P, l.guess[P.sweep_input ? 1 : 0], l.flags);
+            RG_LAUNCH_CHECK("k_vertex_guess_part");
+        }
+        k_line_starts<<<(unsigned)ceil_div((int64_t)P.nl_slots * 32, T), T, 0, st>>>(
             P, l.bbox + 4 * (P.sweep_input ? 1 : 0), l.line_start[p]);
         RG_LAUNCH_CHECK("k_line_starts");
-        const int64_t nthreads = (int64_t)P.nlines * P.nseg;
         k_walk_count<<<(unsigned)ceil_div(nthreads, 128), 128, 0, st>>>(P, l.hist);
         RG_LAUNCH_CHECK("k_walk_count");
-        k_repair<<<(unsigned)ceil_div((int64_t)P.nlines * 32, 128), 128, 0, st>>>(P, l.hist, l.flags);
+        k_repair<<<(unsigned)ceil_div((int64_t)P.nl_slots * 32, 128), 128, 0, st>>>(P, l.hist, l.flags);
         RG_LAUNCH_CHECK("k_repair");
     }
     rc = exclusive_scan_i32_i64(st, l.hist, l.boff, l.Ci, l.scan_scratch);
     if (rc) return rc;
     int64_t total = 0;
     RG_CUDA(cudaMemcpyAsync(&total, l.boff + l.Ci, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+    for (int b = 0; b < n_bounds; b++)
+        RG_CUDA(cudaMemcpyAsync(frag_offsets_host + b, l.boff + cell_bounds_host[b], sizeof(int64_t),
+                                cudaMemcpyDeviceToHost, st));
     RG_CUDA(cudaStreamSynchronize(st));
     if (total >= INT32_MAX) return fail(RG_E_TOO_LARGE, "rg_build2d_count: more than 2^31 fragments");
     *n_fragments_host = total;
     return RG_OK;
+}
+
+extern "C" int rg_build2d_count(int device, void* stream,
+                                int64_t nxi, int64_t nyi, int64_t nxo, int64_t nyo,
+                                const double* xin, const double* yin, const double* xout, const double* yout,
+                                int64_t cell_lo, int64_t cell_hi,
+                                void* workspace, size_t workspace_bytes, int64_t* n_fragments_host)
+{
+    return count_impl(device, stream, nxi, nyi, nxo, nyo, xin, yin, xout, yout, cell_lo, cell_hi, 0, 1,
+                      workspace, workspace_bytes, n_fragments_host, 0, nullptr, nullptr);
 }
 
 extern "C" int rg_build2d_fill(int device, void* stream,
@@ -735,7 +852,8 @@ extern "C" int rg_build2d_fill(int device, void* stream,
                                                                       l.area_in, w_in, l.flags);
         RG_LAUNCH_CHECK("k_walk_emit");
     }
-    k_bucket_sort<<<(unsigned)ceil_div(l.Ci, kSortCells), kSortCells, 0, st>>>(l.boff, l.Ci, frag_key, frag_val, l.nuniq);
+    k_bucket_sort<false><<<(unsigned)ceil_div(l.Ci, kSortCells), kSortCells, 0, st>>>(l.boff, l.Ci, frag_key, frag_val,
+                                                                                       l.nuniq, GatherSrc{});
     RG_LAUNCH_CHECK("k_bucket_sort");
     rc = exclusive_scan_i32_i64(st, l.nuniq, l.colptr, l.Ci, l.scan_scratch);
     if (rc) return rc;
@@ -767,7 +885,7 @@ extern "C" int rg_build2d_emit(int device, void* stream,
     RG_CUDA(cudaSetDevice(device));
     cudaStream_t st = (cudaStream_t)stream;
     if (nnz > 0) {
-        k_bucket_emit<<<(unsigned)ceil_div(l.Ci, 256), 256, 0, st>>>(l.boff, l.colptr, l.Ci, frag_key, frag_val, ii, io, v);
+        k_bucket_emit<<<(unsigned)ceil_div(l.Ci, 256), 256, 0, st>>>(l.boff, 1, 0, l.colptr, l.Ci, frag_key, frag_val, ii, io, v);
         RG_LAUNCH_CHECK("k_bucket_emit");
     }
     return RG_OK;
@@ -783,5 +901,161 @@ extern "C" int rg_build2d_stats(int device, void* stream, int64_t nxi, int64_t n
     RG_CUDA(cudaSetDevice(device));
     RG_CUDA(cudaMemcpyAsync(stats_host, l.flags, sizeof(int32_t) * 8, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
     RG_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+    return RG_OK;
+}
+
+// ---------------------------------------------------------------------------
+// line-sharded build: every rank walks 1/W of the sweep lines of all four passes, fragments travel
+// to the rank that owns their input-row band, which sorts and merges them.  The emission rank inside a
+// fragment key does not depend on who walked the segment, so the merged band is bit-identical to the
+// same rows of a single-GPU build.
+// ---------------------------------------------------------------------------
+extern "C" int rg_build2d_part_count(int device, void* stream,
+                                     int64_t nxi, int64_t nyi, int64_t nxo, int64_t nyo,
+                                     const double* xin, const double* yin, const double* xout, const double* yout,
+                                     int part_rank, int part_world,
+                                     void* workspace, size_t workspace_bytes, int64_t* n_fragments_host,
+                                     int n_bounds, const int64_t* cell_bounds_host, int64_t* frag_offsets_host,
+                                     size_t* counts_offset_host)
+{
+    int rc = count_impl(device, stream, nxi, nyi, nxo, nyo, xin, yin, xout, yout, 0, (nxi - 1) * (nyi - 1),
+                        part_rank, part_world, workspace, workspace_bytes, n_fragments_host,
+                        n_bounds, cell_bounds_host, frag_offsets_host);
+    if (rc) return rc;
+    if (counts_offset_host) {
+        Layout l = make_layout(workspace, nxi, nyi, nxo, nyo);
+        *counts_offset_host = (size_t)((char*)l.hist - (char*)workspace);
+    }
+    return RG_OK;
+}
+
+extern "C" int rg_build2d_part_fill(int device, void* stream,
+                                    int64_t nxi, int64_t nyi, int64_t nxo, int64_t nyo,
+                                    const double* xin, const double* yin, const double* xout, const double* yout,
+                                    const double* w_in, int part_rank, int part_world,
+                                    void* workspace, size_t workspace_bytes,
+                                    uint64_t* frag_key, double* frag_val, int64_t n_fragments)
+{
+    int rc = check_sizes(nxi, nyi, nxo, nyo);
+    if (rc) return rc;
+    if (!workspace || (n_fragments > 0 && (!frag_key || !frag_val)))
+        return fail(RG_E_ARG, "rg_build2d_part_fill: null pointer");
+    if (part_world < 1 || part_rank < 0 || part_rank >= part_world)
+        return fail(RG_E_ARG, "rg_build2d_part_fill: bad line partition");
+    Layout l = make_layout(workspace, nxi, nyi, nxo, nyo);
+    if (workspace_bytes < l.bytes) return fail(RG_E_WORKSPACE, "rg_build2d_part_fill: workspace too small");
+    RG_CUDA(cudaSetDevice(device));
+    cudaStream_t st = (cudaStream_t)stream;
+    RG_CUDA(cudaMemsetAsync(l.cursor, 0, sizeof(int32_t) * (size_t)(l.Ci + 1), st));
+    for (int p = 0; p < 4; p++) {
+        PassParams P = make_pass(l, p, xin, yin, xout, yout, 0, l.Ci, part_rank, part_world);
+        if (P.nl_slots == 0) continue;
+        const int64_t nthreads = (int64_t)P.nl_slots * P.nseg;
+        k_walk_emit<<<(unsigned)ceil_div(nthreads, 128), 128, 0, st>>>(P, l.boff, l.cursor, frag_key, frag_val,
+                                                                      l.area_in, w_in, l.flags);
+        RG_LAUNCH_CHECK("k_walk_emit");
+    }
+    return RG_OK;
+}
+
+namespace rg {
+
+struct MergeLayout {
+    int32_t* cntT;
+    int64_t* src_off;
+    int64_t* dst_off;
+    int32_t* nuniq;
+    int64_t* colptr;
+    int64_t* scan_scratch;
+    size_t bytes;
+};
+
+static MergeLayout make_merge_layout(void* ws, int64_t Cb, int W)
+{
+    MergeLayout m;
+    Carver c(ws);
+    const int64_t n = Cb * W;
+    m.cntT = c.take<int32_t>(n + 1);
+    m.src_off = c.take<int64_t>(n + 1);
+    m.dst_off = c.take<int64_t>(n + 1);
+    m.nuniq = c.take<int32_t>(Cb + 1);
+    m.colptr = c.take<int64_t>(Cb + 1);
+    m.scan_scratch = c.take<int64_t>(scan_scratch_elems(n));
+    m.bytes = c.total();
+    return m;
+}
+
+__global__ void k_merge_transpose(const int32_t* __restrict__ cnt, int32_t* __restrict__ cntT, int64_t Cb, int W)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;  // index into cntT: c * W + s
+    if (i >= Cb * W) return;
+    const int64_t c = i / W;
+    const int s = (int)(i - c * W);
+    cntT[i] = cnt[(int64_t)s * Cb + c];
+}
+
+}  // namespace rg
+
+extern "C" int rg_build2d_merge_workspace_bytes(int64_t n_cells, int n_src, size_t* bytes_host)
+{
+    if (!bytes_host || n_cells < 0 || n_src < 1) return fail(RG_E_ARG, "rg_build2d_merge_workspace_bytes: bad argument");
+    if (n_cells * n_src >= INT32_MAX) return fail(RG_E_TOO_LARGE, "rg_build2d_merge_workspace_bytes: too large");
+    *bytes_host = make_merge_layout(nullptr, n_cells, n_src).bytes;
+    return RG_OK;
+}
+
+extern "C" int rg_build2d_merge(int device, void* stream, int64_t n_cells, int n_src,
+                                const int32_t* counts /* [n_src][n_cells] */,
+                                const uint64_t* recv_key, const double* recv_val, int64_t n_recv,
+                                void* workspace, size_t workspace_bytes,
+                                uint64_t* frag_key, double* frag_val, int64_t* nnz_host)
+{
+    if (n_cells < 0 || n_src < 1 || !workspace || !nnz_host || (n_cells > 0 && !counts) ||
+        (n_recv > 0 && (!recv_key || !recv_val || !frag_key || !frag_val)))
+        return fail(RG_E_ARG, "rg_build2d_merge: bad argument");
+    if (n_cells * n_src >= INT32_MAX || n_recv >= INT32_MAX) return fail(RG_E_TOO_LARGE, "rg_build2d_merge: too large");
+    MergeLayout m = make_merge_layout(workspace, n_cells, n_src);
+    if (workspace_bytes < m.bytes) return fail(RG_E_WORKSPACE, "rg_build2d_merge: workspace too small");
+    RG_CUDA(cudaSetDevice(device));
+    cudaStream_t st = (cudaStream_t)stream;
+    *nnz_host = 0;
+    if (n_cells == 0) return RG_OK;
+    const int64_t n = n_cells * n_src;
+    k_merge_transpose<<<(unsigned)ceil_div(n, 256), 256, 0, st>>>(counts, m.cntT, n_cells, n_src);
+    RG_LAUNCH_CHECK("k_merge_transpose");
+    int rc = exclusive_scan_i32_i64(st, counts, m.src_off, n, m.scan_scratch);
+    if (rc) return rc;
+    rc = exclusive_scan_i32_i64(st, m.cntT, m.dst_off, n, m.scan_scratch);
+    if (rc) return rc;
+    const GatherSrc G{ m.cntT, m.src_off, m.dst_off, recv_key, recv_val, n_src, n_cells };
+    k_bucket_sort<true><<<(unsigned)ceil_div(n_cells, kSortCells), kSortCells, 0, st>>>(m.dst_off, n_cells, frag_key,
+                                                                                     frag_val, m.nuniq, G);
+    RG_LAUNCH_CHECK("k_bucket_sort<gather>");
+    rc = exclusive_scan_i32_i64(st, m.nuniq, m.colptr, n_cells, m.scan_scratch);
+    if (rc) return rc;
+    int64_t nnz = 0, total = 0;
+    RG_CUDA(cudaMemcpyAsync(&nnz, m.colptr + n_cells, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+    RG_CUDA(cudaMemcpyAsync(&total, m.src_off + n, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+    RG_CUDA(cudaStreamSynchronize(st));
+    if (total != n_recv) return fail(RG_E_ARG, "rg_build2d_merge: the counts do not add up to n_recv");
+    *nnz_host = nnz;
+    return RG_OK;
+}
+
+extern "C" int rg_build2d_merge_emit(int device, void* stream, int64_t n_cells, int n_src, int64_t cell_offset,
+                                     void* workspace, size_t workspace_bytes,
+                                     const uint64_t* frag_key, const double* frag_val,
+                                     int64_t* ii, int64_t* io, double* v, int64_t nnz)
+{
+    if (n_cells < 0 || n_src < 1 || !workspace) return fail(RG_E_ARG, "rg_build2d_merge_emit: bad argument");
+    if (nnz > 0 && (!ii || !io || !v || !frag_key || !frag_val)) return fail(RG_E_ARG, "rg_build2d_merge_emit: null pointer");
+    MergeLayout m = make_merge_layout(workspace, n_cells, n_src);
+    if (workspace_bytes < m.bytes) return fail(RG_E_WORKSPACE, "rg_build2d_merge_emit: workspace too small");
+    RG_CUDA(cudaSetDevice(device));
+    if (nnz > 0 && n_cells > 0) {
+        k_bucket_emit<<<(unsigned)ceil_div(n_cells, 256), 256, 0, (cudaStream_t)stream>>>(
+            m.dst_off, n_src, cell_offset, m.colptr, n_cells, frag_key, frag_val, ii, io, v);
+        RG_LAUNCH_CHECK("k_bucket_emit");
+    }
     return RG_OK;
 }

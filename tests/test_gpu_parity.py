@@ -109,6 +109,48 @@ def test_build2d_band_partition_concatenates(rg, dev):
         assert np.array_equal(np.concatenate([p[k] for p in parts]), full[k])
 
 
+@pytest.mark.parametrize("name,world_size", [("dist129", 2), ("dist129", 3), ("dist129", 8), ("fam100", 5)])
+def test_build2d_line_sharded_equals_full(rg, dev, name, world_size):
+    """Line-sharded build (every rank walks 1/W of the sweep lines, fragments exchanged to the band owners,
+    all ranks played on one GPU): the concatenated bands equal the single-GPU build bit for bit."""
+    from regridding_b200 import _parallel
+
+    gi, go, _ = cases.case_2d(name)
+    co = cases.perturb_like_reference(go, (-1, -2), 42)
+    full = rg.device.build_weights_2d(gi[0], gi[1], co[0], co[1], device=dev)
+    bands = _parallel.build_weights_2d_sharded_local(gi[0], gi[1], co[0], co[1], world_size=world_size, device=dev)
+    assert len(bands) == world_size
+    assert sum(b.stats["fragments"] for b in bands) == full.stats["fragments"]
+    assert sum(b.stats["fragments_walked"] for b in bands) == full.stats["fragments"]
+    got = [torch.cat([getattr(b, k) for b in bands]) for k in ("indices_input", "indices_output", "values")]
+    assert torch.equal(got[0], full.indices_input) and torch.equal(got[1], full.indices_output)
+    assert torch.equal(got[2], full.values)
+    bounds = _parallel.band_bounds(gi[0].shape[0] - 1, gi[0].shape[1] - 1, world_size)
+    for r, b in enumerate(bands):
+        if b.nnz:
+            assert bounds[r] <= int(b.indices_input.min()) and int(b.indices_input.max()) < bounds[r + 1]
+
+
+def test_build2d_line_sharded_weights_input_and_more_ranks_than_blocks(rg, dev):
+    """weights_input rides along; with more ranks than 32-line blocks some ranks walk nothing."""
+    from regridding_b200 import _parallel
+
+    gi, go, _ = cases.case_2d("fam100")
+    co = cases.perturb_like_reference(go, (-1, -2), 42)
+    w = np.random.default_rng(5).random((gi[0].shape[0] - 1, gi[0].shape[1] - 1)) + 0.5
+    full = rg.device.build_weights_2d(gi[0], gi[1], co[0], co[1], w, device=dev)
+    bands = _parallel.build_weights_2d_sharded_local(gi[0], gi[1], co[0], co[1], w, world_size=7, device=dev)
+    for k in ("indices_input", "indices_output", "values"):
+        assert torch.equal(torch.cat([getattr(b, k) for b in bands]), getattr(full, k))
+    # coarse output grid: 2 blocks of lines per pass for 7 ranks
+    gi2 = cases.curvilinear(40, 33)
+    go2 = cases.rectilinear_over(gi2[0], gi2[1], 21, 19)
+    full = rg.device.build_weights_2d(gi2[0], gi2[1], go2[0], go2[1], device=dev)
+    bands = _parallel.build_weights_2d_sharded_local(gi2[0], gi2[1], go2[0], go2[1], world_size=7, device=dev)
+    for k in ("indices_input", "indices_output", "values"):
+        assert torch.equal(torch.cat([getattr(b, k) for b in bands]), getattr(full, k))
+
+
 def test_build2d_disjoint_and_tiny_grids(rg, dev, oracle):
     # no overlap at all -> empty weights
     gi = cases.curvilinear(9, 7)
