@@ -55,7 +55,8 @@ int rg_version(void);
  * Protocol (all three calls share one workspace, which must stay untouched between them):
  *   rg_build2d_workspace_bytes -> caller allocates `workspace`
  *   rg_build2d_count           -> *n_fragments_host  (raw fragments before merging)
- *   caller allocates frag_key (uint64[n_fragments]) and frag_val (double[n_fragments])
+ *   caller allocates frags: n_fragments records of 16 bytes, 16-byte aligned
+ *                    ({uint64 key = output cell << 32 | emission rank; double weight})
  *   rg_build2d_fill            -> *nnz_host
  *   caller allocates indices_input/indices_output (int64[nnz]), values (double[nnz])
  *   rg_build2d_emit
@@ -81,14 +82,14 @@ int rg_build2d_fill(int device, void* stream,
                     const double* weights_input_or_null,
                     int64_t cell_lo, int64_t cell_hi,
                     void* workspace, size_t workspace_bytes,
-                    uint64_t* frag_key, double* frag_val, int64_t n_fragments,
+                    void* frags, int64_t n_fragments,
                     int64_t* nnz_host);
 
 int rg_build2d_emit(int device, void* stream,
                     int64_t nx_in, int64_t ny_in, int64_t nx_out, int64_t ny_out,
                     int64_t cell_lo, int64_t cell_hi,
                     void* workspace, size_t workspace_bytes,
-                    const uint64_t* frag_key, const double* frag_val, int64_t n_fragments,
+                    const void* frags, int64_t n_fragments,
                     int64_t* indices_input, int64_t* indices_output, double* values, int64_t nnz);
 
 /* Diagnostics of the last build in `workspace`: stats_host[0] = walk overflow flag,
@@ -105,14 +106,20 @@ int rg_build2d_stats(int device, void* stream, int64_t nx_in, int64_t ny_in, int
  * Rank r of W walks the sweep lines of every W-th block of 32 lines of all four passes
  * (rg_build2d_part_count / _part_fill, same workspace as rg_build2d_*).  Its fragments come out
  * bucketed by input cell, so the fragments of every input-row band are one contiguous range:
- * frag_offsets_host[b] = first fragment of input cell cell_bounds_host[b] (n_bounds bounds, ascending).
+ * frag_offsets_host[b] = first fragment of input cell cell_bounds_host[b] (n_bounds bounds, ascending;
+ * also copied to frag_offsets_dev_or_null, stream-ordered, for peers that read it over NVLink).
  * The per-input-cell fragment counts (int32[(nx_in-1)*(ny_in-1)]) live in the workspace at byte
- * offset *counts_offset_host.  The caller exchanges counts and fragment ranges (all-to-all; NCCL in
- * regridding_b200/_parallel.py) so that every band owner holds, per source rank s, counts[s][c] and the
- * chunks concatenated in source order; rg_build2d_merge gathers the chunks cell by cell, sorts every
- * bucket by (output cell, emission rank) and counts the distinct pairs; rg_build2d_merge_emit writes
- * the band's public triplets (indices_input = cell_offset + band cell).  The emission rank does not
- * depend on which rank walked a segment: the concatenated bands equal the single-GPU result bit for bit.
+ * offset *counts_offset_host.
+ * The owner of a band then needs, per source rank s, the band slice of that rank's counts and of its
+ * fragments.  They either travel by all-to-all (NCCL) or stay where they are and are read in place over
+ * NVLink peer mappings (regridding_b200/_parallel.py does both): rg_build2d_gather_counts copies the W
+ * count slices into counts[s][c]; rg_build2d_merge takes one chunk pointer + size per source
+ * (src_chunks_host[s] = first fragment of the band in source s, device or peer memory), gathers the
+ * chunks cell by cell through shared memory, sorts every bucket by (output cell, emission rank) into
+ * `frags` (sum of the sizes records) and counts the distinct pairs; rg_build2d_merge_emit writes the
+ * band's public triplets (indices_input = cell_offset + band cell).  The emission rank does not depend
+ * on which rank walked a segment: the concatenated bands equal the single-GPU result bit for bit.
+ * n_src <= 16.
  * ------------------------------------------------------------------------------ */
 int rg_build2d_part_count(int device, void* stream,
                           int64_t nx_in, int64_t ny_in, int64_t nx_out, int64_t ny_out,
@@ -122,7 +129,7 @@ int rg_build2d_part_count(int device, void* stream,
                           void* workspace, size_t workspace_bytes,
                           int64_t* n_fragments_host,
                           int n_bounds, const int64_t* cell_bounds_host, int64_t* frag_offsets_host,
-                          size_t* counts_offset_host);
+                          size_t* counts_offset_host, int64_t* frag_offsets_dev_or_null);
 
 int rg_build2d_part_fill(int device, void* stream,
                          int64_t nx_in, int64_t ny_in, int64_t nx_out, int64_t ny_out,
@@ -131,20 +138,25 @@ int rg_build2d_part_fill(int device, void* stream,
                          const double* weights_input_or_null,
                          int part_rank, int part_world,
                          void* workspace, size_t workspace_bytes,
-                         uint64_t* frag_key, double* frag_val, int64_t n_fragments);
+                         void* frags, int64_t n_fragments);
 
 int rg_build2d_merge_workspace_bytes(int64_t n_cells, int n_src, size_t* bytes_host);
 
+int rg_build2d_gather_counts(int device, void* stream, int64_t n_cells, int n_src,
+                             const int32_t* const* src_counts_host /* n_src device pointers */,
+                             int32_t* counts /* [n_src][n_cells] */);
+
 int rg_build2d_merge(int device, void* stream, int64_t n_cells, int n_src,
                      const int32_t* counts /* [n_src][n_cells] */,
-                     const uint64_t* recv_key, const double* recv_val, int64_t n_recv,
+                     const void* const* src_chunks_host /* n_src device pointers */,
+                     const int64_t* src_sizes_host /* n_src record counts */,
                      void* workspace, size_t workspace_bytes,
-                     uint64_t* frag_key /* [n_recv] */, double* frag_val /* [n_recv] */,
+                     void* frags /* sum(src_sizes) records */,
                      int64_t* nnz_host);
 
 int rg_build2d_merge_emit(int device, void* stream, int64_t n_cells, int n_src, int64_t cell_offset,
                           void* workspace, size_t workspace_bytes,
-                          const uint64_t* frag_key, const double* frag_val,
+                          const void* frags,
                           int64_t* indices_input, int64_t* indices_output, double* values, int64_t nnz);
 
 /* Signed cell areas; replaces grid_volume

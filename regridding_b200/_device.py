@@ -22,9 +22,9 @@ I64 = torch.int64
 I32 = torch.int32
 
 # kernel launches of ours per operator call (checked against the ncu launch list in profiles/)
-LAUNCHES_BUILD2D = 37  # area 1, 2 x (bbox 2 + boundary 3), guess 2, 4 x (starts, count, repair), scans 6, emit 4, sort 1, merge 1
-# line-sharded build per rank: area 1, boundaries 10, 4 x (guess, starts, count, repair), scan 3, emit 4, merge: transpose 1, scans 9, sort 1, emit 1
-LAUNCHES_BUILD2D_SHARDED = 46
+LAUNCHES_BUILD2D = 21  # area 1, bbox+boundaries 4, guess 2, starts / count / check / repair 4 (four passes per launch), scans 6, emit walk 1, sort 1, merge 1
+# line-sharded build per rank: walk share 14 (area 1, boundaries 4, guess, starts, count, check, repair, scan 3, emit) + merge 13 (counts 1, transpose 1, scans 9, gather-sort 1, emit 1)
+LAUNCHES_BUILD2D_SHARDED = 27
 LAUNCHES_CSR = 6       # hist, scan 3, fill, rank
 LAUNCHES_APPLY = 1     # one k_apply launch per call (up to 65535 frame tiles)
 
@@ -58,6 +58,11 @@ def to_device(a, device: torch.device, dtype=F64) -> torch.Tensor:
 
 def _workspace(nbytes: int, device) -> torch.Tensor:
     return torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
+
+
+def frags_empty(n: int, device) -> torch.Tensor:
+    """Raw fragment records: 16 bytes each ({uint64 key, float64 weight}), viewed as int64 [n, 2]."""
+    return torch.empty((max(int(n), 1), 2), dtype=I64, device=device)[:int(n)]
 
 
 # ---------------------------------------------------------------------------
@@ -185,18 +190,17 @@ def build_weights_2d(x_in, y_in, x_out, y_out, weights_input=None, cell_band: tu
                                       xo.data_ptr(), yo.data_ptr(), lo, hi, ws.data_ptr(), ws.numel(),
                                       ctypes.byref(nfrag)), "rg_build2d_count")
         nf = nfrag.value
-        fkey = torch.empty(max(nf, 1), dtype=I64, device=device)
-        fval = torch.empty(max(nf, 1), dtype=F64, device=device)
+        frags = frags_empty(nf, device)
         nnz_c = ctypes.c_int64()
         _lib.check(L.rg_build2d_fill(device.index, st, nxi, nyi, nxo, nyo, xi.data_ptr(), yi.data_ptr(),
                                      xo.data_ptr(), yo.data_ptr(), _lib.ptr(w), lo, hi, ws.data_ptr(), ws.numel(),
-                                     fkey.data_ptr(), fval.data_ptr(), nf, ctypes.byref(nnz_c)), "rg_build2d_fill")
+                                     frags.data_ptr(), nf, ctypes.byref(nnz_c)), "rg_build2d_fill")
         nnz = nnz_c.value
         ii = torch.empty(nnz, dtype=I64, device=device)
         io = torch.empty(nnz, dtype=I64, device=device)
         v = torch.empty(nnz, dtype=F64, device=device)
         _lib.check(L.rg_build2d_emit(device.index, st, nxi, nyi, nxo, nyo, lo, hi, ws.data_ptr(), ws.numel(),
-                                     fkey.data_ptr(), fval.data_ptr(), nf,
+                                     frags.data_ptr(), nf,
                                      ii.data_ptr(), io.data_ptr(), v.data_ptr(), nnz), "rg_build2d_emit")
         stats = (ctypes.c_int32 * 8)()
         _lib.check(L.rg_build2d_stats(device.index, st, nxi, nyi, nxo, nyo, ws.data_ptr(), stats), "rg_build2d_stats")
@@ -209,35 +213,46 @@ def build_weights_2d(x_in, y_in, x_out, y_out, weights_input=None, cell_band: tu
 class PartFragments:
     """Fragments one rank produced by walking its share of the sweep lines (line-sharded build):
     bucketed by input cell, so every input-row band is the contiguous range
-    ``[band_offsets[b], band_offsets[b + 1])`` of ``frag_key`` / ``frag_val``."""
+    ``[band_offsets[b], band_offsets[b + 1])`` of ``frags``."""
 
     counts: torch.Tensor        # int32 [n_in]: fragments per input cell (view into the workspace)
-    frag_key: torch.Tensor      # int64 [n_fragments]: output cell << 32 | emission rank
-    frag_val: torch.Tensor      # float64 [n_fragments]
+    counts_offset: int          # byte offset of ``counts`` in the workspace
+    n_fragments: int
     band_offsets: list[int]     # host: first fragment of every band bound
     n_in: int
     n_out: int
     workspace: torch.Tensor
     shape: tuple[int, int, int, int]
+    args: tuple                 # what rg_build2d_part_fill needs again
+    frags: torch.Tensor | None = None   # int64 [n_fragments, 2] 16-byte records (after ``build2d_part_fill``)
 
     def check(self) -> dict:
         """Synchronises; raises if a walk of this rank did not terminate."""
         L = _lib.load()
-        device = self.frag_key.device
+        device = self.workspace.device
         stats = (ctypes.c_int32 * 8)()
         with torch.cuda.device(device):
             _lib.check(L.rg_build2d_stats(device.index, _stream(device), *self.shape, self.workspace.data_ptr(), stats),
                        "rg_build2d_stats")
         if stats[0] or stats[3]:
             raise _lib.RegridB200Error("rg_build2d_part_fill: a sweep walk did not terminate (degenerate or folded grid)")
-        return {"fragments_walked": int(self.frag_key.numel()), "repaired_segments": int(stats[1]),
+        return {"fragments_walked": int(self.n_fragments), "repaired_segments": int(stats[1]),
                 "unknown_guesses": int(stats[2])}
 
 
-def build2d_part_walk(x_in, y_in, x_out, y_out, weights_input, part_rank: int, part_world: int,
-                      cell_bounds: list[int], device=None) -> PartFragments:
-    """Rank ``part_rank`` of ``part_world``: walk every ``part_world``-th block of 32 sweep lines of all four
-    passes (``rg_build2d_part_count`` / ``rg_build2d_part_fill``)."""
+def build2d_workspace_bytes(nxi: int, nyi: int, nxo: int, nyo: int) -> int:
+    nbytes = ctypes.c_size_t()
+    _lib.check(_lib.load().rg_build2d_workspace_bytes(nxi, nyi, nxo, nyo, ctypes.byref(nbytes)),
+               "rg_build2d_workspace_bytes")
+    return int(nbytes.value)
+
+
+def build2d_part_count(x_in, y_in, x_out, y_out, weights_input, part_rank: int, part_world: int,
+                       cell_bounds: list[int], device=None, workspace: torch.Tensor | None = None,
+                       header: torch.Tensor | None = None) -> PartFragments:
+    """Rank ``part_rank`` of ``part_world``: locate, walk and count every ``part_world``-th block of 32 sweep
+    lines of all four passes (``rg_build2d_part_count``).  ``workspace`` / ``header`` (int64, one entry per
+    bound) may live in peer-mapped memory so that the other ranks can read the counts and offsets in place."""
     L = _lib.load()
     device = cuda_device(device if device is not None else (x_in.device if isinstance(x_in, torch.Tensor) else None))
     xi, yi = to_device(x_in, device), to_device(y_in, device)
@@ -255,56 +270,94 @@ def build2d_part_walk(x_in, y_in, x_out, y_out, weights_input, part_rank: int, p
     nb = len(cell_bounds)
     bounds = (ctypes.c_int64 * nb)(*[int(b) for b in cell_bounds])
     offsets = (ctypes.c_int64 * nb)()
+    if header is not None and header.numel() < nb:
+        raise ValueError("header too small for the band bounds")
     with torch.cuda.device(device):
         st = _stream(device)
-        nbytes = ctypes.c_size_t()
-        _lib.check(L.rg_build2d_workspace_bytes(nxi, nyi, nxo, nyo, ctypes.byref(nbytes)), "rg_build2d_workspace_bytes")
-        ws = _workspace(nbytes.value, device)
+        ws = workspace if workspace is not None else _workspace(build2d_workspace_bytes(nxi, nyi, nxo, nyo), device)
         nfrag = ctypes.c_int64()
         coff = ctypes.c_size_t()
         _lib.check(L.rg_build2d_part_count(device.index, st, nxi, nyi, nxo, nyo, xi.data_ptr(), yi.data_ptr(),
                                            xo.data_ptr(), yo.data_ptr(), part_rank, part_world,
                                            ws.data_ptr(), ws.numel(), ctypes.byref(nfrag),
-                                           nb, bounds, offsets, ctypes.byref(coff)), "rg_build2d_part_count")
-        nf = nfrag.value
-        fkey = torch.empty(max(nf, 1), dtype=I64, device=device)[:nf]
-        fval = torch.empty(max(nf, 1), dtype=F64, device=device)[:nf]
-        _lib.check(L.rg_build2d_part_fill(device.index, st, nxi, nyi, nxo, nyo, xi.data_ptr(), yi.data_ptr(),
-                                          xo.data_ptr(), yo.data_ptr(), _lib.ptr(w), part_rank, part_world,
-                                          ws.data_ptr(), ws.numel(), fkey.data_ptr(), fval.data_ptr(), nf),
-                   "rg_build2d_part_fill")
+                                           nb, bounds, offsets, ctypes.byref(coff), _lib.ptr(header)),
+                   "rg_build2d_part_count")
     counts = ws[coff.value:coff.value + 4 * n_in].view(I32)
-    return PartFragments(counts, fkey, fval, [int(o) for o in offsets], n_in, n_out, ws, (nxi, nyi, nxo, nyo))
+    return PartFragments(counts, int(coff.value), int(nfrag.value), [int(o) for o in offsets], n_in, n_out, ws,
+                         (nxi, nyi, nxo, nyo), (xi, yi, xo, yo, w, part_rank, part_world))
 
 
-def build2d_merge(counts: torch.Tensor, recv_key: torch.Tensor, recv_val: torch.Tensor, cell_offset: int,
-                  n_in: int, n_out: int) -> DeviceWeights:
-    """Band owner: ``counts`` int32 ``[n_src, n_band_cells]``, the chunks of all sources concatenated in source
-    order -> the band's public triplets (``rg_build2d_merge`` / ``rg_build2d_merge_emit``)."""
+def build2d_part_fill(part: PartFragments, frags_buffer: torch.Tensor | None = None) -> PartFragments:
+    """Emit walk of the rank's lines into ``frags_buffer`` (>= n_fragments records) or a fresh buffer."""
     L = _lib.load()
-    device = recv_key.device
+    xi, yi, xo, yo, w, part_rank, part_world = part.args
+    device = part.workspace.device
+    nf = part.n_fragments
+    if frags_buffer is None:
+        frags = frags_empty(nf, device)
+    else:
+        if frags_buffer.shape[0] < nf:
+            raise ValueError("fragment buffer too small")
+        frags = frags_buffer[:nf]
+    nxi, nyi, nxo, nyo = part.shape
+    with torch.cuda.device(device):
+        _lib.check(L.rg_build2d_part_fill(device.index, _stream(device), nxi, nyi, nxo, nyo, xi.data_ptr(), yi.data_ptr(),
+                                          xo.data_ptr(), yo.data_ptr(), _lib.ptr(w), part_rank, part_world,
+                                          part.workspace.data_ptr(), part.workspace.numel(), frags.data_ptr(), nf),
+                   "rg_build2d_part_fill")
+    part.frags = frags
+    return part
+
+
+def build2d_part_walk(x_in, y_in, x_out, y_out, weights_input, part_rank: int, part_world: int,
+                      cell_bounds: list[int], device=None) -> PartFragments:
+    """``build2d_part_count`` + ``build2d_part_fill`` with library-allocated buffers."""
+    return build2d_part_fill(build2d_part_count(x_in, y_in, x_out, y_out, weights_input, part_rank, part_world,
+                                                cell_bounds, device=device))
+
+
+def build2d_gather_counts(count_ptrs: list[int], n_cells: int, device) -> torch.Tensor:
+    """``counts[s][c]`` from one device (or peer) pointer per source (``rg_build2d_gather_counts``)."""
+    L = _lib.load()
+    n_src = len(count_ptrs)
+    out = torch.empty((n_src, max(n_cells, 1)), dtype=I32, device=device)[:, :n_cells]
+    arr = (ctypes.c_void_p * n_src)(*count_ptrs)
+    with torch.cuda.device(device):
+        _lib.check(L.rg_build2d_gather_counts(device.index, _stream(device), n_cells, n_src, arr, out.data_ptr()),
+                   "rg_build2d_gather_counts")
+    return out
+
+
+def build2d_merge(counts: torch.Tensor, chunk_ptrs: list[int], chunk_sizes: list[int], cell_offset: int,
+                  n_in: int, n_out: int) -> DeviceWeights:
+    """Band owner: ``counts`` int32 ``[n_src, n_band_cells]`` and one chunk of 16-byte fragment records per source
+    (device or peer pointer + record count) -> the band's public triplets (``rg_build2d_merge`` /
+    ``rg_build2d_merge_emit``)."""
+    L = _lib.load()
+    device = counts.device
     n_src, n_cells = int(counts.shape[0]), int(counts.shape[1])
     counts = counts.contiguous()
-    n_recv = int(recv_key.numel())
+    n_recv = int(sum(chunk_sizes))
+    ptrs = (ctypes.c_void_p * n_src)(*[int(p) if int(s) else None for p, s in zip(chunk_ptrs, chunk_sizes)])
+    sizes = (ctypes.c_int64 * n_src)(*[int(s) for s in chunk_sizes])
     with torch.cuda.device(device):
         st = _stream(device)
         nbytes = ctypes.c_size_t()
         _lib.check(L.rg_build2d_merge_workspace_bytes(n_cells, n_src, ctypes.byref(nbytes)),
                    "rg_build2d_merge_workspace_bytes")
         ws = _workspace(nbytes.value, device)
-        fkey = torch.empty(max(n_recv, 1), dtype=I64, device=device)
-        fval = torch.empty(max(n_recv, 1), dtype=F64, device=device)
+        frags = frags_empty(n_recv, device)
         nnz_c = ctypes.c_int64()
-        _lib.check(L.rg_build2d_merge(device.index, st, n_cells, n_src, counts.data_ptr(),
-                                      recv_key.data_ptr(), recv_val.data_ptr(), n_recv, ws.data_ptr(), ws.numel(),
-                                      fkey.data_ptr(), fval.data_ptr(), ctypes.byref(nnz_c)), "rg_build2d_merge")
+        _lib.check(L.rg_build2d_merge(device.index, st, n_cells, n_src, counts.data_ptr(), ptrs, sizes,
+                                      ws.data_ptr(), ws.numel(), frags.data_ptr(), ctypes.byref(nnz_c)),
+                   "rg_build2d_merge")
         nnz = nnz_c.value
         ii = torch.empty(nnz, dtype=I64, device=device)
         io = torch.empty(nnz, dtype=I64, device=device)
         v = torch.empty(nnz, dtype=F64, device=device)
         _lib.check(L.rg_build2d_merge_emit(device.index, st, n_cells, n_src, int(cell_offset), ws.data_ptr(), ws.numel(),
-                                           fkey.data_ptr(), fval.data_ptr(), ii.data_ptr(), io.data_ptr(),
-                                           v.data_ptr(), nnz), "rg_build2d_merge_emit")
+                                           frags.data_ptr(), ii.data_ptr(), io.data_ptr(), v.data_ptr(), nnz),
+                   "rg_build2d_merge_emit")
     dw = DeviceWeights(ii, io, v, n_in, n_out)
     dw.stats = {"fragments": n_recv, "nnz": nnz}
     return dw

@@ -27,16 +27,17 @@ SIGNATURES: dict[str, list] = {
     "rg_build2d_workspace_bytes": [_i64, _i64, _i64, _i64, _p_sz],
     "rg_build2d_count": [_int, _vp, _i64, _i64, _i64, _i64, _vp, _vp, _vp, _vp, _i64, _i64, _vp, _sz, _p_i64],
     "rg_build2d_fill": [_int, _vp, _i64, _i64, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _vp, _sz,
-                        _vp, _vp, _i64, _p_i64],
-    "rg_build2d_emit": [_int, _vp, _i64, _i64, _i64, _i64, _i64, _i64, _vp, _sz, _vp, _vp, _i64,
+                        _vp, _i64, _p_i64],
+    "rg_build2d_emit": [_int, _vp, _i64, _i64, _i64, _i64, _i64, _i64, _vp, _sz, _vp, _i64,
                         _vp, _vp, _vp, _i64],
     "rg_build2d_part_count": [_int, _vp, _i64, _i64, _i64, _i64, _vp, _vp, _vp, _vp, _int, _int, _vp, _sz, _p_i64,
-                              _int, _p_i64, _p_i64, _p_sz],
+                              _int, _p_i64, _p_i64, _p_sz, _vp],
     "rg_build2d_part_fill": [_int, _vp, _i64, _i64, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _int, _int, _vp, _sz,
-                             _vp, _vp, _i64],
+                             _vp, _i64],
     "rg_build2d_merge_workspace_bytes": [_i64, _int, _p_sz],
-    "rg_build2d_merge": [_int, _vp, _i64, _int, _vp, _vp, _vp, _i64, _vp, _sz, _vp, _vp, _p_i64],
-    "rg_build2d_merge_emit": [_int, _vp, _i64, _int, _i64, _vp, _sz, _vp, _vp, _vp, _vp, _vp, _i64],
+    "rg_build2d_gather_counts": [_int, _vp, _i64, _int, ctypes.POINTER(_vp), _vp],
+    "rg_build2d_merge": [_int, _vp, _i64, _int, _vp, ctypes.POINTER(_vp), _p_i64, _vp, _sz, _vp, _p_i64],
+    "rg_build2d_merge_emit": [_int, _vp, _i64, _int, _i64, _vp, _sz, _vp, _vp, _vp, _vp, _i64],
     "rg_build2d_stats": [_int, _vp, _i64, _i64, _i64, _i64, _vp, _p_i32],
     "rg_grid_area": [_int, _vp, _i64, _i64, _vp, _vp, _vp],
     "rg_find_indices_2d_workspace_bytes": [_i64, _i64, _i64, _p_sz],

@@ -47,40 +47,32 @@ def band_cells(ncx: int, ncy: int, rank: int, world_size: int) -> tuple[int, int
 
 
 def allgather_concat(tensors, group=None):
-    """Variable-length all-gather along dim 0 of one tensor or of a list of tensors that share their
-    dim-0 length: every rank gets ``cat([t_0, ..., t_{W-1}])`` of each.  One small collective for the
-    lengths, then point-to-point copies of every band straight into its place in the result (one
-    NCCL group, no padding, no concatenation pass); works under gloo on CPU too."""
+    """Variable-length all-gather along dim 0 of one tensor or of a list of 1-D 8-byte tensors that share their
+    length: every rank gets ``cat([t_0, ..., t_{W-1}])`` of each.  One small collective for the lengths, then
+    ONE all-gather of the tensors packed side by side and padded to the longest band, then one compaction
+    per tensor; works under gloo on CPU too."""
     single = isinstance(tensors, torch.Tensor)
     ts = [tensors] if single else list(tensors)
     rank, W = world(group)
     if W == 1:
         return tensors
     dev = ts[0].device
+    if any(t.ndim != 1 or t.element_size() != 8 or t.shape[0] != ts[0].shape[0] for t in ts):
+        raise ValueError("allgather_concat expects 1-D tensors of 8-byte elements with one common length")
     n = torch.tensor([ts[0].shape[0]], dtype=torch.int64, device=dev)
     counts = torch.empty(W, dtype=torch.int64, device=dev)
     dist.all_gather_into_tensor(counts, n, group=group)
     counts_h = counts.cpu().tolist()
-    offs = [0]
-    for c in counts_h:
-        offs.append(offs[-1] + c)
-    outs, ops = [], []
-    for t in ts:
-        t = t.contiguous()
-        out = torch.empty((offs[-1],) + tuple(t.shape[1:]), dtype=t.dtype, device=dev)
-        out[offs[rank]:offs[rank + 1]] = t
-        for r in range(W):
-            if r == rank:
-                continue
-            peer = r if group is None else dist.get_global_rank(group, r)
-            if counts_h[rank]:
-                ops.append(dist.P2POp(dist.isend, t, peer, group=group))
-            if counts_h[r]:
-                ops.append(dist.P2POp(dist.irecv, out[offs[r]:offs[r + 1]], peer, group=group))
-        outs.append(out)
-    if ops:
-        for req in dist.batch_isend_irecv(ops):
-            req.wait()
+    most = max(counts_h)
+    if most == 0:
+        return tensors
+    k = len(ts)
+    packed = torch.empty((k, most), dtype=torch.int64, device=dev)
+    for q, t in enumerate(ts):
+        packed[q, :t.shape[0]] = t.contiguous().view(torch.int64)
+    gathered = torch.empty((W, k, most), dtype=torch.int64, device=dev)
+    dist.all_gather_into_tensor(gathered, packed, group=group)
+    outs = [torch.cat([gathered[r, q, :counts_h[r]] for r in range(W)]).view(t.dtype) for q, t in enumerate(ts)]
     return outs[0] if single else outs
 
 
@@ -106,73 +98,178 @@ def band_bounds(ncx: int, ncy: int, world_size: int) -> list[int]:
     return [band_cells(ncx, ncy, r, world_size)[0] for r in range(world_size)] + [ncx * ncy]
 
 
-def _merge_band(rank: int, bounds: list[int], counts_by_src: torch.Tensor, recv_key, recv_val, n_in, n_out):
-    return _device.build2d_merge(counts_by_src, recv_key, recv_val, bounds[rank], n_in, n_out)
+FRAG_BYTES = 16
 
 
-def build_weights_2d_sharded(x_in, y_in, x_out, y_out, weights_input=None, replicate: bool = False,
-                             group=None, device=None) -> _device.DeviceWeights:
-    """Strong-scaling build of ONE large grid pair over the ranks of ``group``.
+class PeerArena:
+    """Peer-mapped (symmetric) memory of one rank for the line-sharded build: the build workspace (it holds the
+    per-cell fragment counts), the fragment buffer and a small header (band offsets), allocated with
+    ``torch.distributed._symmetric_memory`` so that every rank of the group can read them in place over
+    NVLink.  Rendezvous is collective and slow (milliseconds): arenas are cached per (group, shapes)."""
 
-    Every rank holds the full coordinate arrays (134 MB at 2049^2) and walks every W-th block of 32 sweep
-    lines of all four passes; its fragments come out bucketed by input cell, so the share of every
-    input-row band is one contiguous range.  Two all-to-alls follow (the per-cell fragment counts, fixed
-    size; then the fragments themselves, ~1 GB / W^2 per pair of ranks at 2048^2), and each rank merges its
-    band (``rg_build2d_merge``).  Returns this rank's band of the public triplets; with ``replicate`` the
-    bands are all-gathered so that every rank holds the full matrix (equal to the single-GPU build bit
-    for bit)."""
-    rank, W = world(group)
-    if W == 1:
-        return _device.build_weights_2d(x_in, y_in, x_out, y_out, weights_input, device=device)
-    nxi, nyi = x_in.shape
-    bounds = band_bounds(nxi - 1, nyi - 1, W)
+    def __init__(self, group, device: torch.device, shape: tuple[int, int, int, int], capacity: int, n_hdr: int):
+        import torch.distributed._symmetric_memory as symm
+
+        self.shape = shape
+        self.capacity = int(capacity)
+        self.ws_bytes = _device.build2d_workspace_bytes(*shape)
+        al = lambda x: (x + 255) // 256 * 256  # noqa: E731
+        self.off_frags = al(self.ws_bytes)
+        self.off_hdr = self.off_frags + al(FRAG_BYTES * self.capacity)
+        total = self.off_hdr + al(8 * n_hdr)
+        self.n_hdr = n_hdr
+        self.buf = symm.empty(total, dtype=torch.uint8, device=device)
+        self.hdl = symm.rendezvous(self.buf, group if group is not None else dist.group.WORLD)
+        self.base = [int(p) for p in self.hdl.buffer_ptrs]
+        self.workspace = self.buf[:self.ws_bytes]
+        self.frags = self.buf[self.off_frags:self.off_frags + FRAG_BYTES * self.capacity].view(torch.int64).view(-1, 2)
+        self.header = self.buf[self.off_hdr:self.off_hdr + 8 * n_hdr].view(torch.int64)
+
+    def peer_header(self, r: int) -> torch.Tensor:
+        return self.hdl.get_buffer(r, (self.n_hdr,), torch.int64, self.off_hdr // 8)
+
+    def barrier(self, channel: int = 0):
+        self.hdl.barrier(channel=channel)
+
+
+_arenas: dict = {}
+
+
+def _arena(group, device, shape, W, min_capacity: int = 0) -> PeerArena:
+    key = (id(group) if group is not None else 0, device.index, shape)
+    a = _arenas.get(key)
+    ci, co = (shape[0] - 1) * (shape[1] - 1), (shape[2] - 1) * (shape[3] - 1)
+    want = max(int(min_capacity), int(1.3 * 16 * max(ci, co) / W) + 4096)
+    if a is None or a.capacity < min_capacity:
+        _arenas.pop(key, None)
+        a = None  # release the old mapping before the new rendezvous
+        a = PeerArena(group, device, shape, want, W + 1)
+        _arenas[key] = a
+    return a
+
+
+def _sharded_build_p2p(x_in, y_in, x_out, y_out, weights_input, rank, W, bounds, group, device, mark):
+    """Fused exchange: nothing is sent.  Every rank walks into its peer-mapped arena; after one barrier the band
+    owners read the other ranks' counts and fragments in place (NVLink loads inside the gather kernels)."""
+    dev = _device.cuda_device(device if device is not None else (x_in.device if isinstance(x_in, torch.Tensor) else None))
+    shape = (int(x_in.shape[0]), int(x_in.shape[1]), int(x_out.shape[0]), int(x_out.shape[1]))
+    need = 0
+    while True:
+        arena = _arena(group, dev, shape, W, need)
+        part = _device.build2d_part_count(x_in, y_in, x_out, y_out, weights_input, rank, W, bounds, device=dev,
+                                          workspace=arena.workspace, header=arena.header)
+        if part.n_fragments <= arena.capacity:
+            _device.build2d_part_fill(part, arena.frags)
+        mark("walk")
+        arena.barrier(0)  # every rank's walk and header are complete (stream-ordered)
+        hdr = torch.stack([arena.peer_header(r) for r in range(W)]).cpu()  # [W, W + 1]; the one host sync
+        most = int(hdr[:, W].max())
+        if most <= arena.capacity:
+            break
+        arena.barrier(1)
+        need = int(most * 1.25) + 4096  # same decision on every rank: grow the arenas together and walk again
+    cb = bounds[rank + 1] - bounds[rank]
+    sizes = [int(hdr[s, rank + 1] - hdr[s, rank]) for s in range(W)]
+    chunk_ptrs = [arena.base[s] + arena.off_frags + FRAG_BYTES * int(hdr[s, rank]) for s in range(W)]
+    count_ptrs = [arena.base[s] + part.counts_offset + 4 * bounds[rank] for s in range(W)]
+    counts_by_src = _device.build2d_gather_counts(count_ptrs, cb, dev)
+    mark("exchange")
+    dw = _device.build2d_merge(counts_by_src, chunk_ptrs, sizes, bounds[rank], part.n_in, part.n_out)
+    arena.barrier(1)  # nobody starts overwriting its arena while a peer still reads it
+    dw.stats.update(part.check())
+    mark("merge")
+    return dw
+
+
+def _sharded_build_nccl(x_in, y_in, x_out, y_out, weights_input, rank, W, bounds, group, device, mark):
+    """Exchange by NCCL all-to-all: the per-cell counts (fixed sizes), then the 16-byte fragment records."""
     part = _device.build2d_part_walk(x_in, y_in, x_out, y_out, weights_input, rank, W, bounds, device=device)
-    dev = part.frag_key.device
+    mark("walk")
+    dev = part.frags.device
     band_sizes = [bounds[r + 1] - bounds[r] for r in range(W)]
     cb = band_sizes[rank]
-    # 1. counts: my counts of band d -> rank d; I receive [W, cb]
     counts_by_src = torch.empty(W * cb, dtype=torch.int32, device=dev)
     dist.all_to_all_single(counts_by_src, part.counts, output_split_sizes=[cb] * W,
                            input_split_sizes=band_sizes, group=group)
     counts_by_src = counts_by_src.view(W, cb)
     recv_sizes = counts_by_src.sum(dim=1, dtype=torch.int64).cpu().tolist()  # the one host sync of the exchange
     send_sizes = [part.band_offsets[r + 1] - part.band_offsets[r] for r in range(W)]
-    # 2. fragments
-    n_recv = int(sum(recv_sizes))
-    recv_key = torch.empty(n_recv, dtype=torch.int64, device=dev)
-    recv_val = torch.empty(n_recv, dtype=torch.float64, device=dev)
-    dist.all_to_all_single(recv_key, part.frag_key, output_split_sizes=recv_sizes, input_split_sizes=send_sizes,
-                           group=group)
-    dist.all_to_all_single(recv_val, part.frag_val, output_split_sizes=recv_sizes, input_split_sizes=send_sizes,
-                           group=group)
-    dw = _merge_band(rank, bounds, counts_by_src, recv_key, recv_val, part.n_in, part.n_out)
+    recv = _device.frags_empty(int(sum(recv_sizes)), dev)
+    dist.all_to_all_single(recv, part.frags, output_split_sizes=recv_sizes, input_split_sizes=send_sizes, group=group)
+    mark("exchange")
+    offs = [0]
+    for n in recv_sizes:
+        offs.append(offs[-1] + n)
+    ptrs = [recv.data_ptr() + FRAG_BYTES * offs[s] for s in range(W)]
+    dw = _device.build2d_merge(counts_by_src, ptrs, recv_sizes, bounds[rank], part.n_in, part.n_out)
     dw.stats.update(part.check())
-    if not replicate:
-        return dw
-    ii, io, v = allgather_concat([dw.indices_input, dw.indices_output, dw.values], group)
-    out = _device.DeviceWeights(ii, io, v, dw.n_in, dw.n_out)
-    out.stats = dw.stats
-    return out
+    mark("merge")
+    return dw
+
+
+def build_weights_2d_sharded(x_in, y_in, x_out, y_out, weights_input=None, replicate: bool = False,
+                             group=None, device=None, exchange: str = "p2p",
+                             phases: dict | None = None) -> _device.DeviceWeights:
+    """Strong-scaling build of ONE large grid pair over the ranks of ``group``.
+
+    Every rank holds the full coordinate arrays (134 MB at 2049^2) and walks every W-th block of 32 sweep
+    lines of all four passes; its fragments come out bucketed by input cell, so the share of every
+    input-row band is one contiguous range.  The owner of a band then merges the W shares of its band
+    (``rg_build2d_merge``): with ``exchange="p2p"`` it reads them in place from the other ranks' peer-mapped
+    memory over NVLink (one barrier, no send); with ``exchange="nccl"`` they travel by all-to-all first.
+    Returns this rank's band of the public triplets; with ``replicate`` the bands are all-gathered so that
+    every rank holds the full matrix (equal to the single-GPU build bit for bit).
+    ``phases`` (development) receives the milliseconds of walk / exchange / merge."""
+    rank, W = world(group)
+    if W == 1:
+        return _device.build_weights_2d(x_in, y_in, x_out, y_out, weights_input, device=device)
+    if exchange not in ("p2p", "nccl"):
+        raise ValueError(f"exchange must be 'p2p' or 'nccl', got {exchange!r}")
+    nxi, nyi = x_in.shape
+    bounds = band_bounds(nxi - 1, nyi - 1, W)
+    marks = []
+
+    def mark(name):
+        if phases is not None:
+            e = torch.cuda.Event(enable_timing=True)
+            e.record()
+            marks.append((name, e))
+
+    mark("start")
+    impl = _sharded_build_p2p if exchange == "p2p" else _sharded_build_nccl
+    dw = impl(x_in, y_in, x_out, y_out, weights_input, rank, W, bounds, group, device, mark)
+    if replicate:
+        ii, io, v = allgather_concat([dw.indices_input, dw.indices_output, dw.values], group)
+        out = _device.DeviceWeights(ii, io, v, dw.n_in, dw.n_out)
+        out.stats = dw.stats
+        dw = out
+        mark("allgather")
+    if phases is not None:
+        torch.cuda.synchronize(dw.device)
+        for (_, a), (name, b) in zip(marks[:-1], marks[1:]):
+            phases[name] = phases.get(name, 0.0) + a.elapsed_time(b)
+    return dw
 
 
 def build_weights_2d_sharded_local(x_in, y_in, x_out, y_out, weights_input=None, world_size: int = 2,
                                    device=None) -> list[_device.DeviceWeights]:
     """The line-sharded build with all ``world_size`` ranks played one after the other on ONE GPU and the
-    all-to-all replaced by slicing: the same kernels and the same merge as ``build_weights_2d_sharded``,
-    used to validate the partition on a single device (tests) and to time the per-rank share."""
+    exchange replaced by pointers into the other "ranks'" buffers (what the p2p exchange does over NVLink):
+    the same kernels and the same merge as ``build_weights_2d_sharded``, used to validate the partition on a
+    single device (tests) and to time the per-rank share."""
     W = int(world_size)
     nxi, nyi = x_in.shape
     bounds = band_bounds(nxi - 1, nyi - 1, W)
     parts = [_device.build2d_part_walk(x_in, y_in, x_out, y_out, weights_input, r, W, bounds, device=device)
              for r in range(W)]
+    dev = parts[0].workspace.device
     out = []
     for d in range(W):
-        lo, hi = bounds[d], bounds[d + 1]
-        counts_by_src = torch.stack([p.counts[lo:hi] for p in parts])
-        recv_key = torch.cat([p.frag_key[p.band_offsets[d]:p.band_offsets[d + 1]] for p in parts])
-        recv_val = torch.cat([p.frag_val[p.band_offsets[d]:p.band_offsets[d + 1]] for p in parts])
-        dw = _merge_band(d, bounds, counts_by_src, recv_key, recv_val, parts[0].n_in, parts[0].n_out)
-        out.append(dw)
+        cb = bounds[d + 1] - bounds[d]
+        counts = _device.build2d_gather_counts([p.counts.data_ptr() + 4 * bounds[d] for p in parts], cb, dev)
+        sizes = [p.band_offsets[d + 1] - p.band_offsets[d] for p in parts]
+        ptrs = [p.frags.data_ptr() + FRAG_BYTES * p.band_offsets[d] for p in parts]
+        out.append(_device.build2d_merge(counts, ptrs, sizes, bounds[d], parts[0].n_in, parts[0].n_out))
     for d, p in enumerate(parts):
         out[d].stats.update(p.check())
     return out

@@ -43,44 +43,14 @@ __device__ __forceinline__ void atomic_max_double(double* addr, double v)
     } while (assumed != old);
 }
 
-static __global__ void k_bbox_init(double* bbox)
-{
-    if (threadIdx.x < 4) bbox[threadIdx.x] = (threadIdx.x < 2) ? INFINITY : -INFINITY;
-}
-
-static __global__ void k_bbox(GridView g, double* __restrict__ bbox /* xlo, ylo, xhi, yhi */)
-{
-    const int64_t n = (int64_t)g.nx * g.ny;
-    double xlo = INFINITY, ylo = INFINITY, xhi = -INFINITY, yhi = -INFINITY;
-    for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < n; q += (int64_t)gridDim.x * blockDim.x) {
-        const double x = g.x[q], y = g.y[q];
-        xlo = fmin(xlo, x); xhi = fmax(xhi, x);
-        ylo = fmin(ylo, y); yhi = fmax(yhi, y);
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        xlo = fmin(xlo, __shfl_xor_sync(0xffffffffu, xlo, o));
-        ylo = fmin(ylo, __shfl_xor_sync(0xffffffffu, ylo, o));
-        xhi = fmax(xhi, __shfl_xor_sync(0xffffffffu, xhi, o));
-        yhi = fmax(yhi, __shfl_xor_sync(0xffffffffu, yhi, o));
-    }
-    if ((threadIdx.x & 31) == 0) {
-        atomic_min_double(&bbox[0], xlo);
-        atomic_min_double(&bbox[1], ylo);
-        atomic_max_double(&bbox[2], xhi);
-        atomic_max_double(&bbox[3], yhi);
-    }
-}
-
 // ---------------------------------------------------------------------------
 // K2: boundary edges in the scan order of _step_outside_static (c2d.py:462-483):
 //   axis 0: faces i = 0 then i = nx-1, edge m joins (i_face, m)-(i_face, m+1), enters cell (0 | ncx-1, m)
 //   axis 1: faces j = 0 then j = ny-1, edge m joins (m, j_face)-(m+1, j_face), enters cell (m, 0 | ncy-1)
 // ---------------------------------------------------------------------------
-static __global__ void k_boundary_edges(GridView g, Boundary b)
+__device__ __forceinline__ void boundary_edge(const GridView& g, const Boundary& b, int s,
+                                              double& x3, double& y3, double& x4, double& y4, int& cell)
 {
-    const int s = blockIdx.x * blockDim.x + threadIdx.x;
-    if (s >= b.n_edges) return;
     const int ncx = g.nx - 1, ncy = g.ny - 1;
     int axis, face, m;
     if (s < 2 * b.ne_a0) {
@@ -104,36 +74,97 @@ static __global__ void k_boundary_edges(GridView g, Boundary b)
         ci = m;
         cj = face ? ncy - 1 : 0;
     }
-    b.x3[s] = g.x[v3]; b.y3[s] = g.y[v3];
-    b.x4[s] = g.x[v4]; b.y4[s] = g.y[v4];
-    b.cell[s] = ci * ncy + cj;
+    x3 = g.x[v3]; y3 = g.y[v3];
+    x4 = g.x[v4]; y4 = g.y[v4];
+    cell = ci * ncy + cj;
 }
 
-static __global__ void k_boundary_bb1(Boundary b)
+// Up to two grids per launch (blockIdx.y): the build prepares the input and the output grid together.
+struct BoundarySet {
+    GridView g[2];
+    Boundary b[2];
+    double* bbox[2];
+    int n;
+};
+
+static __global__ void k_bbox_init(BoundarySet S)
 {
-    const int gi = blockIdx.x * blockDim.x + threadIdx.x;
-    if (gi >= b.n_g1) return;
-    BBox r = { INFINITY, INFINITY, -INFINITY, -INFINITY };
-    const int e1 = min(b.n_edges, (gi + 1) * 32);
-    for (int s = gi * 32; s < e1; s++) {
-        r.xlo = fmin(r.xlo, fmin(b.x3[s], b.x4[s])); r.xhi = fmax(r.xhi, fmax(b.x3[s], b.x4[s]));
-        r.ylo = fmin(r.ylo, fmin(b.y3[s], b.y4[s])); r.yhi = fmax(r.yhi, fmax(b.y3[s], b.y4[s]));
-    }
-    b.bb1[gi] = r;
+    if (threadIdx.x < 4 * S.n) S.bbox[threadIdx.x >> 2][threadIdx.x & 3] = ((threadIdx.x & 3) < 2) ? INFINITY : -INFINITY;
 }
 
-static __global__ void k_boundary_bb2(Boundary b)
+static __global__ void k_bbox(const __grid_constant__ BoundarySet S)
 {
-    const int gi = blockIdx.x * blockDim.x + threadIdx.x;
-    if (gi >= b.n_g2) return;
-    BBox r = { INFINITY, INFINITY, -INFINITY, -INFINITY };
-    const int e1 = min(b.n_g1, (gi + 1) * 32);
-    for (int s = gi * 32; s < e1; s++) {
-        const BBox q = b.bb1[s];
-        r.xlo = fmin(r.xlo, q.xlo); r.xhi = fmax(r.xhi, q.xhi);
-        r.ylo = fmin(r.ylo, q.ylo); r.yhi = fmax(r.yhi, q.yhi);
+    const GridView& g = S.g[blockIdx.y];
+    double* bbox = S.bbox[blockIdx.y];  // xlo, ylo, xhi, yhi
+    const int64_t n = (int64_t)g.nx * g.ny;
+    double xlo = INFINITY, ylo = INFINITY, xhi = -INFINITY, yhi = -INFINITY;
+    for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < n; q += (int64_t)gridDim.x * blockDim.x) {
+        const double x = g.x[q], y = g.y[q];
+        xlo = fmin(xlo, x); xhi = fmax(xhi, x);
+        ylo = fmin(ylo, y); yhi = fmax(yhi, y);
     }
-    b.bb2[gi] = r;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        xlo = fmin(xlo, __shfl_xor_sync(0xffffffffu, xlo, o));
+        ylo = fmin(ylo, __shfl_xor_sync(0xffffffffu, ylo, o));
+        xhi = fmax(xhi, __shfl_xor_sync(0xffffffffu, xhi, o));
+        yhi = fmax(yhi, __shfl_xor_sync(0xffffffffu, yhi, o));
+    }
+    if ((threadIdx.x & 31) == 0) {
+        atomic_min_double(&bbox[0], xlo);
+        atomic_min_double(&bbox[1], ylo);
+        atomic_max_double(&bbox[2], xhi);
+        atomic_max_double(&bbox[3], yhi);
+    }
+}
+
+// one warp per group of 32 edges: lane = edge; the group's bounding box by shuffles
+static __global__ void k_boundary_edges_bb1(const __grid_constant__ BoundarySet S)
+{
+    const GridView& g = S.g[blockIdx.y];
+    const Boundary& b = S.b[blockIdx.y];
+    const int lane = threadIdx.x & 31;
+    const int g1 = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+    if (g1 >= b.n_g1) return;
+    const int s = g1 * 32 + lane;
+    BBox r = { INFINITY, INFINITY, -INFINITY, -INFINITY };
+    if (s < b.n_edges) {
+        double x3, y3, x4, y4;
+        int cell;
+        boundary_edge(g, b, s, x3, y3, x4, y4, cell);
+        b.x3[s] = x3; b.y3[s] = y3;
+        b.x4[s] = x4; b.y4[s] = y4;
+        b.cell[s] = cell;
+        r.xlo = fmin(x3, x4); r.xhi = fmax(x3, x4);
+        r.ylo = fmin(y3, y4); r.yhi = fmax(y3, y4);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        r.xlo = fmin(r.xlo, __shfl_xor_sync(0xffffffffu, r.xlo, o));
+        r.ylo = fmin(r.ylo, __shfl_xor_sync(0xffffffffu, r.ylo, o));
+        r.xhi = fmax(r.xhi, __shfl_xor_sync(0xffffffffu, r.xhi, o));
+        r.yhi = fmax(r.yhi, __shfl_xor_sync(0xffffffffu, r.yhi, o));
+    }
+    if (lane == 0) b.bb1[g1] = r;
+}
+
+static __global__ void k_boundary_bb2(const __grid_constant__ BoundarySet S)
+{
+    const Boundary& b = S.b[blockIdx.y];
+    const int lane = threadIdx.x & 31;
+    const int g2 = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+    if (g2 >= b.n_g2) return;
+    const int s = g2 * 32 + lane;
+    BBox r = { INFINITY, INFINITY, -INFINITY, -INFINITY };
+    if (s < b.n_g1) r = b.bb1[s];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        r.xlo = fmin(r.xlo, __shfl_xor_sync(0xffffffffu, r.xlo, o));
+        r.ylo = fmin(r.ylo, __shfl_xor_sync(0xffffffffu, r.ylo, o));
+        r.xhi = fmax(r.xhi, __shfl_xor_sync(0xffffffffu, r.xhi, o));
+        r.yhi = fmax(r.yhi, __shfl_xor_sync(0xffffffffu, r.yhi, o));
+    }
+    if (lane == 0) b.bb2[g2] = r;
 }
 
 __device__ __forceinline__ int edge_local_id(const Boundary& b, int s)
@@ -222,18 +253,31 @@ static void carve_boundary(Carver& c, Boundary& b, int64_t nx, int64_t ny)
 }
 
 
-// builds the boundary structure and the bbox (xlo, ylo, xhi, yhi) of a grid
-static inline int build_boundary(cudaStream_t st, const GridView& g, const Boundary& b, double* bbox)
+// builds the boundary structures and the bboxes (xlo, ylo, xhi, yhi) of one or two grids: 4 launches
+static inline int build_boundaries(cudaStream_t st, int n, const GridView* g, const Boundary* b, double* const* bbox)
 {
     const int T = 256;
-    k_bbox_init<<<1, 32, 0, st>>>(bbox);
-    k_bbox<<<kNumSM * 2, T, 0, st>>>(g, bbox);
+    BoundarySet S;
+    memset(&S, 0, sizeof(S));
+    S.n = n;
+    int g1max = 0, g2max = 0;
+    for (int q = 0; q < n; q++) {
+        S.g[q] = g[q]; S.b[q] = b[q]; S.bbox[q] = bbox[q];
+        g1max = b[q].n_g1 > g1max ? b[q].n_g1 : g1max;
+        g2max = b[q].n_g2 > g2max ? b[q].n_g2 : g2max;
+    }
+    k_bbox_init<<<1, 32, 0, st>>>(S);
+    k_bbox<<<dim3(kNumSM * 2, n), T, 0, st>>>(S);
     RG_LAUNCH_CHECK("k_bbox");
-    k_boundary_edges<<<(unsigned)ceil_div(b.n_edges, T), T, 0, st>>>(g, b);
-    k_boundary_bb1<<<(unsigned)ceil_div(b.n_g1, T), T, 0, st>>>(b);
-    k_boundary_bb2<<<(unsigned)ceil_div(b.n_g2, T), T, 0, st>>>(b);
+    k_boundary_edges_bb1<<<dim3((unsigned)ceil_div((int64_t)g1max * 32, T), n), T, 0, st>>>(S);
+    k_boundary_bb2<<<dim3((unsigned)ceil_div((int64_t)g2max * 32, T), n), T, 0, st>>>(S);
     RG_LAUNCH_CHECK("k_boundary");
     return RG_OK;
+}
+
+static inline int build_boundary(cudaStream_t st, const GridView& g, const Boundary& b, double* bbox)
+{
+    return build_boundaries(st, 1, &g, &b, &bbox);
 }
 
 }  // namespace rg

@@ -48,8 +48,9 @@ struct PassParams {
     int nlines, nseg;
     int ncy_in, ncy_out;
     int ncx_st, ncy_st;
-    const int32_t* guess;       // [sweep vertices] guessed state at each sweep vertex
-    const int32_t* line_start;  // [nlines] exact state at the first vertex of each line
+    int32_t* guess;             // [sweep vertices] guessed state at each sweep vertex
+    int32_t* line_start;        // [nlines] exact state at the first vertex of each line
+    int32_t* line_bad;          // [nlines] does the chain of segment states of the line need a repair?
     int32_t* seg_start;         // [sweep vertices] state each segment starts from
     int32_t* seg_end;           // [sweep vertices] state each segment ends in
     int max_iter;
@@ -59,6 +60,29 @@ struct PassParams {
     // line-sharded builds: this rank walks the sweep lines of every part_world-th block of 32 lines
     int part_rank, part_world;
     int nl_slots;               // line slots of this rank (== nlines when part_world == 1)
+};
+
+// The four sweep passes are independent of each other: every phase launches them together.
+struct Pass4 {
+    PassParams p[4];
+    int64_t tstart[5];  // first thread of every pass in the per-segment launches (multiples of 256)
+    int lstart[5];      // first line slot of every pass in the per-line launches
+};
+
+__device__ __forceinline__ int pass_of_thread(const Pass4& Q, int64_t tid)
+{
+    return (tid >= Q.tstart[1]) + (tid >= Q.tstart[2]) + (tid >= Q.tstart[3]);
+}
+__device__ __forceinline__ int pass_of_slot(const Pass4& Q, int slot)
+{
+    return (slot >= Q.lstart[1]) + (slot >= Q.lstart[2]) + (slot >= Q.lstart[3]);
+}
+
+// One raw fragment: key = output cell << 32 | emission rank, val = weight.  16-byte records: one store per
+// fragment in the emit walk, one all-to-all (or one peer read) per band in sharded builds.
+struct __align__(16) Frag {
+    uint64_t key;
+    double val;
 };
 
 constexpr int kStateOutside = -1;
@@ -231,8 +255,7 @@ struct CountSink {
 struct EmitSink {
     const int64_t* boff;
     int32_t* cursor;
-    uint64_t* fkey;
-    double* fval;
+    Frag* frag;
     const double* area_in;
     const double* w_in;
     int32_t* flags;
@@ -256,22 +279,24 @@ struct EmitSink {
             // comes before the cell left of line L+1), then piece order inside the segment.
             const uint32_t seq = ((uint32_t)P.pass << 30) | (pc.side[q] == 0 ? (1u << 29) : 0u) | (uint32_t)piece_idx;
             const int64_t slot = boff[pc.in[q]] + atomicAdd(&cursor[pc.in[q]], 1);
-            fkey[slot] = ((uint64_t)pc.out[q] << 32) | seq;
-            fval[slot] = w;
+            frag[slot] = Frag{ ((uint64_t)pc.out[q] << 32) | seq, w };
         }
     }
 };
 
 // ---------------------------------------------------------------------------
-// K2: exact line-start states (c2d.py:293-322).  One warp per line.
+// K2: exact line-start states (c2d.py:293-322).  One CTA per line: the boundary winding number is
+// latency bound (the boundary has 4 (n - 1) edges), so 256 threads share it.
 // ---------------------------------------------------------------------------
-__global__ void k_line_starts(PassParams P, const double* __restrict__ bbox_static, int32_t* __restrict__ out)
+__global__ void __launch_bounds__(256) k_line_starts(const __grid_constant__ Pass4 Q, const double* __restrict__ bbox2)
 {
-    const int lane = threadIdx.x & 31;
-    const int slot = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
-    if (slot >= P.nl_slots) return;
-    const int L = line_of_slot(P, slot);
+    __shared__ double s_w[8];
+    const int p = pass_of_slot(Q, (int)blockIdx.x);
+    const PassParams& P = Q.p[p];
+    const int L = line_of_slot(P, (int)blockIdx.x - Q.lstart[p]);
     if (L >= P.nlines) return;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const double* bbox_static = bbox2 + 4 * (P.sweep_input ? 1 : 0);
     const int64_t v0 = vertex_of(P, L, 0);
     const double px = P.sweep.x[v0], py = P.sweep.y[v0];
     // point_is_inside_box_2d (geometry.py:64-105)
@@ -282,7 +307,7 @@ __global__ void k_line_starts(PassParams P, const double* __restrict__ bbox_stat
         // the scan-order edges of the i = 0 face and of the j = ny-1 face run the other way round.
         const Boundary& b = P.bnd;
         double w = 0.0;
-        for (int s = lane; s < b.n_edges; s += 32) {
+        for (int s = threadIdx.x; s < b.n_edges; s += 256) {
             double x0 = dsub(b.x3[s], px), y0 = dsub(b.y3[s], py);
             double x1 = dsub(b.x4[s], px), y1 = dsub(b.y4[s], py);
             const bool reversed = (s < b.ne_a0) || (s >= 2 * b.ne_a0 + b.ne_a1);
@@ -290,6 +315,12 @@ __global__ void k_line_starts(PassParams P, const double* __restrict__ bbox_stat
         }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) w += __shfl_xor_sync(0xffffffffu, w, o);  // halves: exact in any order
+        if (lane == 0) s_w[warp] = w;
+        __syncthreads();
+        if (warp != 0) return;
+        w = 0.0;
+#pragma unroll
+        for (int q = 0; q < 8; q++) w += s_w[q];
         if (w != 0.0) {
             int found = kLocUnknown;
             if (lane == 0) found = locate_newton(P.stat, px, py, 0.5 * P.stat.nx, 0.5 * P.stat.ny);
@@ -310,7 +341,10 @@ __global__ void k_line_starts(PassParams P, const double* __restrict__ bbox_stat
             state = found;
         }
     }
-    if (lane == 0) out[L] = state;
+    if (threadIdx.x == 0) {
+        P.line_start[L] = state;
+        P.line_bad[L] = 0;
+    }
 }
 
 // K2: guessed state of every sweep vertex
@@ -338,11 +372,15 @@ __device__ __forceinline__ bool segment_of_thread(const PassParams& P, int64_t t
 }
 
 // K2 (line-sharded builds): guessed state at the first vertex of every segment this rank walks
-__global__ void k_vertex_guess_part(PassParams P, int32_t* __restrict__ guess, int32_t* flags)
+__global__ void k_vertex_guess_part(const __grid_constant__ Pass4 Q, int32_t* flags)
 {
-    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t gtid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gtid >= Q.tstart[4]) return;
+    const int p = pass_of_thread(Q, gtid);
+    const PassParams& P = Q.p[p];
+    int32_t* guess = P.guess;
     int L, k;
-    if (!segment_of_thread(P, tid, L, k)) return;
+    if (!segment_of_thread(P, gtid - Q.tstart[p], L, k)) return;
     if (k == 0) return;  // the line start is located exactly by k_line_starts
     const int64_t v = vertex_of(P, L, k);
     const int r = locate_newton(P.stat, P.sweep.x[v], P.sweep.y[v], 0.5 * P.stat.nx, 0.5 * P.stat.ny);
@@ -350,11 +388,14 @@ __global__ void k_vertex_guess_part(PassParams P, int32_t* __restrict__ guess, i
     if (r == kLocUnknown) atomicAdd(&flags[kFlagUnknown], 1);
 }
 
-__global__ void __launch_bounds__(128) k_walk_count(PassParams P, int32_t* __restrict__ hist)
+__global__ void __launch_bounds__(128) k_walk_count(const __grid_constant__ Pass4 Q, int32_t* __restrict__ hist)
 {
-    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t gtid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gtid >= Q.tstart[4]) return;
+    const int p = pass_of_thread(Q, gtid);
+    const PassParams& P = Q.p[p];
     int L, k;
-    if (!segment_of_thread(P, tid, L, k)) return;
+    if (!segment_of_thread(P, gtid - Q.tstart[p], L, k)) return;
     const int64_t v = vertex_of(P, L, k), v2 = v + vertex_step(P);
     const int start = (k == 0) ? P.line_start[L] : P.guess[v];
     P.seg_start[v] = start;
@@ -369,14 +410,32 @@ __global__ void __launch_bounds__(128) k_walk_count(PassParams P, int32_t* __res
     if (P.banded) P.seg_hit[v] = sink.total > 0;
 }
 
-// One warp per line: make the chain of states equal to the sequential walk.
-__global__ void k_repair(PassParams P, int32_t* __restrict__ hist, int32_t* __restrict__ flags)
+// Does every segment start from the state its predecessor ended in?  (Thread per segment; the common answer
+// is yes for every line, and then k_repair has nothing to do.)
+__global__ void k_chain_check(const __grid_constant__ Pass4 Q)
+{
+    const int64_t gtid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gtid >= Q.tstart[4]) return;
+    const int p = pass_of_thread(Q, gtid);
+    const PassParams& P = Q.p[p];
+    int L, k;
+    if (!segment_of_thread(P, gtid - Q.tstart[p], L, k)) return;
+    if (k == 0) return;
+    const int64_t v = vertex_of(P, L, k);
+    if (P.seg_end[v - vertex_step(P)] != P.seg_start[v]) P.line_bad[L] = 1;
+}
+
+// One warp per flagged line: make the chain of states equal to the sequential walk.
+__global__ void k_repair(const __grid_constant__ Pass4 Q, int32_t* __restrict__ hist, int32_t* __restrict__ flags)
 {
     const int lane = threadIdx.x & 31;
-    const int slot = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
-    if (slot >= P.nl_slots) return;
-    const int L = line_of_slot(P, slot);
+    const int gslot = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+    if (gslot >= Q.lstart[4]) return;
+    const int p = pass_of_slot(Q, gslot);
+    const PassParams& P = Q.p[p];
+    const int L = line_of_slot(P, gslot - Q.lstart[p]);
     if (L >= P.nlines) return;
+    if (!P.line_bad[L]) return;
     const int64_t step = vertex_step(P);
     for (int base = 1; base < P.nseg; base += 32) {
         const int k = base + lane;
@@ -411,16 +470,19 @@ __global__ void k_repair(PassParams P, int32_t* __restrict__ hist, int32_t* __re
 }
 
 __global__ void __launch_bounds__(128)
-k_walk_emit(PassParams P, const int64_t* __restrict__ boff, int32_t* __restrict__ cursor,
-            uint64_t* __restrict__ fkey, double* __restrict__ fval,
+k_walk_emit(const __grid_constant__ Pass4 Q, const int64_t* __restrict__ boff, int32_t* __restrict__ cursor,
+            Frag* __restrict__ frag,
             const double* __restrict__ area_in, const double* __restrict__ w_in, int32_t* __restrict__ flags)
 {
-    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t gtid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gtid >= Q.tstart[4]) return;
+    const int p = pass_of_thread(Q, gtid);
+    const PassParams& P = Q.p[p];
     int L, k;
-    if (!segment_of_thread(P, tid, L, k)) return;
+    if (!segment_of_thread(P, gtid - Q.tstart[p], L, k)) return;
     const int64_t v = vertex_of(P, L, k), v2 = v + vertex_step(P);
     if (P.banded && !P.seg_hit[v]) return;  // the count walk saw nothing of this segment inside the band
-    EmitSink sink{ boff, cursor, fkey, fval, area_in, w_in, flags, L, k };
+    EmitSink sink{ boff, cursor, frag, area_in, w_in, flags, L, k };
     bool overflow = false;
     walk_segment(P, P.sweep.x[v], P.sweep.y[v], P.sweep.x[v2], P.sweep.y[v2], P.seg_start[v], sink, overflow);
     if (overflow) atomicOr(&flags[kFlagOverflow], 1);
@@ -437,125 +499,76 @@ k_walk_emit(PassParams P, const int64_t* __restrict__ boff, int32_t* __restrict_
 // sort in global memory: one lane per bucket, the whole warp (odd-even transposition) for the long ones.
 constexpr int kSortCells = 128;
 constexpr int kSortCap = 3040;  // fragments staged per CTA (just under the 48 KB of static shared memory)
+constexpr int kMaxSrc = 16;     // source ranks of a sharded build
 
 // Line-sharded builds: the fragments of a band arrive as one chunk per source rank, each chunk bucketed by
 // input cell.  cntT[c * W + s] = fragments of band cell c in the chunk of source s; src_off = exclusive scan of
-// the counts in [s][c] order (position in the concatenated chunks), dst_off = exclusive scan in [c][s] order
-// (position in the merged bucket array).  The sort kernel then gathers instead of staging a contiguous range.
+// the counts in [s][c] order, dst_off = exclusive scan in [c][s] order (position in the merged bucket array).
+// src[s] points at the chunk of source s MINUS src_off[s * Cb] records (so that src[s][src_off[s * Cb + c]] is
+// the first fragment of cell c from source s); the chunks may live in peer memory (NVLink loads).
 struct GatherSrc {
     const int32_t* cntT;
     const int64_t* src_off;
     const int64_t* dst_off;
-    const uint64_t* rkey;
-    const double* rval;
+    const Frag* src[kMaxSrc];
     int W;
     int64_t Cb;
 };
 
-template <bool kGather>
-__global__ void __launch_bounds__(kSortCells)
-k_bucket_sort(const int64_t* __restrict__ boff, int64_t n_cells,
-              uint64_t* __restrict__ fkey, double* __restrict__ fval,
-              int32_t* __restrict__ nuniq, GatherSrc G)
+__device__ __forceinline__ Frag load_frag_nc(const Frag* p)
 {
-    __shared__ uint64_t s_key[kSortCap];
-    __shared__ double s_val[kSortCap];
-    __shared__ int s_long;
+    const ulonglong2 q = __ldg(reinterpret_cast<const ulonglong2*>(p));
+    return Frag{ q.x, __longlong_as_double((long long)q.y) };
+}
+
+// 16-byte asynchronous global -> shared copy (LDGSTS): all the copies of a staging loop are in flight together
+__device__ __forceinline__ void cp_async_frag(Frag* smem_dst, const Frag* gsrc)
+{
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all()
+{
+    asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
+}
+
+__device__ __forceinline__ void insert_sorted_shared(Frag* s, int b, int e, const Frag x)
+{
+    int f = e - 1;
+    while (f >= b && s[f].key > x.key) {
+        s[f + 1] = s[f];
+        f--;
+    }
+    s[f + 1] = x;
+}
+
+__device__ __forceinline__ int32_t count_unique_shared(const Frag* s, int b, int n_mine)
+{
+    int32_t u = 0;
+    uint32_t prev = 0xffffffffu;
+    for (int e = b; e < b + n_mine; e++) {
+        const uint32_t o = (uint32_t)(s[e].key >> 32);
+        u += (e == b) || (o != prev);
+        prev = o;
+    }
+    return u;
+}
+
+// global-memory fallback: buckets already in place in `frag`
+__device__ inline void sort_buckets_global(Frag* __restrict__ frag, int64_t beg, int64_t end, bool valid,
+                                           int32_t* __restrict__ nuniq, int64_t c)
+{
     const int lane = threadIdx.x & 31;
-    const int64_t c0 = (int64_t)blockIdx.x * kSortCells;
-    const int64_t c = c0 + threadIdx.x;
-    const int64_t bstride = kGather ? G.W : 1;  // boff == dst_off in gather mode
-    int64_t beg = 0, end = 0;
-    if (c < n_cells) {
-        beg = boff[c * bstride];
-        end = boff[(c + 1) * bstride];
-    }
     const int64_t len = end - beg;
-    const int64_t lo = boff[c0 * bstride], hi = boff[min(c0 + (int64_t)kSortCells, n_cells) * bstride];
-    if (threadIdx.x == 0) s_long = 0;
-    __syncthreads();
-    if (len > 64) s_long = 1;
-    __syncthreads();
-    if (hi - lo <= kSortCap && !s_long) {
-        const int n = (int)(hi - lo);
-        const int b = (int)(beg - lo), n_mine = (int)len;
-        if (kGather) {
-            if (c < n_cells) {
-                int w = b;
-                for (int s = 0; s < G.W; s++) {
-                    const int ns = G.cntT[c * G.W + s];
-                    const int64_t src = G.src_off[(int64_t)s * G.Cb + c];
-                    for (int e = 0; e < ns; e++) {
-                        s_key[w] = G.rkey[src + e];
-                        s_val[w] = G.rval[src + e];
-                        w++;
-                    }
-                }
-            }
-        } else {
-            for (int e = threadIdx.x; e < n; e += kSortCells) {
-                s_key[e] = fkey[lo + e];
-                s_val[e] = fval[lo + e];
-            }
-            __syncthreads();
-        }
-        for (int e = b + 1; e < b + n_mine; e++) {
-            const uint64_t key = s_key[e];
-            const double val = s_val[e];
-            int f = e - 1;
-            while (f >= b && s_key[f] > key) {
-                s_key[f + 1] = s_key[f];
-                s_val[f + 1] = s_val[f];
-                f--;
-            }
-            s_key[f + 1] = key;
-            s_val[f + 1] = val;
-        }
-        if (c < n_cells) {
-            int32_t u = 0;
-            uint32_t prev = 0xffffffffu;
-            for (int e = b; e < b + n_mine; e++) {
-                const uint32_t o = (uint32_t)(s_key[e] >> 32);
-                u += (e == b) || (o != prev);
-                prev = o;
-            }
-            nuniq[c] = u;
-        }
-        __syncthreads();
-        for (int e = threadIdx.x; e < n; e += kSortCells) {
-            fkey[lo + e] = s_key[e];
-            fval[lo + e] = s_val[e];
-        }
-        return;
-    }
-    // ---- global-memory path ----
-    if (kGather) {
-        if (c < n_cells) {
-            int64_t w = beg;
-            for (int s = 0; s < G.W; s++) {
-                const int ns = G.cntT[c * G.W + s];
-                const int64_t src = G.src_off[(int64_t)s * G.Cb + c];
-                for (int e = 0; e < ns; e++) {
-                    fkey[w] = G.rkey[src + e];
-                    fval[w] = G.rval[src + e];
-                    w++;
-                }
-            }
-        }
-        __syncwarp();
-    }
     if (len <= 64) {
         for (int64_t e = beg + 1; e < end; e++) {
-            const uint64_t key = fkey[e];
-            const double val = fval[e];
+            const Frag x = frag[e];
             int64_t f = e - 1;
-            while (f >= beg && fkey[f] > key) {
-                fkey[f + 1] = fkey[f];
-                fval[f + 1] = fval[f];
+            while (f >= beg && frag[f].key > x.key) {
+                frag[f + 1] = frag[f];
                 f--;
             }
-            fkey[f + 1] = key;
-            fval[f + 1] = val;
+            frag[f + 1] = x;
         }
     }
     unsigned longmask = __ballot_sync(0xffffffffu, len > 64);
@@ -566,22 +579,21 @@ k_bucket_sort(const int64_t* __restrict__ boff, int64_t n_cells,
         const int64_t n = __shfl_sync(0xffffffffu, end, src) - b;
         for (int64_t phase = 0; phase < n; phase++) {
             for (int64_t p = (phase & 1) + 2 * lane; p + 1 < n; p += 64) {
-                const uint64_t k0 = fkey[b + p], k1 = fkey[b + p + 1];
-                if (k0 > k1) {
-                    fkey[b + p] = k1; fkey[b + p + 1] = k0;
-                    const double t0 = fval[b + p];
-                    fval[b + p] = fval[b + p + 1]; fval[b + p + 1] = t0;
+                const Frag f0 = frag[b + p], f1 = frag[b + p + 1];
+                if (f0.key > f1.key) {
+                    frag[b + p] = f1;
+                    frag[b + p + 1] = f0;
                 }
             }
             __syncwarp();
         }
     }
     __syncwarp();
-    if (c < n_cells) {
+    if (valid) {
         int32_t u = 0;
         uint32_t prev = 0xffffffffu;
         for (int64_t e = beg; e < end; e++) {
-            const uint32_t o = (uint32_t)(fkey[e] >> 32);
+            const uint32_t o = (uint32_t)(frag[e].key >> 32);
             u += (e == beg) || (o != prev);
             prev = o;
         }
@@ -589,11 +601,132 @@ k_bucket_sort(const int64_t* __restrict__ boff, int64_t n_cells,
     }
 }
 
+__global__ void __launch_bounds__(kSortCells)
+k_bucket_sort(const int64_t* __restrict__ boff, int64_t n_cells, Frag* __restrict__ frag, int32_t* __restrict__ nuniq)
+{
+    __shared__ Frag s_frag[kSortCap];
+    __shared__ int s_long;
+    const int64_t c0 = (int64_t)blockIdx.x * kSortCells;
+    const int64_t c = c0 + threadIdx.x;
+    int64_t beg = 0, end = 0;
+    if (c < n_cells) {
+        beg = boff[c];
+        end = boff[c + 1];
+    }
+    const int64_t len = end - beg;
+    const int64_t lo = boff[c0], hi = boff[min(c0 + (int64_t)kSortCells, n_cells)];
+    if (threadIdx.x == 0) s_long = 0;
+    __syncthreads();
+    if (len > 64) s_long = 1;
+    __syncthreads();
+    if (hi - lo <= kSortCap && !s_long) {
+        const int n = (int)(hi - lo);
+        for (int e = threadIdx.x; e < n; e += kSortCells) cp_async_frag(&s_frag[e], frag + lo + e);
+        cp_async_wait_all();
+        __syncthreads();
+        const int b = (int)(beg - lo), n_mine = (int)len;
+        for (int e = b + 1; e < b + n_mine; e++) insert_sorted_shared(s_frag, b, e, s_frag[e]);
+        if (c < n_cells) nuniq[c] = count_unique_shared(s_frag, b, n_mine);
+        __syncthreads();
+        for (int e = threadIdx.x; e < n; e += kSortCells) frag[lo + e] = s_frag[e];
+        return;
+    }
+    sort_buckets_global(frag, beg, end, c < n_cells, nuniq, c);
+}
+
+// Sharded builds: gather the band's buckets from the W source chunks, then sort as above.  Every source's
+// share of the CTA's 128 cells is ONE contiguous range of its chunk: the CTA copies the W ranges into a staging
+// area with 16-byte asynchronous copies (all in flight together -- they may cross NVLink), then every thread
+// inserts its own pieces into its bucket.  Dynamic shared memory: stage + buckets (Frag[kSortCap] each).
+constexpr size_t kGatherSmem = (size_t)kSortCap * sizeof(Frag) * 2;
+
+__global__ void __launch_bounds__(kSortCells)
+k_bucket_gather_sort(const __grid_constant__ GatherSrc G, int64_t n_cells, Frag* __restrict__ frag,
+                     int32_t* __restrict__ nuniq)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    Frag* s_stage = reinterpret_cast<Frag*>(smem_raw);
+    Frag* s_frag = s_stage + kSortCap;
+    __shared__ int s_long;
+    __shared__ int s_base[kMaxSrc + 1];
+    const int W = G.W;
+    const int64_t c0 = (int64_t)blockIdx.x * kSortCells;
+    const int64_t c1 = min(c0 + (int64_t)kSortCells, n_cells);
+    const int64_t c = c0 + threadIdx.x;
+    int64_t beg = 0, end = 0;
+    if (c < n_cells) {
+        beg = G.dst_off[c * W];
+        end = G.dst_off[(c + 1) * W];
+    }
+    const int64_t len = end - beg;
+    const int64_t lo = G.dst_off[c0 * W], hi = G.dst_off[c1 * W];
+    if (threadIdx.x == 0) s_long = 0;
+    if (threadIdx.x <= W) {
+        // s_base[s] = fragments of the sources before s inside this CTA's cells
+        int acc = 0;
+        for (int s = 0; s < (int)threadIdx.x; s++)
+            acc += (int)min(G.src_off[(int64_t)s * G.Cb + c1] - G.src_off[(int64_t)s * G.Cb + c0], (int64_t)kSortCap + 1);
+        s_base[threadIdx.x] = acc;
+    }
+    __syncthreads();
+    if (len > 64) s_long = 1;
+    __syncthreads();
+    if (hi - lo <= kSortCap && !s_long) {
+        const int n = (int)(hi - lo);
+        for (int s = 0; s < W; s++) {
+            const Frag* src = G.src[s] + G.src_off[(int64_t)s * G.Cb + c0];
+            const int ns = s_base[s + 1] - s_base[s];
+            for (int e = threadIdx.x; e < ns; e += kSortCells) cp_async_frag(&s_stage[s_base[s] + e], src + e);
+        }
+        const int b = (int)(beg - lo), n_mine = (int)len;
+        // per-source position of this cell's pieces in the stage, while the copies fly
+        int at[kMaxSrc], cnt[kMaxSrc];
+        if (c < n_cells) {
+#pragma unroll
+            for (int s = 0; s < kMaxSrc; s++) {
+                if (s < W) {
+                    cnt[s] = G.cntT[c * W + s];
+                    at[s] = s_base[s] + (int)(G.src_off[(int64_t)s * G.Cb + c] - G.src_off[(int64_t)s * G.Cb + c0]);
+                }
+            }
+        }
+        cp_async_wait_all();
+        __syncthreads();
+        if (c < n_cells) {
+            int w = b;
+#pragma unroll
+            for (int s = 0; s < kMaxSrc; s++) {
+                if (s < W) {
+                    for (int e = 0; e < cnt[s]; e++) {
+                        insert_sorted_shared(s_frag, b, w, s_stage[at[s] + e]);
+                        w++;
+                    }
+                }
+            }
+            nuniq[c] = count_unique_shared(s_frag, b, n_mine);
+        }
+        __syncthreads();
+        for (int e = threadIdx.x; e < n; e += kSortCells) frag[lo + e] = s_frag[e];
+        return;
+    }
+    // ---- global-memory path ----
+    if (c < n_cells) {
+        int64_t w = beg;
+        for (int s = 0; s < W; s++) {
+            const int ns = G.cntT[c * W + s];
+            const Frag* src = G.src[s] + G.src_off[(int64_t)s * G.Cb + c];
+            for (int e = 0; e < ns; e++) frag[w++] = load_frag_nc(src + e);
+        }
+    }
+    __syncwarp();
+    sort_buckets_global(frag, beg, end, c < n_cells, nuniq, c);
+}
+
 // Merge the runs of equal (input, output) pair: np.add.reduceat association over the
 // emission order (warr.py:59-72) and write the public arrays.
 __global__ void k_bucket_emit(const int64_t* __restrict__ boff, int64_t bstride, int64_t cell_offset,
                               const int64_t* __restrict__ colptr, int64_t n_cells,
-                              const uint64_t* __restrict__ fkey, const double* __restrict__ fval,
+                              const Frag* __restrict__ frag,
                               int64_t* __restrict__ ii, int64_t* __restrict__ io, double* __restrict__ vv)
 {
     const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -602,12 +735,12 @@ __global__ void k_bucket_emit(const int64_t* __restrict__ boff, int64_t bstride,
     int64_t w = colptr[c];
     int64_t s = beg;
     while (s < end) {
-        const uint32_t o = (uint32_t)(fkey[s] >> 32);
+        const uint32_t o = (uint32_t)(frag[s].key >> 32);
         int64_t e = s + 1;
-        while (e < end && (uint32_t)(fkey[e] >> 32) == o) e++;
+        while (e < end && (uint32_t)(frag[e].key >> 32) == o) e++;
         ii[w] = c + cell_offset;
         io[w] = (int64_t)o;
-        vv[w] = np_reduceat_segment(fval + s, e - s);
+        vv[w] = np_reduceat_segment<2>(&frag[s].val, e - s);
         w++;
         s = e;
     }
@@ -625,6 +758,7 @@ struct Layout {
     Boundary bnd[2];
     int32_t* guess[2];       // [0]: output vertices located in the input grid, [1]: input vertices in the output grid
     int32_t* line_start[4];
+    int32_t* line_bad[4];
     int32_t* seg_start[4];
     int32_t* seg_end[4];
     uint8_t* seg_hit[4];
@@ -656,6 +790,7 @@ static Layout make_layout(void* ws, int64_t nxi, int64_t nyi, int64_t nxo, int64
         const int64_t nx = sweep_in ? nxi : nxo, ny = sweep_in ? nyi : nyo;
         const int axis = p & 1;
         l.line_start[p] = c.take<int32_t>(axis ? nx : ny);
+        l.line_bad[p] = c.take<int32_t>(axis ? nx : ny);
         l.seg_start[p] = c.take<int32_t>(nx * ny);
         l.seg_end[p] = c.take<int32_t>(nx * ny);
         l.seg_hit[p] = c.take<uint8_t>(nx * ny);
@@ -700,6 +835,7 @@ static PassParams make_pass(const Layout& l, int p, const double* xin, const dou
     P.ncy_st = P.stat.ny - 1;
     P.guess = l.guess[P.sweep_input ? 1 : 0];
     P.line_start = l.line_start[p];
+    P.line_bad = l.line_bad[p];
     P.seg_start = l.seg_start[p];
     P.seg_end = l.seg_end[p];
     P.max_iter = 4 * (P.ncx_st + P.ncy_st) + 64;
@@ -717,6 +853,20 @@ static PassParams make_pass(const Layout& l, int p, const double* xin, const dou
         P.nl_slots = mine * 32;
     }
     return P;
+}
+
+static Pass4 make_pass4(const Layout& l, const double* xin, const double* yin, const double* xout, const double* yout,
+                        int64_t cell_lo, int64_t cell_hi, int part_rank, int part_world)
+{
+    Pass4 Q;
+    Q.tstart[0] = 0;
+    Q.lstart[0] = 0;
+    for (int p = 0; p < 4; p++) {
+        Q.p[p] = make_pass(l, p, xin, yin, xout, yout, cell_lo, cell_hi, part_rank, part_world);
+        Q.tstart[p + 1] = Q.tstart[p] + ceil_div((int64_t)Q.p[p].nl_slots * Q.p[p].nseg, 256) * 256;
+        Q.lstart[p + 1] = Q.lstart[p] + Q.p[p].nl_slots;
+    }
+    return Q;
 }
 
 }  // namespace rg
@@ -778,32 +928,30 @@ static int count_impl(int device, void* stream,
     k_cell_area<<<(unsigned)ceil_div(l.Ci, T), T, 0, st>>>(gin, l.area_in);
     RG_LAUNCH_CHECK("k_cell_area");
     // bounding boxes + boundaries of both grids
-    for (int g = 0; g < 2; g++) {
-        const GridView& gv = g ? gout : gin;
-        rc = build_boundary(st, gv, l.bnd[g], l.bbox + 4 * g);
+    {
+        const GridView gv[2] = { gin, gout };
+        double* const bb[2] = { l.bbox, l.bbox + 4 };
+        rc = build_boundaries(st, 2, gv, l.bnd, bb);
         if (rc) return rc;
     }
-    if (part_world == 1) {
-        // vertex guesses: output vertices in the input grid, input vertices in the output grid
-        k_vertex_guess<<<(unsigned)ceil_div(l.Vo, T), T, 0, st>>>(gout, gin, l.guess[0], l.flags);
-        k_vertex_guess<<<(unsigned)ceil_div(l.Vi, T), T, 0, st>>>(gin, gout, l.guess[1], l.flags);
-        RG_LAUNCH_CHECK("k_vertex_guess");
-    }
-    for (int p = 0; p < 4; p++) {
-        PassParams P = make_pass(l, p, xin, yin, xout, yout, cell_lo, cell_hi, part_rank, part_world);
-        if (P.nl_slots == 0) continue;
-        const int64_t nthreads = (int64_t)P.nl_slots * P.nseg;
-        if (part_world > 1) {
+    const Pass4 Q = make_pass4(l, xin, yin, xout, yout, cell_lo, cell_hi, part_rank, part_world);
+    if (Q.lstart[4] > 0 && Q.tstart[4] > 0) {
+        if (part_world == 1) {
+            // vertex guesses: output vertices in the input grid, input vertices in the output grid
+            k_vertex_guess<<<(unsigned)ceil_div(l.Vo, T), T, 0, st>>>(gout, gin, l.guess[0], l.flags);
+            k_vertex_guess<<<(unsigned)ceil_div(l.Vi, T), T, 0, st>>>(gin, gout, l.guess[1], l.flags);
+        } else {
             // only the vertices on this rank's lines (the two axis passes of a grid use different lines)
-            k_vertex_guess_part<<<(unsigned)ceil_div(nthreads, T), T, 0, st>>>(P, l.guess[P.sweep_input ? 1 : 0], l.flags);
-            RG_LAUNCH_CHECK("k_vertex_guess_part");
+            k_vertex_guess_part<<<(unsigned)ceil_div(Q.tstart[4], T), T, 0, st>>>(Q, l.flags);
         }
-        k_line_starts<<<(unsigned)ceil_div((int64_t)P.nl_slots * 32, T), T, 0, st>>>(
-            P, l.bbox + 4 * (P.sweep_input ? 1 : 0), l.line_start[p]);
+        RG_LAUNCH_CHECK("k_vertex_guess");
+        k_line_starts<<<(unsigned)Q.lstart[4], 256, 0, st>>>(Q, l.bbox);
         RG_LAUNCH_CHECK("k_line_starts");
-        k_walk_count<<<(unsigned)ceil_div(nthreads, 128), 128, 0, st>>>(P, l.hist);
+        k_walk_count<<<(unsigned)ceil_div(Q.tstart[4], 128), 128, 0, st>>>(Q, l.hist);
         RG_LAUNCH_CHECK("k_walk_count");
-        k_repair<<<(unsigned)ceil_div((int64_t)P.nl_slots * 32, 128), 128, 0, st>>>(P, l.hist, l.flags);
+        k_chain_check<<<(unsigned)ceil_div(Q.tstart[4], T), T, 0, st>>>(Q);
+        RG_LAUNCH_CHECK("k_chain_check");
+        k_repair<<<(unsigned)ceil_div((int64_t)Q.lstart[4] * 32, 128), 128, 0, st>>>(Q, l.hist, l.flags);
         RG_LAUNCH_CHECK("k_repair");
     }
     rc = exclusive_scan_i32_i64(st, l.hist, l.boff, l.Ci, l.scan_scratch);
@@ -834,26 +982,24 @@ extern "C" int rg_build2d_fill(int device, void* stream,
                                const double* xin, const double* yin, const double* xout, const double* yout,
                                const double* w_in, int64_t cell_lo, int64_t cell_hi,
                                void* workspace, size_t workspace_bytes,
-                               uint64_t* frag_key, double* frag_val, int64_t n_fragments, int64_t* nnz_host)
+                               void* frags, int64_t n_fragments, int64_t* nnz_host)
 {
     int rc = check_sizes(nxi, nyi, nxo, nyo);
     if (rc) return rc;
-    if (!workspace || !nnz_host || (n_fragments > 0 && (!frag_key || !frag_val)))
+    if (!workspace || !nnz_host || (n_fragments > 0 && !frags))
         return fail(RG_E_ARG, "rg_build2d_fill: null pointer");
     Layout l = make_layout(workspace, nxi, nyi, nxo, nyo);
     if (workspace_bytes < l.bytes) return fail(RG_E_WORKSPACE, "rg_build2d_fill: workspace too small");
     RG_CUDA(cudaSetDevice(device));
     cudaStream_t st = (cudaStream_t)stream;
     RG_CUDA(cudaMemsetAsync(l.cursor, 0, sizeof(int32_t) * (size_t)(l.Ci + 1), st));
-    for (int p = 0; p < 4; p++) {
-        PassParams P = make_pass(l, p, xin, yin, xout, yout, cell_lo, cell_hi);
-        const int64_t nthreads = (int64_t)P.nlines * P.nseg;
-        k_walk_emit<<<(unsigned)ceil_div(nthreads, 128), 128, 0, st>>>(P, l.boff, l.cursor, frag_key, frag_val,
-                                                                      l.area_in, w_in, l.flags);
+    {
+        const Pass4 Q = make_pass4(l, xin, yin, xout, yout, cell_lo, cell_hi, 0, 1);
+        k_walk_emit<<<(unsigned)ceil_div(Q.tstart[4], 128), 128, 0, st>>>(Q, l.boff, l.cursor, (Frag*)frags,
+                                                                         l.area_in, w_in, l.flags);
         RG_LAUNCH_CHECK("k_walk_emit");
     }
-    k_bucket_sort<false><<<(unsigned)ceil_div(l.Ci, kSortCells), kSortCells, 0, st>>>(l.boff, l.Ci, frag_key, frag_val,
-                                                                                       l.nuniq, GatherSrc{});
+    k_bucket_sort<<<(unsigned)ceil_div(l.Ci, kSortCells), kSortCells, 0, st>>>(l.boff, l.Ci, (Frag*)frags, l.nuniq);
     RG_LAUNCH_CHECK("k_bucket_sort");
     rc = exclusive_scan_i32_i64(st, l.nuniq, l.colptr, l.Ci, l.scan_scratch);
     if (rc) return rc;
@@ -872,20 +1018,20 @@ extern "C" int rg_build2d_emit(int device, void* stream,
                                int64_t nxi, int64_t nyi, int64_t nxo, int64_t nyo,
                                int64_t cell_lo, int64_t cell_hi,
                                void* workspace, size_t workspace_bytes,
-                               const uint64_t* frag_key, const double* frag_val, int64_t n_fragments,
+                               const void* frags, int64_t n_fragments,
                                int64_t* ii, int64_t* io, double* v, int64_t nnz)
 {
     (void)cell_lo; (void)cell_hi; (void)n_fragments;
     int rc = check_sizes(nxi, nyi, nxo, nyo);
     if (rc) return rc;
     if (!workspace) return fail(RG_E_ARG, "rg_build2d_emit: null workspace");
-    if (nnz > 0 && (!ii || !io || !v || !frag_key || !frag_val)) return fail(RG_E_ARG, "rg_build2d_emit: null pointer");
+    if (nnz > 0 && (!ii || !io || !v || !frags)) return fail(RG_E_ARG, "rg_build2d_emit: null pointer");
     Layout l = make_layout(workspace, nxi, nyi, nxo, nyo);
     if (workspace_bytes < l.bytes) return fail(RG_E_WORKSPACE, "rg_build2d_emit: workspace too small");
     RG_CUDA(cudaSetDevice(device));
     cudaStream_t st = (cudaStream_t)stream;
     if (nnz > 0) {
-        k_bucket_emit<<<(unsigned)ceil_div(l.Ci, 256), 256, 0, st>>>(l.boff, 1, 0, l.colptr, l.Ci, frag_key, frag_val, ii, io, v);
+        k_bucket_emit<<<(unsigned)ceil_div(l.Ci, 256), 256, 0, st>>>(l.boff, 1, 0, l.colptr, l.Ci, (const Frag*)frags, ii, io, v);
         RG_LAUNCH_CHECK("k_bucket_emit");
     }
     return RG_OK;
@@ -916,7 +1062,7 @@ extern "C" int rg_build2d_part_count(int device, void* stream,
                                      int part_rank, int part_world,
                                      void* workspace, size_t workspace_bytes, int64_t* n_fragments_host,
                                      int n_bounds, const int64_t* cell_bounds_host, int64_t* frag_offsets_host,
-                                     size_t* counts_offset_host)
+                                     size_t* counts_offset_host, int64_t* frag_offsets_dev_or_null)
 {
     int rc = count_impl(device, stream, nxi, nyi, nxo, nyo, xin, yin, xout, yout, 0, (nxi - 1) * (nyi - 1),
                         part_rank, part_world, workspace, workspace_bytes, n_fragments_host,
@@ -926,6 +1072,9 @@ extern "C" int rg_build2d_part_count(int device, void* stream,
         Layout l = make_layout(workspace, nxi, nyi, nxo, nyo);
         *counts_offset_host = (size_t)((char*)l.hist - (char*)workspace);
     }
+    if (frag_offsets_dev_or_null && n_bounds > 0)  // for the peers of a P2P exchange (they read it after a barrier)
+        RG_CUDA(cudaMemcpyAsync(frag_offsets_dev_or_null, frag_offsets_host, sizeof(int64_t) * n_bounds,
+                                cudaMemcpyHostToDevice, (cudaStream_t)stream));
     return RG_OK;
 }
 
@@ -934,11 +1083,11 @@ extern "C" int rg_build2d_part_fill(int device, void* stream,
                                     const double* xin, const double* yin, const double* xout, const double* yout,
                                     const double* w_in, int part_rank, int part_world,
                                     void* workspace, size_t workspace_bytes,
-                                    uint64_t* frag_key, double* frag_val, int64_t n_fragments)
+                                    void* frags, int64_t n_fragments)
 {
     int rc = check_sizes(nxi, nyi, nxo, nyo);
     if (rc) return rc;
-    if (!workspace || (n_fragments > 0 && (!frag_key || !frag_val)))
+    if (!workspace || (n_fragments > 0 && !frags))
         return fail(RG_E_ARG, "rg_build2d_part_fill: null pointer");
     if (part_world < 1 || part_rank < 0 || part_rank >= part_world)
         return fail(RG_E_ARG, "rg_build2d_part_fill: bad line partition");
@@ -947,13 +1096,13 @@ extern "C" int rg_build2d_part_fill(int device, void* stream,
     RG_CUDA(cudaSetDevice(device));
     cudaStream_t st = (cudaStream_t)stream;
     RG_CUDA(cudaMemsetAsync(l.cursor, 0, sizeof(int32_t) * (size_t)(l.Ci + 1), st));
-    for (int p = 0; p < 4; p++) {
-        PassParams P = make_pass(l, p, xin, yin, xout, yout, 0, l.Ci, part_rank, part_world);
-        if (P.nl_slots == 0) continue;
-        const int64_t nthreads = (int64_t)P.nl_slots * P.nseg;
-        k_walk_emit<<<(unsigned)ceil_div(nthreads, 128), 128, 0, st>>>(P, l.boff, l.cursor, frag_key, frag_val,
-                                                                      l.area_in, w_in, l.flags);
-        RG_LAUNCH_CHECK("k_walk_emit");
+    {
+        const Pass4 Q = make_pass4(l, xin, yin, xout, yout, 0, l.Ci, part_rank, part_world);
+        if (Q.tstart[4] > 0) {
+            k_walk_emit<<<(unsigned)ceil_div(Q.tstart[4], 128), 128, 0, st>>>(Q, l.boff, l.cursor, (Frag*)frags,
+                                                                             l.area_in, w_in, l.flags);
+            RG_LAUNCH_CHECK("k_walk_emit");
+        }
     }
     return RG_OK;
 }
@@ -994,25 +1143,63 @@ __global__ void k_merge_transpose(const int32_t* __restrict__ cnt, int32_t* __re
     cntT[i] = cnt[(int64_t)s * Cb + c];
 }
 
+struct CountSrc {
+    const int32_t* src[kMaxSrc];
+};
+
+// counts[s][c] = src[s][c]: the band slices of the sources' per-cell counts (possibly peer memory)
+__global__ void k_gather_counts(const __grid_constant__ CountSrc S, int64_t Cb, int32_t* __restrict__ counts)
+{
+    const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= Cb) return;
+    counts[(int64_t)blockIdx.y * Cb + c] = __ldg(S.src[blockIdx.y] + c);
+}
+
 }  // namespace rg
 
 extern "C" int rg_build2d_merge_workspace_bytes(int64_t n_cells, int n_src, size_t* bytes_host)
 {
-    if (!bytes_host || n_cells < 0 || n_src < 1) return fail(RG_E_ARG, "rg_build2d_merge_workspace_bytes: bad argument");
+    if (!bytes_host || n_cells < 0 || n_src < 1 || n_src > kMaxSrc)
+        return fail(RG_E_ARG, "rg_build2d_merge_workspace_bytes: bad argument");
     if (n_cells * n_src >= INT32_MAX) return fail(RG_E_TOO_LARGE, "rg_build2d_merge_workspace_bytes: too large");
     *bytes_host = make_merge_layout(nullptr, n_cells, n_src).bytes;
     return RG_OK;
 }
 
+extern "C" int rg_build2d_gather_counts(int device, void* stream, int64_t n_cells, int n_src,
+                                        const int32_t* const* src_counts_host, int32_t* counts)
+{
+    if (n_cells < 0 || n_src < 1 || n_src > kMaxSrc || !src_counts_host || (n_cells > 0 && !counts))
+        return fail(RG_E_ARG, "rg_build2d_gather_counts: bad argument");
+    RG_CUDA(cudaSetDevice(device));
+    if (n_cells == 0) return RG_OK;
+    CountSrc S;
+    memset(&S, 0, sizeof(S));
+    for (int s = 0; s < n_src; s++) {
+        if (!src_counts_host[s]) return fail(RG_E_ARG, "rg_build2d_gather_counts: null source");
+        S.src[s] = src_counts_host[s];
+    }
+    k_gather_counts<<<dim3((unsigned)ceil_div(n_cells, 256), n_src), 256, 0, (cudaStream_t)stream>>>(S, n_cells, counts);
+    RG_LAUNCH_CHECK("k_gather_counts");
+    return RG_OK;
+}
+
 extern "C" int rg_build2d_merge(int device, void* stream, int64_t n_cells, int n_src,
                                 const int32_t* counts /* [n_src][n_cells] */,
-                                const uint64_t* recv_key, const double* recv_val, int64_t n_recv,
+                                const void* const* src_chunks_host, const int64_t* src_sizes_host,
                                 void* workspace, size_t workspace_bytes,
-                                uint64_t* frag_key, double* frag_val, int64_t* nnz_host)
+                                void* frags, int64_t* nnz_host)
 {
-    if (n_cells < 0 || n_src < 1 || !workspace || !nnz_host || (n_cells > 0 && !counts) ||
-        (n_recv > 0 && (!recv_key || !recv_val || !frag_key || !frag_val)))
+    if (n_cells < 0 || n_src < 1 || n_src > kMaxSrc || !workspace || !nnz_host || (n_cells > 0 && !counts) ||
+        !src_chunks_host || !src_sizes_host)
         return fail(RG_E_ARG, "rg_build2d_merge: bad argument");
+    int64_t n_recv = 0;
+    for (int s = 0; s < n_src; s++) {
+        if (src_sizes_host[s] < 0 || (src_sizes_host[s] > 0 && !src_chunks_host[s]))
+            return fail(RG_E_ARG, "rg_build2d_merge: bad source chunk");
+        n_recv += src_sizes_host[s];
+    }
+    if (n_recv > 0 && !frags) return fail(RG_E_ARG, "rg_build2d_merge: null fragment buffer");
     if (n_cells * n_src >= INT32_MAX || n_recv >= INT32_MAX) return fail(RG_E_TOO_LARGE, "rg_build2d_merge: too large");
     MergeLayout m = make_merge_layout(workspace, n_cells, n_src);
     if (workspace_bytes < m.bytes) return fail(RG_E_WORKSPACE, "rg_build2d_merge: workspace too small");
@@ -1020,6 +1207,11 @@ extern "C" int rg_build2d_merge(int device, void* stream, int64_t n_cells, int n
     cudaStream_t st = (cudaStream_t)stream;
     *nnz_host = 0;
     if (n_cells == 0) return RG_OK;
+    static bool smem_set = false;  // idempotent attribute; a race only repeats the call
+    if (!smem_set) {
+        RG_CUDA(cudaFuncSetAttribute(k_bucket_gather_sort, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGatherSmem));
+        smem_set = true;
+    }
     const int64_t n = n_cells * n_src;
     k_merge_transpose<<<(unsigned)ceil_div(n, 256), 256, 0, st>>>(counts, m.cntT, n_cells, n_src);
     RG_LAUNCH_CHECK("k_merge_transpose");
@@ -1027,34 +1219,41 @@ extern "C" int rg_build2d_merge(int device, void* stream, int64_t n_cells, int n
     if (rc) return rc;
     rc = exclusive_scan_i32_i64(st, m.cntT, m.dst_off, n, m.scan_scratch);
     if (rc) return rc;
-    const GatherSrc G{ m.cntT, m.src_off, m.dst_off, recv_key, recv_val, n_src, n_cells };
-    k_bucket_sort<true><<<(unsigned)ceil_div(n_cells, kSortCells), kSortCells, 0, st>>>(m.dst_off, n_cells, frag_key,
-                                                                                     frag_val, m.nuniq, G);
-    RG_LAUNCH_CHECK("k_bucket_sort<gather>");
+    GatherSrc G;
+    memset(&G, 0, sizeof(G));
+    G.cntT = m.cntT; G.src_off = m.src_off; G.dst_off = m.dst_off; G.W = n_src; G.Cb = n_cells;
+    int64_t before = 0;
+    for (int s = 0; s < n_src; s++) {
+        G.src[s] = (const Frag*)src_chunks_host[s] - before;  // src_off[s * Cb] == fragments of the sources before s
+        before += src_sizes_host[s];
+    }
+    k_bucket_gather_sort<<<(unsigned)ceil_div(n_cells, kSortCells), kSortCells, kGatherSmem, st>>>(
+        G, n_cells, (Frag*)frags, m.nuniq);
+    RG_LAUNCH_CHECK("k_bucket_gather_sort");
     rc = exclusive_scan_i32_i64(st, m.nuniq, m.colptr, n_cells, m.scan_scratch);
     if (rc) return rc;
     int64_t nnz = 0, total = 0;
     RG_CUDA(cudaMemcpyAsync(&nnz, m.colptr + n_cells, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
     RG_CUDA(cudaMemcpyAsync(&total, m.src_off + n, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
     RG_CUDA(cudaStreamSynchronize(st));
-    if (total != n_recv) return fail(RG_E_ARG, "rg_build2d_merge: the counts do not add up to n_recv");
+    if (total != n_recv) return fail(RG_E_ARG, "rg_build2d_merge: the counts do not add up to the chunk sizes");
     *nnz_host = nnz;
     return RG_OK;
 }
 
 extern "C" int rg_build2d_merge_emit(int device, void* stream, int64_t n_cells, int n_src, int64_t cell_offset,
                                      void* workspace, size_t workspace_bytes,
-                                     const uint64_t* frag_key, const double* frag_val,
+                                     const void* frags,
                                      int64_t* ii, int64_t* io, double* v, int64_t nnz)
 {
-    if (n_cells < 0 || n_src < 1 || !workspace) return fail(RG_E_ARG, "rg_build2d_merge_emit: bad argument");
-    if (nnz > 0 && (!ii || !io || !v || !frag_key || !frag_val)) return fail(RG_E_ARG, "rg_build2d_merge_emit: null pointer");
+    if (n_cells < 0 || n_src < 1 || n_src > kMaxSrc || !workspace) return fail(RG_E_ARG, "rg_build2d_merge_emit: bad argument");
+    if (nnz > 0 && (!ii || !io || !v || !frags)) return fail(RG_E_ARG, "rg_build2d_merge_emit: null pointer");
     MergeLayout m = make_merge_layout(workspace, n_cells, n_src);
     if (workspace_bytes < m.bytes) return fail(RG_E_WORKSPACE, "rg_build2d_merge_emit: workspace too small");
     RG_CUDA(cudaSetDevice(device));
     if (nnz > 0 && n_cells > 0) {
         k_bucket_emit<<<(unsigned)ceil_div(n_cells, 256), 256, 0, (cudaStream_t)stream>>>(
-            m.dst_off, n_src, cell_offset, m.colptr, n_cells, frag_key, frag_val, ii, io, v);
+            m.dst_off, n_src, cell_offset, m.colptr, n_cells, (const Frag*)frags, ii, io, v);
         RG_LAUNCH_CHECK("k_bucket_emit");
     }
     return RG_OK;

@@ -80,36 +80,39 @@ __device__ __forceinline__ double dfma(double a, double b, double c) { return __
 
 // NumPy pairwise summation (numpy/_core/src/umath/loops_utils.h.src, @TYPE@_pairwise_sum),
 // the association np.add.reduceat uses per segment (reference: _weights_arrays.py:72).
+// `S` = stride of the operands in doubles (fragments are stored as 16-byte (key, value) records: S = 2).
+template <int S = 1>
 __device__ inline double np_pairwise_sum(const double* a, int64_t n)
 {
     if (n < 8) {
         double res = -0.0;
-        for (int64_t i = 0; i < n; i++) res = dadd(res, a[i]);
+        for (int64_t i = 0; i < n; i++) res = dadd(res, a[i * S]);
         return res;
     } else if (n <= 128) {
         double r[8];
 #pragma unroll
-        for (int q = 0; q < 8; q++) r[q] = a[q];
+        for (int q = 0; q < 8; q++) r[q] = a[q * S];
         int64_t i;
         for (i = 8; i < n - (n % 8); i += 8) {
 #pragma unroll
-            for (int q = 0; q < 8; q++) r[q] = dadd(r[q], a[i + q]);
+            for (int q = 0; q < 8; q++) r[q] = dadd(r[q], a[(i + q) * S]);
         }
         double res = dadd(dadd(dadd(r[0], r[1]), dadd(r[2], r[3])), dadd(dadd(r[4], r[5]), dadd(r[6], r[7])));
-        for (; i < n; i++) res = dadd(res, a[i]);
+        for (; i < n; i++) res = dadd(res, a[i * S]);
         return res;
     } else {
         int64_t n2 = n / 2;
         n2 -= n2 % 8;
-        return dadd(np_pairwise_sum(a, n2), np_pairwise_sum(a + n2, n - n2));
+        return dadd(np_pairwise_sum<S>(a, n2), np_pairwise_sum<S>(a + n2 * S, n - n2));
     }
 }
 
 // one segment of np.add.reduceat: out = a[0]; out += pairwise_sum(a[1:])
+template <int S = 1>
 __device__ inline double np_reduceat_segment(const double* a, int64_t n)
 {
     double out = a[0];
-    if (n > 1) out = dadd(out, np_pairwise_sum(a + 1, n - 1));
+    if (n > 1) out = dadd(out, np_pairwise_sum<S>(a + S, n - 1));
     return out;
 }
 

@@ -40,9 +40,12 @@ if "RANK" not in os.environ:
     if os.environ.get("NCU"):  # launch list of rank 0 of 8: run under ncu --metrics gpu__time_duration.sum
         W = 8
         bounds = _parallel.band_bounds(n - 1, n - 1, W)
-        p = _device.build2d_part_walk(xi, yi, xo, yo, None, 0, W, bounds, device=dev)
-        cnt = torch.stack([p.counts[bounds[0]:bounds[1]]] * 1)
-        _device.build2d_merge(cnt, p.frag_key[:p.band_offsets[1]], p.frag_val[:p.band_offsets[1]], 0, p.n_in, p.n_out)
+        parts = [_device.build2d_part_walk(xi, yi, xo, yo, None, r, W, bounds, device=dev) for r in range(W)]
+        torch.cuda.synchronize()
+        print("merge of band 0 from 8 sources", flush=True)
+        cnt = _device.build2d_gather_counts([p.counts.data_ptr() for p in parts], bounds[1], dev)
+        _device.build2d_merge(cnt, [p.frags.data_ptr() for p in parts], [p.band_offsets[1] for p in parts], 0,
+                              parts[0].n_in, parts[0].n_out)
         torch.cuda.synchronize()
         sys.exit(0)
     for W in [int(a) for a in sys.argv[1:]] or [2, 4, 8]:
@@ -52,15 +55,18 @@ if "RANK" not in os.environ:
         for r in range(W):
             ms, p = ev_time(lambda: _device.build2d_part_walk(xi, yi, xo, yo, None, r, W, bounds, device=dev), reps=3, warm=1)
             walk_ms.append(ms)
-            frag_share.append(p.frag_key.numel())
+            frag_share.append(p.n_fragments)
             parts.append(p)
         merge_ms = []
         for d in range(W):
             lo, hi = bounds[d], bounds[d + 1]
-            cnt = torch.stack([p.counts[lo:hi] for p in parts])
-            rk = torch.cat([p.frag_key[p.band_offsets[d]:p.band_offsets[d + 1]] for p in parts])
-            rv = torch.cat([p.frag_val[p.band_offsets[d]:p.band_offsets[d + 1]] for p in parts])
-            ms, dw = ev_time(lambda: _device.build2d_merge(cnt, rk, rv, lo, parts[0].n_in, parts[0].n_out), reps=3, warm=1)
+            sizes = [p.band_offsets[d + 1] - p.band_offsets[d] for p in parts]
+            ptrs = [p.frags.data_ptr() + 16 * p.band_offsets[d] for p in parts]
+
+            def merge():
+                cnt = _device.build2d_gather_counts([p.counts.data_ptr() + 4 * lo for p in parts], hi - lo, dev)
+                return _device.build2d_merge(cnt, ptrs, sizes, lo, parts[0].n_in, parts[0].n_out)
+            ms, dw = ev_time(merge, reps=3, warm=1)
             merge_ms.append(ms)
         print(f"W={W}: walk share per rank ms {['%.2f' % m for m in walk_ms]} (fragments {frag_share}); "
               f"merge per band ms {['%.2f' % m for m in merge_ms]}; "
@@ -91,15 +97,24 @@ def timeit(fn, reps=5):
 
 
 ms_full, full = timeit(lambda: _device.build_weights_2d(xi, yi, xo, yo, device=dev))
-ms_sh, dw = timeit(lambda: _parallel.build_weights_2d_sharded(xi, yi, xo, yo, replicate=False, device=dev))
-ms_rep, dwr = timeit(lambda: _parallel.build_weights_2d_sharded(xi, yi, xo, yo, replicate=True, device=dev))
-bounds = _parallel.band_bounds(n - 1, n - 1, world)
-ms_walk, part = timeit(lambda: _device.build2d_part_walk(xi, yi, xo, yo, None, rank, world, bounds, device=dev))
-ok = bool(torch.equal(dwr.indices_input, full.indices_input) and torch.equal(dwr.indices_output, full.indices_output)
-          and torch.equal(dwr.values, full.values))
-oks = torch.tensor([int(ok)], device=dev)
-dist.all_reduce(oks, op=dist.ReduceOp.MIN)
-if rank == 0:
-    print(f"world {world}: full build {ms_full:.2f} ms | line-sharded {ms_sh:.2f} ms ({ms_full / ms_sh:.2f}x) | "
-          f"+ all-gather {ms_rep:.2f} ms | walk share only {ms_walk:.2f} ms | replicated == single-GPU build on every rank: {bool(oks.item())}")
+for ex in (os.environ.get("EXCHANGE", "p2p,nccl")).split(","):
+    try:
+        ms_sh, dw = timeit(lambda: _parallel.build_weights_2d_sharded(xi, yi, xo, yo, replicate=False, device=dev, exchange=ex))
+    except Exception as e:  # report and carry on with the other exchange
+        if rank == 0:
+            print(f"exchange {ex} failed: {type(e).__name__}: {e}")
+        continue
+    ms_rep, dwr = timeit(lambda: _parallel.build_weights_2d_sharded(xi, yi, xo, yo, replicate=True, device=dev, exchange=ex))
+    ph = {}
+    for _ in range(5):
+        _parallel.build_weights_2d_sharded(xi, yi, xo, yo, replicate=False, device=dev, exchange=ex, phases=ph)
+    ph = {k: round(v / 5, 3) for k, v in ph.items()}
+    ok = bool(torch.equal(dwr.indices_input, full.indices_input) and torch.equal(dwr.indices_output, full.indices_output)
+              and torch.equal(dwr.values, full.values))
+    oks = torch.tensor([int(ok)], device=dev)
+    dist.all_reduce(oks, op=dist.ReduceOp.MIN)
+    if rank == 0:
+        print(f"world {world} [{ex}]: full build {ms_full:.2f} ms | line-sharded {ms_sh:.2f} ms ({ms_full / ms_sh:.2f}x) | "
+              f"+ all-gather {ms_rep:.2f} ms | replicated == single-GPU build on every rank: {bool(oks.item())}")
+        print("   phases on rank 0 (ms):", ph)
 dist.destroy_process_group()
