@@ -49,6 +49,12 @@
 #ifndef RG_CTAS
 #define RG_CTAS 2
 #endif
+#ifndef RG_CP_MODE
+#define RG_CP_MODE "cg.shared.global"   // footprint copies: L2 -> shared memory, bypassing L1
+#endif
+#ifndef RG_TAIL_OUT
+#define RG_TAIL_OUT 1   // stage the outputs in the unused tail of the footprint buffer (one barrier per sub-block)
+#endif
 
 
 namespace rg {
@@ -69,7 +75,10 @@ constexpr int kZeroOdd = kCP - 1;    // the targets of padding entries, one per 
 constexpr int kNnzMax = 1280;    // max CSR entries per tile
 constexpr int kPadMax = 1536;    // max SLOT entries per tile (4 cells x padded, aligned slots of every quad)
 constexpr int kAlignMax = 16;    // rows up to this length take part in the bank-parity alignment
-constexpr int kOutStride = kCP;  // staged output frame t lives in slots [0, 128) of staged input frame t
+constexpr int kOutStride = kCP;  // staged output frame t lives in slots [0, 128) of staged input frame t ...
+constexpr int kTailOut = kCellsMax - kTileCells;  // ... or, when the footprint has at most this many cells, in slots
+                                 // [kTailOut, kTailOut + 128): the footprint part of the buffer is then free for the
+                                 // next fill as soon as the compute is over, and two of three block barriers go
 constexpr int kStagedThreads = 512;   // 2 CTAs per SM: their load / compute / store phases overlap
 constexpr int kCopyPairs = kCellsMax / 2;            // 16-byte pieces of one staged frame
 constexpr int kPairsPerLane = (kCopyPairs + 31) / 32;  // ... of which a lane copies up to this many per sub-block
@@ -567,7 +576,7 @@ k_apply_staged(int64_t n_frames, int64_t w_in, int64_t n_in, int64_t h_out, int6
                         "{\n.reg .pred p;\n.reg .u64 a;\n"
                         "setp.ge.s32 p, %2, 0;\n"
                         "mad.wide.u32 a, %2, 8, %1;\n"
-                        "@p cp.async.cg.shared.global [%0], [a], 16;\n}\n" ::"r"(dst + j * 32 * 16),
+                        "@p cp.async." RG_CP_MODE " [%0], [a], 16;\n}\n" ::"r"(dst + j * 32 * 16),
                         "l"(src), "r"(pair_off[j]));
             }
         }
@@ -584,6 +593,7 @@ k_apply_staged(int64_t n_frames, int64_t w_in, int64_t n_in, int64_t h_out, int6
     for (int k = 0; k < 2; k++) o_local[k] = 2 * (int)S.pair_of[2 * (2 * warp + k) + (q >> 1)] + (q & 1);
     // full-width tiles of 16-byte aligned output rows are written with 16-byte stores
     const bool vec_store = tw == kTW && th >= 2 && (w_out & 1) == 0 && ((uintptr_t)vout & 15) == 0;
+    const int out_off = (RG_TAIL_OUT && RG_NBUF > 1 && cells <= kTailOut) ? kTailOut : 0;  // uniform over the CTA
     for (int s = 0; s < nsub; s++) {
         const int64_t f0 = f_begin + (int64_t)s * kT;
         const int buf = (RG_NBUF > 1) ? (s & 1) : 0;
@@ -640,13 +650,17 @@ k_apply_staged(int64_t n_frames, int64_t w_in, int64_t n_in, int64_t h_out, int6
             }
             acc[0][0] = a0; acc[0][1] = a1; acc[1][0] = b0; acc[1][1] = b1;
         }
-        __syncthreads();  // everyone is done reading in_s[buf]: frame t's slots [0,128) now take its outputs
+        if (out_off == 0) __syncthreads();  // everyone is done reading in_s[buf]: slots [0,128) now take the outputs
 #pragma unroll
         for (int k = 0; k < 2; k++) {
-            in[t * kOutStride + o_local[k]] = acc[k][0];
-            in[(t + 8) * kOutStride + o_local[k]] = acc[k][1];
+            in[t * kOutStride + out_off + o_local[k]] = acc[k][0];
+            in[(t + 8) * kOutStride + out_off + o_local[k]] = acc[k][1];
         }
         __syncthreads();
+        // tail staging: the footprint slots are free now, the outputs sit beyond them -> refill at once.  (The
+        // outputs of this sub-block are read below; the next write to this tail happens two sub-blocks later,
+        // after the barrier of the next sub-block, which every warp reaches only after its write-out here.)
+        if (out_off != 0 && s + RG_NBUF < nsub) prefetch(f0 + RG_NBUF * kT, buf);
         // ---- write-out: warp w stores frame w; 16 B per lane, two tile rows (2 x 256 B) per instruction ----
         {
             const int64_t f = f0 + tt_p;
@@ -654,20 +668,22 @@ k_apply_staged(int64_t n_frames, int64_t w_in, int64_t n_in, int64_t h_out, int6
                 if (vec_store) {
                     const int hr = lane >> 4, c2 = (lane & 15) * 2;  // half-warp -> tile row, lane -> 2 cells
                     double* o = vout + f * n_out + out_base + (int64_t)hr * w_out + c2;
-                    const double* si = in + tt_p * kOutStride + hr * kTW + c2;
+                    const double* si = in + tt_p * kOutStride + out_off + hr * kTW + c2;
                     const double2 r0 = *reinterpret_cast<const double2*>(si);
                     const double2 r1 = *reinterpret_cast<const double2*>(si + 2 * kTW);
                     *reinterpret_cast<double2*>(o) = r0;
                     if (hr + 2 < th) *reinterpret_cast<double2*>(o + 2 * w_out) = r1;
                 } else if (lane < tw) {
                     double* o = vout + f * n_out + out_base + lane;
-                    const double* si = in + tt_p * kOutStride + lane;
+                    const double* si = in + tt_p * kOutStride + out_off + lane;
                     for (int tr = 0; tr < th; tr++) o[(int64_t)tr * w_out] = si[tr * kTW];
                 }
             }
         }
-        __syncthreads();  // outputs consumed: the buffer may be refilled
-        if (s + RG_NBUF < nsub) prefetch(f0 + RG_NBUF * kT, buf);
+        if (out_off == 0) {
+            __syncthreads();  // outputs consumed: the buffer may be refilled
+            if (s + RG_NBUF < nsub) prefetch(f0 + RG_NBUF * kT, buf);
+        }
     }
 }
 

@@ -498,7 +498,7 @@ k_walk_emit(const __grid_constant__ Pass4 Q, const int64_t* __restrict__ boff, i
 // and the range is written back coalesced.  CTAs whose range does not fit (or that hold a bucket longer than 64)
 // sort in global memory: one lane per bucket, the whole warp (odd-even transposition) for the long ones.
 constexpr int kSortCells = 128;
-constexpr int kSortCap = 3040;  // fragments staged per CTA (just under the 48 KB of static shared memory)
+constexpr int kSortCap = 3000;  // fragments staged per CTA (~56 KB of shared memory with the maps: 4 CTAs per SM)
 constexpr int kMaxSrc = 16;     // source ranks of a sharded build
 
 // Line-sharded builds: the fragments of a band arrive as one chunk per source rank, each chunk bucketed by
@@ -530,28 +530,6 @@ __device__ __forceinline__ void cp_async_frag(Frag* smem_dst, const Frag* gsrc)
 __device__ __forceinline__ void cp_async_wait_all()
 {
     asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
-}
-
-__device__ __forceinline__ void insert_sorted_shared(Frag* s, int b, int e, const Frag x)
-{
-    int f = e - 1;
-    while (f >= b && s[f].key > x.key) {
-        s[f + 1] = s[f];
-        f--;
-    }
-    s[f + 1] = x;
-}
-
-__device__ __forceinline__ int32_t count_unique_shared(const Frag* s, int b, int n_mine)
-{
-    int32_t u = 0;
-    uint32_t prev = 0xffffffffu;
-    for (int e = b; e < b + n_mine; e++) {
-        const uint32_t o = (uint32_t)(s[e].key >> 32);
-        u += (e == b) || (o != prev);
-        prev = o;
-    }
-    return u;
 }
 
 // global-memory fallback: buckets already in place in `frag`
@@ -601,11 +579,28 @@ __device__ inline void sort_buckets_global(Frag* __restrict__ frag, int64_t beg,
     }
 }
 
+// Shared-memory layout of the two sort kernels (dynamic): the staged fragments, the bucket (local cell) of
+// every staged fragment, and per local cell: first slot, length, distinct output cells.
+struct SortSmem {
+    Frag frag[kSortCap];
+    uint16_t cell[kSortCap];
+    int beg[kSortCells];
+    int len[kSortCells];
+    int uniq[kSortCells];
+    // gather variant only: stage position of the k-th fragment of every bucket (bucket b owns pos[beg .. beg + len))
+    uint16_t pos[kSortCap];
+    int base[kMaxSrc + 1];
+    int is_long;
+};
+
+// Rank sort, one thread per FRAGMENT: keys are unique inside a bucket, so the final slot of a fragment is the
+// number of smaller keys in its bucket.  No dependent stores, no divergence between the lanes of a bucket (they
+// read the same keys: shared-memory broadcasts), and the sorted records go straight to global memory.
 __global__ void __launch_bounds__(kSortCells)
 k_bucket_sort(const int64_t* __restrict__ boff, int64_t n_cells, Frag* __restrict__ frag, int32_t* __restrict__ nuniq)
 {
-    __shared__ Frag s_frag[kSortCap];
-    __shared__ int s_long;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    SortSmem& S = *reinterpret_cast<SortSmem*>(smem_raw);
     const int64_t c0 = (int64_t)blockIdx.x * kSortCells;
     const int64_t c = c0 + threadIdx.x;
     int64_t beg = 0, end = 0;
@@ -615,40 +610,51 @@ k_bucket_sort(const int64_t* __restrict__ boff, int64_t n_cells, Frag* __restric
     }
     const int64_t len = end - beg;
     const int64_t lo = boff[c0], hi = boff[min(c0 + (int64_t)kSortCells, n_cells)];
-    if (threadIdx.x == 0) s_long = 0;
+    if (threadIdx.x == 0) S.is_long = 0;
     __syncthreads();
-    if (len > 64) s_long = 1;
+    if (len > 64) S.is_long = 1;
     __syncthreads();
-    if (hi - lo <= kSortCap && !s_long) {
+    if (hi - lo <= kSortCap && !S.is_long) {
         const int n = (int)(hi - lo);
-        for (int e = threadIdx.x; e < n; e += kSortCells) cp_async_frag(&s_frag[e], frag + lo + e);
+        for (int e = threadIdx.x; e < n; e += kSortCells) cp_async_frag(&S.frag[e], frag + lo + e);
+        const int b = (int)(beg - lo), n_mine = (int)len;
+        S.beg[threadIdx.x] = b;
+        S.len[threadIdx.x] = n_mine;
+        S.uniq[threadIdx.x] = 0;
+        for (int e = b; e < b + n_mine; e++) S.cell[e] = (uint16_t)threadIdx.x;
         cp_async_wait_all();
         __syncthreads();
-        const int b = (int)(beg - lo), n_mine = (int)len;
-        for (int e = b + 1; e < b + n_mine; e++) insert_sorted_shared(s_frag, b, e, s_frag[e]);
-        if (c < n_cells) nuniq[c] = count_unique_shared(s_frag, b, n_mine);
+        for (int e = threadIdx.x; e < n; e += kSortCells) {
+            const int cl = S.cell[e];
+            const int bb = S.beg[cl], m = S.len[cl];
+            const Frag x = S.frag[e];
+            const uint32_t o = (uint32_t)(x.key >> 32);
+            int rank = 0, dup = 0;
+            for (int f = 0; f < m; f++) {
+                const uint64_t k2 = S.frag[bb + f].key;
+                rank += k2 < x.key;
+                dup += (k2 < x.key) && ((uint32_t)(k2 >> 32) == o);
+            }
+            frag[lo + bb + rank] = x;
+            if (!dup) atomicAdd(&S.uniq[cl], 1);  // the first fragment of its (input, output) pair
+        }
         __syncthreads();
-        for (int e = threadIdx.x; e < n; e += kSortCells) frag[lo + e] = s_frag[e];
+        if (c < n_cells) nuniq[c] = S.uniq[threadIdx.x];
         return;
     }
     sort_buckets_global(frag, beg, end, c < n_cells, nuniq, c);
 }
 
-// Sharded builds: gather the band's buckets from the W source chunks, then sort as above.  Every source's
-// share of the CTA's 128 cells is ONE contiguous range of its chunk: the CTA copies the W ranges into a staging
-// area with 16-byte asynchronous copies (all in flight together -- they may cross NVLink), then every thread
-// inserts its own pieces into its bucket.  Dynamic shared memory: stage + buckets (Frag[kSortCap] each).
-constexpr size_t kGatherSmem = (size_t)kSortCap * sizeof(Frag) * 2;
-
+// Sharded builds: gather the band's buckets from the W source chunks and rank-sort them.  Every source's share
+// of the CTA's 128 cells is ONE contiguous range of its chunk: the CTA copies the W ranges into the stage with
+// 16-byte asynchronous copies (all in flight together -- they may cross NVLink); a bucket is then the union of
+// its W pieces in the stage.
 __global__ void __launch_bounds__(kSortCells)
 k_bucket_gather_sort(const __grid_constant__ GatherSrc G, int64_t n_cells, Frag* __restrict__ frag,
                      int32_t* __restrict__ nuniq)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    Frag* s_stage = reinterpret_cast<Frag*>(smem_raw);
-    Frag* s_frag = s_stage + kSortCap;
-    __shared__ int s_long;
-    __shared__ int s_base[kMaxSrc + 1];
+    SortSmem& S = *reinterpret_cast<SortSmem*>(smem_raw);
     const int W = G.W;
     const int64_t c0 = (int64_t)blockIdx.x * kSortCells;
     const int64_t c1 = min(c0 + (int64_t)kSortCells, n_cells);
@@ -660,53 +666,73 @@ k_bucket_gather_sort(const __grid_constant__ GatherSrc G, int64_t n_cells, Frag*
     }
     const int64_t len = end - beg;
     const int64_t lo = G.dst_off[c0 * W], hi = G.dst_off[c1 * W];
-    if (threadIdx.x == 0) s_long = 0;
-    if (threadIdx.x <= W) {
-        // s_base[s] = fragments of the sources before s inside this CTA's cells
-        int acc = 0;
-        for (int s = 0; s < (int)threadIdx.x; s++)
-            acc += (int)min(G.src_off[(int64_t)s * G.Cb + c1] - G.src_off[(int64_t)s * G.Cb + c0], (int64_t)kSortCap + 1);
-        s_base[threadIdx.x] = acc;
+    if (threadIdx.x == 0) S.is_long = 0;
+    if (threadIdx.x < W)  // fragments of source s inside this CTA's cells
+        S.base[threadIdx.x + 1] = (int)min(G.src_off[(int64_t)threadIdx.x * G.Cb + c1] -
+                                           G.src_off[(int64_t)threadIdx.x * G.Cb + c0], (int64_t)kSortCap + 1);
+    // this cell's pieces: count and first fragment (relative to the CTA's first cell) per source
+    int p_cnt[kMaxSrc], p_off[kMaxSrc];
+#pragma unroll
+    for (int s = 0; s < kMaxSrc; s++) {
+        p_cnt[s] = 0;
+        p_off[s] = 0;
+        if (s < W && c < n_cells) {
+            p_cnt[s] = G.cntT[c * W + s];
+            p_off[s] = (int)min(G.src_off[(int64_t)s * G.Cb + c] - G.src_off[(int64_t)s * G.Cb + c0], (int64_t)kSortCap + 1);
+        }
     }
     __syncthreads();
-    if (len > 64) s_long = 1;
+    if (len > 64) S.is_long = 1;
+    if (threadIdx.x == 0) {  // base[s] = fragments of the sources before s
+        int acc = 0;
+        S.base[0] = 0;
+        for (int s = 1; s <= W; s++) {
+            acc = min(acc + S.base[s], kSortCap + 1);
+            S.base[s] = acc;
+        }
+    }
     __syncthreads();
-    if (hi - lo <= kSortCap && !s_long) {
+    if (hi - lo <= kSortCap && !S.is_long) {
         const int n = (int)(hi - lo);
         for (int s = 0; s < W; s++) {
             const Frag* src = G.src[s] + G.src_off[(int64_t)s * G.Cb + c0];
-            const int ns = s_base[s + 1] - s_base[s];
-            for (int e = threadIdx.x; e < ns; e += kSortCells) cp_async_frag(&s_stage[s_base[s] + e], src + e);
+            const int ns = S.base[s + 1] - S.base[s];
+            for (int e = threadIdx.x; e < ns; e += kSortCells) cp_async_frag(&S.frag[S.base[s] + e], src + e);
         }
-        const int b = (int)(beg - lo), n_mine = (int)len;
-        // per-source position of this cell's pieces in the stage, while the copies fly
-        int at[kMaxSrc], cnt[kMaxSrc];
-        if (c < n_cells) {
+        // while the copies fly: where the pieces of this thread's cell land in the stage
+        const int b = (int)(beg - lo);
+        S.beg[threadIdx.x] = b;
+        S.len[threadIdx.x] = (int)len;
+        S.uniq[threadIdx.x] = 0;
+        {
+            int k = b;
 #pragma unroll
             for (int s = 0; s < kMaxSrc; s++) {
-                if (s < W) {
-                    cnt[s] = G.cntT[c * W + s];
-                    at[s] = s_base[s] + (int)(G.src_off[(int64_t)s * G.Cb + c] - G.src_off[(int64_t)s * G.Cb + c0]);
+                const int at = S.base[s < W ? s : 0] + p_off[s];
+                for (int e = 0; e < p_cnt[s]; e++) {
+                    S.cell[at + e] = (uint16_t)threadIdx.x;
+                    S.pos[k++] = (uint16_t)(at + e);
                 }
             }
         }
         cp_async_wait_all();
         __syncthreads();
-        if (c < n_cells) {
-            int w = b;
-#pragma unroll
-            for (int s = 0; s < kMaxSrc; s++) {
-                if (s < W) {
-                    for (int e = 0; e < cnt[s]; e++) {
-                        insert_sorted_shared(s_frag, b, w, s_stage[at[s] + e]);
-                        w++;
-                    }
-                }
+        for (int e = threadIdx.x; e < n; e += kSortCells) {
+            const int cl = S.cell[e];
+            const int bb = S.beg[cl], m = S.len[cl];
+            const Frag x = S.frag[e];
+            const uint32_t o = (uint32_t)(x.key >> 32);
+            int rank = 0, dup = 0;
+            for (int f = 0; f < m; f++) {
+                const uint64_t k2 = S.frag[S.pos[bb + f]].key;
+                rank += k2 < x.key;
+                dup += (k2 < x.key) && ((uint32_t)(k2 >> 32) == o);
             }
-            nuniq[c] = count_unique_shared(s_frag, b, n_mine);
+            frag[lo + bb + rank] = x;
+            if (!dup) atomicAdd(&S.uniq[cl], 1);
         }
         __syncthreads();
-        for (int e = threadIdx.x; e < n; e += kSortCells) frag[lo + e] = s_frag[e];
+        if (c < n_cells) nuniq[c] = S.uniq[threadIdx.x];
         return;
     }
     // ---- global-memory path ----
@@ -855,6 +881,14 @@ static PassParams make_pass(const Layout& l, int p, const double* xin, const dou
     return P;
 }
 
+// the sort kernels use more than the 48 KB of shared memory a kernel gets by default (per device, idempotent)
+static int sort_smem_opt_in()
+{
+    RG_CUDA(cudaFuncSetAttribute(k_bucket_sort, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SortSmem)));
+    RG_CUDA(cudaFuncSetAttribute(k_bucket_gather_sort, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SortSmem)));
+    return RG_OK;
+}
+
 static Pass4 make_pass4(const Layout& l, const double* xin, const double* yin, const double* xout, const double* yout,
                         int64_t cell_lo, int64_t cell_hi, int part_rank, int part_world)
 {
@@ -999,7 +1033,10 @@ extern "C" int rg_build2d_fill(int device, void* stream,
                                                                          l.area_in, w_in, l.flags);
         RG_LAUNCH_CHECK("k_walk_emit");
     }
-    k_bucket_sort<<<(unsigned)ceil_div(l.Ci, kSortCells), kSortCells, 0, st>>>(l.boff, l.Ci, (Frag*)frags, l.nuniq);
+    rc = sort_smem_opt_in();
+    if (rc) return rc;
+    k_bucket_sort<<<(unsigned)ceil_div(l.Ci, kSortCells), kSortCells, sizeof(SortSmem), st>>>(l.boff, l.Ci, (Frag*)frags,
+                                                                                           l.nuniq);
     RG_LAUNCH_CHECK("k_bucket_sort");
     rc = exclusive_scan_i32_i64(st, l.nuniq, l.colptr, l.Ci, l.scan_scratch);
     if (rc) return rc;
@@ -1207,11 +1244,8 @@ extern "C" int rg_build2d_merge(int device, void* stream, int64_t n_cells, int n
     cudaStream_t st = (cudaStream_t)stream;
     *nnz_host = 0;
     if (n_cells == 0) return RG_OK;
-    static bool smem_set = false;  // idempotent attribute; a race only repeats the call
-    if (!smem_set) {
-        RG_CUDA(cudaFuncSetAttribute(k_bucket_gather_sort, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGatherSmem));
-        smem_set = true;
-    }
+    int rc0 = sort_smem_opt_in();
+    if (rc0) return rc0;
     const int64_t n = n_cells * n_src;
     k_merge_transpose<<<(unsigned)ceil_div(n, 256), 256, 0, st>>>(counts, m.cntT, n_cells, n_src);
     RG_LAUNCH_CHECK("k_merge_transpose");
@@ -1227,7 +1261,7 @@ extern "C" int rg_build2d_merge(int device, void* stream, int64_t n_cells, int n
         G.src[s] = (const Frag*)src_chunks_host[s] - before;  // src_off[s * Cb] == fragments of the sources before s
         before += src_sizes_host[s];
     }
-    k_bucket_gather_sort<<<(unsigned)ceil_div(n_cells, kSortCells), kSortCells, kGatherSmem, st>>>(
+    k_bucket_gather_sort<<<(unsigned)ceil_div(n_cells, kSortCells), kSortCells, sizeof(SortSmem), st>>>(
         G, n_cells, (Frag*)frags, m.nuniq);
     RG_LAUNCH_CHECK("k_bucket_gather_sort");
     rc = exclusive_scan_i32_i64(st, m.nuniq, m.colptr, n_cells, m.scan_scratch);
