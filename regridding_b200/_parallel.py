@@ -70,8 +70,9 @@ def allgather_concat(tensors, group=None):
     packed = torch.empty((k, most), dtype=torch.int64, device=dev)
     for q, t in enumerate(ts):
         packed[q, :t.shape[0]] = t.contiguous().view(torch.int64)
-    gathered = torch.empty((W, k, most), dtype=torch.int64, device=dev)
-    dist.all_gather_into_tensor(gathered, packed, group=group)
+    flat = torch.empty(W * k * most, dtype=torch.int64, device=dev)
+    dist.all_gather_into_tensor(flat, packed.view(-1), group=group)
+    gathered = flat.view(W, k, most)
     outs = [torch.cat([gathered[r, q, :counts_h[r]] for r in range(W)]).view(t.dtype) for q, t in enumerate(ts)]
     return outs[0] if single else outs
 
