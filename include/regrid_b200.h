@@ -182,6 +182,29 @@ int rg_find_indices_2d(int device, void* stream, int64_t nx, int64_t ny,
                        void* workspace, size_t workspace_bytes);
 
 /* ------------------------------------------------------------------------------
+ * 2D multilinear (bilinear) weights on a curvilinear vertex grid + their application
+ * (BASELINE config 5).  The reference stops at 1D (regridding/_weights/_weights_multilinear.py:128-131
+ * raises for 2D); this extends its 1D rule (wml.py:105-119, 185-202) to two axes: values live on the
+ * VERTICES, an output point takes the four vertices of its containing cell (cell_flat from
+ * rg_find_indices_2d, `fill` = outside) with weights (1-u)(1-v), (1-u)v, u(1-v), uv, (u, v) solving the
+ * cell's bilinear map.  bounds_mode: 0 = extrapolate (bilinear map of the nearest border cell continued),
+ * 1 = nan (weights of outside points are NaN), 2 = raise (as nan; the caller raises when *n_outside_dev > 0).
+ * idx4: int64[n_points][4] flat vertex indices in ascending order; w4: double[n_points][4]; both 32-byte
+ * aligned.  n_outside_dev: device int32 counter (stream-ordered).
+ * rg_ell4_apply: values_out[f][p] = sum_k w4[p][k] * values_in[f][idx4[p][k]] (k ascending, separately
+ * rounded multiply and add from +0.0 -- the accumulation order of
+ * regridding/_regrid/_regrid_from_weights.py:179-182 on the sorted triplets).
+ * ------------------------------------------------------------------------------ */
+int rg_multilinear2d_weights(int device, void* stream, int64_t nx, int64_t ny,
+                             const double* x, const double* y,
+                             int64_t n_points, const double* px, const double* py,
+                             const int64_t* cell_flat, int64_t fill, int bounds_mode,
+                             int64_t* idx4, double* w4, int32_t* n_outside_dev);
+
+int rg_ell4_apply(int device, void* stream, int64_t n_frames, int64_t n_in, int64_t n_points,
+                  const int64_t* idx4, const double* w4, const double* values_in, double* values_out);
+
+/* ------------------------------------------------------------------------------
  * shared-weights apply
  * replaces: _regrid_from_weights(weights, values_input, values_output)
  *           regridding/_regrid/_regrid_from_weights.py:165-182

@@ -221,3 +221,47 @@ def transpose_weights_conservative_values(indices_input, indices_output, values,
     if weights_input is not None:
         v = v / np.square(weights_input[indices_input])
     return v * volume_input[indices_input] / volume_output[indices_output]
+
+
+def multilinear2d_weights(x, y, px, py, cells_flat):
+    """NumPy restatement of the 2D multilinear (bilinear) rule (test infrastructure; the reference has no 2D
+    multilinear, regridding/_weights/_weights_multilinear.py:128-131 raises -- this extends its 1D rule,
+    wml.py:105-119, 185-202): for every point, (u, v) of the bilinear map of its containing cell (flat cell
+    index ``cells_flat``, u along axis 0) by Newton from (1/2, 1/2), and the weights
+    ``(1-u)(1-v), (1-u)v, u(1-v), uv`` at the flat vertex indices ``a, a+1, a+ny, a+ny+1`` (ascending).
+    Returns ``(idx4 int64 [P, 4], w4 float64 [P, 4])``.  Points with a negative cell index get NaN weights."""
+    x, y = _f64(x), _f64(y)
+    px, py = _f64(px).reshape(-1), _f64(py).reshape(-1)
+    cells = np.asarray(cells_flat, dtype=np.int64).reshape(-1)
+    nx, ny = x.shape
+    ncy = ny - 1
+    ok = cells >= 0
+    c = np.where(ok, cells, 0)
+    ci, cj = c // ncy, c % ncy
+    a = ci * ny + cj
+    xf, yf = x.reshape(-1), y.reshape(-1)
+    x00, x01, x10, x11 = xf[a], xf[a + 1], xf[a + ny], xf[a + ny + 1]
+    y00, y01, y10, y11 = yf[a], yf[a + 1], yf[a + ny], yf[a + ny + 1]
+    ax, bx, cx = x10 - x00, x01 - x00, ((x00 - x10) - x01) + x11
+    ay, by, cy = y10 - y00, y01 - y00, ((y00 - y10) - y01) + y11
+    u = np.full(px.shape, 0.5)
+    v = np.full(px.shape, 0.5)
+    active = np.ones(px.shape, dtype=bool)
+    with np.errstate(all="ignore"):
+        for _ in range(24):
+            ex = (((x00 + u * ax) + v * bx) + (u * v) * cx) - px
+            ey = (((y00 + u * ay) + v * by) + (u * v) * cy) - py
+            xu, xv = ax + v * cx, bx + u * cx
+            yu, yv = ay + v * cy, by + u * cy
+            det = xu * yv - xv * yu
+            du = (yv * ex - xv * ey) / det
+            dv = (xu * ey - yu * ex) / det
+            u = np.where(active, u - du, u)
+            v = np.where(active, v - dv, v)
+            active &= ~((np.abs(du) < 1e-14) & (np.abs(dv) < 1e-14))
+            if not active.any():
+                break
+    w4 = np.stack(((1 - u) * (1 - v), (1 - u) * v, u * (1 - v), u * v), axis=1)
+    w4[~ok] = np.nan
+    idx4 = np.stack((a, a + 1, a + ny, a + ny + 1), axis=1)
+    return idx4, w4

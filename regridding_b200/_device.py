@@ -567,3 +567,45 @@ def find_indices_2d(x: torch.Tensor, y: torch.Tensor, px: torch.Tensor, py: torc
                                         px.data_ptr(), py.data_ptr(), int(fill_value), out.data_ptr(),
                                         ws.data_ptr(), ws.numel()), "rg_find_indices_2d")
     return out
+
+
+BOUNDS_MODES = {"extrapolate": 0, "nan": 1, "raise": 2}
+
+
+def multilinear2d_weights(x: torch.Tensor, y: torch.Tensor, px: torch.Tensor, py: torch.Tensor,
+                          bounds: str = "extrapolate") -> tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+    """Bilinear weights of the points (px, py) on the curvilinear VERTEX grid (x, y): cell location
+    (``rg_find_indices_2d``) + inverse bilinear map (``rg_multilinear2d_weights``).
+    Returns ``idx4`` int64 [P, 4] (flat vertex indices, ascending), ``w4`` float64 [P, 4] and the device
+    counter of points outside the grid (int32 [1]; reading it synchronises)."""
+    L = _lib.load()
+    if bounds not in BOUNDS_MODES:
+        raise ValueError(f"Unrecognized {bounds=}, expected one of ('extrapolate', 'nan', 'raise').")
+    device = x.device
+    P = int(px.numel())
+    px, py = px.reshape(-1).contiguous(), py.reshape(-1).contiguous()
+    cell = find_indices_2d(x, y, px, py, -1)
+    idx4 = torch.empty((max(P, 1), 4), dtype=I64, device=device)[:P]
+    w4 = torch.empty((max(P, 1), 4), dtype=F64, device=device)[:P]
+    n_out = torch.zeros(1, dtype=I32, device=device)
+    nx, ny = x.shape
+    with torch.cuda.device(device):
+        _lib.check(L.rg_multilinear2d_weights(device.index, _stream(device), nx, ny, x.data_ptr(), y.data_ptr(), P,
+                                              px.data_ptr(), py.data_ptr(), cell.data_ptr(), -1, BOUNDS_MODES[bounds],
+                                              idx4.data_ptr(), w4.data_ptr(), n_out.data_ptr()),
+                   "rg_multilinear2d_weights")
+    return idx4, w4, n_out
+
+
+def ell4_apply(idx4: torch.Tensor, w4: torch.Tensor, values_in: torch.Tensor, out: torch.Tensor | None = None) -> torch.Tensor:
+    """values_in (F, n_vertices) -> (F, P): four weighted vertices per output point (``rg_ell4_apply``)."""
+    L = _lib.load()
+    device = values_in.device
+    F, n_in = values_in.shape
+    P = int(idx4.shape[0])
+    if out is None:
+        out = torch.empty((F, P), dtype=F64, device=device)
+    with torch.cuda.device(device):
+        _lib.check(L.rg_ell4_apply(device.index, _stream(device), F, n_in, P, idx4.data_ptr(), w4.data_ptr(),
+                                   values_in.data_ptr(), out.data_ptr()), "rg_ell4_apply")
+    return out

@@ -42,6 +42,8 @@ SIGNATURES: dict[str, list] = {
     "rg_grid_area": [_int, _vp, _i64, _i64, _vp, _vp, _vp],
     "rg_find_indices_2d_workspace_bytes": [_i64, _i64, _i64, _p_sz],
     "rg_find_indices_2d": [_int, _vp, _i64, _i64, _vp, _vp, _i64, _vp, _vp, _i64, _vp, _vp, _sz],
+    "rg_multilinear2d_weights": [_int, _vp, _i64, _i64, _vp, _vp, _i64, _vp, _vp, _vp, _i64, _int, _vp, _vp, _vp],
+    "rg_ell4_apply": [_int, _vp, _i64, _i64, _i64, _vp, _vp, _vp, _vp],
     "rg_csr_workspace_bytes": [_i64, _i64, _p_sz],
     "rg_csr_from_coo": [_int, _vp, _i64, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz],
     "rg_apply_csr": [_int, _vp, _i64, _i64, _i64, _vp, _vp, _vp, _vp, _vp],

@@ -219,6 +219,10 @@ def regrid(
             isinstance(values_input, torch.Tensor) and values_input.is_cuda):
         return _regrid_conservative_1d_fused(coordinates_input, coordinates_output, values_input, values_output,
                                              axis_input, axis_output, perturb, seed)
+    if method == "multilinear" and n_coordinates == 2 and all(
+            np.ndim(c) == 2 for c in (*coordinates_input, *coordinates_output)):
+        return _regrid_multilinear_2d_fused(coordinates_input, coordinates_output, values_input, values_output,
+                                            axis_input, axis_output, bounds)
     if method == "conservative":
         elements, shape_in, shape_out, shape_orth = _weights_conservative_device(
             coordinates_input, coordinates_output, axis_input, axis_output, None, perturb, seed)
@@ -296,3 +300,64 @@ def _regrid_conservative_1d_fused(coordinates_input, coordinates_output, values_
     if unit is None:
         return result
     return result << unit
+
+
+def _regrid_multilinear_2d_fused(coordinates_input, coordinates_output, values_input, values_output,
+                                 axis_input, axis_output, bounds):
+    """``regrid(method="multilinear")`` between two 2D grids shared by every orthogonal slice of the values
+    (BASELINE config 5): cell location, bilinear weights and the four-point gather all stay on the GPU and no
+    triplets are materialised (``rg_find_indices_2d`` -> ``rg_multilinear2d_weights`` -> ``rg_ell4_apply``).
+    Same numbers as ``weights(method="multilinear")`` + ``regrid_from_weights`` (same accumulation order)."""
+    if bounds not in ("extrapolate", "nan", "raise"):
+        raise ValueError(f"Unrecognized {bounds=}, expected one of ('extrapolate', 'nan', 'raise').")
+    unit = getattr(values_input, "unit", None)
+    if unit is not None:
+        values_input = values_input.value
+    (coords_in, coords_out, axis_in, axis_out, shape_in, shape_out, _orth) = \
+        _util.normalize_input_output_coordinates(coordinates_input, coordinates_output, axis_input, axis_output)
+    device = _device.cuda_device()
+    x, y = (_device.to_device(np.asarray(getattr(c, "value", c), dtype=np.float64), device) for c in coords_in)
+    px, py = (_device.to_device(np.asarray(getattr(c, "value", c), dtype=np.float64), device) for c in coords_out)
+    grid_in, grid_out = tuple(x.shape), tuple(px.shape)
+    on_device = isinstance(values_input, torch.Tensor) and values_input.is_cuda
+    vals = values_input if on_device else np.asarray(values_input, dtype=np.float64)
+    nd = vals.ndim
+    a_in = tuple(sorted(a % nd for a in (axis_input if axis_input is not None else (-2, -1))))
+    a_out = tuple(sorted(a % nd for a in (axis_output if axis_output is not None else (-2, -1))))
+    if tuple(vals.shape[a] for a in a_in) != grid_in:
+        raise ValueError(f"values_input has shape {tuple(vals.shape)} along {a_in=}, expected the vertex grid {grid_in}")
+    idx4, w4, n_outside = _device.multilinear2d_weights(x, y, px, py, bounds)
+    if bounds == "raise":
+        n_bad = int(n_outside.item())
+        if n_bad:
+            raise ValueError(f"{n_bad} of the output points fall outside the input grid, and {bounds=}.")
+    last = (-2, -1)
+    if on_device:
+        moved = torch.movedim(vals.to(torch.float64), a_in, last)
+        orth = tuple(moved.shape[:-2])
+        F = int(np.prod(orth, dtype=np.int64))
+        res = _device.ell4_apply(idx4, w4, moved.reshape(F, -1).contiguous())
+        res = torch.movedim(res.reshape(*orth, *grid_out), last, a_out)
+        if values_output is not None:
+            values_output.copy_(res)
+            return values_output
+        return res
+    moved = np.moveaxis(vals, a_in, last)
+    orth = moved.shape[:-2]
+    F = int(np.prod(orth, dtype=np.int64))
+    flat = np.ascontiguousarray(moved.reshape(F, -1))
+    out_h = np.empty((F, grid_out[0] * grid_out[1]), dtype=float)
+    per = max(1, min(F, (1 << 30) // (8 * (flat.shape[1] + out_h.shape[1]))))
+    for f in range(0, F, per):
+        e = min(F, f + per)
+        res = _device.ell4_apply(idx4, w4, _device.to_device(flat[f:e], device))
+        torch.from_numpy(out_h[f:e]).copy_(res)
+    full_out = np.moveaxis(out_h.reshape(*orth, *grid_out), last, a_out)
+    if values_output is not None:
+        if values_output.shape != full_out.shape:
+            raise ValueError(f"{values_output.shape=} should be equal to {full_out.shape}")
+        values_output[...] = full_out
+        full_out = values_output
+    if unit is None:
+        return full_out
+    return full_out << unit

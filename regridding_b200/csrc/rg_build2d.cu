@@ -882,10 +882,13 @@ static PassParams make_pass(const Layout& l, int p, const double* xin, const dou
 }
 
 // the sort kernels use more than the 48 KB of shared memory a kernel gets by default (per device, idempotent)
-static int sort_smem_opt_in()
+static int sort_smem_opt_in(int device)
 {
+    static bool done[64] = {};  // per device; the attribute is idempotent, so a race only repeats the calls
+    if (device >= 0 && device < 64 && done[device]) return RG_OK;
     RG_CUDA(cudaFuncSetAttribute(k_bucket_sort, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SortSmem)));
     RG_CUDA(cudaFuncSetAttribute(k_bucket_gather_sort, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SortSmem)));
+    if (device >= 0 && device < 64) done[device] = true;
     return RG_OK;
 }
 
@@ -1033,7 +1036,7 @@ extern "C" int rg_build2d_fill(int device, void* stream,
                                                                          l.area_in, w_in, l.flags);
         RG_LAUNCH_CHECK("k_walk_emit");
     }
-    rc = sort_smem_opt_in();
+    rc = sort_smem_opt_in(device);
     if (rc) return rc;
     k_bucket_sort<<<(unsigned)ceil_div(l.Ci, kSortCells), kSortCells, sizeof(SortSmem), st>>>(l.boff, l.Ci, (Frag*)frags,
                                                                                            l.nuniq);
@@ -1244,7 +1247,7 @@ extern "C" int rg_build2d_merge(int device, void* stream, int64_t n_cells, int n
     cudaStream_t st = (cudaStream_t)stream;
     *nnz_host = 0;
     if (n_cells == 0) return RG_OK;
-    int rc0 = sort_smem_opt_in();
+    int rc0 = sort_smem_opt_in(device);
     if (rc0) return rc0;
     const int64_t n = n_cells * n_src;
     k_merge_transpose<<<(unsigned)ceil_div(n, 256), 256, 0, st>>>(counts, m.cntT, n_cells, n_src);

@@ -76,7 +76,23 @@ for name, scale in (("inside_0.7_bbox", 0.7), ("full_bbox", 1.0)):
     inside = float((idx >= 0).double().mean())
     out["config5_" + name] = {"points": m * m, "ms": ms, "Mpoints_per_s": m * m / ms / 1e3, "fraction_inside": inside,
                               "algorithmic_GBps": (16 + 8) * m * m / ms / 1e6}
-    del px, py, idx
+    del idx
+    # ... + bilinear weights (4 per point) + the four-point gather of one frame of vertex values
+    vals5 = torch.rand((1, 4096 * 4096), dtype=torch.float64, device=dev)
+    pxf, pyf = px.reshape(-1), py.reshape(-1)
+
+    def ml():
+        idx4, w4, _ = _device.multilinear2d_weights(X, Y, pxf, pyf, "nan")
+        return _device.ell4_apply(idx4, w4, vals5)
+    ms_ml, res = timed(ml, reps=2, warm=1)
+    idx4, w4, _ = _device.multilinear2d_weights(X, Y, pxf, pyf, "nan")
+    ms_ap, _ = timed(lambda: _device.ell4_apply(idx4, w4, vals5), reps=3, warm=1)
+    out["config5_" + name].update({
+        "multilinear_regrid_ms_locate_weights_apply": ms_ml, "multilinear_Mpoints_per_s": m * m / ms_ml / 1e3,
+        "apply_only_ms_per_frame": ms_ap,
+        "apply_algorithmic_GBps": (64 + 8) * m * m / ms_ap / 1e6,  # idx4 + w4 read, one value written; gathers hit L2
+        "nan_fraction": float(torch.isnan(res).double().mean())})
+    del px, py, pxf, pyf, idx4, w4, res, vals5
 print(json.dumps(out, indent=1))
 if len(sys.argv) > 1:
     pathlib.Path(sys.argv[1]).write_text(json.dumps(out, indent=1))
