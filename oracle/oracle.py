@@ -247,6 +247,7 @@ def multilinear2d_weights(x, y, px, py, cells_flat):
     u = np.full(px.shape, 0.5)
     v = np.full(px.shape, 0.5)
     active = np.ones(px.shape, dtype=bool)
+    prev = np.full(px.shape, np.inf)
     with np.errstate(all="ignore"):
         for _ in range(24):
             ex = (((x00 + u * ax) + v * bx) + (u * v) * cx) - px
@@ -258,7 +259,11 @@ def multilinear2d_weights(x, y, px, py, cells_flat):
             dv = (xu * ey - yu * ex) / det
             u = np.where(active, u - du, u)
             v = np.where(active, v - dv, v)
-            active &= ~((np.abs(du) < 1e-14) & (np.abs(dv) < 1e-14))
+            # converged, or stagnating at the rounding noise of the residual
+            step = np.fmax(np.abs(du), np.abs(dv))
+            stop = (step < 1e-14) | ((step < 1e-6) & (step >= prev))
+            prev = np.where(active, step, prev)
+            active &= ~stop
             if not active.any():
                 break
     w4 = np.stack(((1 - u) * (1 - v), (1 - u) * v, u * (1 - v), u * v), axis=1)

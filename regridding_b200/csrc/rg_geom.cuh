@@ -142,6 +142,15 @@ __device__ inline int locate_newton(const GridView& g, double px, double py, dou
     if (!converged) return kLocUnknown;
     int ic = (int)floor(fmin(fmax(i, -2.0), (double)ncx + 2.0));
     int jc = (int)floor(fmin(fmax(j, -2.0), (double)ncy + 2.0));
+    // Fast path: the solution sits well inside cell (ic, jc) in index space (the Newton step was < 1e-9) and the
+    // exact containment test agrees.  In a mesh without overlapping cells no other cell contains the point then,
+    // so the lowest-index scan of the 3x3 neighbourhood below would return the same cell.
+    if (ic >= 0 && jc >= 0 && ic < ncx && jc < ncy) {
+        const double fu = i - ic, fv = j - jc;
+        constexpr double kMargin = 1e-6;
+        if (fu > kMargin && fu < 1.0 - kMargin && fv > kMargin && fv < 1.0 - kMargin && cell_contains(g, ic, jc, px, py))
+            return ic * ncy + jc;
+    }
     int found = locate_local(g, px, py, min(max(ic, 0), ncx - 1), min(max(jc, 0), ncy - 1));
     if (found >= 0) return found;
     if (i < 0.0 || j < 0.0 || i > (double)ncx || j > (double)ncy) return kLocOutside;

@@ -97,6 +97,7 @@ __global__ void k_bilinear_weights(GridView g, int64_t n, const double* __restri
         const double y00 = g.y[a], y01 = g.y[a + 1], y10 = g.y[a + g.ny], y11 = g.y[a + g.ny + 1];
         const double ax = dsub(x10, x00), bx = dsub(x01, x00), cx = dadd(dsub(dsub(x00, x10), x01), x11);
         const double ay = dsub(y10, y00), by = dsub(y01, y00), cy = dadd(dsub(dsub(y00, y10), y01), y11);
+        double prev = INFINITY;
         for (int it = 0; it < 24; it++) {
             const double ex = dsub(dadd(dadd(dadd(x00, dmul(u, ax)), dmul(v, bx)), dmul(dmul(u, v), cx)), x);
             const double ey = dsub(dadd(dadd(dadd(y00, dmul(u, ay)), dmul(v, by)), dmul(dmul(u, v), cy)), y);
@@ -111,7 +112,10 @@ __global__ void k_bilinear_weights(GridView g, int64_t n, const double* __restri
             const double dv = ddiv(dsub(dmul(xu, ey), dmul(yu, ex)), det);
             u = dsub(u, du);
             v = dsub(v, dv);
-            if (fabs(du) < 1e-14 && fabs(dv) < 1e-14) break;
+            // converged, or stagnating at the rounding noise of the residual (~ eps * |x| / cell size)
+            const double step = fmax(fabs(du), fabs(dv));
+            if (step < 1e-14 || (step < 1e-6 && step >= prev)) break;
+            prev = step;
         }
     }
     double w00, w01, w10, w11;
