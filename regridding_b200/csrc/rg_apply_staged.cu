@@ -52,6 +52,9 @@
 #ifndef RG_CP_MODE
 #define RG_CP_MODE "cg.shared.global"   // footprint copies: L2 -> shared memory, bypassing L1
 #endif
+#ifndef RG_WARP_REFILL
+#define RG_WARP_REFILL 1   // a warp refills its own frame row right after writing it out (no third block barrier)
+#endif
 #ifndef RG_TAIL_OUT
 #define RG_TAIL_OUT 1   // stage the outputs in the unused tail of the footprint buffer (one barrier per sub-block)
 #endif
@@ -681,7 +684,11 @@ k_apply_staged(int64_t n_frames, int64_t w_in, int64_t n_in, int64_t h_out, int6
             }
         }
         if (out_off == 0) {
-            __syncthreads();  // outputs consumed: the buffer may be refilled
+            // Frame row w of this buffer holds the outputs of frame w, which only warp w reads (just above), and warp
+            // w is also the one that refills row w: program order inside the warp is enough, no block barrier.  (The
+            // loads above have completed -- their values were stored -- before the asynchronous copies are issued;
+            // nobody else touches the buffer before the "filled" mbarrier of sub-block s + 2.)
+            if (!RG_WARP_REFILL) __syncthreads();  // outputs consumed: the buffer may be refilled
             if (s + RG_NBUF < nsub) prefetch(f0 + RG_NBUF * kT, buf);
         }
     }

@@ -497,7 +497,8 @@ k_walk_emit(const __grid_constant__ Pass4 Q, const int64_t* __restrict__ boff, i
 // memory with coalesced loads, every thread insertion-sorts its own bucket there (buckets hold ~14 fragments),
 // and the range is written back coalesced.  CTAs whose range does not fit (or that hold a bucket longer than 64)
 // sort in global memory: one lane per bucket, the whole warp (odd-even transposition) for the long ones.
-constexpr int kSortCells = 128;
+constexpr int kSortCells = 128;   // buckets per CTA
+constexpr int kSortThreads = 256; // threads per CTA: one per bucket for the bookkeeping, all of them for the per-fragment phases
 constexpr int kSortCap = 3000;  // fragments staged per CTA (~56 KB of shared memory with the maps: 4 CTAs per SM)
 constexpr int kMaxSrc = 16;     // source ranks of a sharded build
 
@@ -596,15 +597,16 @@ struct SortSmem {
 // Rank sort, one thread per FRAGMENT: keys are unique inside a bucket, so the final slot of a fragment is the
 // number of smaller keys in its bucket.  No dependent stores, no divergence between the lanes of a bucket (they
 // read the same keys: shared-memory broadcasts), and the sorted records go straight to global memory.
-__global__ void __launch_bounds__(kSortCells)
+__global__ void __launch_bounds__(kSortThreads)
 k_bucket_sort(const int64_t* __restrict__ boff, int64_t n_cells, Frag* __restrict__ frag, int32_t* __restrict__ nuniq)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     SortSmem& S = *reinterpret_cast<SortSmem*>(smem_raw);
     const int64_t c0 = (int64_t)blockIdx.x * kSortCells;
+    const bool owner = threadIdx.x < kSortCells;  // this thread keeps the books of bucket c
     const int64_t c = c0 + threadIdx.x;
     int64_t beg = 0, end = 0;
-    if (c < n_cells) {
+    if (owner && c < n_cells) {
         beg = boff[c];
         end = boff[c + 1];
     }
@@ -616,15 +618,17 @@ k_bucket_sort(const int64_t* __restrict__ boff, int64_t n_cells, Frag* __restric
     __syncthreads();
     if (hi - lo <= kSortCap && !S.is_long) {
         const int n = (int)(hi - lo);
-        for (int e = threadIdx.x; e < n; e += kSortCells) cp_async_frag(&S.frag[e], frag + lo + e);
-        const int b = (int)(beg - lo), n_mine = (int)len;
-        S.beg[threadIdx.x] = b;
-        S.len[threadIdx.x] = n_mine;
-        S.uniq[threadIdx.x] = 0;
-        for (int e = b; e < b + n_mine; e++) S.cell[e] = (uint16_t)threadIdx.x;
+        for (int e = threadIdx.x; e < n; e += kSortThreads) cp_async_frag(&S.frag[e], frag + lo + e);
+        if (owner) {
+            const int b = (int)(beg - lo), n_mine = (int)len;
+            S.beg[threadIdx.x] = b;
+            S.len[threadIdx.x] = n_mine;
+            S.uniq[threadIdx.x] = 0;
+            for (int e = b; e < b + n_mine; e++) S.cell[e] = (uint16_t)threadIdx.x;
+        }
         cp_async_wait_all();
         __syncthreads();
-        for (int e = threadIdx.x; e < n; e += kSortCells) {
+        for (int e = threadIdx.x; e < n; e += kSortThreads) {
             const int cl = S.cell[e];
             const int bb = S.beg[cl], m = S.len[cl];
             const Frag x = S.frag[e];
@@ -639,17 +643,17 @@ k_bucket_sort(const int64_t* __restrict__ boff, int64_t n_cells, Frag* __restric
             if (!dup) atomicAdd(&S.uniq[cl], 1);  // the first fragment of its (input, output) pair
         }
         __syncthreads();
-        if (c < n_cells) nuniq[c] = S.uniq[threadIdx.x];
+        if (owner && c < n_cells) nuniq[c] = S.uniq[threadIdx.x];
         return;
     }
-    sort_buckets_global(frag, beg, end, c < n_cells, nuniq, c);
+    if (owner) sort_buckets_global(frag, beg, end, c < n_cells, nuniq, c);  // warps 0..3 are complete
 }
 
 // Sharded builds: gather the band's buckets from the W source chunks and rank-sort them.  Every source's share
 // of the CTA's 128 cells is ONE contiguous range of its chunk: the CTA copies the W ranges into the stage with
 // 16-byte asynchronous copies (all in flight together -- they may cross NVLink); a bucket is then the union of
 // its W pieces in the stage.
-__global__ void __launch_bounds__(kSortCells)
+__global__ void __launch_bounds__(kSortThreads)
 k_bucket_gather_sort(const __grid_constant__ GatherSrc G, int64_t n_cells, Frag* __restrict__ frag,
                      int32_t* __restrict__ nuniq)
 {
@@ -658,9 +662,10 @@ k_bucket_gather_sort(const __grid_constant__ GatherSrc G, int64_t n_cells, Frag*
     const int W = G.W;
     const int64_t c0 = (int64_t)blockIdx.x * kSortCells;
     const int64_t c1 = min(c0 + (int64_t)kSortCells, n_cells);
+    const bool owner = threadIdx.x < kSortCells;  // this thread keeps the books of bucket c
     const int64_t c = c0 + threadIdx.x;
     int64_t beg = 0, end = 0;
-    if (c < n_cells) {
+    if (owner && c < n_cells) {
         beg = G.dst_off[c * W];
         end = G.dst_off[(c + 1) * W];
     }
@@ -676,7 +681,7 @@ k_bucket_gather_sort(const __grid_constant__ GatherSrc G, int64_t n_cells, Frag*
     for (int s = 0; s < kMaxSrc; s++) {
         p_cnt[s] = 0;
         p_off[s] = 0;
-        if (s < W && c < n_cells) {
+        if (s < W && owner && c < n_cells) {
             p_cnt[s] = G.cntT[c * W + s];
             p_off[s] = (int)min(G.src_off[(int64_t)s * G.Cb + c] - G.src_off[(int64_t)s * G.Cb + c0], (int64_t)kSortCap + 1);
         }
@@ -697,14 +702,14 @@ k_bucket_gather_sort(const __grid_constant__ GatherSrc G, int64_t n_cells, Frag*
         for (int s = 0; s < W; s++) {
             const Frag* src = G.src[s] + G.src_off[(int64_t)s * G.Cb + c0];
             const int ns = S.base[s + 1] - S.base[s];
-            for (int e = threadIdx.x; e < ns; e += kSortCells) cp_async_frag(&S.frag[S.base[s] + e], src + e);
+            for (int e = threadIdx.x; e < ns; e += kSortThreads) cp_async_frag(&S.frag[S.base[s] + e], src + e);
         }
         // while the copies fly: where the pieces of this thread's cell land in the stage
-        const int b = (int)(beg - lo);
-        S.beg[threadIdx.x] = b;
-        S.len[threadIdx.x] = (int)len;
-        S.uniq[threadIdx.x] = 0;
-        {
+        if (owner) {
+            const int b = (int)(beg - lo);
+            S.beg[threadIdx.x] = b;
+            S.len[threadIdx.x] = (int)len;
+            S.uniq[threadIdx.x] = 0;
             int k = b;
 #pragma unroll
             for (int s = 0; s < kMaxSrc; s++) {
@@ -717,7 +722,7 @@ k_bucket_gather_sort(const __grid_constant__ GatherSrc G, int64_t n_cells, Frag*
         }
         cp_async_wait_all();
         __syncthreads();
-        for (int e = threadIdx.x; e < n; e += kSortCells) {
+        for (int e = threadIdx.x; e < n; e += kSortThreads) {
             const int cl = S.cell[e];
             const int bb = S.beg[cl], m = S.len[cl];
             const Frag x = S.frag[e];
@@ -732,10 +737,11 @@ k_bucket_gather_sort(const __grid_constant__ GatherSrc G, int64_t n_cells, Frag*
             if (!dup) atomicAdd(&S.uniq[cl], 1);
         }
         __syncthreads();
-        if (c < n_cells) nuniq[c] = S.uniq[threadIdx.x];
+        if (owner && c < n_cells) nuniq[c] = S.uniq[threadIdx.x];
         return;
     }
     // ---- global-memory path ----
+    if (!owner) return;  // warps 0..3 are complete
     if (c < n_cells) {
         int64_t w = beg;
         for (int s = 0; s < W; s++) {
@@ -1038,7 +1044,7 @@ extern "C" int rg_build2d_fill(int device, void* stream,
     }
     rc = sort_smem_opt_in(device);
     if (rc) return rc;
-    k_bucket_sort<<<(unsigned)ceil_div(l.Ci, kSortCells), kSortCells, sizeof(SortSmem), st>>>(l.boff, l.Ci, (Frag*)frags,
+    k_bucket_sort<<<(unsigned)ceil_div(l.Ci, kSortCells), kSortThreads, sizeof(SortSmem), st>>>(l.boff, l.Ci, (Frag*)frags,
                                                                                            l.nuniq);
     RG_LAUNCH_CHECK("k_bucket_sort");
     rc = exclusive_scan_i32_i64(st, l.nuniq, l.colptr, l.Ci, l.scan_scratch);
@@ -1264,7 +1270,7 @@ extern "C" int rg_build2d_merge(int device, void* stream, int64_t n_cells, int n
         G.src[s] = (const Frag*)src_chunks_host[s] - before;  // src_off[s * Cb] == fragments of the sources before s
         before += src_sizes_host[s];
     }
-    k_bucket_gather_sort<<<(unsigned)ceil_div(n_cells, kSortCells), kSortCells, sizeof(SortSmem), st>>>(
+    k_bucket_gather_sort<<<(unsigned)ceil_div(n_cells, kSortCells), kSortThreads, sizeof(SortSmem), st>>>(
         G, n_cells, (Frag*)frags, m.nuniq);
     RG_LAUNCH_CHECK("k_bucket_gather_sort");
     rc = exclusive_scan_i32_i64(st, m.nuniq, m.colptr, n_cells, m.scan_scratch);
