@@ -101,7 +101,11 @@ def regrid_from_weights(
     axis_input: None | int | Sequence[int] = None,
     axis_output: None | int | Sequence[int] = None,
 ):
-    """Drop-in for ``regridding.regrid_from_weights``."""
+    """Drop-in for ``regridding.regrid_from_weights``; ``weights`` may also be a ``PackedWeights``."""
+    from ._packed import PackedWeights
+
+    if isinstance(weights, PackedWeights):
+        weights = weights.to_reference()[0]
     on_device = isinstance(values_input, torch.Tensor) and values_input.is_cuda
     unit = getattr(values_input, "unit", None)
     if unit is not None:

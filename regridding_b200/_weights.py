@@ -21,7 +21,7 @@ import torch
 
 from . import _cache, _device, _util
 
-__all__ = ["weights"]
+__all__ = ["weights", "weights_packed"]
 
 
 def weights(
@@ -60,6 +60,38 @@ def weights(
             _cache.remember(triple, dw)
         result[k] = triple
     return result.reshape(shape_orth), shape_in, shape_out
+
+
+def weights_packed(
+    coordinates_input,
+    coordinates_output,
+    axis_input: None | int | Sequence[int] = None,
+    axis_output: None | int | Sequence[int] = None,
+    weights_input=None,
+    method: Literal["multilinear", "conservative"] = "multilinear",
+    bounds: Literal["extrapolate", "nan", "raise"] = "extrapolate",
+    perturb: None | bool = None,
+    seed: "None | int | np.random.Generator" = _util.SEED_DEFAULT,
+):
+    """Same arguments and same numbers as ``weights()``, returned as ``PackedWeights`` (four flat arrays instead
+    of one Python tuple per orthogonal slice; ``.to_reference()`` gives the reference layout, ``.save()`` /
+    ``PackedWeights.load()`` a memory-mappable file).  SURVEY section 8 row f2: with one grid per spectrum or per
+    frame (BASELINE configs 2 and 4) the tuples, not the kernels, are the cost of the reference layout."""
+    from ._packed import pack_elements
+
+    if getattr(weights_input, "unit", None) is not None:
+        raise ValueError("weights_packed does not carry units; pass plain arrays")
+    if method == "multilinear":
+        from ._multilinear import weights_multilinear
+
+        elements, shape_in, shape_out, shape_orth = weights_multilinear(
+            coordinates_input, coordinates_output, axis_input, axis_output, weights_input, bounds, perturb, seed)
+    elif method == "conservative":
+        elements, shape_in, shape_out, shape_orth = _weights_conservative_device(
+            coordinates_input, coordinates_output, axis_input, axis_output, weights_input, perturb, seed)
+    else:
+        raise ValueError(f"unrecognized method '{method}'")
+    return pack_elements(elements, shape_in, shape_out, shape_orth)
 
 
 def _weights_conservative_device(

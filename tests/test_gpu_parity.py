@@ -641,3 +641,32 @@ def test_apply_degenerate_sizes(rg, dev):
     empty = torch.empty((0, dw.n_in), dtype=torch.float64, device=dev)
     assert rg.device.apply_planned(plan, empty).shape == (0, dw.n_out)
     assert rg.device.apply_csr(dw.csr(), empty).shape == (0, dw.n_out)
+
+
+def test_weights_packed_equals_weights(rg, dev, tmp_path):
+    """weights_packed (four flat arrays) holds exactly what weights() returns, survives its file
+    format, and regrid_from_weights takes it directly."""
+    # per-slice 2D grids (config-4 layout at small size)
+    gis, gos = cases.case_2d_batched()
+    W = rg.weights(gis, gos, axis_input=(-2, -1), axis_output=(-2, -1), method="conservative")
+    P = rg.weights_packed(gis, gos, axis_input=(-2, -1), axis_output=(-2, -1), method="conservative")
+    assert len(P) == W[0].size and P.shape_input == W[1] and P.shape_output == W[2]
+    back = P.to_reference()[0]
+    for idx in np.ndindex(*W[0].shape):
+        for a, b in zip(back[idx], W[0][idx]):
+            assert np.array_equal(a, b)
+    P.save(tmp_path / "w.rgpw")
+    Q = rg.PackedWeights.load(tmp_path / "w.rgpw")
+    vals = np.random.default_rng(0).random(W[1])
+    r0 = rg.regrid_from_weights(W[0], W[1], W[2], vals, axis_input=(-2, -1), axis_output=(-2, -1))
+    r1 = rg.regrid_from_weights(Q, Q.shape_input, Q.shape_output, vals, axis_input=(-2, -1), axis_output=(-2, -1))
+    assert np.array_equal(r0, r1)
+    dws = Q.to_device(dev)
+    assert len(dws) == len(Q) and all(d.nnz == int(Q.offsets[k + 1] - Q.offsets[k]) for k, d in enumerate(dws))
+    # per-spectrum 1D grids (config-2 layout)
+    xin, xout, _ = cases.cases_1d()["spectra"]
+    W1 = rg.weights(xin, xout, axis_input=-1, axis_output=-1, method="conservative")
+    P1 = rg.weights_packed(xin, xout, axis_input=-1, axis_output=-1, method="conservative")
+    for k in range(W1[0].size):
+        for a, b in zip(P1.element(k), W1[0].reshape(-1)[k]):
+            assert np.array_equal(a, b)

@@ -112,3 +112,38 @@ def test_shard_ranges_cover_exactly():
             sizes = [b - a for a, b in parts]
             assert max(sizes) - min(sizes) <= 1
     assert _parallel.band_cells(2048, 2048, 3, 8) == (3 * 256 * 2048, 4 * 256 * 2048)
+
+
+def test_packed_weights_roundtrip(tmp_path):
+    """PackedWeights <-> reference layout (object ndarray of tuples) and the memory-mapped file format."""
+    from regridding_b200._packed import PackedWeights
+
+    rng = np.random.default_rng(0)
+    shape_orth = (2, 3)
+    w = np.empty(shape_orth, dtype=object)
+    for idx in np.ndindex(*shape_orth):
+        k = int(rng.integers(0, 6))  # some slices are empty
+        w[idx] = (rng.integers(-4, 9, k), rng.integers(0, 7, k), rng.random(k))
+    ref = (w, (2, 3, 9), (2, 3, 7))
+    p = PackedWeights.from_reference(ref)
+    assert len(p) == 6 and p.nnz == sum(len(e[2]) for e in w.reshape(-1))
+    back, s_in, s_out = p.to_reference()
+    assert back.shape == shape_orth and s_in == (2, 3, 9) and s_out == (2, 3, 7)
+    for idx in np.ndindex(*shape_orth):
+        for a, b in zip(back[idx], w[idx]):
+            assert a.dtype == b.dtype and np.array_equal(a, b)
+    path = tmp_path / "weights.rgpw"
+    p.save(path)
+    for mmap in (True, False):
+        q = PackedWeights.load(path, mmap=mmap)
+        assert q.shape_input == p.shape_input and q.shape_output == p.shape_output and q.shape_orthogonal == shape_orth
+        for name in ("offsets", "indices_input", "indices_output", "values"):
+            assert np.array_equal(getattr(q, name), getattr(p, name))
+    # an all-empty weights object and a corrupted file
+    e = PackedWeights.from_reference((np.array((np.empty(0, np.int64), np.empty(0, np.int64), np.empty(0)), dtype=object)[None][:0].reshape(0), (0, 4), (0, 5)))
+    assert len(e) == 0 and e.nnz == 0
+    path.write_bytes(b"not a weights file")
+    with pytest.raises(ValueError):
+        PackedWeights.load(path)
+    with pytest.raises(ValueError):
+        PackedWeights(np.array([0, 2]), np.zeros(1), np.zeros(1), np.zeros(1), (3,), (3,), ())
