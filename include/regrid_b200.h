@@ -205,6 +205,19 @@ int rg_ell4_apply(int device, void* stream, int64_t n_frames, int64_t n_in, int6
                   const int64_t* idx4, const double* w4, const double* values_in, double* values_out);
 
 /* ------------------------------------------------------------------------------
+ * fill(method="gauss_seidel"): red-black Gauss-Seidel relaxation of missing cells
+ * replaces: _fill_gauss_seidel_2d / _iteration_gauss_seidel_2d  regridding/_fill/_gauss_seidel.py:83-139
+ *           (called from fill_gauss_seidel, regridding/_fill/_gauss_seidel.py:13-59)
+ * a: double[num_t][num_y][num_x], updated in place (the guess already stored in the missing cells), periodic in
+ * both axes.  idx_lists_host: 6 device pointers [colour][level] to int32 flat indices of the missing cells with
+ * (i + j) & 1 == colour and level = (i == num_x-1 && num_x odd) + (j == num_y-1 && num_y odd) -- the levels
+ * reproduce the order of the reference's sequential sweep across the periodic wrap; counts_host: their lengths.
+ * One cooperative launch runs all iterations; the result equals the reference's bit for bit.
+ * ------------------------------------------------------------------------------ */
+int rg_fill_gauss_seidel_2d(int device, void* stream, double* a, int64_t num_t, int64_t num_y, int64_t num_x,
+                            const int32_t* const* idx_lists_host, const int64_t* counts_host, int64_t num_iterations);
+
+/* ------------------------------------------------------------------------------
  * shared-weights apply
  * replaces: _regrid_from_weights(weights, values_input, values_output)
  *           regridding/_regrid/_regrid_from_weights.py:165-182

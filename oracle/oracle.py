@@ -270,3 +270,45 @@ def multilinear2d_weights(x, y, px, py, cells_flat):
     w4[~ok] = np.nan
     idx4 = np.stack((a, a + 1, a + ny, a + ny + 1), axis=1)
     return idx4, w4
+
+
+def fill_gauss_seidel_2d(a, where, num_iterations: int) -> np.ndarray:
+    """``_fill_gauss_seidel_2d`` (regridding/_fill/_gauss_seidel.py:83-139): ``a`` (T, ny, nx) with the guess
+    already in place, ``where`` boolean (T, ny, nx); returns the relaxed copy."""
+    L = lib()
+    a = np.array(a, dtype=np.float64, order="C", copy=True)
+    w = np.ascontiguousarray(where, dtype=np.uint8)
+    assert a.ndim == 3 and w.shape == a.shape
+    L.orc_fill_gauss_seidel_2d.argtypes = [_c_double_p, ctypes.POINTER(ctypes.c_ubyte), ctypes.c_int64, ctypes.c_int64,
+                                           ctypes.c_int64, ctypes.c_int64]
+    L.orc_fill_gauss_seidel_2d.restype = None
+    L.orc_fill_gauss_seidel_2d(_d(a), w.ctypes.data_as(ctypes.POINTER(ctypes.c_ubyte)), a.shape[0], a.shape[1],
+                               a.shape[2], int(num_iterations))
+    return a
+
+
+def fill(a, where=None, axis=None, guess=None, num_iterations: int = 100) -> np.ndarray:
+    """``regridding.fill(method="gauss_seidel")`` host logic (``_fill.py:10-109``, ``_gauss_seidel.py:13-81``)
+    around the C relaxation: NaN mask by default, median guess, axis bookkeeping."""
+    a = np.array(a, dtype=np.float64, copy=True)
+    if where is None:
+        where = np.isnan(a)
+    a, where = np.broadcast_arrays(a, where)
+    a = a.copy()
+    nd = a.ndim
+    ax = tuple(range(nd)) if axis is None else tuple(np.lib.array_utils.normalize_axis_tuple(axis, nd))
+    if len(ax) != 2:
+        raise ValueError(f"The number of interpolation axes, {len(ax)},is not supported")
+    if guess is None:
+        masked = np.where(where, np.nan, a)
+        import warnings
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore", category=RuntimeWarning)
+            guess = np.nanmedian(masked, axis=ax, keepdims=True)
+        guess = np.where(np.isnan(guess), 0, guess)
+    a[where] = np.broadcast_to(guess, a.shape)[where]
+    am = np.moveaxis(a, ax, (-2, -1))
+    wm = np.moveaxis(where, ax, (-2, -1))
+    shape_moved = am.shape
+    res = fill_gauss_seidel_2d(am.reshape(-1, *shape_moved[-2:]), wm.reshape(-1, *shape_moved[-2:]), num_iterations)
+    return np.moveaxis(res.reshape(shape_moved), (-2, -1), ax)

@@ -949,3 +949,42 @@ void orc_find_indices_searchsorted_1d(int64_t D, int64_t n, int64_t m, const dou
         }
     }
 }
+
+/* _fill/_gauss_seidel.py:83-139  red-black Gauss-Seidel relaxation of the cells flagged in `where`
+ * (uint8, 1 = missing) on a periodic (num_y, num_x) grid, num_t independent frames, in place.
+ * The sweep is sequential (j outer, i inner) inside a colour exactly like the reference: with an odd
+ * size the periodic wrap joins two cells of the SAME colour, so the order decides which of them sees
+ * the other's new value.  The JIT (fastmath) folds dcent into the two constants and contracts
+ *     (dxxinv * (a_w + a_e) + dyyinv * (a_s + a_n)) * dcent
+ * into fma(dyyinv * dcent, a_s + a_n, (dxxinv * dcent) * (a_w + a_e)); measured against the reference
+ * (tests/golden/golden_fill.npz) -- strict mode evaluates the source expression as written. */
+void orc_fill_gauss_seidel_2d(double* a, const unsigned char* where, int64_t num_t, int64_t num_y, int64_t num_x,
+                              int64_t num_iterations)
+{
+    const double dx = (1.0 - -1.0) / (double)(num_x - 1);
+    const double dy = (1.0 - -1.0) / (double)(num_y - 1);
+    const double dxxinv = 1.0 / (dx * dx);
+    const double dyyinv = 1.0 / (dy * dy);
+    const double dcent = 1.0 / (2.0 * (dxxinv + dyyinv));
+    const double cx = dxxinv * dcent, cy = dyyinv * dcent;
+    const int strict = orc_get_mode() == 0;
+#pragma omp parallel for schedule(static)
+    for (int64_t t = 0; t < num_t; t++) {
+        double* at = a + t * num_y * num_x;
+        const unsigned char* wt = where + t * num_y * num_x;
+        for (int64_t k = 0; k < num_iterations; k++) {
+            for (int odd = 0; odd < 2; odd++) {
+                for (int64_t j = 0; j < num_y; j++) {
+                    for (int64_t i = 0; i < num_x; i++) {
+                        if (((i + j) & 1) != odd || !wt[j * num_x + i]) continue;
+                        const int64_t i9 = (i - 1 + num_x) % num_x, i1 = (i + 1) % num_x;
+                        const int64_t j9 = (j - 1 + num_y) % num_y, j1 = (j + 1) % num_y;
+                        const double sx = at[j * num_x + i9] + at[j * num_x + i1];
+                        const double sy = at[j9 * num_x + i] + at[j1 * num_x + i];
+                        at[j * num_x + i] = strict ? (dxxinv * sx + dyyinv * sy) * dcent : fma(cy, sy, cx * sx);
+                    }
+                }
+            }
+        }
+    }
+}

@@ -12,9 +12,10 @@ from ._find_indices import find_indices
 from ._regrid import regrid, regrid_from_weights
 from ._weights import weights, weights_packed
 from ._packed import PackedWeights
+from ._fill import fill
 from ._transposed import transpose_weights, transpose_weights_conservative
 from . import _device as device  # device-resident operators (torch CUDA tensors in / out)
 
 __all__ = ["regrid", "weights", "regrid_from_weights", "find_indices", "transpose_weights",
-           "transpose_weights_conservative", "weights_packed", "PackedWeights", "device"]
+           "transpose_weights_conservative", "weights_packed", "PackedWeights", "fill", "device"]
 __version__ = "0.1.0"
