@@ -352,7 +352,7 @@ __global__ void k_vertex_guess(GridView sweep, GridView stat, int32_t* __restric
 {
     const int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (v >= (int64_t)sweep.nx * sweep.ny) return;
-    const int r = locate_newton(stat, sweep.x[v], sweep.y[v], 0.5 * stat.nx, 0.5 * stat.ny);
+    const int r = locate_guess(stat, sweep.x[v], sweep.y[v]);
     guess[v] = r;
     if (r == kLocUnknown) atomicAdd(&flags[kFlagUnknown], 1);
 }
@@ -383,7 +383,7 @@ __global__ void k_vertex_guess_part(const __grid_constant__ Pass4 Q, int32_t* fl
     if (!segment_of_thread(P, gtid - Q.tstart[p], L, k)) return;
     if (k == 0) return;  // the line start is located exactly by k_line_starts
     const int64_t v = vertex_of(P, L, k);
-    const int r = locate_newton(P.stat, P.sweep.x[v], P.sweep.y[v], 0.5 * P.stat.nx, 0.5 * P.stat.ny);
+    const int r = locate_guess(P.stat, P.sweep.x[v], P.sweep.y[v]);
     guess[v] = r;
     if (r == kLocUnknown) atomicAdd(&flags[kFlagUnknown], 1);
 }

@@ -157,4 +157,59 @@ __device__ inline int locate_newton(const GridView& g, double px, double py, dou
     return kLocUnknown;
 }
 
+// Cheap variant for the walk-state GUESSES of the 2D build (k_vertex_guess*): wrong guesses only cost a repair,
+// so the iteration starts from the affine map through three corners of the grid, stops as soon as the Newton step
+// is below 1e-4 cells and accepts the cell when the point is 1e-3 cells away from its edges AND the exact
+// containment test agrees; anything else continues with the full-precision locate_newton from where it stands.
+__device__ inline int locate_guess(const GridView& g, double px, double py)
+{
+    const int ncx = g.nx - 1, ncy = g.ny - 1;
+    const double x00 = g.x[0], y00 = g.y[0];
+    const double ax = (g.x[(int64_t)ncx * g.ny] - x00) / ncx, ay = (g.y[(int64_t)ncx * g.ny] - y00) / ncx;
+    const double bx = (g.x[ncy] - x00) / ncy, by = (g.y[ncy] - y00) / ncy;
+    const double det0 = ax * by - bx * ay;
+    double i = 0.5 * g.nx, j = 0.5 * g.ny;
+    if (det0 != 0.0 && det0 == det0) {
+        i = ((px - x00) * by - (py - y00) * bx) / det0;
+        j = ((py - y00) * ax - (px - x00) * ay) / det0;
+        i = fmin(fmax(i, -1.0), (double)ncx + 1.0);
+        j = fmin(fmax(j, -1.0), (double)ncy + 1.0);
+    }
+    for (int it = 0; it < 12; it++) {
+        int i0 = (int)floor(i), j0 = (int)floor(j);
+        i0 = min(max(i0, 0), ncx - 1);
+        j0 = min(max(j0, 0), ncy - 1);
+        const int64_t a = (int64_t)i0 * g.ny + j0;
+        const double x00c = g.x[a], x01 = g.x[a + 1], x10 = g.x[a + g.ny], x11 = g.x[a + g.ny + 1];
+        const double y00c = g.y[a], y01 = g.y[a + 1], y10 = g.y[a + g.ny], y11 = g.y[a + g.ny + 1];
+        const double u = i - i0, v = j - j0;
+        const double X = (x00c * (1 - u) + x10 * u) * (1 - v) + (x01 * (1 - u) + x11 * u) * v;
+        const double Y = (y00c * (1 - u) + y10 * u) * (1 - v) + (y01 * (1 - u) + y11 * u) * v;
+        const double ex = X - px, ey = Y - py;
+        const double dxdi = (x10 - x00c) * (1 - v) + (x11 - x01) * v;
+        const double dxdj = (x01 - x00c) * (1 - u) + (x11 - x10) * u;
+        const double dydi = (y10 - y00c) * (1 - v) + (y11 - y01) * v;
+        const double dydj = (y01 - y00c) * (1 - u) + (y11 - y10) * u;
+        const double det = dxdi * dydj - dxdj * dydi;
+        if (det == 0.0 || !(det == det)) break;
+        double di = (dydj * ex - dxdj * ey) / det;
+        double dj = (-dydi * ex + dxdi * ey) / det;
+        di = fmin(fmax(di, -(double)g.nx), (double)g.nx);
+        dj = fmin(fmax(dj, -(double)g.ny), (double)g.ny);
+        i -= di;
+        j -= dj;
+        if (fabs(di) < 1e-4 && fabs(dj) < 1e-4) {
+            const int ic = (int)floor(i), jc = (int)floor(j);
+            if (ic >= 0 && jc >= 0 && ic < ncx && jc < ncy) {
+                const double fu = i - ic, fv = j - jc;
+                if (fu > 1e-3 && fu < 1.0 - 1e-3 && fv > 1e-3 && fv < 1.0 - 1e-3 && cell_contains(g, ic, jc, px, py))
+                    return ic * ncy + jc;
+            }
+            break;
+        }
+    }
+    if (!(i == i) || !(j == j)) { i = 0.5 * g.nx; j = 0.5 * g.ny; }
+    return locate_newton(g, px, py, i, j);
+}
+
 }  // namespace rg
