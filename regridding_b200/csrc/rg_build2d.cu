@@ -497,9 +497,21 @@ k_walk_emit(const __grid_constant__ Pass4 Q, const int64_t* __restrict__ boff, i
 // memory with coalesced loads, every thread insertion-sorts its own bucket there (buckets hold ~14 fragments),
 // and the range is written back coalesced.  CTAs whose range does not fit (or that hold a bucket longer than 64)
 // sort in global memory: one lane per bucket, the whole warp (odd-even transposition) for the long ones.
-constexpr int kSortCells = 128;   // buckets per CTA
-constexpr int kSortThreads = 256; // threads per CTA: one per bucket for the bookkeeping, all of them for the per-fragment phases
-constexpr int kSortCap = 3000;  // fragments staged per CTA (~56 KB of shared memory with the maps: 4 CTAs per SM)
+#ifndef RG_SORT_CELLS
+#define RG_SORT_CELLS 64
+#endif
+#ifndef RG_SORT_THREADS
+#define RG_SORT_THREADS 128
+#endif
+#ifndef RG_SORT_CAP
+#define RG_SORT_CAP 1500
+#endif
+constexpr int kSortCells = RG_SORT_CELLS;     // buckets per CTA
+constexpr int kSortThreads = RG_SORT_THREADS; // threads per CTA: one per bucket for the bookkeeping, all of them for the
+                                              // per-fragment phases
+constexpr int kSortCap = RG_SORT_CAP;  // fragments staged per CTA (~31 KB of shared memory with the maps: 7 CTAs per SM;
+                                       // smaller tiles hide the NVLink latency of the sharded gather better: -9 % merge time)
+static_assert(kSortThreads >= kSortCells && kSortThreads % 32 == 0 && kSortCells % 32 == 0, "sort CTA shape");
 constexpr int kMaxSrc = 16;     // source ranks of a sharded build
 
 // Line-sharded builds: the fragments of a band arrive as one chunk per source rank, each chunk bucketed by
@@ -650,7 +662,7 @@ k_bucket_sort(const int64_t* __restrict__ boff, int64_t n_cells, Frag* __restric
 }
 
 // Sharded builds: gather the band's buckets from the W source chunks and rank-sort them.  Every source's share
-// of the CTA's 128 cells is ONE contiguous range of its chunk: the CTA copies the W ranges into the stage with
+// of the CTA's kSortCells cells is ONE contiguous range of its chunk: the CTA copies the W ranges into the stage with
 // 16-byte asynchronous copies (all in flight together -- they may cross NVLink); a bucket is then the union of
 // its W pieces in the stage.
 __global__ void __launch_bounds__(kSortThreads)
