@@ -57,6 +57,12 @@ struct PassParams {
     int64_t cell_lo, cell_hi;   // input-cell band
     uint8_t* seg_hit;           // [sweep vertices] banded builds: does the segment emit anything inside the band?
     int banded;
+    // piece cache: what the count walk found, so that the emit walk does not repeat the geometry
+    uint8_t* pc_n;              // [sweep vertices] cached entries of the segment, kPieceNone: walk again
+    int32_t* pc_cell;           // [kPieceCache][sweep vertices] static cell of the piece; -1: "move to" (re-entry point)
+    double* pc_x;               // [kPieceCache][sweep vertices] end point of the piece / the point moved to
+    double* pc_y;
+    int64_t pc_stride;          // sweep vertices
     // line-sharded builds: this rank walks the sweep lines of every part_world-th block of 32 lines
     int part_rank, part_world;
     int nl_slots;               // line slots of this rank (== nlines when part_world == 1)
@@ -84,6 +90,9 @@ struct __align__(16) Frag {
     uint64_t key;
     double val;
 };
+
+constexpr int kPieceCache = 4;      // cached entries per segment (a segment makes 1.8 pieces on average)
+constexpr int kPieceNone = 255;
 
 constexpr int kStateOutside = -1;
 constexpr int kStateUnknown = -2;
@@ -244,11 +253,32 @@ struct CountSink {
     int32_t* hist;
     int L, k, delta;
     int total;  // fragments of this segment that fall inside the band
-    __device__ __forceinline__ void piece(const PassParams& P, double, double, double, double, int ci, int cj, int)
+    // piece cache (v < 0: off): entries written so far and the point the last one ended at
+    int64_t v;
+    int n_cached;
+    double cx, cy;
+    __device__ __forceinline__ void push(const PassParams& P, int cell, double x, double y)
+    {
+        if (n_cached < kPieceCache) {
+            const int64_t at = (int64_t)n_cached * P.pc_stride + v;
+            P.pc_cell[at] = cell;
+            P.pc_x[at] = x;
+            P.pc_y[at] = y;
+        }
+        n_cached++;
+    }
+    __device__ __forceinline__ void piece(const PassParams& P, double x1, double y1, double x2, double y2,
+                                          int ci, int cj, int)
     {
         const PieceCells pc = piece_cells(P, L, k, ci, cj);
         for (int q = 0; q < pc.n; q++) atomicAdd(&hist[pc.in[q]], delta);
         total += pc.n;
+        if (v >= 0) {
+            if (x1 != cx || y1 != cy) push(P, -1, x1, y1);  // the piece starts at a re-entry point
+            push(P, ci * P.ncy_st + cj, x2, y2);
+            cx = x2;
+            cy = y2;
+        }
     }
 };
 
@@ -402,12 +432,15 @@ __global__ void __launch_bounds__(128) k_walk_count(const __grid_constant__ Pass
     if (start == kStateUnknown) {
         P.seg_end[v] = kStateInvalid;
         if (P.banded) P.seg_hit[v] = 1;  // decided by the repair pass
+        P.pc_n[v] = kPieceNone;
         return;
     }
-    CountSink sink{ hist, L, k, 1, 0 };
+    const double x1 = P.sweep.x[v], y1 = P.sweep.y[v];
+    CountSink sink{ hist, L, k, 1, 0, v, 0, x1, y1 };
     bool overflow = false;
-    P.seg_end[v] = walk_segment(P, P.sweep.x[v], P.sweep.y[v], P.sweep.x[v2], P.sweep.y[v2], start, sink, overflow);
+    P.seg_end[v] = walk_segment(P, x1, y1, P.sweep.x[v2], P.sweep.y[v2], start, sink, overflow);
     if (P.banded) P.seg_hit[v] = sink.total > 0;
+    P.pc_n[v] = (uint8_t)((sink.n_cached <= kPieceCache && !overflow) ? sink.n_cached : kPieceNone);
 }
 
 // Does every segment start from the state its predecessor ended in?  (Thread per segment; the common answer
@@ -452,13 +485,14 @@ __global__ void k_repair(const __grid_constant__ Pass4 Q, int32_t* __restrict__ 
                 const double x1 = P.sweep.x[v], y1 = P.sweep.y[v], x2 = P.sweep.x[v2], y2 = P.sweep.y[v2];
                 bool overflow = false;
                 if (old_start != kStateUnknown) {
-                    CountSink undo{ hist, L, k, -1, 0 };
+                    CountSink undo{ hist, L, k, -1, 0, -1, 0, 0.0, 0.0 };
                     walk_segment(P, x1, y1, x2, y2, old_start, undo, overflow);
                 }
-                CountSink redo{ hist, L, k, 1, 0 };
+                CountSink redo{ hist, L, k, 1, 0, -1, 0, 0.0, 0.0 };
                 const int e = walk_segment(P, x1, y1, x2, y2, new_start, redo, overflow);
                 P.seg_start[v] = new_start;
                 P.seg_end[v] = e;
+                P.pc_n[v] = kPieceNone;  // the cached pieces belong to the wrong start: the emit walk redoes them
                 if (P.banded) P.seg_hit[v] = redo.total > 0;
                 atomicAdd(&flags[kFlagRepairs], 1);
                 __threadfence();
@@ -483,6 +517,25 @@ k_walk_emit(const __grid_constant__ Pass4 Q, const int64_t* __restrict__ boff, i
     const int64_t v = vertex_of(P, L, k), v2 = v + vertex_step(P);
     if (P.banded && !P.seg_hit[v]) return;  // the count walk saw nothing of this segment inside the band
     EmitSink sink{ boff, cursor, frag, area_in, w_in, flags, L, k };
+    const int nc = P.pc_n[v];
+    if (nc != kPieceNone) {
+        // replay the pieces the count walk recorded: same points, same cells, same order -- no geometry
+        double x1 = P.sweep.x[v], y1 = P.sweep.y[v];
+        int piece = 0;
+        for (int e = 0; e < nc; e++) {
+            const int64_t at = (int64_t)e * P.pc_stride + v;
+            const int cell = P.pc_cell[at];
+            const double x = P.pc_x[at], y = P.pc_y[at];
+            if (cell >= 0) {
+                const int ci = cell / P.ncy_st;
+                sink.piece(P, x1, y1, x, y, ci, cell - ci * P.ncy_st, piece);
+                piece++;
+            }
+            x1 = x;
+            y1 = y;
+        }
+        return;
+    }
     bool overflow = false;
     walk_segment(P, P.sweep.x[v], P.sweep.y[v], P.sweep.x[v2], P.sweep.y[v2], P.seg_start[v], sink, overflow);
     if (overflow) atomicOr(&flags[kFlagOverflow], 1);
@@ -806,6 +859,10 @@ struct Layout {
     int32_t* seg_start[4];
     int32_t* seg_end[4];
     uint8_t* seg_hit[4];
+    uint8_t* pc_n[4];
+    int32_t* pc_cell[4];
+    double* pc_x[4];
+    double* pc_y[4];
     int32_t* hist;
     int64_t* boff;
     int32_t* cursor;
@@ -838,6 +895,10 @@ static Layout make_layout(void* ws, int64_t nxi, int64_t nyi, int64_t nxo, int64
         l.seg_start[p] = c.take<int32_t>(nx * ny);
         l.seg_end[p] = c.take<int32_t>(nx * ny);
         l.seg_hit[p] = c.take<uint8_t>(nx * ny);
+        l.pc_n[p] = c.take<uint8_t>(nx * ny);
+        l.pc_cell[p] = c.take<int32_t>(kPieceCache * nx * ny);
+        l.pc_x[p] = c.take<double>(kPieceCache * nx * ny);
+        l.pc_y[p] = c.take<double>(kPieceCache * nx * ny);
     }
     l.hist = c.take<int32_t>(l.Ci + 1);
     l.boff = c.take<int64_t>(l.Ci + 1);
@@ -886,6 +947,11 @@ static PassParams make_pass(const Layout& l, int p, const double* xin, const dou
     P.cell_lo = cell_lo;
     P.cell_hi = cell_hi;
     P.seg_hit = l.seg_hit[p];
+    P.pc_n = l.pc_n[p];
+    P.pc_cell = l.pc_cell[p];
+    P.pc_x = l.pc_x[p];
+    P.pc_y = l.pc_y[p];
+    P.pc_stride = (int64_t)P.sweep.nx * P.sweep.ny;
     P.banded = (cell_lo > 0 || cell_hi < l.Ci) ? 1 : 0;
     P.part_rank = part_rank;
     P.part_world = part_world;
