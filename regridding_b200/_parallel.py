@@ -140,7 +140,12 @@ def _arena(group, device, shape, W, min_capacity: int = 0) -> PeerArena:
     key = (id(group) if group is not None else 0, device.index, shape)
     a = _arenas.get(key)
     ci, co = (shape[0] - 1) * (shape[1] - 1), (shape[2] - 1) * (shape[3] - 1)
-    want = max(int(min_capacity), int(1.3 * 16 * max(ci, co) / W) + 4096)
+    # first guess: 16 fragments per cell of the finer grid, shared by W ranks, + 30 %; REGRID_B200_ARENA_FRAGS_PER_CELL
+    # overrides the 16 (tests use a tiny value to exercise the growth path)
+    import os
+
+    per_cell = float(os.environ.get("REGRID_B200_ARENA_FRAGS_PER_CELL", "16"))
+    want = max(int(min_capacity), int(1.3 * per_cell * max(ci, co) / W) + 64)
     if a is None or a.capacity < min_capacity:
         _arenas.pop(key, None)
         a = None  # release the old mapping before the new rendezvous

@@ -41,6 +41,14 @@ def _worker(rank, world, port, ret):
             lo, hi = _parallel.band_cells(gi[0].shape[0] - 1, gi[0].shape[1] - 1, rank, world)
             sel = (full.indices_input >= lo) & (full.indices_input < hi)
             ok = ok and torch.equal(band.values, full.values[sel]) and torch.equal(band.indices_output, full.indices_output[sel])
+        # arena growth: start with room for 1 fragment per cell -> every rank overflows, all grow together, walk again
+        os.environ["REGRID_B200_ARENA_FRAGS_PER_CELL"] = "1"
+        _parallel._arenas.clear()
+        rep = _parallel.build_weights_2d_sharded(*t, replicate=True, device=dev, exchange="p2p")
+        ok = ok and torch.equal(rep.values, full.values) and torch.equal(rep.indices_input, full.indices_input)
+        grown = next(iter(_parallel._arenas.values())).capacity
+        ok = ok and grown >= full.stats["fragments"] // world // 2
+        os.environ.pop("REGRID_B200_ARENA_FRAGS_PER_CELL")
         ret[rank] = bool(ok)
     finally:
         dist.destroy_process_group()
