@@ -300,16 +300,31 @@ struct EmitSink {
         const double neg2 = dfma(-x1, y2, dmul(x2, y1));
         const double area = dmul(neg2, P.axis == 0 ? 0.5 : -0.5);
         if (piece_idx >= (1 << 29)) atomicOr(&flags[kFlagSeqOverflow], 1);
-        for (int q = 0; q < pc.n; q++) {
-            const double a = pc.side[q] ? -area : area;
-            double w;
-            if (w_in) w = ddiv(dmul(a, w_in[pc.in[q]]), area_in[pc.in[q]]);  // fastmath reassociation seen in the JIT
-            else w = ddiv(a, area_in[pc.in[q]]);
-            // emission rank inside one (input, output) pair: pass, then line (the cell right of line L
-            // comes before the cell left of line L+1), then piece order inside the segment.
-            const uint32_t seq = ((uint32_t)P.pass << 30) | (pc.side[q] == 0 ? (1u << 29) : 0u) | (uint32_t)piece_idx;
-            const int64_t slot = boff[pc.in[q]] + atomicAdd(&cursor[pc.in[q]], 1);
-            frag[slot] = Frag{ ((uint64_t)pc.out[q] << 32) | seq, w };
+        // both sides of the line: all loads and the two slot reservations are issued before anything is used
+        // (this code is bound by the latency of these accesses, not by arithmetic)
+        const bool two = pc.n > 1;
+        const int64_t in0 = pc.in[0], in1 = pc.in[two ? 1 : 0];
+        const double vol0 = area_in[in0];
+        const double vol1 = area_in[in1];
+        const int64_t base0 = boff[in0];
+        const int64_t base1 = boff[in1];
+        double wi0 = 1.0, wi1 = 1.0;
+        if (w_in) { wi0 = w_in[in0]; wi1 = w_in[in1]; }
+        const int old0 = atomicAdd(&cursor[in0], 1);
+        const int old1 = two ? atomicAdd(&cursor[in1], 1) : 0;
+        // emission rank inside one (input, output) pair: pass, then line (the cell right of line L
+        // comes before the cell left of line L+1), then piece order inside the segment.
+        const uint32_t seq = ((uint32_t)P.pass << 30) | (uint32_t)piece_idx;
+        {
+            const double a = pc.side[0] ? -area : area;
+            // with weights_input: (area * w) / vol, the fastmath reassociation seen in the JIT
+            const double w = w_in ? ddiv(dmul(a, wi0), vol0) : ddiv(a, vol0);
+            frag[base0 + old0] = Frag{ ((uint64_t)pc.out[0] << 32) | seq | (pc.side[0] == 0 ? (1u << 29) : 0u), w };
+        }
+        if (two) {
+            const double a = pc.side[1] ? -area : area;
+            const double w = w_in ? ddiv(dmul(a, wi1), vol1) : ddiv(a, vol1);
+            frag[base1 + old1] = Frag{ ((uint64_t)pc.out[1] << 32) | seq | (pc.side[1] == 0 ? (1u << 29) : 0u), w };
         }
     }
 };
@@ -522,10 +537,20 @@ k_walk_emit(const __grid_constant__ Pass4 Q, const int64_t* __restrict__ boff, i
         // replay the pieces the count walk recorded: same points, same cells, same order -- no geometry
         double x1 = P.sweep.x[v], y1 = P.sweep.y[v];
         int piece = 0;
-        for (int e = 0; e < nc; e++) {
+        // all entries are loaded before the first one is used (independent loads in flight together)
+        int cells[kPieceCache];
+        double xs[kPieceCache], ys[kPieceCache];
+#pragma unroll
+        for (int e = 0; e < kPieceCache; e++) {
             const int64_t at = (int64_t)e * P.pc_stride + v;
-            const int cell = P.pc_cell[at];
-            const double x = P.pc_x[at], y = P.pc_y[at];
+            cells[e] = -1; xs[e] = 0.0; ys[e] = 0.0;
+            if (e < nc) { cells[e] = P.pc_cell[at]; xs[e] = P.pc_x[at]; ys[e] = P.pc_y[at]; }
+        }
+#pragma unroll
+        for (int e = 0; e < kPieceCache; e++) {
+            if (e >= nc) break;
+            const int cell = cells[e];
+            const double x = xs[e], y = ys[e];
             if (cell >= 0) {
                 const int ci = cell / P.ncy_st;
                 sink.piece(P, x1, y1, x, y, ci, cell - ci * P.ncy_st, piece);
