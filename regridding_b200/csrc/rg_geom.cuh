@@ -159,8 +159,9 @@ __device__ inline int locate_newton(const GridView& g, double px, double py, dou
 
 // Cheap variant for the walk-state GUESSES of the 2D build (k_vertex_guess*): wrong guesses only cost a repair,
 // so the iteration starts from the affine map through three corners of the grid, stops as soon as the Newton step
-// is below 1e-4 cells and accepts the cell when the point is 1e-3 cells away from its edges AND the exact
-// containment test agrees; anything else continues with the full-precision locate_newton from where it stands.
+// is below 1e-4 cells and accepts the cell when the point is 1e-3 cells away from its edges (or "outside" when it
+// is 1e-3 cells beyond the border); anything else continues with the full-precision locate_newton from where it
+// stands.
 __device__ inline int locate_guess(const GridView& g, double px, double py)
 {
     const int ncx = g.nx - 1, ncy = g.ny - 1;
@@ -202,8 +203,11 @@ __device__ inline int locate_guess(const GridView& g, double px, double py)
             const int ic = (int)floor(i), jc = (int)floor(j);
             if (ic >= 0 && jc >= 0 && ic < ncx && jc < ncy) {
                 const double fu = i - ic, fv = j - jc;
-                if (fu > 1e-3 && fu < 1.0 - 1e-3 && fv > 1e-3 && fv < 1.0 - 1e-3 && cell_contains(g, ic, jc, px, py))
-                    return ic * ncy + jc;
+                // (no exact containment test here: with the step below 1e-4 the solution is ~1e-8 cells from the
+                // root, so 1e-3 cells inside the unit square of a convex cell is inside the cell)
+                if (fu > 1e-3 && fu < 1.0 - 1e-3 && fv > 1e-3 && fv < 1.0 - 1e-3) return ic * ncy + jc;
+            } else if (i < -1e-3 || j < -1e-3 || i > ncx + 1e-3 || j > ncy + 1e-3) {
+                return kLocOutside;  // clearly beyond the border cells: a guess needs no exact verification
             }
             break;
         }
