@@ -64,10 +64,10 @@ def build_bytes(v_in: int, v_out: int, nnz: int) -> int:
 
 
 # dram__bytes_read.sum + dram__bytes_write.sum of one launch of the dominant kernel from the committed
-# `ncu --set full` capture (profiles/), scaled to the launch the bench times; None until measured.
-# profiles/r1_apply_tuning.md (gpurun_out/prof_apply_r1h.ncu-rep): 9.689 GB read + 8.535 GB written for a 256-frame
-# launch at config 3 = 71.19 MB per frame; the weights part (slot arrays, ~0.19 GB) is inside and negligible.
-TRAFFIC_NCU: dict = {"apply_bytes_per_frame": (9.688984e9 + 8.534854e9) / 256}
+# `ncu --set full` capture, scaled to the launch the bench times; None until measured.
+# profiles/r1e_apply_ncu_summary.txt: 9.685 GB read + 8.535 GB written for a 256-frame launch at config 3
+# = 71.17 MB per frame (1.05x the algorithmic bytes); the weights part (slot arrays, ~0.19 GB) is inside.
+TRAFFIC_NCU: dict = {"apply_bytes_per_frame": (9.685029e9 + 8.534865e9) / 256}
 
 
 def hbm_peak():
@@ -402,7 +402,7 @@ def run_ours(args):
         "roofline": {"bound": "hbm", "achieved": per_gpu, "peak": peak, "unit": "GB/s", "frac": per_gpu / peak,
                      "traffic": (TRAFFIC_NCU["apply_bytes_per_frame"] * F if n == 2049 else None),
                      "traffic_source": "ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum of one 256-frame "
-                                       "launch, scaled to this launch's frames (profiles/r1_apply_tuning.md)",
+                                       "launch, scaled to this launch's frames (profiles/r1e_apply_ncu_summary.txt)",
                      "peak_source": peak_src, "kernel": "rg::k_apply_staged",
                      "algorithmic_bytes_per_launch": abytes},
         "e2e": {"value": e2e_value, "unit": UNIT, "frames": Fe,
