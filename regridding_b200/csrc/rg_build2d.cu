@@ -854,17 +854,34 @@ __global__ void k_bucket_emit(const int64_t* __restrict__ boff, int64_t bstride,
     const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= n_cells) return;
     const int64_t beg = boff[c * bstride], end = boff[(c + 1) * bstride];
+    if (beg >= end) return;
     int64_t w = colptr[c];
-    int64_t s = beg;
-    while (s < end) {
-        const uint32_t o = (uint32_t)(frag[s].key >> 32);
-        int64_t e = s + 1;
-        while (e < end && (uint32_t)(frag[e].key >> 32) == o) e++;
+    // One 16-byte load per fragment (the kernel is bound by the L1 wavefronts of these uncoalesced loads): the run
+    // sum is accumulated while scanning.  np.add.reduceat of a run a[0..n) is a[0] + pairwise_sum(a[1..n)), and the
+    // pairwise sum of fewer than 8 values is the sequential sum from -0.0; longer runs (rare) are summed again
+    // from memory in NumPy's blocked order.
+    Frag x = frag[beg];
+    uint32_t o = (uint32_t)(x.key >> 32);
+    double a0 = x.val, rest = -0.0;
+    int64_t run = beg;
+    for (int64_t e = beg + 1; e <= end; e++) {
+        const bool more = e < end;
+        Frag y = x;
+        if (more) y = frag[e];
+        const uint32_t oy = (uint32_t)(y.key >> 32);
+        if (more && oy == o) {
+            rest = dadd(rest, y.val);
+            continue;
+        }
+        const int64_t n = e - run;
         ii[w] = c + cell_offset;
         io[w] = (int64_t)o;
-        vv[w] = np_reduceat_segment<2>(&frag[s].val, e - s);
+        vv[w] = n == 1 ? a0 : (n - 1 < 8 ? dadd(a0, rest) : np_reduceat_segment<2>(&frag[run].val, n));
         w++;
-        s = e;
+        o = oy;
+        a0 = y.val;
+        rest = -0.0;
+        run = e;
     }
 }
 
