@@ -22,7 +22,7 @@ I64 = torch.int64
 I32 = torch.int32
 
 # kernel launches of ours per operator call (checked against the ncu launch list in profiles/)
-LAUNCHES_BUILD2D = 21  # area 1, bbox+boundaries 4, guess 2, starts / count / check / repair 4 (four passes per launch), scans 6, emit walk 1, sort 1, merge 1
+LAUNCHES_BUILD2D = 20  # area 1, bbox+boundaries 4, guess 2, starts / count / check / repair 4 (four passes per launch), scans 6, emit walk 1, sort 1, merge 1
 # line-sharded build per rank: walk share 14 (area 1, boundaries 4, guess, starts, count, check, repair, scan 3, emit) + merge 13 (counts 1, transpose 1, scans 9, gather-sort 1, emit 1)
 LAUNCHES_BUILD2D_SHARDED = 27
 LAUNCHES_CSR = 6       # hist, scan 3, fill, rank
