@@ -433,7 +433,7 @@ __global__ void k_vertex_guess_part(const __grid_constant__ Pass4 Q, int32_t* fl
     if (r == kLocUnknown) atomicAdd(&flags[kFlagUnknown], 1);
 }
 
-__global__ void __launch_bounds__(128) k_walk_count(const __grid_constant__ Pass4 Q, int32_t* __restrict__ hist)
+__global__ void __launch_bounds__(128, 8) k_walk_count(const __grid_constant__ Pass4 Q, int32_t* __restrict__ hist)
 {
     const int64_t gtid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (gtid >= Q.tstart[4]) return;
@@ -518,7 +518,7 @@ __global__ void k_repair(const __grid_constant__ Pass4 Q, int32_t* __restrict__ 
     }
 }
 
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, 8)
 k_walk_emit(const __grid_constant__ Pass4 Q, const int64_t* __restrict__ boff, int32_t* __restrict__ cursor,
             Frag* __restrict__ frag,
             const double* __restrict__ area_in, const double* __restrict__ w_in, int32_t* __restrict__ flags)
