@@ -147,3 +147,25 @@ def test_packed_weights_roundtrip(tmp_path):
         PackedWeights.load(path)
     with pytest.raises(ValueError):
         PackedWeights(np.array([0, 2]), np.zeros(1), np.zeros(1), np.zeros(1), (3,), (3,), ())
+
+
+def test_band_bounds_partition_the_input_cells():
+    """Input-row bands of the sharded build: contiguous, ordered, covering every cell once, empty bands allowed."""
+    for ncx, ncy, w in [(2048, 2048, 8), (99, 100, 5), (3, 7, 8), (1, 1, 2)]:
+        b = _parallel.band_bounds(ncx, ncy, w)
+        assert len(b) == w + 1 and b[0] == 0 and b[-1] == ncx * ncy
+        assert all(b[r] <= b[r + 1] and b[r] % ncy == 0 for r in range(w))
+        assert [b[r + 1] - b[r] for r in range(w)] == [
+            (_parallel.shard_range(ncx, r, w)[1] - _parallel.shard_range(ncx, r, w)[0]) * ncy for r in range(w)]
+        for r in range(w):
+            assert _parallel.band_cells(ncx, ncy, r, w) == (b[r], b[r + 1])
+
+
+def test_sharded_build_rejects_unknown_exchange(monkeypatch):
+    import torch.distributed as dist
+
+    monkeypatch.setattr(_parallel, "world", lambda group=None: (0, 2))
+    with pytest.raises(ValueError, match="exchange"):
+        _parallel.build_weights_2d_sharded(np.zeros((3, 3)), np.zeros((3, 3)), np.zeros((3, 3)), np.zeros((3, 3)),
+                                           exchange="carrier-pigeon")
+    del dist
