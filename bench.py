@@ -70,6 +70,13 @@ def build_bytes(v_in: int, v_out: int, nnz: int) -> int:
 TRAFFIC_NCU: dict = {"apply_bytes_per_frame": (9.685029e9 + 8.534865e9) / 256}
 
 
+# The reference's own Numba implementation (as shipped, warm JIT cache) measured in the build container
+# (8 vCPU, numba 0.65, OpenMP layer; SURVEY.md section 6 / BASELINE.md): printed beside the port's numbers because the
+# CPU arm of this bench is the C/OpenMP port of the same algorithm, which is several times faster than Numba.
+NUMBA_FIGURES = {"apply_GBps": 6.0, "build_Mcells_per_s": 0.058, "cores": 8,
+                 "source": "SURVEY.md section 6 (2048^2 cells: sweep 64.7 s + coalesce 7.2 s; apply 16 frames 0.240 s)"}
+
+
 def hbm_peak():
     p = ROOT / "MEASURED_PEAKS.json"
     if p.exists():
@@ -172,12 +179,15 @@ def run_reference(args):
     if rank != 0:
         return
     from oracle import oracle
+    from tests import cases
 
     oracle.build()
-    cores = oracle.num_threads()
+    # torch.distributed.run exports OMP_NUM_THREADS=1 to its workers: use every core this process may run on
+    cores = oracle.set_num_threads()
     n = args.n
     n_in = n_out = (n - 1) ** 2
     tri, t_sweep, t_coal = cpu_build_sample(n)
+    weights_sha = cases.sha(*tri)
     frames = args.ref_frames
     vals = np.random.default_rng(0).random((frames, n_in))
     for _ in range(args.warmup):
@@ -200,6 +210,9 @@ def run_reference(args):
                   "sweep_s": t_sweep, "coalesce_s": t_coal, "cores": cores, "kind": "port",
                   "sample": "full 2048^2-cell build, 1 repetition"},
         "gpu_launches": 0,
+        # SHA-256 of the reference algorithm's (ii, io, v) for this config: the GPU arm prints the same key
+        "weights_sha256": weights_sha,
+        "reference_numba_on_8_vcpu": NUMBA_FIGURES,
     }
     print(json.dumps(line), flush=True)
 
@@ -283,6 +296,7 @@ def run_ours(args):
     dw, build_ms = time_build(False)
     build_stats = dict(dw.stats or {})
     sharded_ms = replicated_ms = None
+    sharded_equal = None
     if world > 1:
         # peer-mapped exchange needs torch symmetric memory on every rank; agree on the fallback together
         ok = 1
@@ -295,8 +309,24 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MIN)
         if int(t.item()) == 0:
             exchange["mode"] = "nccl"
-        _, sharded_ms = time_build(True)
-        dw, replicated_ms = time_build(True, replicate=True)
+        dw_band, sharded_ms = time_build(True)
+        dw_rep, replicated_ms = time_build(True, replicate=True)
+        # parity before any number is reported: this rank's band and the replicated matrix equal the single-GPU
+        # build bit for bit (indices AND weights)
+        lo, hi = _parallel.band_cells(n - 1, n - 1, rank, world)
+        sel = (dw.indices_input >= lo) & (dw.indices_input < hi)
+        same = int(torch.equal(dw_band.indices_input, dw.indices_input[sel]) and
+                   torch.equal(dw_band.indices_output, dw.indices_output[sel]) and
+                   torch.equal(dw_band.values, dw.values[sel]) and
+                   torch.equal(dw_rep.indices_input, dw.indices_input) and
+                   torch.equal(dw_rep.indices_output, dw.indices_output) and
+                   torch.equal(dw_rep.values, dw.values))
+        t = torch.tensor([same], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MIN)
+        sharded_equal = bool(int(t.item()))
+        assert sharded_equal, "sharded / replicated build differs from the single-GPU build"
+        del dw_band, sel
+        dw = dw_rep
     nnz = dw.nnz
     csr = dw.csr()
     plan = dw.plan((n - 1, n - 1), (n - 1, n - 1))  # per-tile footprints of the shared-memory staged apply
@@ -337,6 +367,7 @@ def run_ours(args):
     from regridding_b200 import _cache
 
     _cache.remember(weights_host[()], dw)
+    weights_sha = cases.sha(*weights_host[()]) if rank == 0 else None
     shape_in = shape_out = (n - 1, n - 1)
     pin_in = torch.empty((Fe, n - 1, n - 1), dtype=torch.float64, pin_memory=True)
     pin_in.uniform_(0.0, 1.0)
@@ -373,6 +404,7 @@ def run_ours(args):
         from oracle import oracle
 
         oracle.build()
+        oracle.set_num_threads()
         ii_h, io_h, v_h = weights_host[()]
         frames_cpu = args.cpu_frames
         cpu_val, cpu_t = cpu_apply_sample(ii_h, io_h, v_h, n_in, n_out, frames_cpu)
@@ -429,6 +461,7 @@ def run_ours(args):
                 "n_gpus": world, "ms": sharded_ms, "value": n_in / (sharded_ms * 1e-3) / 1e6, "unit": "Mcells/s",
                 "speedup_vs_this_runs_1gpu_build": build_ms / sharded_ms,
                 "scaling": "strong", "exchange": exchange["mode"],
+                "equals_single_gpu_build_bitwise_on_every_rank": sharded_equal,
                 "result": "every rank holds its input-row band of the public triplets (no collective on the data path "
                           "with exchange=p2p: band owners read peer memory over NVLink)",
                 "replicated_ms": replicated_ms,
@@ -440,6 +473,9 @@ def run_ours(args):
             "cpu_baseline": cpu_build,
         },
         "checksum": checksum,
+        # SHA-256 of the public (ii, io, v): `--impl reference` prints the same key for the CPU oracle's triplets
+        "weights_sha256": weights_sha,
+        "reference_numba_on_8_vcpu": NUMBA_FIGURES,
     }
     print(json.dumps(line), flush=True)
     if world > 1:

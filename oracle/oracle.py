@@ -104,6 +104,37 @@ def num_threads() -> int:
     return int(lib().orc_num_threads())
 
 
+def set_num_threads(n: int | None = None) -> int:
+    """Use ``n`` OpenMP threads (default: every core this process may run on), whatever ``OMP_NUM_THREADS``
+    says -- ``torch.distributed.run`` exports ``OMP_NUM_THREADS=1`` to its workers."""
+    import os
+
+    if n is None:
+        try:
+            n = len(os.sched_getaffinity(0))
+        except AttributeError:
+            n = os.cpu_count() or 1
+    L = lib()
+    L.orc_set_num_threads.argtypes = [ctypes.c_int]
+    L.orc_set_num_threads(int(n))
+    return num_threads()
+
+
+def index_of_points(x, y, px, py, fill_value: int, method: str = "secant") -> np.ndarray:
+    """Flat cell index ``i * (ny - 1) + j`` of the lowest-index cell containing each point, else ``fill_value``
+    (c2d/_grids.py:223-279 brute, 356-463 secant), OpenMP over the points."""
+    x, y = _f64(x), _f64(y)
+    px, py = _f64(px).reshape(-1), _f64(py).reshape(-1)
+    out = np.empty(px.size, dtype=np.int64)
+    L = lib()
+    L.orc_index_of_points.argtypes = [ctypes.c_int, _c_double_p, _c_double_p, ctypes.c_int64, ctypes.c_int64,
+                                      ctypes.c_int64, _c_double_p, _c_double_p, ctypes.c_int64, _c_int64_p]
+    L.orc_index_of_points.restype = None
+    L.orc_index_of_points(0 if method == "secant" else 1, _d(x), _d(y), x.shape[0], x.shape[1], px.size,
+                          _d(px), _d(py), int(fill_value), _i(out))
+    return out
+
+
 def point_is_inside_polygon(x, y, vertices_x, vertices_y) -> bool:
     vx, vy = _f64(vertices_x), _f64(vertices_y)
     return bool(lib().orc_point_in_polygon(float(x), float(y), _d(vx), _d(vy), vx.size))

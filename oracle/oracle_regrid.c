@@ -58,6 +58,15 @@ int orc_num_threads(void)
     return 1;
 #endif
 }
+/* bench.py's reference arm: torchrun exports OMP_NUM_THREADS=1, which would starve the CPU baseline */
+void orc_set_num_threads(int n)
+{
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}
 void orc_free(void* p) { free(p); }
 
 /* ------------------------------------------------------------------------ */
@@ -375,6 +384,24 @@ void orc_index_of_point_brute(const double* x, const double* y, int64_t nx, int6
                               double px, double py, int64_t* out)
 {
     index_of_point_brute(grid_make(x, y, nx, ny), px, py, &out[0], &out[1]);
+}
+
+/* Many points against one grid (test harness for the 2D find_indices extension): flat cell index
+ * i*(ny-1)+j per point, `fill` when no cell contains it.  method 0 = secant (c2d/_grids.py:356-463),
+ * 1 = brute (c2d/_grids.py:223-279). */
+void orc_index_of_points(int method, const double* x, const double* y, int64_t nx, int64_t ny,
+                         int64_t npts, const double* px, const double* py, int64_t fill, int64_t* out)
+{
+    const grid_t g = grid_make(x, y, nx, ny);
+#pragma omp parallel for schedule(dynamic, 64)
+    for (int64_t p = 0; p < npts; p++) {
+        int64_t i, j;
+        if (method == 0)
+            orc_index_of_point_secant_g(g, px[p], py[p], &i, &j);
+        else
+            index_of_point_brute(g, px[p], py[p], &i, &j);
+        out[p] = (i == ORC_MAXSIZE || j == ORC_MAXSIZE) ? fill : i * (ny - 1) + j;
+    }
 }
 
 /* ------------------------------------------------------------------------ */

@@ -1,0 +1,298 @@
+// bulk_probe.cu -- development probe (not part of the product): how fast can 1-D bulk copies (cp.async.bulk,
+// SASS UBLKCP) stream the apply's footprints (one copy per (frame, input row) of a tile) and write the output tiles
+// back (one copy per (frame, tile row)), as a function of the tile shape?  Copy-only: no compute.
+//
+// Geometry = config 3 without the small distortion: input grid rotated by 0.4 rad, output rectilinear over its
+// bounding box (1.31 input cells per output cell), 2048^2 cells on both sides.  The footprint of a TH x TW output
+// tile is computed exactly (parallelogram clipped row by row, +-1 cell of halo, spans made even).
+//
+//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o bulk_probe bulk_probe.cu && ./bulk_probe
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <algorithm>
+#include <vector>
+
+#define CK(x) do { cudaError_t e = (x); if (e != cudaSuccess) { printf("%s: %s\n", #x, cudaGetErrorString(e)); exit(1); } } while (0)
+
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, unsigned bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity)
+{
+    asm volatile(
+        "{\n.reg .pred p;\nWAIT_%=:\nmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n@p bra DONE_%=;\nbra WAIT_%=;\nDONE_%=:\n}\n" ::"r"(
+            smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void bulk_load(unsigned dst, const void* src, unsigned bytes, uint64_t* bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(dst), "l"(src),
+                 "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_store(void* dst, unsigned src, unsigned bytes)
+{
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;\n" ::"l"(dst), "r"(src), "r"(bytes) : "memory");
+}
+
+constexpr int kMaxRows = 96;
+struct TileRec {
+    int32_t nrows;      // 0: zero tile
+    int32_t cells;      // staged cells per frame
+    int32_t ty, tx;
+    int32_t src[kMaxRows];    // source offset (doubles) inside a frame
+    uint16_t dst[kMaxRows];   // destination offset (doubles) inside a staged frame
+    uint16_t len[kMaxRows];   // cells
+};
+
+// consumers: NCW warps; producer: 1 warp.  T frames per stage, NST stages.
+template <int TH, int TW, int T, int NST, int NCW, int CTAS, int CP, int NOB, int NPW>
+__global__ void __launch_bounds__((NCW + NPW) * 32, CTAS)
+k_probe(const TileRec* __restrict__ tiles, int n_frames, int64_t n_in, int64_t w_out, int64_t n_out,
+        const double* __restrict__ vin, double* __restrict__ vout, int store_mode)
+{
+    extern __shared__ __align__(128) unsigned char smem[];
+    constexpr int kStage = T * CP * 8;
+    constexpr int kOutStride = TH * TW + 2;   // doubles per staged output frame
+    double* out_s = reinterpret_cast<double*>(smem + NST * kStage);          // [2][T][kOutStride]
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + NST * kStage + NOB * T * kOutStride * 8);
+    uint64_t* empty = full + NST;
+    const TileRec& R = tiles[blockIdx.x];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t out_base = (int64_t)R.ty * TH * w_out + (int64_t)R.tx * TW;
+    if (R.nrows == 0) {
+        // zero tile: plain 16-byte stores
+        if (warp < NCW) {
+            const double2 z = make_double2(0.0, 0.0);
+            for (int64_t f = warp; f < n_frames; f += NCW)
+                for (int k = lane; k < TH * TW / 2; k += 32) {
+                    const int r = (2 * k) / TW, c = (2 * k) % TW;
+                    *reinterpret_cast<double2*>(vout + f * n_out + out_base + (int64_t)r * w_out + c) = z;
+                }
+        }
+        return;
+    }
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < NST; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], NCW); }
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    }
+    __syncthreads();
+    const int nsub = (n_frames + T - 1) / T;
+    if (warp >= NCW) {
+        const int pw = warp - NCW;
+        // ---- producer ----
+        constexpr int RPL = (kMaxRows + 31) / 32;
+        int32_t src[RPL];
+        unsigned dst[RPL], len[RPL];
+#pragma unroll
+        for (int j = 0; j < RPL; j++) {
+            const int r = lane + 32 * j;
+            const bool ok = r < R.nrows;
+            src[j] = ok ? R.src[r] : 0;
+            dst[j] = ok ? R.dst[r] * 8u : 0;
+            len[j] = ok ? R.len[r] * 8u : 0;
+        }
+        const unsigned stage_bytes = (unsigned)R.cells * 8u * T;
+        for (int s = 0; s < nsub; s++) {
+            const int st = s % NST;
+            if (s >= NST) mbar_wait(&empty[st], (unsigned)((s / NST - 1) & 1));
+            if (lane == 0 && pw == 0) mbar_expect_tx(&full[st], stage_bytes);
+            __syncwarp();
+            const unsigned sbase = smem_u32(smem) + st * kStage;
+            const int64_t f0 = (int64_t)s * T;
+#pragma unroll 1
+            for (int t = pw; t < T; t += NPW) {
+                int64_t f = f0 + t;
+                if (f >= n_frames) f = n_frames - 1;   // tail: re-read the last frame (keeps the tx count fixed)
+                const double* fr = vin + f * n_in;
+#pragma unroll
+                for (int j = 0; j < RPL; j++)
+                    if (len[j]) bulk_load(sbase + t * (CP * 8) + dst[j], fr + src[j], len[j], &full[st]);
+            }
+        }
+    } else {
+        // ---- consumers ----
+        for (int s = 0; s < nsub; s++) {
+            const int st = s % NST;
+            mbar_wait(&full[st], (unsigned)((s / NST) & 1));
+            const int64_t f0 = (int64_t)s * T;
+            if (store_mode == 1) {
+                // bulk stores: one per (frame, tile row); rows dealt to (warp, lane)
+                double* ob = out_s + (s % NOB) * T * kOutStride;
+                if (NOB > 1) asm volatile("cp.async.bulk.wait_group.read 1;\n" ::: "memory"); else asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory");
+                for (int k = warp * 32 + lane; k < T * TH; k += NCW * 32) {
+                    const int t = k / TH, r = k % TH;
+                    const int64_t f = f0 + t;
+                    if (f < n_frames)
+                        bulk_store(vout + f * n_out + out_base + (int64_t)r * w_out, smem_u32(ob + t * kOutStride + r * TW), TW * 8);
+                }
+                asm volatile("cp.async.bulk.commit_group;\n" ::: "memory");
+            } else if (store_mode == 2) {
+                // plain 16-byte stores from the staging area
+                const double* ob = out_s + (s % NOB) * T * kOutStride;
+                for (int k = warp * 32 + lane; k < T * TH * TW / 2; k += NCW * 32) {
+                    const int t = k / (TH * TW / 2), rc = k % (TH * TW / 2);
+                    const int r = (2 * rc) / TW, c = (2 * rc) % TW;
+                    const int64_t f = f0 + t;
+                    if (f < n_frames)
+                        *reinterpret_cast<double2*>(vout + f * n_out + out_base + (int64_t)r * w_out + c) =
+                            *reinterpret_cast<const double2*>(ob + t * kOutStride + r * TW + c);
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty[st]);
+        }
+        asm volatile("cp.async.bulk.wait_group 0;\n" ::: "memory");
+    }
+}
+
+// ---- host: exact footprints of the rotated geometry ----
+struct Geo {
+    int N = 2048;
+    double theta = 0.4;
+    void map(double io, double jo, double& fi, double& fj) const
+    {
+        const double c = cos(theta), s = sin(theta), ext = c + s;   // output bbox = [-ext, ext]^2
+        const double X = -ext + 2 * ext * io / N, Y = -ext + 2 * ext * jo / N;
+        const double x = X * c + Y * s, y = -X * s + Y * c;          // inverse rotation
+        fi = (x + 1) * 0.5 * N;
+        fj = (y + 1) * 0.5 * N;
+    }
+};
+
+static void make_tiles(int TH, int TW, int CPmax, std::vector<TileRec>& out, double& cells_per_out, double& rows_avg, int& too_big)
+{
+    Geo G;
+    const int N = G.N, tiles_y = N / TH, tiles_x = N / TW;
+    std::vector<TileRec> recs((size_t)tiles_y * tiles_x);
+    double tot_cells = 0, tot_rows = 0;
+    int64_t staged = 0;
+    too_big = 0;
+    for (int ty = 0; ty < tiles_y; ty++)
+        for (int tx = 0; tx < tiles_x; tx++) {
+            TileRec& R = recs[(size_t)ty * tiles_x + tx];
+            R.ty = ty; R.tx = tx; R.nrows = 0; R.cells = 0;
+            double pi[4], pj[4];
+            const double ci[4] = {(double)ty * TH, (double)ty * TH + TH, (double)ty * TH + TH, (double)ty * TH};
+            const double cj[4] = {(double)tx * TW, (double)tx * TW, (double)tx * TW + TW, (double)tx * TW + TW};
+            double imin = 1e30, imax = -1e30;
+            for (int k = 0; k < 4; k++) { G.map(ci[k], cj[k], pi[k], pj[k]); imin = std::min(imin, pi[k]); imax = std::max(imax, pi[k]); }
+            const int r0 = std::max(0, (int)floor(imin)), r1 = std::min(N - 1, (int)floor(imax));
+            int off = 0, nr = 0;
+            for (int r = r0; r <= r1; r++) {
+                // j-extent of the parallelogram inside the strip [r, r+1]
+                double jmin = 1e30, jmax = -1e30;
+                for (int k = 0; k < 4; k++) {
+                    const int k2 = (k + 1) & 3;
+                    if (pi[k] >= r && pi[k] <= r + 1) { jmin = std::min(jmin, pj[k]); jmax = std::max(jmax, pj[k]); }
+                    for (int side = 0; side < 2; side++) {
+                        const double lv = r + side;
+                        if ((pi[k] - lv) * (pi[k2] - lv) < 0) {
+                            const double t = (lv - pi[k]) / (pi[k2] - pi[k]);
+                            const double j = pj[k] + t * (pj[k2] - pj[k]);
+                            jmin = std::min(jmin, j); jmax = std::max(jmax, j);
+                        }
+                    }
+                }
+                if (jmax < jmin) continue;
+                int c0 = (int)floor(jmin), c1 = (int)floor(jmax);
+                if (c1 < 0 || c0 > N - 1) continue;
+                c0 = std::max(c0, 0) & ~1;
+                c1 = std::min(c1, N - 1) | 1;
+                if (nr >= kMaxRows) { nr = kMaxRows + 1; break; }
+                R.src[nr] = r * N + c0;
+                R.dst[nr] = (uint16_t)off;
+                R.len[nr] = (uint16_t)(c1 - c0 + 1);
+                off += c1 - c0 + 1;
+                nr++;
+            }
+            if (nr > kMaxRows || off > CPmax) { too_big++; nr = 0; off = 0; }
+            R.nrows = nr; R.cells = off;
+            if (nr) { tot_cells += off; tot_rows += nr; staged++; }
+        }
+    // patch-major order: patches of ~12 x 12 tiles
+    const int PR = 12, PC = 12;
+    out.clear();
+    for (int py = 0; py < (tiles_y + PR - 1) / PR; py++)
+        for (int px = 0; px < (tiles_x + PC - 1) / PC; px++)
+            for (int y = py * PR; y < std::min(tiles_y, (py + 1) * PR); y++)
+                for (int x = px * PC; x < std::min(tiles_x, (px + 1) * PC); x++) out.push_back(recs[(size_t)y * tiles_x + x]);
+    cells_per_out = staged ? tot_cells / ((double)staged * TH * TW) : 0;
+    rows_avg = staged ? tot_rows / staged : 0;
+}
+
+template <int TH, int TW, int T, int NST, int NCW, int CTAS, int CP, int NOB, int NPW>
+static void run(const double* vin, double* vout, int F)
+{
+    std::vector<TileRec> tiles;
+    double cpo, rows;
+    int too_big;
+    make_tiles(TH, TW, CP - 2, tiles, cpo, rows, too_big);
+    TileRec* d_tiles;
+    CK(cudaMalloc(&d_tiles, tiles.size() * sizeof(TileRec)));
+    CK(cudaMemcpy(d_tiles, tiles.data(), tiles.size() * sizeof(TileRec), cudaMemcpyHostToDevice));
+    const int N = 2048;
+    const size_t smem = (size_t)NST * T * CP * 8 + NOB * T * (TH * TW + 2) * 8 + 2 * NST * 8 + 64;
+    auto kern = k_probe<TH, TW, T, NST, NCW, CTAS, CP, NOB, NPW>;
+    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0));
+    CK(cudaEventCreate(&e1));
+    for (int mode = 0; mode < 3; mode++) {
+        for (int it = 0; it < 2; it++)
+            kern<<<(unsigned)tiles.size(), (NCW + NPW) * 32, smem>>>(d_tiles, F, (int64_t)N * N, N, (int64_t)N * N, vin, vout, mode);
+        CK(cudaDeviceSynchronize());
+        CK(cudaEventRecord(e0));
+        const int reps = 5;
+        for (int it = 0; it < reps; it++)
+            kern<<<(unsigned)tiles.size(), (NCW + NPW) * 32, smem>>>(d_tiles, F, (int64_t)N * N, N, (int64_t)N * N, vin, vout, mode);
+        CK(cudaEventRecord(e1));
+        CK(cudaDeviceSynchronize());
+        float ms;
+        CK(cudaEventElapsedTime(&ms, e0, e1));
+        ms /= reps;
+        const double bytes = 8.0 * F * (double)N * N * (mode ? 2 : 1);
+        printf("tile %2dx%2d T=%2d stages=%d warps=%d+%d ctas=%d smem=%6zu  rows/tile %.1f  staged cells/out cell %.2f  too_big %d  "
+               "store=%s : %.3f ms  %.0f GB/s\n",
+               TH, TW, T, NST, NCW, NPW, CTAS, smem, rows, cpo, too_big, mode == 0 ? "none" : mode == 1 ? "bulk" : "stg ", ms, bytes / ms / 1e6);
+    }
+    CK(cudaFree(d_tiles));
+}
+
+int main()
+{
+    const int F = 256, N = 2048;
+    double *vin, *vout;
+    CK(cudaMalloc(&vin, (size_t)F * N * N * 8));
+    CK(cudaMalloc(&vout, (size_t)F * N * N * 8));
+    CK(cudaMemset(vin, 0, (size_t)F * N * N * 8));
+    CK(cudaMemset(vout, 0, (size_t)F * N * N * 8));
+    //   TH  TW   T NST NCW CTAS  CP NOB NPW
+    run<4, 32, 16, 2, 16, 2, 386, 2, 1>(vin, vout, F);     // the geometry of k_apply_staged (v9)
+    run<8, 32, 16, 2, 16, 1, 706, 1, 1>(vin, vout, F);
+    run<8, 32, 8, 3, 16, 1, 706, 2, 1>(vin, vout, F);
+    run<8, 32, 8, 3, 16, 1, 706, 2, 2>(vin, vout, F);
+    run<8, 32, 8, 2, 8, 2, 706, 2, 1>(vin, vout, F);
+    run<16, 32, 8, 2, 16, 1, 1186, 2, 1>(vin, vout, F);
+    run<16, 32, 8, 2, 16, 1, 1186, 2, 2>(vin, vout, F);
+    run<16, 32, 8, 2, 16, 1, 1186, 2, 4>(vin, vout, F);
+    run<16, 32, 4, 4, 16, 1, 1186, 2, 2>(vin, vout, F);
+    run<8, 64, 8, 2, 16, 1, 1186, 2, 2>(vin, vout, F);
+    run<16, 64, 4, 2, 16, 1, 2210, 2, 2>(vin, vout, F);
+    run<32, 32, 4, 2, 16, 1, 2210, 2, 2>(vin, vout, F);
+    return 0;
+}
