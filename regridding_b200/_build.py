@@ -14,7 +14,7 @@ HERE = pathlib.Path(__file__).resolve().parent
 CSRC = HERE / "csrc"
 LIB = HERE / "libregrid_b200.so"
 
-SOURCES = ["rg_util.cu", "rg_apply.cu", "rg_apply_staged.cu", "rg_build2d.cu", "rg_locate.cu", "rg_cons1d.cu", "rg_multilinear2d.cu", "rg_fill.cu"]
+SOURCES = ["rg_util.cu", "rg_apply.cu", "rg_apply_bulk.cu", "rg_build2d.cu", "rg_locate.cu", "rg_cons1d.cu", "rg_multilinear2d.cu", "rg_fill.cu"]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
@@ -40,13 +40,14 @@ def needs_build() -> bool:
 
 
 def build(force: bool = False, verbose: bool = False, defines: list[str] | None = None,
-          out: pathlib.Path | None = None) -> pathlib.Path:
-    """``defines``/``out`` build a tuning variant next to the product library (development only)."""
+          out: pathlib.Path | None = None, replace: dict[str, str] | None = None) -> pathlib.Path:
+    """``defines``/``out``/``replace`` (source file substitutions) build a tuning variant next to the product
+    library (development only)."""
     if out is None and not force and not needs_build():
         return LIB
     out = out or LIB
     cmd = [nvcc(), *NVCC_FLAGS, *[f"-D{d}" for d in (defines or [])], "-ccbin", "/usr/bin/g++", "-o", str(out),
-           *[str(CSRC / s) for s in SOURCES]]
+           *[str(CSRC / (replace or {}).get(s, s)) for s in SOURCES]]
     if verbose:
         cmd.insert(1, "-Xptxas")
         cmd.insert(2, "-v")

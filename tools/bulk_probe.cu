@@ -273,6 +273,152 @@ static void run(const double* vin, double* vout, int F)
     CK(cudaFree(d_tiles));
 }
 
+
+// ---------------------------------------------------------------------------
+// 2-D tensor-map boxes {W cells, T frames}: one TMA instruction per row piece for ALL frames of a stage
+// ---------------------------------------------------------------------------
+#include <cuda.h>
+typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                             const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                             CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+__device__ __forceinline__ void tma_load_2d(unsigned dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar)
+{
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];\n" ::"r"(dst),
+                 "l"(map), "r"(c0), "r"(c1), "r"(smem_u32(bar))
+                 : "memory");
+}
+constexpr int kMaxBox = 352;
+struct BoxRec {
+    int32_t nbox, ty, tx, pad;
+    int32_t src[kMaxBox];
+};
+template <int TH, int TW, int T, int NST, int NCW, int NPW, int W, int MAXB>
+__global__ void __launch_bounds__((NCW + NPW) * 32, 1)
+k_box(const __grid_constant__ CUtensorMap map, const BoxRec* __restrict__ tiles, int n_frames, int64_t w_out, int64_t n_out,
+      double* __restrict__ vout, int store_mode)
+{
+    extern __shared__ __align__(128) unsigned char smem[];
+    constexpr int kBox = W * 8 * T;
+    constexpr int kStage = MAXB * kBox;
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + NST * kStage);
+    uint64_t* empty = full + NST;
+    const BoxRec& R = tiles[blockIdx.x];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t out_base = (int64_t)R.ty * TH * w_out + (int64_t)R.tx * TW;
+    if (R.nbox == 0) {
+        if (warp < NCW) {
+            const double2 z = make_double2(0.0, 0.0);
+            for (int64_t f = warp; f < n_frames; f += NCW)
+                for (int k = lane; k < TH * TW / 2; k += 32) {
+                    const int r = (2 * k) / TW, c = (2 * k) % TW;
+                    *reinterpret_cast<double2*>(vout + f * n_out + out_base + (int64_t)r * w_out + c) = z;
+                }
+        }
+        return;
+    }
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < NST; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], NCW); }
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    }
+    __syncthreads();
+    const int nsub = (n_frames + T - 1) / T;
+    if (warp >= NCW) {
+        const int pw = warp - NCW;
+        for (int s = 0; s < nsub; s++) {
+            const int st = s % NST;
+            if (s >= NST) mbar_wait(&empty[st], (unsigned)((s / NST - 1) & 1));
+            if (lane == 0 && pw == 0) mbar_expect_tx(&full[st], (unsigned)R.nbox * kBox);
+            __syncwarp();
+            const unsigned sbase = smem_u32(smem) + st * kStage;
+            for (int b = pw * 32 + lane; b < R.nbox; b += NPW * 32)
+                tma_load_2d(sbase + b * kBox, &map, R.src[b], s * T, &full[st]);
+        }
+    } else {
+        for (int s = 0; s < nsub; s++) {
+            const int st = s % NST;
+            mbar_wait(&full[st], (unsigned)((s / NST) & 1));
+            const int64_t f0 = (int64_t)s * T;
+            if (store_mode == 2) {
+                const double* ob = reinterpret_cast<const double*>(smem + st * kStage);
+                for (int k = warp * 32 + lane; k < T * TH * TW / 2; k += NCW * 32) {
+                    const int t = k / (TH * TW / 2), rc = k % (TH * TW / 2);
+                    const int r = (2 * rc) / TW, c = (2 * rc) % TW;
+                    const int64_t f = f0 + t;
+                    if (f < n_frames)
+                        *reinterpret_cast<double2*>(vout + f * n_out + out_base + (int64_t)r * w_out + c) =
+                            *reinterpret_cast<const double2*>(ob + 2 * k);
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty[st]);
+        }
+    }
+}
+
+template <int TH, int TW, int T, int NST, int NCW, int NPW, int W, int MAXB>
+static void run_box(EncodeFn enc, const double* vin, double* vout, int F, CUtensorMapSwizzle swz, const char* swz_name)
+{
+    std::vector<TileRec> tiles;
+    double cpo, rows;
+    int too_big;
+    make_tiles(TH, TW, 100000, tiles, cpo, rows, too_big);
+    const int N = 2048;
+    std::vector<BoxRec> boxes(tiles.size());
+    double nb_tot = 0, live = 0;
+    int nb_max = 0;
+    for (size_t i = 0; i < tiles.size(); i++) {
+        BoxRec& B = boxes[i];
+        B.ty = tiles[i].ty; B.tx = tiles[i].tx; B.nbox = 0; B.pad = 0;
+        for (int r = 0; r < tiles[i].nrows; r++)
+            for (int c = 0; c < tiles[i].len[r]; c += W) {
+                if (B.nbox < MAXB) B.src[B.nbox] = std::min(tiles[i].src[r] + c, N * N - W);
+                B.nbox++;
+            }
+        if (B.nbox > MAXB) { printf("too many boxes %d\n", B.nbox); B.nbox = MAXB; }
+        if (B.nbox) { nb_tot += B.nbox; live++; nb_max = std::max(nb_max, B.nbox); }
+    }
+    BoxRec* d_tiles;
+    CK(cudaMalloc(&d_tiles, boxes.size() * sizeof(BoxRec)));
+    CK(cudaMemcpy(d_tiles, boxes.data(), boxes.size() * sizeof(BoxRec), cudaMemcpyHostToDevice));
+    CUtensorMap map;
+    {
+        cuuint64_t dims[2] = {(cuuint64_t)N * N, (cuuint64_t)F};
+        cuuint64_t strides[1] = {(cuuint64_t)N * N * 8};
+        cuuint32_t box[2] = {W, T};
+        cuuint32_t es[2] = {1, 1};
+        CUresult r = enc(&map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, (void*)vin, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                         swz, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) { printf("encode failed %d (W=%d %s)\n", (int)r, W, swz_name); return; }
+    }
+    constexpr int kBox = W * 8 * T;
+    const size_t smem = (size_t)NST * MAXB * kBox + 2 * NST * 8 + 64;
+    if (smem > 227 * 1024) { printf("smem too large\n"); return; }
+    auto kern = k_box<TH, TW, T, NST, NCW, NPW, W, MAXB>;
+    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0));
+    CK(cudaEventCreate(&e1));
+    for (int mode = 0; mode < 3; mode += 2) {
+        for (int it = 0; it < 2; it++)
+            kern<<<(unsigned)boxes.size(), (NCW + NPW) * 32, smem>>>(map, d_tiles, F, N, (int64_t)N * N, vout, mode);
+        CK(cudaDeviceSynchronize());
+        CK(cudaEventRecord(e0));
+        const int reps = 5;
+        for (int it = 0; it < reps; it++)
+            kern<<<(unsigned)boxes.size(), (NCW + NPW) * 32, smem>>>(map, d_tiles, F, N, (int64_t)N * N, vout, mode);
+        CK(cudaEventRecord(e1));
+        CK(cudaDeviceSynchronize());
+        float ms;
+        CK(cudaEventElapsedTime(&ms, e0, e1));
+        ms /= reps;
+        const double bytes = 8.0 * F * (double)N * N * (mode ? 2 : 1);
+        printf("BOX tile %2dx%2d T=%d stages=%d warps=%d+%d W=%2d swz=%s smem=%zu boxes/tile %.1f max %d staged cells/out %.2f store=%s : %.3f ms  %.0f GB/s\n",
+               TH, TW, T, NST, NCW, NPW, W, swz_name, smem, nb_tot / live, nb_max, nb_tot * W / (live * TH * TW),
+               mode == 0 ? "none" : "stg ", ms, bytes / ms / 1e6);
+    }
+    CK(cudaFree(d_tiles));
+}
+
 int main()
 {
     const int F = 256, N = 2048;
@@ -281,18 +427,27 @@ int main()
     CK(cudaMalloc(&vout, (size_t)F * N * N * 8));
     CK(cudaMemset(vin, 0, (size_t)F * N * N * 8));
     CK(cudaMemset(vout, 0, (size_t)F * N * N * 8));
+    EncodeFn enc = nullptr;
+    {
+        cudaDriverEntryPointQueryResult qres;
+        void* fn = nullptr;
+        CK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+        enc = (EncodeFn)fn;
+    }
+    //      TH  TW  T NST NCW NPW  W
+    run_box<16, 32, 8, 2, 16, 1, 8, 200>(enc, vin, vout, F, CU_TENSOR_MAP_SWIZZLE_64B, "64B");
+    run_box<16, 32, 8, 2, 16, 2, 8, 200>(enc, vin, vout, F, CU_TENSOR_MAP_SWIZZLE_64B, "64B");
+    run_box<16, 32, 8, 2, 16, 4, 8, 200>(enc, vin, vout, F, CU_TENSOR_MAP_SWIZZLE_64B, "64B");
+    run_box<16, 32, 8, 2, 16, 8, 8, 200>(enc, vin, vout, F, CU_TENSOR_MAP_SWIZZLE_64B, "64B");
+    run_box<16, 32, 8, 2, 16, 4, 8, 200>(enc, vin, vout, F, CU_TENSOR_MAP_SWIZZLE_NONE, "none");
+    run_box<12, 32, 8, 2, 16, 4, 8, 170>(enc, vin, vout, F, CU_TENSOR_MAP_SWIZZLE_64B, "64B");
+    run_box<8, 32, 8, 2, 16, 4, 8, 130>(enc, vin, vout, F, CU_TENSOR_MAP_SWIZZLE_64B, "64B");
+    run_box<8, 32, 8, 3, 16, 4, 8, 130>(enc, vin, vout, F, CU_TENSOR_MAP_SWIZZLE_64B, "64B");
+    run_box<8, 32, 8, 2, 16, 4, 16, 100>(enc, vin, vout, F, CU_TENSOR_MAP_SWIZZLE_128B, "128B");
+    run_box<12, 32, 8, 2, 16, 4, 16, 100>(enc, vin, vout, F, CU_TENSOR_MAP_SWIZZLE_128B, "128B");
+    run_box<16, 32, 8, 2, 16, 4, 4, 340>(enc, vin, vout, F, CU_TENSOR_MAP_SWIZZLE_32B, "32B");
+    run_box<16, 32, 8, 2, 16, 8, 4, 340>(enc, vin, vout, F, CU_TENSOR_MAP_SWIZZLE_32B, "32B");
     //   TH  TW   T NST NCW CTAS  CP NOB NPW
-    run<4, 32, 16, 2, 16, 2, 386, 2, 1>(vin, vout, F);     // the geometry of k_apply_staged (v9)
-    run<8, 32, 16, 2, 16, 1, 706, 1, 1>(vin, vout, F);
-    run<8, 32, 8, 3, 16, 1, 706, 2, 1>(vin, vout, F);
-    run<8, 32, 8, 3, 16, 1, 706, 2, 2>(vin, vout, F);
-    run<8, 32, 8, 2, 8, 2, 706, 2, 1>(vin, vout, F);
-    run<16, 32, 8, 2, 16, 1, 1186, 2, 1>(vin, vout, F);
-    run<16, 32, 8, 2, 16, 1, 1186, 2, 2>(vin, vout, F);
-    run<16, 32, 8, 2, 16, 1, 1186, 2, 4>(vin, vout, F);
-    run<16, 32, 4, 4, 16, 1, 1186, 2, 2>(vin, vout, F);
-    run<8, 64, 8, 2, 16, 1, 1186, 2, 2>(vin, vout, F);
-    run<16, 64, 4, 2, 16, 1, 2210, 2, 2>(vin, vout, F);
-    run<32, 32, 4, 2, 16, 1, 2210, 2, 2>(vin, vout, F);
+    run<16, 32, 8, 2, 16, 1, 1186, 2, 8>(vin, vout, F);
     return 0;
 }
