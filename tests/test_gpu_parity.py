@@ -630,63 +630,48 @@ def test_find_indices_2d_config5_shape_properties(rg, dev):
 
 
 def test_apply_degenerate_sizes(rg, dev):
-    """Zero frames and odd (not 16-byte friendly) grid widths take the generic paths and stay correct."""
-    gi = cases.curvilinear(12, 10)                     # 11 x 9 cells: odd input width
+    """Odd (not 16-byte friendly) grid sizes are staged too -- odd frames one cell later, the unpaired last frame
+    through the generic kernel -- misaligned value pointers take the generic path; zero frames are a no-op."""
+    gi = cases.curvilinear(12, 10)                     # 11 x 9 = 99 cells: odd input width and odd n_in
     go = cases.rectilinear_over(gi[0], gi[1], 8, 8)    # 7 x 7 cells: odd output width
     dw = rg.device.build_weights_2d(gi[0], gi[1], go[0], go[1], device=dev)
     plan = dw.plan((11, 9), (7, 7))
-    assert plan.n_generic_tiles == plan.n_tiles  # odd widths cannot be moved in 16-byte pieces
-    x = torch.rand((5, dw.n_in), dtype=torch.float64, device=dev)
+    assert plan.n_generic_tiles == 0  # no odd-width cliff: the bulk-copy kernel stages flat, even-aligned spans
+    for F in (1, 2, 5, 8, 9, 16, 23):
+        x = torch.rand((F, dw.n_in), dtype=torch.float64, device=dev)
+        assert torch.equal(rg.device.apply_planned(plan, x), rg.device.apply_csr(dw.csr(), x)), F
+    # values that start 8 bytes off a 16-byte boundary
+    big = torch.rand((7, dw.n_in), dtype=torch.float64, device=dev)
+    x = big[1:]
+    assert x.data_ptr() % 16 == 8 and x.is_contiguous()
     assert torch.equal(rg.device.apply_planned(plan, x), rg.device.apply_csr(dw.csr(), x))
+    # output rows that start 8 bytes off (odd w_out and a misaligned out buffer)
+    outbuf = torch.empty((7, dw.n_out), dtype=torch.float64, device=dev)
+    x = torch.rand((6, dw.n_in), dtype=torch.float64, device=dev)
+    got = rg.device.apply_planned(plan, x, out=outbuf[1:])
+    assert torch.equal(got, rg.device.apply_csr(dw.csr(), x))
     empty = torch.empty((0, dw.n_in), dtype=torch.float64, device=dev)
     assert rg.device.apply_planned(plan, empty).shape == (0, dw.n_out)
     assert rg.device.apply_csr(dw.csr(), empty).shape == (0, dw.n_out)
 
 
-def test_weights_packed_equals_weights(rg, dev, tmp_path):
-    """weights_packed (four flat arrays) holds exactly what weights() returns, survives its file
-    format, and regrid_from_weights takes it directly."""
-    # per-slice 2D grids (config-4 layout at small size)
-    gis, gos = cases.case_2d_batched()
-    W = rg.weights(gis, gos, axis_input=(-2, -1), axis_output=(-2, -1), method="conservative")
-    P = rg.weights_packed(gis, gos, axis_input=(-2, -1), axis_output=(-2, -1), method="conservative")
-    assert len(P) == W[0].size and P.shape_input == W[1] and P.shape_output == W[2]
-    back = P.to_reference()[0]
-    for idx in np.ndindex(*W[0].shape):
-        for a, b in zip(back[idx], W[0][idx]):
-            assert np.array_equal(a, b)
-    P.save(tmp_path / "w.rgpw")
-    Q = rg.PackedWeights.load(tmp_path / "w.rgpw")
-    vals = np.random.default_rng(0).random(W[1])
-    r0 = rg.regrid_from_weights(W[0], W[1], W[2], vals, axis_input=(-2, -1), axis_output=(-2, -1))
-    r1 = rg.regrid_from_weights(Q, Q.shape_input, Q.shape_output, vals, axis_input=(-2, -1), axis_output=(-2, -1))
-    assert np.array_equal(r0, r1)
-    dws = Q.to_device(dev)
-    assert len(dws) == len(Q) and all(d.nnz == int(Q.offsets[k + 1] - Q.offsets[k]) for k, d in enumerate(dws))
-    # per-spectrum 1D grids (config-2 layout)
-    xin, xout, _ = cases.cases_1d()["spectra"]
-    W1 = rg.weights(xin, xout, axis_input=-1, axis_output=-1, method="conservative")
-    P1 = rg.weights_packed(xin, xout, axis_input=-1, axis_output=-1, method="conservative")
-    for k in range(W1[0].size):
-        for a, b in zip(P1.element(k), W1[0].reshape(-1)[k]):
-            assert np.array_equal(a, b)
-
-
-@pytest.mark.parametrize("seed,amp", [(11, 0.45), (12, 0.48), (13, 0.48)])
-def test_build2d_concave_cells_bit_exact(rg, dev, oracle, seed, amp):
-    """Grids with CONCAVE cells (vertex jitter of almost half a cell): the walk-state guesses of the build take
-    shortcuts that assume convex cells, so some may be wrong here -- the chain repair must still reproduce the
-    reference's sequential walk exactly (in both roles: jittered grid as input and as output)."""
-    rng = np.random.default_rng(seed)
-    gi = cases.curvilinear(24, 21)
-    h = np.hypot(gi[0][1, 0] - gi[0][0, 0], gi[1][1, 0] - gi[1][0, 0])
-    xi = gi[0] + amp * h * rng.uniform(-1, 1, gi[0].shape)
-    yi = gi[1] + amp * h * rng.uniform(-1, 1, gi[1].shape)
-    go = cases.rectilinear_over(xi, yi, 19, 23)
+@pytest.mark.parametrize("shape_in,shape_out", [((100, 100), (120, 80)), ((101, 98), (57, 131)), ((64, 333), (200, 31))])
+def test_apply_bulk_odd_and_ragged_shapes(rg, dev, oracle, shape_in, shape_out):
+    """Vertex counts that make n_in / w_in / w_out odd in every combination, with partial tiles on both output axes:
+    staged apply == generic apply == oracle, for frame counts around the 8-frame stage and the 512-frame block."""
+    gi = cases.curvilinear(*shape_in, distort=0.01)
+    go = cases.rectilinear_over(gi[0], gi[1], *shape_out)
     co = cases.perturb_like_reference(go, (-1, -2), 42)
-    for a, b in (((xi, yi), co), (co, (xi, yi))):
-        dw = rg.device.build_weights_2d(a[0], a[1], b[0], b[1], device=dev)
-        oi, oo, ov = oracle.coalesce(*oracle.weights_conservative_2d(a, b))
-        ii, io, v = dw.to_host()
-        assert np.array_equal(ii, oi) and np.array_equal(io, oo)
-        assert np.array_equal(v, ov)
+    dw = rg.device.build_weights_2d(gi[0], gi[1], co[0], co[1], device=dev)
+    cin = (shape_in[0] - 1, shape_in[1] - 1)
+    cout = (shape_out[0] - 1, shape_out[1] - 1)
+    plan = dw.plan(cin, cout)
+    assert plan.n_generic_tiles == 0
+    for F in (3, 8, 15, 513):
+        x = torch.rand((F, dw.n_in), dtype=torch.float64, device=dev)
+        a = rg.device.apply_planned(plan, x)
+        assert torch.equal(a, rg.device.apply_csr(dw.csr(), x)), F
+    ii, io, v = dw.to_host()
+    vals = np.random.default_rng(1).random((9, dw.n_in))
+    ref = oracle.regrid_from_weights(ii, io, v, vals, dw.n_out)
+    assert np.array_equal(rg.device.apply_planned(plan, T(vals, dev)).cpu().numpy(), ref)
