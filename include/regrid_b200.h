@@ -98,6 +98,24 @@ int rg_build2d_emit(int device, void* stream,
 int rg_build2d_stats(int device, void* stream, int64_t nx_in, int64_t ny_in, int64_t nx_out, int64_t ny_out,
                      void* workspace, int32_t* stats_host);
 
+/* Band build for multi-GPU strong scaling of ONE grid pair (the reference's parallel axis is the sweep line,
+ * _weights_conservative_2d.py:286; its result layout is sorted by input cell, _weights_arrays.py:54-59, so bands
+ * of input rows concatenate).  Rank r passes its band of input rows [row_lo, row_hi) and gets that band's public
+ * triplets; it walks only the sweep segments whose bounding box meets a cell of the band (exact, see
+ * rg_build2d.cu).  Stream-ordered, NO host synchronisation: `frags` (16-byte records) and ii / io / v are sized
+ * by the caller's estimate; counts_dev[0] = fragments, [1] = triplets, [2..7] = status flags
+ * (2 walk overflow, 3 repairs, 4 unknown guesses, 5 rank overflow, 6 CHAIN MISMATCH -> the caller must OR this
+ * over the ranks and, if set anywhere, rebuild with rg_build2d_count/_fill/_emit on the same band,
+ * 7 CAPACITY -> buffers too small: reallocate from counts_dev[0..1] and call again). */
+int rg_build2d_band(int device, void* stream,
+                    int64_t nx_in, int64_t ny_in, int64_t nx_out, int64_t ny_out,
+                    const double* x_in, const double* y_in, const double* x_out, const double* y_out,
+                    const double* weights_input_or_null, int64_t row_lo, int64_t row_hi,
+                    void* workspace, size_t workspace_bytes,
+                    void* frags, int64_t frag_capacity,
+                    int64_t* indices_input, int64_t* indices_output, double* values, int64_t nnz_capacity,
+                    int64_t* counts_dev);
+
 /* ------------------------------------------------------------------------------
  * Line-sharded 2D build (strong scaling of ONE large build over W ranks).
  * replaces the same reference code as rg_build2d_* (the reference parallelises the sweep lines with

@@ -209,6 +209,108 @@ def build_weights_2d(x_in, y_in, x_out, y_out, weights_input=None, cell_band: tu
     return dw
 
 
+# learned buffer sizes of band builds: (shape, band) -> (fragments, triplets) of the previous build
+_band_caps: dict = {}
+
+
+@dataclasses.dataclass
+class BandBuild:
+    """One enqueued ``rg_build2d_band``: nothing has been synchronised yet.  ``counts`` (device int64[8]) holds
+    fragments, triplets and the status flags once the stream has run; ``finish()`` reads it."""
+
+    ii: torch.Tensor
+    io: torch.Tensor
+    v: torch.Tensor
+    counts: torch.Tensor
+    frag_capacity: int
+    nnz_capacity: int
+    n_in: int
+    n_out: int
+    key: tuple
+    keep: tuple  # buffers the enqueued kernels still use
+
+    MISMATCH, CAPACITY = 6, 7
+
+    def finish(self, counts_host=None):
+        """-> (DeviceWeights | None, status): status is "ok", "mismatch" (use the sequentially verified build) or
+        "capacity" (buffers were too small: the learned sizes are updated, build again)."""
+        c = (self.counts.cpu() if counts_host is None else counts_host).tolist()
+        nfrag, nnz = int(c[0]), int(c[1])
+        if c[2] or c[5]:
+            raise _lib.RegridB200Error("rg_build2d_band: a sweep walk did not terminate (degenerate or folded grid)")
+        if c[self.CAPACITY]:
+            _band_caps[self.key] = (max(int(nfrag * 1.05) + 1024, self.frag_capacity),
+                                    max(int(nfrag * 0.55) + 1024, self.nnz_capacity))
+            return None, "capacity"
+        if c[self.MISMATCH]:
+            return None, "mismatch"
+        _band_caps[self.key] = (int(nfrag * 1.02) + 1024, int(nnz * 1.02) + 1024)
+        dw = DeviceWeights(self.ii[:nnz], self.io[:nnz], self.v[:nnz], self.n_in, self.n_out)
+        dw.stats = {"fragments": nfrag, "nnz": nnz, "repaired_segments": 0, "unknown_guesses": int(c[4])}
+        return dw, "ok"
+
+
+def build2d_band_enqueue(x_in, y_in, x_out, y_out, weights_input, row_lo: int, row_hi: int, device=None) -> BandBuild:
+    """Enqueue the band build of input rows ``[row_lo, row_hi)`` (``rg_build2d_band``); no host synchronisation."""
+    L = _lib.load()
+    device = cuda_device(device if device is not None else (x_in.device if isinstance(x_in, torch.Tensor) else None))
+    xi, yi = to_device(x_in, device), to_device(y_in, device)
+    xo, yo = to_device(x_out, device), to_device(y_out, device)
+    if xi.ndim != 2 or xi.shape != yi.shape or xo.ndim != 2 or xo.shape != yo.shape:
+        raise ValueError("grids must be 2D arrays with matching x / y shapes")
+    nxi, nyi = xi.shape
+    nxo, nyo = xo.shape
+    n_in, n_out = (nxi - 1) * (nyi - 1), (nxo - 1) * (nyo - 1)
+    w = None
+    if weights_input is not None:
+        w = to_device(weights_input, device)
+        if tuple(w.shape) != (nxi - 1, nyi - 1):
+            raise ValueError(f"weights_input must have the input cell shape {(nxi - 1, nyi - 1)}, got {tuple(w.shape)}")
+    key = (nxi, nyi, nxo, nyo, int(row_lo), int(row_hi))
+    nb = (int(row_hi) - int(row_lo)) * (nyi - 1)
+    if key in _band_caps:
+        fcap, ncap = _band_caps[key]
+    else:
+        share = nb / max(n_in, 1)
+        fcap = int(10 * (nb + n_out * share)) + 4096
+        ncap = fcap // 2
+    with torch.cuda.device(device):
+        st = _stream(device)
+        ws = _workspace(build2d_workspace_bytes(nxi, nyi, nxo, nyo), device)
+        frags = frags_empty(fcap, device)
+        ii = torch.empty(ncap, dtype=I64, device=device)
+        io = torch.empty(ncap, dtype=I64, device=device)
+        v = torch.empty(ncap, dtype=F64, device=device)
+        counts = torch.empty(8, dtype=I64, device=device)
+        _lib.check(L.rg_build2d_band(device.index, st, nxi, nyi, nxo, nyo, xi.data_ptr(), yi.data_ptr(),
+                                     xo.data_ptr(), yo.data_ptr(), _lib.ptr(w), int(row_lo), int(row_hi),
+                                     ws.data_ptr(), ws.numel(), frags.data_ptr(), fcap,
+                                     ii.data_ptr(), io.data_ptr(), v.data_ptr(), ncap, counts.data_ptr()),
+                   "rg_build2d_band")
+    return BandBuild(ii, io, v, counts, fcap, ncap, n_in, n_out, key, (ws, frags, xi, yi, xo, yo, w))
+
+
+def build_weights_2d_band(x_in, y_in, x_out, y_out, weights_input=None, row_band: tuple[int, int] | None = None,
+                          device=None) -> DeviceWeights:
+    """The band ``row_band = (row_lo, row_hi)`` of input rows of the 2D conservative weights, by the exchange-free
+    band build; falls back to the sequentially verified banded build if a chain of walk states does not verify."""
+    nxi, nyi = x_in.shape
+    lo, hi = (0, nxi - 1) if row_band is None else (int(row_band[0]), int(row_band[1]))
+    if lo >= hi:
+        dev = cuda_device(device if device is not None else (x_in.device if isinstance(x_in, torch.Tensor) else None))
+        e = torch.empty(0, dtype=I64, device=dev)
+        return DeviceWeights(e, e.clone(), torch.empty(0, dtype=F64, device=dev), (nxi - 1) * (nyi - 1),
+                             (x_out.shape[0] - 1) * (x_out.shape[1] - 1))
+    for _ in range(3):
+        dw, status = build2d_band_enqueue(x_in, y_in, x_out, y_out, weights_input, lo, hi, device=device).finish()
+        if status == "ok":
+            return dw
+        if status == "mismatch":
+            break
+    return build_weights_2d(x_in, y_in, x_out, y_out, weights_input, cell_band=(lo * (nyi - 1), hi * (nyi - 1)),
+                            device=device)
+
+
 @dataclasses.dataclass
 class PartFragments:
     """Fragments one rank produced by walking its share of the sweep lines (line-sharded build):

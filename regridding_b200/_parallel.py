@@ -213,24 +213,57 @@ def _sharded_build_nccl(x_in, y_in, x_out, y_out, weights_input, rank, W, bounds
     return dw
 
 
+def _sharded_build_band(x_in, y_in, x_out, y_out, weights_input, rank, W, group, device, mark):
+    """Exchange-free band build: rank r builds the band of input rows ``shard_range(ncx, r, W)`` by walking only the
+    sweep segments that can reach it (``rg_build2d_band``).  The only collective is an 16-byte all-reduce (MAX) of the
+    status flags: a chain of walk states that does not verify on ANY rank sends every rank to the sequentially
+    verified banded build, a too-small buffer anywhere repeats the build with the learned sizes."""
+    nxi, nyi = x_in.shape
+    lo, hi = shard_range(nxi - 1, rank, W)
+    dev = _device.cuda_device(device if device is not None else (x_in.device if isinstance(x_in, torch.Tensor) else None))
+    status = "mismatch"
+    dw = None
+    for _ in range(4):
+        bb = _device.build2d_band_enqueue(x_in, y_in, x_out, y_out, weights_input, lo, hi, device=dev) if hi > lo else None
+        counts = bb.counts if bb is not None else torch.zeros(8, dtype=torch.int64, device=dev)
+        flags = counts[6:8].clone()
+        dist.all_reduce(flags, op=dist.ReduceOp.MAX, group=group)
+        host = torch.cat([counts[:6], flags]).cpu()  # the one host synchronisation of the build
+        if bb is None:
+            status = "mismatch" if host[6] else ("capacity" if host[7] else "ok")
+        else:
+            dw, status = bb.finish(host)
+        if status != "capacity":
+            break
+    mark("band")
+    if status != "ok":
+        ncy = nyi - 1
+        dw = _device.build_weights_2d(x_in, y_in, x_out, y_out, weights_input, cell_band=(lo * ncy, hi * ncy), device=dev)
+        mark("fallback")
+    elif dw is None:
+        e = torch.empty(0, dtype=torch.int64, device=dev)
+        dw = _device.DeviceWeights(e, e.clone(), torch.empty(0, dtype=torch.float64, device=dev),
+                                   (nxi - 1) * (nyi - 1), (x_out.shape[0] - 1) * (x_out.shape[1] - 1))
+    return dw
+
+
 def build_weights_2d_sharded(x_in, y_in, x_out, y_out, weights_input=None, replicate: bool = False,
-                             group=None, device=None, exchange: str = "p2p",
+                             group=None, device=None, exchange: str = "band",
                              phases: dict | None = None) -> _device.DeviceWeights:
     """Strong-scaling build of ONE large grid pair over the ranks of ``group``.
 
-    Every rank holds the full coordinate arrays (134 MB at 2049^2) and walks every W-th block of 32 sweep
-    lines of all four passes; its fragments come out bucketed by input cell, so the share of every
-    input-row band is one contiguous range.  The owner of a band then merges the W shares of its band
-    (``rg_build2d_merge``): with ``exchange="p2p"`` it reads them in place from the other ranks' peer-mapped
-    memory over NVLink (one barrier, no send); with ``exchange="nccl"`` they travel by all-to-all first.
+    Every rank holds the full coordinate arrays (134 MB at 2049^2).  ``exchange="band"`` (default): rank r builds its
+    band of input rows and walks only the sweep segments that can reach it -- no fragments are exchanged at all
+    (``rg_build2d_band``).  ``exchange="p2p"`` / ``"nccl"``: the older line-sharded build (every rank walks every W-th
+    block of 32 sweep lines, the band owners gather the fragments over NVLink peer memory or by all-to-all and merge).
     Returns this rank's band of the public triplets; with ``replicate`` the bands are all-gathered so that
     every rank holds the full matrix (equal to the single-GPU build bit for bit).
-    ``phases`` (development) receives the milliseconds of walk / exchange / merge."""
+    ``phases`` (development) receives the milliseconds of the phases."""
     rank, W = world(group)
     if W == 1:
         return _device.build_weights_2d(x_in, y_in, x_out, y_out, weights_input, device=device)
-    if exchange not in ("p2p", "nccl"):
-        raise ValueError(f"exchange must be 'p2p' or 'nccl', got {exchange!r}")
+    if exchange not in ("band", "p2p", "nccl"):
+        raise ValueError(f"exchange must be 'band', 'p2p' or 'nccl', got {exchange!r}")
     nxi, nyi = x_in.shape
     bounds = band_bounds(nxi - 1, nyi - 1, W)
     marks = []
@@ -242,8 +275,11 @@ def build_weights_2d_sharded(x_in, y_in, x_out, y_out, weights_input=None, repli
             marks.append((name, e))
 
     mark("start")
-    impl = _sharded_build_p2p if exchange == "p2p" else _sharded_build_nccl
-    dw = impl(x_in, y_in, x_out, y_out, weights_input, rank, W, bounds, group, device, mark)
+    if exchange == "band":
+        dw = _sharded_build_band(x_in, y_in, x_out, y_out, weights_input, rank, W, group, device, mark)
+    else:
+        impl = _sharded_build_p2p if exchange == "p2p" else _sharded_build_nccl
+        dw = impl(x_in, y_in, x_out, y_out, weights_input, rank, W, bounds, group, device, mark)
     if replicate:
         ii, io, v = allgather_concat([dw.indices_input, dw.indices_output, dw.values], group)
         out = _device.DeviceWeights(ii, io, v, dw.n_in, dw.n_out)

@@ -103,6 +103,8 @@ constexpr int kFlagOverflow = 0;   // a verified walk exceeded max_iter
 constexpr int kFlagRepairs = 1;    // number of re-walked segments
 constexpr int kFlagUnknown = 2;    // number of vertices whose guess was "unknown"
 constexpr int kFlagSeqOverflow = 3;  // piece index overflowed the 29-bit rank field
+constexpr int kFlagBandMismatch = 4; // band build: a walked segment did not start in the state its predecessor ended in
+constexpr int kFlagCapacity = 5;     // band build: the caller's fragment / triplet buffers are too small
 
 __device__ __forceinline__ int64_t vertex_of(const PassParams& P, int L, int k)
 {
@@ -147,6 +149,29 @@ __global__ void k_cell_area(GridView g, double* __restrict__ area)
     const double A0 = tri_area(y00, x00, y10, x10, b == 0);
     const double A1 = tri_area(y01, x01, y11, x11, false);
     // axis 1: lines i = a, a+1 ; edge from (i, b) to (i, b+1)
+    const double B0 = tri_area(x00, y00, x01, y01, a == 0);
+    const double B1 = tri_area(x10, y10, x11, y11, false);
+    double r = dsub(0.0, A0);
+    r = dadd(r, A1);
+    r = dsub(r, B0);
+    r = dadd(r, B1);
+    area[c] = r;
+}
+
+// the same for the cells [c_lo, c_hi) only (band builds); area[] is indexed by the global cell id
+__global__ void k_cell_area_range(GridView g, int64_t c_lo, int64_t c_hi, double* __restrict__ area)
+{
+    const int ncy = g.ny - 1;
+    const int64_t c = c_lo + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= c_hi) return;
+    const int a = (int)(c / ncy), b = (int)(c % ncy);
+    const int64_t v = (int64_t)a * g.ny + b;
+    const double x00 = g.x[v], y00 = g.y[v];
+    const double x01 = g.x[v + 1], y01 = g.y[v + 1];
+    const double x10 = g.x[v + g.ny], y10 = g.y[v + g.ny];
+    const double x11 = g.x[v + g.ny + 1], y11 = g.y[v + g.ny + 1];
+    const double A0 = tri_area(y00, x00, y10, x10, b == 0);
+    const double A1 = tri_area(y01, x01, y11, x11, false);
     const double B0 = tri_area(x00, y00, x01, y01, a == 0);
     const double B1 = tri_area(x10, y10, x11, y11, false);
     double r = dsub(0.0, A0);
@@ -290,6 +315,7 @@ struct EmitSink {
     const double* w_in;
     int32_t* flags;
     int L, k;
+    int64_t cap = INT64_MAX;  // records the fragment buffer holds (band builds size it by estimate)
     __device__ __forceinline__ void piece(const PassParams& P, double x1, double y1, double x2, double y2,
                                           int ci, int cj, int piece_idx)
     {
@@ -312,6 +338,10 @@ struct EmitSink {
         if (w_in) { wi0 = w_in[in0]; wi1 = w_in[in1]; }
         const int old0 = atomicAdd(&cursor[in0], 1);
         const int old1 = two ? atomicAdd(&cursor[in1], 1) : 0;
+        if (base0 + old0 >= cap || base1 + old1 >= cap) {
+            atomicOr(&flags[kFlagCapacity], 1);
+            return;
+        }
         // emission rank inside one (input, output) pair: pass, then line (the cell right of line L
         // comes before the cell left of line L+1), then piece order inside the segment.
         const uint32_t seq = ((uint32_t)P.pass << 30) | (uint32_t)piece_idx;
@@ -333,13 +363,8 @@ struct EmitSink {
 // K2: exact line-start states (c2d.py:293-322).  One CTA per line: the boundary winding number is
 // latency bound (the boundary has 4 (n - 1) edges), so 256 threads share it.
 // ---------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_line_starts(const __grid_constant__ Pass4 Q, const double* __restrict__ bbox2)
+__device__ inline void line_start_body(const PassParams& P, int L, const double* __restrict__ bbox2, double* s_w)
 {
-    __shared__ double s_w[8];
-    const int p = pass_of_slot(Q, (int)blockIdx.x);
-    const PassParams& P = Q.p[p];
-    const int L = line_of_slot(P, (int)blockIdx.x - Q.lstart[p]);
-    if (L >= P.nlines) return;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const double* bbox_static = bbox2 + 4 * (P.sweep_input ? 1 : 0);
     const int64_t v0 = vertex_of(P, L, 0);
@@ -390,6 +415,16 @@ __global__ void __launch_bounds__(256) k_line_starts(const __grid_constant__ Pas
         P.line_start[L] = state;
         P.line_bad[L] = 0;
     }
+}
+
+__global__ void __launch_bounds__(256) k_line_starts(const __grid_constant__ Pass4 Q, const double* __restrict__ bbox2)
+{
+    __shared__ double s_w[8];
+    const int p = pass_of_slot(Q, (int)blockIdx.x);
+    const PassParams& P = Q.p[p];
+    const int L = line_of_slot(P, (int)blockIdx.x - Q.lstart[p]);
+    if (L >= P.nlines) return;
+    line_start_body(P, L, bbox2, s_w);
 }
 
 // K2: guessed state of every sweep vertex
@@ -688,10 +723,12 @@ struct SortSmem {
 // number of smaller keys in its bucket.  No dependent stores, no divergence between the lanes of a bucket (they
 // read the same keys: shared-memory broadcasts), and the sorted records go straight to global memory.
 __global__ void __launch_bounds__(kSortThreads)
-k_bucket_sort(const int64_t* __restrict__ boff, int64_t n_cells, Frag* __restrict__ frag, int32_t* __restrict__ nuniq)
+k_bucket_sort(const int64_t* __restrict__ boff, int64_t n_cells, Frag* __restrict__ frag, int32_t* __restrict__ nuniq,
+              const int32_t* __restrict__ abort_flag = nullptr)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     SortSmem& S = *reinterpret_cast<SortSmem*>(smem_raw);
+    if (abort_flag && *abort_flag) return;  // band builds: the fragment buffer was too small, nothing valid to sort
     const int64_t c0 = (int64_t)blockIdx.x * kSortCells;
     const bool owner = threadIdx.x < kSortCells;  // this thread keeps the books of bucket c
     const int64_t c = c0 + threadIdx.x;
@@ -849,10 +886,12 @@ k_bucket_gather_sort(const __grid_constant__ GatherSrc G, int64_t n_cells, Frag*
 __global__ void k_bucket_emit(const int64_t* __restrict__ boff, int64_t bstride, int64_t cell_offset,
                               const int64_t* __restrict__ colptr, int64_t n_cells,
                               const Frag* __restrict__ frag,
-                              int64_t* __restrict__ ii, int64_t* __restrict__ io, double* __restrict__ vv)
+                              int64_t* __restrict__ ii, int64_t* __restrict__ io, double* __restrict__ vv,
+                              const int32_t* __restrict__ abort_flag = nullptr)
 {
     const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= n_cells) return;
+    if (abort_flag && *abort_flag) return;
     const int64_t beg = boff[c * bstride], end = boff[(c + 1) * bstride];
     if (beg >= end) return;
     int64_t w = colptr[c];
@@ -912,7 +951,18 @@ struct Layout {
     int64_t* colptr;
     int64_t* scan_scratch;
     int32_t* flags;
+    // band builds (rg_build2d_band)
+    uint8_t* raster;         // [kRasterN^2] does a cell of the band touch this cell of the raster over the input bbox?
+    uint8_t* rel[2];         // [output vertices] can the pass-0 / pass-1 segment starting here have a piece in the band?
+    struct BandInfo* info;
     size_t bytes;
+};
+
+constexpr int kRasterN = 512;
+struct BandInfo {            // device memory, written by k_band_finalize
+    int32_t rect[4][4];      // per pass: first line, lines, first segment, segments of the rectangle that is walked
+    int64_t tstart[5];       // first thread of every pass in the per-segment launches (multiples of 256)
+    int32_t ext[2][4];       // scratch: per OUTPUT pass the extent (Lmin, Lmax, kmin, kmax) of its relevant segments
 };
 
 static Layout make_layout(void* ws, int64_t nxi, int64_t nyi, int64_t nxo, int64_t nyo)
@@ -949,6 +999,10 @@ static Layout make_layout(void* ws, int64_t nxi, int64_t nyi, int64_t nxo, int64
     l.colptr = c.take<int64_t>(l.Ci + 1);
     l.scan_scratch = c.take<int64_t>(scan_scratch_elems(l.Ci));
     l.flags = c.take<int32_t>(8);
+    l.raster = c.take<uint8_t>((size_t)kRasterN * kRasterN);
+    l.rel[0] = c.take<uint8_t>(l.Vo);
+    l.rel[1] = c.take<uint8_t>(l.Vo);
+    l.info = c.take<BandInfo>(1);
     l.bytes = c.total();
     return l;
 }
@@ -1419,5 +1473,440 @@ extern "C" int rg_build2d_merge_emit(int device, void* stream, int64_t n_cells, 
             m.dst_off, n_src, cell_offset, m.colptr, n_cells, (const Frag*)frags, ii, io, v);
         RG_LAUNCH_CHECK("k_bucket_emit");
     }
+    return RG_OK;
+}
+
+// ===========================================================================
+// Band build: ONE large grid pair built by W ranks with no exchange of fragments (rg_build2d_band).
+//
+// Rank r owns a band of input rows [row_lo, row_hi).  The public layout is sorted by input cell first
+// (_weights_arrays.py:54-59), so the bands concatenate in rank order.  A rank only walks the sweep segments that
+// can produce a piece inside its band:
+//   * INPUT-line passes: the lines / segments bounding the band's cells (closed form in index space);
+//   * OUTPUT-line passes: a piece inside band cell C lies inside C, so a segment can only contribute if its
+//     bounding box meets the bounding box of some cell of the band.  The band's cells are rasterised into a
+//     kRasterN^2 bitmap over the input grid's bbox (every cell marks every raster cell its bbox touches) and a
+//     segment is RELEVANT iff the raster cells under its own bbox contain a mark: exact and conservative.
+// Exactness of the walk states: the reference walks a line sequentially (c2d.py:324-387); here every walked
+// segment starts from the located cell of its first vertex, and the chain "end state of k-1 == start state of k"
+// is verified for every walked pair -- the predecessor of a relevant segment is always walked too (halo), and
+// the end state of a relevant segment is compared with the located state of the next vertex.  Every pair of a
+// line with a possible piece is therefore verified by the rank(s) that own one of the two; pairs nobody
+// walks lie outside every cell bbox of the static grid (state "outside" on both sides by geometry).  Any
+// mismatch (never observed: it needs a vertex exactly on a cell edge) raises kFlagBandMismatch; the caller
+// ORs the flag over the ranks and falls back to the sequentially verified banded build (rg_build2d_count/_fill).
+//
+// No host synchronisation inside: buffers are sized by the caller's estimate, overflow raises kFlagCapacity
+// and the counts come back in `counts_dev` (the caller reads them once, after everything was enqueued).
+// ===========================================================================
+namespace rg {
+
+struct BandParams {
+    int row_lo, row_hi;        // band of input rows
+    const uint8_t* rel[2];     // relevance of the pass-0 / pass-1 segment starting at each output vertex
+    const BandInfo* info;
+};
+
+__device__ __forceinline__ int raster_index(double x, double lo, double scale)
+{
+    const double t = floor((x - lo) * scale);   // monotone in x: overlapping intervals give overlapping index ranges
+    return (int)fmin(fmax(t, 0.0), (double)(kRasterN - 1));
+}
+
+// every cell of the band marks the raster cells its bounding box touches
+__global__ void k_band_raster(GridView g, int row_lo, int row_hi, const double* __restrict__ bbox, uint8_t* __restrict__ raster)
+{
+    const int ncy = g.ny - 1;
+    const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= (int64_t)(row_hi - row_lo) * ncy) return;
+    const int a = row_lo + (int)(c / ncy), b = (int)(c % ncy);
+    const int64_t v = (int64_t)a * g.ny + b;
+    const double x0 = g.x[v], x1 = g.x[v + 1], x2 = g.x[v + g.ny], x3 = g.x[v + g.ny + 1];
+    const double y0 = g.y[v], y1 = g.y[v + 1], y2 = g.y[v + g.ny], y3 = g.y[v + g.ny + 1];
+    const double sx = kRasterN / (bbox[2] - bbox[0]), sy = kRasterN / (bbox[3] - bbox[1]);
+    const int ix0 = raster_index(fmin(fmin(x0, x1), fmin(x2, x3)), bbox[0], sx);
+    const int ix1 = raster_index(fmax(fmax(x0, x1), fmax(x2, x3)), bbox[0], sx);
+    const int iy0 = raster_index(fmin(fmin(y0, y1), fmin(y2, y3)), bbox[1], sy);
+    const int iy1 = raster_index(fmax(fmax(y0, y1), fmax(y2, y3)), bbox[1], sy);
+    for (int ix = ix0; ix <= ix1; ix++)
+        for (int iy = iy0; iy <= iy1; iy++) raster[ix * kRasterN + iy] = 1;
+}
+
+__device__ __forceinline__ bool raster_hit(const uint8_t* __restrict__ raster, const double* __restrict__ bbox,
+                                           double sx, double sy, double xlo, double ylo, double xhi, double yhi)
+{
+    if (!(xlo <= bbox[2] && bbox[0] <= xhi && ylo <= bbox[3] && bbox[1] <= yhi)) return false;  // misses the input grid's bbox
+    const int ix0 = raster_index(xlo, bbox[0], sx), ix1 = raster_index(xhi, bbox[0], sx);
+    const int iy0 = raster_index(ylo, bbox[1], sy), iy1 = raster_index(yhi, bbox[1], sy);
+    for (int ix = ix0; ix <= ix1; ix++)
+        for (int iy = iy0; iy <= iy1; iy++)
+            if (raster[ix * kRasterN + iy]) return true;
+    return false;
+}
+
+// Thread per OUTPUT vertex (i, j): relevance of the two segments that start there (pass 1: to (i, j+1); pass 0: to
+// (i+1, j)) and the extent of the relevant segments in (line, segment) space.
+__global__ void k_band_relevance(GridView gout, const uint8_t* __restrict__ raster,
+                                 const double* __restrict__ bbox_in, uint8_t* __restrict__ rel0, uint8_t* __restrict__ rel1,
+                                 BandInfo* __restrict__ info)
+{
+    const int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t nv = (int64_t)gout.nx * gout.ny;
+    int ext[8] = { INT32_MAX, -1, INT32_MAX, -1, INT32_MAX, -1, INT32_MAX, -1 };  // pass 0: Lmin Lmax kmin kmax; pass 1
+    if (v < nv) {
+        const int i = (int)(v / gout.ny), j = (int)(v % gout.ny);
+        const double x = gout.x[v], y = gout.y[v];
+        // the same expressions as in k_band_raster (the index ranges of overlapping intervals must overlap)
+        const double sx = kRasterN / (bbox_in[2] - bbox_in[0]), sy = kRasterN / (bbox_in[3] - bbox_in[1]);
+        bool r1 = false, r0 = false;
+        if (j + 1 < gout.ny) {
+            const double xb = gout.x[v + 1], yb = gout.y[v + 1];
+            r1 = raster_hit(raster, bbox_in, sx, sy, fmin(x, xb), fmin(y, yb), fmax(x, xb), fmax(y, yb));
+        }
+        if (i + 1 < gout.nx) {
+            const double xb = gout.x[v + gout.ny], yb = gout.y[v + gout.ny];
+            r0 = raster_hit(raster, bbox_in, sx, sy, fmin(x, xb), fmin(y, yb), fmax(x, xb), fmax(y, yb));
+        }
+        rel0[v] = r0;
+        rel1[v] = r1;
+        if (r0) { ext[0] = ext[1] = j; ext[2] = ext[3] = i; }   // pass 0 (axis 0): line = j, segment = i
+        if (r1) { ext[4] = ext[5] = i; ext[6] = ext[7] = j; }   // pass 1 (axis 1): line = i, segment = j
+    }
+    if (!__any_sync(0xffffffffu, ext[1] >= 0 || ext[5] >= 0)) return;  // nothing relevant in this warp (the common case)
+#pragma unroll
+    for (int q = 0; q < 8; q++) {
+        int e = ext[q];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const int other = __shfl_xor_sync(0xffffffffu, e, o);
+            e = (q & 1) ? max(e, other) : min(e, other);
+        }
+        if ((threadIdx.x & 31) == 0 && e != ((q & 1) ? -1 : INT32_MAX)) {
+            if (q & 1) atomicMax(&info->ext[q >> 2][q & 3], e);
+            else atomicMin(&info->ext[q >> 2][q & 3], e);
+        }
+    }
+}
+
+__global__ void k_band_info_init(BandInfo* info)
+{
+    if (threadIdx.x < 8) info->ext[threadIdx.x >> 2][threadIdx.x & 3] = (threadIdx.x & 1) ? -1 : INT32_MAX;
+}
+
+// Located state of every output vertex that starts a walked segment (relevant, or the halo before a relevant one) or
+// ends a relevant one, of either output pass: thread per vertex of the bounding rectangle of the two passes.
+__global__ void k_band_guess_out(GridView gout, GridView gin, const uint8_t* __restrict__ rel0,
+                                 const uint8_t* __restrict__ rel1, const BandInfo* __restrict__ info,
+                                 int32_t* __restrict__ guess, int32_t* __restrict__ flags)
+{
+    // pass 0 (axis 0): line = j, segment = i; pass 1 (axis 1): line = i, segment = j
+    const int* r0 = info->rect[0];
+    const int* r1 = info->rect[1];
+    int i_lo = INT32_MAX, i_hi = -1, j_lo = INT32_MAX, j_hi = -1;
+    if (r0[1] > 0) { j_lo = min(j_lo, r0[0]); j_hi = max(j_hi, r0[0] + r0[1] - 1); i_lo = min(i_lo, r0[2]); i_hi = max(i_hi, r0[2] + r0[3]); }
+    if (r1[1] > 0) { i_lo = min(i_lo, r1[0]); i_hi = max(i_hi, r1[0] + r1[1] - 1); j_lo = min(j_lo, r1[2]); j_hi = max(j_hi, r1[2] + r1[3]); }
+    if (i_hi < i_lo || j_hi < j_lo) return;
+    i_hi = min(i_hi, gout.nx - 1);
+    j_hi = min(j_hi, gout.ny - 1);
+    const int ni = i_hi - i_lo + 1, nj = j_hi - j_lo + 1;
+    const int64_t total = (int64_t)ni * nj;
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+        const int i = i_lo + (int)(t / nj), j = j_lo + (int)(t % nj);
+        const int64_t v = (int64_t)i * gout.ny + j;
+        const int ny = gout.ny;
+        bool need = rel1[v] || rel0[v];                                   // starts a relevant segment
+        if (j + 1 < ny) need = need || rel1[v + 1];                      // starts the halo of pass 1
+        if (i + 1 < gout.nx) need = need || rel0[v + ny];                // starts the halo of pass 0
+        if (j > 0) need = need || rel1[v - 1];                           // ends a relevant segment of pass 1
+        if (i > 0) need = need || rel0[v - ny];                          // ends a relevant segment of pass 0
+        int r = kStateInvalid;  // never read by a walked segment (an invalid start raises the mismatch flag)
+        if (need) {
+            r = locate_guess(gin, gout.x[v], gout.y[v]);
+            if (r == kLocUnknown) atomicAdd(&flags[kFlagUnknown], 1);
+        }
+        guess[v] = r;
+    }
+}
+
+// located states of the input vertices around the band (the sweep vertices of passes 2 and 3)
+__global__ void k_band_guess_in(GridView gin, GridView gout, int64_t v_lo, int64_t v_hi, int32_t* __restrict__ guess,
+                                int32_t* __restrict__ flags)
+{
+    const int64_t v = v_lo + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= v_hi) return;
+    const int r = locate_guess(gout, gin.x[v], gin.y[v]);
+    guess[v] = r;
+    if (r == kLocUnknown) atomicAdd(&flags[kFlagUnknown], 1);
+}
+
+// rectangles in (line, segment) space that the per-segment kernels cover, per pass
+__global__ void k_band_finalize(const __grid_constant__ Pass4 Q, int row_lo, int row_hi, BandInfo* info)
+{
+    if (threadIdx.x != 0) return;
+    for (int p = 0; p < 4; p++) {
+        const PassParams& P = Q.p[p];
+        int L0 = 0, nL = 0, k0 = 0, nK = 0;
+        if (!P.sweep_input) {
+            const int* e = info->ext[P.axis];  // ext[0]: pass 0 (axis 0), ext[1]: pass 1 (axis 1)
+            if (e[1] >= e[0] && e[3] >= e[2]) {
+                L0 = e[0]; nL = e[1] - e[0] + 1;
+                k0 = max(e[2] - 1, 0);            // halo: the predecessor of the first relevant segment
+                nK = e[3] - k0 + 1;
+            }
+        } else if (P.axis) {   // pass 3: line = input vertex row; lines row_lo .. row_hi bound the band's cells
+            L0 = row_lo; nL = min(row_hi, P.nlines - 1) - row_lo + 1; k0 = 0; nK = P.nseg;
+        } else {               // pass 2: segment = input row
+            L0 = 0; nL = P.nlines; k0 = max(row_lo - 1, 0); nK = row_hi - k0;
+        }
+        if (nL <= 0 || nK <= 0) { nL = 0; nK = 0; }
+        info->rect[p][0] = L0; info->rect[p][1] = nL; info->rect[p][2] = k0; info->rect[p][3] = nK;
+    }
+    info->tstart[0] = 0;
+    for (int p = 0; p < 4; p++)
+        info->tstart[p + 1] = info->tstart[p] + ((int64_t)info->rect[p][1] * info->rect[p][3] + 255) / 256 * 256;
+}
+
+__device__ __forceinline__ bool band_relevant(const PassParams& P, const BandParams& B, int L, int k, int64_t v)
+{
+    if (P.sweep_input) return P.axis ? (L >= B.row_lo && L <= B.row_hi) : (k >= B.row_lo && k < B.row_hi);
+    return B.rel[P.axis][v] != 0;
+}
+// a segment is walked when it is relevant or the predecessor (halo) of a relevant one
+__device__ __forceinline__ bool band_walked(const PassParams& P, const BandParams& B, int L, int k, int64_t v)
+{
+    return band_relevant(P, B, L, k, v) || (k + 1 < P.nseg && band_relevant(P, B, L, k + 1, v + vertex_step(P)));
+}
+
+__device__ __forceinline__ bool band_segment(const Pass4& Q, const BandInfo& I, int64_t gtid, int& p, int& L, int& k)
+{
+    p = (gtid >= I.tstart[1]) + (gtid >= I.tstart[2]) + (gtid >= I.tstart[3]);
+    const int64_t t = gtid - I.tstart[p];
+    const int L0 = I.rect[p][0], nL = I.rect[p][1], k0 = I.rect[p][2], nK = I.rect[p][3];
+    if (t >= (int64_t)nL * nK) return false;
+    // consecutive lanes take consecutive memory: along the line for axis 1, across lines for axis 0
+    int slot;
+    if (Q.p[p].axis) { slot = (int)(t / nK); k = k0 + (int)(t % nK); }
+    else             { k = k0 + (int)(t / nL); slot = (int)(t % nL); }
+    L = L0 + slot;
+    return true;
+}
+
+// exact start state of the lines whose first segment is walked (CTA per line of every pass)
+__global__ void __launch_bounds__(256) k_band_line_starts(const __grid_constant__ Pass4 Q, const BandParams B,
+                                                          const double* __restrict__ bbox2)
+{
+    __shared__ double s_w[8];
+    const int p = pass_of_slot(Q, (int)blockIdx.x);
+    const PassParams& P = Q.p[p];
+    const int L = (int)blockIdx.x - Q.lstart[p];
+    if (L >= P.nlines) return;
+    const int* r = B.info->rect[p];
+    if (L < r[0] || L >= r[0] + r[1] || r[2] != 0 || r[3] <= 0) return;
+    if (!band_walked(P, B, L, 0, vertex_of(P, L, 0))) return;
+    line_start_body(P, L, bbox2, s_w);
+}
+
+__global__ void __launch_bounds__(128, 8) k_band_walk_count(const __grid_constant__ Pass4 Q, const BandParams B,
+                                                            int32_t* __restrict__ hist, int32_t* __restrict__ flags)
+{
+    const BandInfo& I = *B.info;
+    const int64_t total = I.tstart[4];
+    for (int64_t gtid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; gtid < total; gtid += (int64_t)gridDim.x * blockDim.x) {
+        int p, L, k;
+        if (!band_segment(Q, I, gtid, p, L, k)) continue;
+        const PassParams& P = Q.p[p];
+        const int64_t v = vertex_of(P, L, k), v2 = v + vertex_step(P);
+        const bool relevant = band_relevant(P, B, L, k, v);
+        if (!relevant && !(k + 1 < P.nseg && band_relevant(P, B, L, k + 1, v2))) continue;
+        const int start = (k == 0) ? P.line_start[L] : P.guess[v];
+        P.seg_start[v] = start;
+        if (start <= kStateUnknown) {   // unknown or never located: the sequentially verified build decides
+            P.seg_end[v] = kStateInvalid;
+            atomicOr(&flags[kFlagBandMismatch], 1);
+            continue;
+        }
+        const double x1 = P.sweep.x[v], y1 = P.sweep.y[v];
+        CountSink sink{ hist, L, k, 1, 0, relevant ? v : (int64_t)-1, 0, x1, y1 };
+        bool overflow = false;
+        P.seg_end[v] = walk_segment(P, x1, y1, P.sweep.x[v2], P.sweep.y[v2], start, sink, overflow);
+        P.seg_hit[v] = sink.total > 0;
+        P.pc_n[v] = (uint8_t)((relevant && sink.n_cached <= kPieceCache && !overflow) ? sink.n_cached : kPieceNone);
+        if (overflow) atomicOr(&flags[kFlagOverflow], 1);
+    }
+}
+
+__global__ void k_band_chain_check(const __grid_constant__ Pass4 Q, const BandParams B, int32_t* __restrict__ flags)
+{
+    const BandInfo& I = *B.info;
+    const int64_t total = I.tstart[4];
+    for (int64_t gtid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; gtid < total; gtid += (int64_t)gridDim.x * blockDim.x) {
+        int p, L, k;
+        if (!band_segment(Q, I, gtid, p, L, k)) continue;
+        const PassParams& P = Q.p[p];
+        const int64_t step = vertex_step(P), v = vertex_of(P, L, k);
+        if (!band_walked(P, B, L, k, v)) continue;
+        bool bad = false;
+        // (the predecessor of a RELEVANT segment is always walked; a halo segment's own start is verified by the rank
+        // whose band its predecessor touches, or is "outside" by geometry)
+        if (k >= 1 && band_walked(P, B, L, k - 1, v - step)) bad = P.seg_end[v - step] != P.seg_start[v];
+        if (band_relevant(P, B, L, k, v) && k + 1 < P.nseg && !band_walked(P, B, L, k + 1, v + step))
+            bad = bad || (P.seg_end[v] != P.guess[v + step]);
+        if (bad) atomicOr(&flags[kFlagBandMismatch], 1);
+    }
+}
+
+__global__ void __launch_bounds__(128, 8)
+k_band_walk_emit(const __grid_constant__ Pass4 Q, const BandParams B, const int64_t* __restrict__ boff,
+                 int32_t* __restrict__ cursor, Frag* __restrict__ frag, int64_t frag_capacity,
+                 const double* __restrict__ area_in, const double* __restrict__ w_in, int32_t* __restrict__ flags)
+{
+    if (flags[kFlagCapacity]) return;
+    const BandInfo& I = *B.info;
+    const int64_t total = I.tstart[4];
+    for (int64_t gtid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; gtid < total; gtid += (int64_t)gridDim.x * blockDim.x) {
+        int p, L, k;
+        if (!band_segment(Q, I, gtid, p, L, k)) continue;
+        const PassParams& P = Q.p[p];
+        const int64_t v = vertex_of(P, L, k), v2 = v + vertex_step(P);
+        if (!band_relevant(P, B, L, k, v) || !P.seg_hit[v]) continue;
+        EmitSink sink{ boff, cursor, frag, area_in, w_in, flags, L, k, frag_capacity };
+        const int nc = P.pc_n[v];
+        if (nc != kPieceNone) {
+            double x1 = P.sweep.x[v], y1 = P.sweep.y[v];
+            int piece = 0;
+            int cells[kPieceCache];
+            double xs[kPieceCache], ys[kPieceCache];
+#pragma unroll
+            for (int e = 0; e < kPieceCache; e++) {
+                const int64_t at = (int64_t)e * P.pc_stride + v;
+                cells[e] = -1; xs[e] = 0.0; ys[e] = 0.0;
+                if (e < nc) { cells[e] = P.pc_cell[at]; xs[e] = P.pc_x[at]; ys[e] = P.pc_y[at]; }
+            }
+#pragma unroll
+            for (int e = 0; e < kPieceCache; e++) {
+                if (e >= nc) break;
+                const int cell = cells[e];
+                const double x = xs[e], y = ys[e];
+                if (cell >= 0) {
+                    const int ci = cell / P.ncy_st;
+                    sink.piece(P, x1, y1, x, y, ci, cell - ci * P.ncy_st, piece);
+                    piece++;
+                }
+                x1 = x;
+                y1 = y;
+            }
+            continue;
+        }
+        bool overflow = false;
+        walk_segment(P, P.sweep.x[v], P.sweep.y[v], P.sweep.x[v2], P.sweep.y[v2], P.seg_start[v], sink, overflow);
+        if (overflow) atomicOr(&flags[kFlagOverflow], 1);
+    }
+}
+
+// counts[0] = fragments of the band, counts[1] = triplets; capacity flags (stage 0: after the count scan, 1: after the
+// unique-pair scan, 2: final report of all flags)
+__global__ void k_band_counts(int stage, const int64_t* __restrict__ total, int64_t capacity, int64_t* __restrict__ counts,
+                              int32_t* __restrict__ flags)
+{
+    if (threadIdx.x != 0) return;
+    if (stage < 2) {
+        counts[stage] = *total;
+        if (*total > capacity || *total >= INT32_MAX) flags[kFlagCapacity] = 1;
+    } else {
+        for (int q = 0; q < 6; q++) counts[2 + q] = flags[q];
+    }
+}
+
+}  // namespace rg
+
+extern "C" int rg_build2d_band(int device, void* stream,
+                               int64_t nxi, int64_t nyi, int64_t nxo, int64_t nyo,
+                               const double* xin, const double* yin, const double* xout, const double* yout,
+                               const double* w_in, int64_t row_lo, int64_t row_hi,
+                               void* workspace, size_t workspace_bytes,
+                               void* frags, int64_t frag_capacity,
+                               int64_t* ii, int64_t* io, double* v, int64_t nnz_capacity,
+                               int64_t* counts_dev /* [8] */)
+{
+    int rc = check_sizes(nxi, nyi, nxo, nyo);
+    if (rc) return rc;
+    if (!xin || !yin || !xout || !yout || !workspace || !counts_dev || !frags || !ii || !io || !v)
+        return fail(RG_E_ARG, "rg_build2d_band: null pointer");
+    if (row_lo < 0 || row_hi > nxi - 1 || row_lo >= row_hi) return fail(RG_E_ARG, "rg_build2d_band: bad row band");
+    if (frag_capacity < 1 || nnz_capacity < 1) return fail(RG_E_ARG, "rg_build2d_band: bad capacity");
+    Layout l = make_layout(workspace, nxi, nyi, nxo, nyo);
+    if (workspace_bytes < l.bytes) return fail(RG_E_WORKSPACE, "rg_build2d_band: workspace too small");
+    RG_CUDA(cudaSetDevice(device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const GridView gin{ xin, yin, (int)nxi, (int)nyi };
+    const GridView gout{ xout, yout, (int)nxo, (int)nyo };
+    const int T = 256;
+    const int64_t ncy = nyi - 1;
+    const int64_t cell_lo = row_lo * ncy, cell_hi = row_hi * ncy, nb = cell_hi - cell_lo;
+
+    RG_CUDA(cudaMemsetAsync(l.flags, 0, sizeof(int32_t) * 8, st));
+    RG_CUDA(cudaMemsetAsync(l.hist + cell_lo, 0, sizeof(int32_t) * (size_t)(nb + 1), st));
+    RG_CUDA(cudaMemsetAsync(l.cursor + cell_lo, 0, sizeof(int32_t) * (size_t)(nb + 1), st));
+    RG_CUDA(cudaMemsetAsync(l.raster, 0, (size_t)kRasterN * kRasterN, st));
+    RG_CUDA(cudaMemsetAsync(counts_dev, 0, sizeof(int64_t) * 8, st));
+    k_band_info_init<<<1, 32, 0, st>>>(l.info);
+    // areas of the band's cells (k_cell_area works on the rows [row_lo, row_hi) of the grid: a view of those rows would
+    // move the peeled first-edge pattern of grid_volume, so the full-grid kernel runs on the band's cell range)
+    {
+        GridView gb = gin;
+        k_cell_area_range<<<(unsigned)ceil_div(nb, T), T, 0, st>>>(gb, cell_lo, cell_hi, l.area_in);
+        RG_LAUNCH_CHECK("k_cell_area_range");
+    }
+    {
+        const GridView gv[2] = { gin, gout };
+        double* const bb[2] = { l.bbox, l.bbox + 4 };
+        rc = build_boundaries(st, 2, gv, l.bnd, bb);
+        if (rc) return rc;
+    }
+    const Pass4 Q = make_pass4(l, xin, yin, xout, yout, cell_lo, cell_hi, 0, 1);
+    BandParams B;
+    B.row_lo = (int)row_lo; B.row_hi = (int)row_hi;
+    B.rel[0] = l.rel[0]; B.rel[1] = l.rel[1];
+    B.info = l.info;
+    k_band_raster<<<(unsigned)ceil_div(nb, T), T, 0, st>>>(gin, (int)row_lo, (int)row_hi, l.bbox, l.raster);
+    RG_LAUNCH_CHECK("k_band_raster");
+    k_band_relevance<<<(unsigned)ceil_div(l.Vo, T), T, 0, st>>>(gout, l.raster, l.bbox, l.rel[0], l.rel[1], l.info);
+    RG_LAUNCH_CHECK("k_band_relevance");
+    {
+        // input vertices of rows row_lo - 1 .. row_hi + 1: every start / end vertex of a walked segment of passes 2, 3
+        const int64_t r0 = row_lo > 0 ? row_lo - 1 : 0, r1 = (row_hi + 2 < nxi ? row_hi + 2 : nxi);
+        const int64_t v_lo = r0 * nyi, v_hi = r1 * nyi;
+        k_band_guess_in<<<(unsigned)ceil_div(v_hi - v_lo, T), T, 0, st>>>(gin, gout, v_lo, v_hi, l.guess[1], l.flags);
+        RG_LAUNCH_CHECK("k_band_guess_in");
+    }
+    k_band_finalize<<<1, 32, 0, st>>>(Q, (int)row_lo, (int)row_hi, l.info);
+    k_band_guess_out<<<kNumSM * 8, T, 0, st>>>(gout, gin, l.rel[0], l.rel[1], l.info, l.guess[0], l.flags);
+    RG_LAUNCH_CHECK("k_band_guess_out");
+    k_band_line_starts<<<(unsigned)Q.lstart[4], 256, 0, st>>>(Q, B, l.bbox);
+    RG_LAUNCH_CHECK("k_band_line_starts");
+    const unsigned walk_grid = kNumSM * 16;   // grid-stride: the amount of work is only known on the device
+    k_band_walk_count<<<walk_grid, 128, 0, st>>>(Q, B, l.hist, l.flags);
+    RG_LAUNCH_CHECK("k_band_walk_count");
+    k_band_chain_check<<<kNumSM * 8, T, 0, st>>>(Q, B, l.flags);
+    RG_LAUNCH_CHECK("k_band_chain_check");
+    rc = exclusive_scan_i32_i64(st, l.hist + cell_lo, l.boff + cell_lo, nb, l.scan_scratch);
+    if (rc) return rc;
+    k_band_counts<<<1, 32, 0, st>>>(0, l.boff + cell_hi, frag_capacity, counts_dev, l.flags);
+    // boff of the band starts at 0: cells index it globally (boff[cell]), fragments locally
+    k_band_walk_emit<<<walk_grid, 128, 0, st>>>(Q, B, l.boff, l.cursor, (Frag*)frags, frag_capacity, l.area_in, w_in, l.flags);
+    RG_LAUNCH_CHECK("k_band_walk_emit");
+    rc = sort_smem_opt_in(device);
+    if (rc) return rc;
+    k_bucket_sort<<<(unsigned)ceil_div(nb, kSortCells), kSortThreads, sizeof(SortSmem), st>>>(
+        l.boff + cell_lo, nb, (Frag*)frags, l.nuniq + cell_lo, l.flags + kFlagCapacity);
+    RG_LAUNCH_CHECK("k_bucket_sort");
+    rc = exclusive_scan_i32_i64(st, l.nuniq + cell_lo, l.colptr + cell_lo, nb, l.scan_scratch);
+    if (rc) return rc;
+    k_band_counts<<<1, 32, 0, st>>>(1, l.colptr + cell_hi, nnz_capacity, counts_dev, l.flags);
+    k_bucket_emit<<<(unsigned)ceil_div(nb, 256), 256, 0, st>>>(l.boff + cell_lo, 1, cell_lo, l.colptr + cell_lo, nb,
+                                                              (const Frag*)frags, ii, io, v, l.flags + kFlagCapacity);
+    RG_LAUNCH_CHECK("k_bucket_emit");
+    k_band_counts<<<1, 32, 0, st>>>(2, nullptr, 0, counts_dev, l.flags);
+    RG_LAUNCH_CHECK("k_band_counts");
     return RG_OK;
 }

@@ -1,4 +1,4 @@
-"""The real multi-process line-sharded build (NCCL + peer-mapped memory) on 2 GPUs of one box; skipped on
+"""The real multi-process sharded builds (exchange-free band build; line-sharded with NCCL / peer-mapped memory) on 2 GPUs of one box; skipped on
 single-GPU boxes (there the same kernels are covered by test_build2d_line_sharded_equals_full, which plays all
 ranks on one device)."""
 
@@ -33,7 +33,7 @@ def _worker(rank, world, port, ret):
         t = [torch.from_numpy(a).to(dev) for a in (*gi, *co)]
         full = _device.build_weights_2d(*t, device=dev)
         ok = True
-        for exchange in ("p2p", "nccl"):
+        for exchange in ("band", "p2p", "nccl"):
             rep = _parallel.build_weights_2d_sharded(*t, replicate=True, device=dev, exchange=exchange)
             ok = ok and all(torch.equal(getattr(rep, k), getattr(full, k))
                             for k in ("indices_input", "indices_output", "values"))
@@ -41,6 +41,11 @@ def _worker(rank, world, port, ret):
             lo, hi = _parallel.band_cells(gi[0].shape[0] - 1, gi[0].shape[1] - 1, rank, world)
             sel = (full.indices_input >= lo) & (full.indices_input < hi)
             ok = ok and torch.equal(band.values, full.values[sel]) and torch.equal(band.indices_output, full.indices_output[sel])
+        # band build with buffers that are too small at first: every rank repeats the build with the learned sizes
+        for key in list(_device._band_caps):
+            _device._band_caps[key] = (1000, 500)
+        rep = _parallel.build_weights_2d_sharded(*t, replicate=True, device=dev, exchange="band")
+        ok = ok and torch.equal(rep.values, full.values) and torch.equal(rep.indices_input, full.indices_input)
         # arena growth: start with room for 1 fragment per cell -> every rank overflows, all grow together, walk again
         os.environ["REGRID_B200_ARENA_FRAGS_PER_CELL"] = "1"
         _parallel._arenas.clear()
