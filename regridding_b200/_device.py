@@ -211,6 +211,8 @@ def build_weights_2d(x_in, y_in, x_out, y_out, weights_input=None, cell_band: tu
 
 # learned buffer sizes of band builds: (shape, band) -> (fragments, triplets) of the previous build
 _band_caps: dict = {}
+# scratch of the last band build shape: (workspace, fragment buffer); stream-ordered reuse on the current stream
+_band_scratch: dict = {}
 
 
 @dataclasses.dataclass
@@ -276,8 +278,14 @@ def build2d_band_enqueue(x_in, y_in, x_out, y_out, weights_input, row_lo: int, r
         ncap = fcap // 2
     with torch.cuda.device(device):
         st = _stream(device)
-        ws = _workspace(build2d_workspace_bytes(nxi, nyi, nxo, nyo), device)
-        frags = frags_empty(fcap, device)
+        # workspace and fragment buffer are scratch: kept per (device, shape) so that repeated builds allocate nothing
+        skey = (device.index, st, nxi, nyi, nxo, nyo)
+        scratch = _band_scratch.get(skey)
+        if scratch is None or scratch[1].shape[0] < fcap:
+            _band_scratch.clear()
+            scratch = (_workspace(build2d_workspace_bytes(nxi, nyi, nxo, nyo), device), frags_empty(fcap, device))
+            _band_scratch[skey] = scratch
+        ws, frags = scratch
         ii = torch.empty(ncap, dtype=I64, device=device)
         io = torch.empty(ncap, dtype=I64, device=device)
         v = torch.empty(ncap, dtype=F64, device=device)

@@ -963,6 +963,7 @@ struct BandInfo {            // device memory, written by k_band_finalize
     int32_t rect[4][4];      // per pass: first line, lines, first segment, segments of the rectangle that is walked
     int64_t tstart[5];       // first thread of every pass in the per-segment launches (multiples of 256)
     int32_t ext[2][4];       // scratch: per OUTPUT pass the extent (Lmin, Lmax, kmin, kmax) of its relevant segments
+    double sx, sy;           // raster cells per unit length over the input grid's bbox
 };
 
 static Layout make_layout(void* ws, int64_t nxi, int64_t nyi, int64_t nxo, int64_t nyo)
@@ -1514,7 +1515,8 @@ __device__ __forceinline__ int raster_index(double x, double lo, double scale)
 }
 
 // every cell of the band marks the raster cells its bounding box touches
-__global__ void k_band_raster(GridView g, int row_lo, int row_hi, const double* __restrict__ bbox, uint8_t* __restrict__ raster)
+__global__ void k_band_raster(GridView g, int row_lo, int row_hi, const double* __restrict__ bbox,
+                              const BandInfo* __restrict__ info, uint8_t* __restrict__ raster)
 {
     const int ncy = g.ny - 1;
     const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -1523,25 +1525,13 @@ __global__ void k_band_raster(GridView g, int row_lo, int row_hi, const double* 
     const int64_t v = (int64_t)a * g.ny + b;
     const double x0 = g.x[v], x1 = g.x[v + 1], x2 = g.x[v + g.ny], x3 = g.x[v + g.ny + 1];
     const double y0 = g.y[v], y1 = g.y[v + 1], y2 = g.y[v + g.ny], y3 = g.y[v + g.ny + 1];
-    const double sx = kRasterN / (bbox[2] - bbox[0]), sy = kRasterN / (bbox[3] - bbox[1]);
+    const double sx = info->sx, sy = info->sy;
     const int ix0 = raster_index(fmin(fmin(x0, x1), fmin(x2, x3)), bbox[0], sx);
     const int ix1 = raster_index(fmax(fmax(x0, x1), fmax(x2, x3)), bbox[0], sx);
     const int iy0 = raster_index(fmin(fmin(y0, y1), fmin(y2, y3)), bbox[1], sy);
     const int iy1 = raster_index(fmax(fmax(y0, y1), fmax(y2, y3)), bbox[1], sy);
     for (int ix = ix0; ix <= ix1; ix++)
         for (int iy = iy0; iy <= iy1; iy++) raster[ix * kRasterN + iy] = 1;
-}
-
-__device__ __forceinline__ bool raster_hit(const uint8_t* __restrict__ raster, const double* __restrict__ bbox,
-                                           double sx, double sy, double xlo, double ylo, double xhi, double yhi)
-{
-    if (!(xlo <= bbox[2] && bbox[0] <= xhi && ylo <= bbox[3] && bbox[1] <= yhi)) return false;  // misses the input grid's bbox
-    const int ix0 = raster_index(xlo, bbox[0], sx), ix1 = raster_index(xhi, bbox[0], sx);
-    const int iy0 = raster_index(ylo, bbox[1], sy), iy1 = raster_index(yhi, bbox[1], sy);
-    for (int ix = ix0; ix <= ix1; ix++)
-        for (int iy = iy0; iy <= iy1; iy++)
-            if (raster[ix * kRasterN + iy]) return true;
-    return false;
 }
 
 // Thread per OUTPUT vertex (i, j): relevance of the two segments that start there (pass 1: to (i, j+1); pass 0: to
@@ -1555,18 +1545,20 @@ __global__ void k_band_relevance(GridView gout, const uint8_t* __restrict__ rast
     int ext[8] = { INT32_MAX, -1, INT32_MAX, -1, INT32_MAX, -1, INT32_MAX, -1 };  // pass 0: Lmin Lmax kmin kmax; pass 1
     if (v < nv) {
         const int i = (int)(v / gout.ny), j = (int)(v % gout.ny);
-        const double x = gout.x[v], y = gout.y[v];
-        // the same expressions as in k_band_raster (the index ranges of overlapping intervals must overlap)
-        const double sx = kRasterN / (bbox_in[2] - bbox_in[0]), sy = kRasterN / (bbox_in[3] - bbox_in[1]);
+        // raster cell of the vertex and of its two successors; a segment is relevant iff a raster cell under its bounding
+        // box is marked (indices are clamped to the raster: segments beyond the input grid's bbox can only over-report)
+        const double sx = info->sx, sy = info->sy, x0 = bbox_in[0], y0 = bbox_in[1];
+        const int ix = raster_index(gout.x[v], x0, sx), iy = raster_index(gout.y[v], y0, sy);
+        auto marked = [&](int ixb, int iyb) {
+            const int xa = min(ix, ixb), xb = max(ix, ixb), ya = min(iy, iyb), yb = max(iy, iyb);
+            for (int a = xa; a <= xb; a++)
+                for (int b = ya; b <= yb; b++)
+                    if (raster[a * kRasterN + b]) return true;
+            return false;
+        };
         bool r1 = false, r0 = false;
-        if (j + 1 < gout.ny) {
-            const double xb = gout.x[v + 1], yb = gout.y[v + 1];
-            r1 = raster_hit(raster, bbox_in, sx, sy, fmin(x, xb), fmin(y, yb), fmax(x, xb), fmax(y, yb));
-        }
-        if (i + 1 < gout.nx) {
-            const double xb = gout.x[v + gout.ny], yb = gout.y[v + gout.ny];
-            r0 = raster_hit(raster, bbox_in, sx, sy, fmin(x, xb), fmin(y, yb), fmax(x, xb), fmax(y, yb));
-        }
+        if (j + 1 < gout.ny) r1 = marked(raster_index(gout.x[v + 1], x0, sx), raster_index(gout.y[v + 1], y0, sy));
+        if (i + 1 < gout.nx) r0 = marked(raster_index(gout.x[v + gout.ny], x0, sx), raster_index(gout.y[v + gout.ny], y0, sy));
         rel0[v] = r0;
         rel1[v] = r1;
         if (r0) { ext[0] = ext[1] = j; ext[2] = ext[3] = i; }   // pass 0 (axis 0): line = j, segment = i
@@ -1588,9 +1580,15 @@ __global__ void k_band_relevance(GridView gout, const uint8_t* __restrict__ rast
     }
 }
 
-__global__ void k_band_info_init(BandInfo* info)
+// after the bounding boxes: extents reset, raster scales (ONE evaluation shared by the kernels that mark and that
+// look up, so that overlapping intervals always map to overlapping index ranges)
+__global__ void k_band_info_init(BandInfo* info, const double* __restrict__ bbox_in)
 {
     if (threadIdx.x < 8) info->ext[threadIdx.x >> 2][threadIdx.x & 3] = (threadIdx.x & 1) ? -1 : INT32_MAX;
+    if (threadIdx.x == 0) {
+        info->sx = kRasterN / (bbox_in[2] - bbox_in[0]);
+        info->sy = kRasterN / (bbox_in[3] - bbox_in[1]);
+    }
 }
 
 // Located state of every output vertex that starts a walked segment (relevant, or the halo before a relevant one) or
@@ -1700,6 +1698,7 @@ __global__ void __launch_bounds__(256) k_band_line_starts(const __grid_constant_
     const PassParams& P = Q.p[p];
     const int L = (int)blockIdx.x - Q.lstart[p];
     if (L >= P.nlines) return;
+    if (P.sweep_input && (P.axis ? (L < B.row_lo || L > B.row_hi) : (B.row_lo > 1))) return;  // known without the rectangle
     const int* r = B.info->rect[p];
     if (L < r[0] || L >= r[0] + r[1] || r[2] != 0 || r[3] <= 0) return;
     if (!band_walked(P, B, L, 0, vertex_of(P, L, 0))) return;
@@ -1849,7 +1848,6 @@ extern "C" int rg_build2d_band(int device, void* stream,
     RG_CUDA(cudaMemsetAsync(l.cursor + cell_lo, 0, sizeof(int32_t) * (size_t)(nb + 1), st));
     RG_CUDA(cudaMemsetAsync(l.raster, 0, (size_t)kRasterN * kRasterN, st));
     RG_CUDA(cudaMemsetAsync(counts_dev, 0, sizeof(int64_t) * 8, st));
-    k_band_info_init<<<1, 32, 0, st>>>(l.info);
     // areas of the band's cells (k_cell_area works on the rows [row_lo, row_hi) of the grid: a view of those rows would
     // move the peeled first-edge pattern of grid_volume, so the full-grid kernel runs on the band's cell range)
     {
@@ -1868,7 +1866,8 @@ extern "C" int rg_build2d_band(int device, void* stream,
     B.row_lo = (int)row_lo; B.row_hi = (int)row_hi;
     B.rel[0] = l.rel[0]; B.rel[1] = l.rel[1];
     B.info = l.info;
-    k_band_raster<<<(unsigned)ceil_div(nb, T), T, 0, st>>>(gin, (int)row_lo, (int)row_hi, l.bbox, l.raster);
+    k_band_info_init<<<1, 32, 0, st>>>(l.info, l.bbox);
+    k_band_raster<<<(unsigned)ceil_div(nb, T), T, 0, st>>>(gin, (int)row_lo, (int)row_hi, l.bbox, l.info, l.raster);
     RG_LAUNCH_CHECK("k_band_raster");
     k_band_relevance<<<(unsigned)ceil_div(l.Vo, T), T, 0, st>>>(gout, l.raster, l.bbox, l.rel[0], l.rel[1], l.info);
     RG_LAUNCH_CHECK("k_band_relevance");
