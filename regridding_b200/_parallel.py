@@ -67,6 +67,18 @@ def allgather_concat(tensors, group=None):
     if most == 0:
         return tensors
     k = len(ts)
+    if dev.type == "cuda":
+        # NCCL gathers uneven shares straight into views of the result (one grouped broadcast per rank): no padding,
+        # no compaction pass
+        outs = []
+        offs = [0]
+        for c in counts_h:
+            offs.append(offs[-1] + c)
+        for t in ts:
+            full = torch.empty(offs[-1], dtype=t.dtype, device=dev)
+            dist.all_gather([full[offs[r]:offs[r + 1]] for r in range(W)], t.contiguous(), group=group)
+            outs.append(full)
+        return outs[0] if single else outs
     packed = torch.empty((k, most), dtype=torch.int64, device=dev)
     for q, t in enumerate(ts):
         packed[q, :t.shape[0]] = t.contiguous().view(torch.int64)
@@ -226,9 +238,8 @@ def _sharded_build_band(x_in, y_in, x_out, y_out, weights_input, rank, W, group,
     for _ in range(4):
         bb = _device.build2d_band_enqueue(x_in, y_in, x_out, y_out, weights_input, lo, hi, device=dev) if hi > lo else None
         counts = bb.counts if bb is not None else torch.zeros(8, dtype=torch.int64, device=dev)
-        flags = counts[6:8].clone()
-        dist.all_reduce(flags, op=dist.ReduceOp.MAX, group=group)
-        host = torch.cat([counts[:6], flags]).cpu()  # the one host synchronisation of the build
+        dist.all_reduce(counts[6:8], op=dist.ReduceOp.MAX, group=group)  # mismatch / capacity flags, in place
+        host = counts.cpu()  # the one host synchronisation of the build
         if bb is None:
             status = "mismatch" if host[6] else ("capacity" if host[7] else "ok")
         else:
