@@ -223,6 +223,28 @@ int rg_ell4_apply(int device, void* stream, int64_t n_frames, int64_t n_in, int6
                   const int64_t* idx4, const double* w4, const double* values_in, double* values_out);
 
 /* ------------------------------------------------------------------------------
+ * 1D multilinear weights (weights()'s default method) and the saved-weights ordering of raw triplets
+ * replaces  _weights_multilinear / _weights_from_indices_multilinear(_1d)
+ *           regridding/_weights/_weights_multilinear.py:9-206 (searchsorted location, clamp / "below" fix-up,
+ *           w1 = (x - x0) / (x1 - x0), w0 = 1 - w1, weights_input factors, bounds)
+ *           and the ordering of _coalesce, regridding/_weights/_weights_arrays.py:44-73 (stable sort by
+ *           (indices_input, indices_output); multilinear elements hold no repeated pair).
+ * x_in (D, n) and x_out (D, m) row-major; the D elements come back one after the other, 2 m triplets each, sorted
+ * by (input, output); bounds: 0 extrapolate, 1 nan, 2 raise (the count of outside points is returned and the caller
+ * raises).  At most 65535 spectra and 2^31 triplets per call. */
+int rg_multilinear1d_workspace_bytes(int64_t D, int64_t m, size_t* bytes_host);
+int rg_multilinear1d_weights(int device, void* stream, int64_t D, int64_t n, int64_t m,
+                             const double* x_in, const double* x_out, const double* weights_input_or_null, int bounds,
+                             int64_t* indices_input, int64_t* indices_output, double* values,
+                             int64_t* n_outside_host_or_null, void* workspace, size_t workspace_bytes);
+/* raw triplets of ONE element (n of them, flat indices below n_in / n_out) -> sorted by (input, output), stable */
+int rg_sort_triplets_workspace_bytes(int64_t n, size_t* bytes_host);
+int rg_sort_triplets(int device, void* stream, int64_t n, int64_t n_in, int64_t n_out,
+                     const int64_t* indices_input, const int64_t* indices_output, const double* values,
+                     int64_t* out_indices_input, int64_t* out_indices_output, double* out_values,
+                     void* workspace, size_t workspace_bytes);
+
+/* ------------------------------------------------------------------------------
  * fill(method="gauss_seidel"): red-black Gauss-Seidel relaxation of missing cells
  * replaces: _fill_gauss_seidel_2d / _iteration_gauss_seidel_2d  regridding/_fill/_gauss_seidel.py:83-139
  *           (called from fill_gauss_seidel, regridding/_fill/_gauss_seidel.py:13-59)

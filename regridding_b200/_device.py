@@ -116,6 +116,15 @@ class DeviceWeights:
     def device(self) -> torch.device:
         return self.values.device
 
+    def device_bytes(self) -> int:
+        """Device memory this object keeps alive (COO + CSR + apply plans)."""
+        n = sum(t.numel() * t.element_size() for t in (self.indices_input, self.indices_output, self.values))
+        if self._csr is not None:
+            n += sum(t.numel() * t.element_size() for t in (self._csr.row_ptr, self._csr.col, self._csr.val))
+        for p in self._plans.values():
+            n += sum(t.numel() * t.element_size() for t in (p.tile_info, p.tile_rows, p.slot_val, p.slot_lidx))
+        return n
+
     def csr(self) -> CSR:
         if self._csr is None:
             ii, io = self.indices_input, self.indices_output
@@ -150,6 +159,22 @@ class DeviceWeights:
             raise IndexError("weights index out of range for the given shapes")
         v = np.ascontiguousarray(np.asarray(values), dtype=np.float64)
         return cls(to_device(ii, device, I64), to_device(io, device, I64), to_device(v, device, F64), n_in, n_out)
+
+
+class HostWeights:
+    """One saved-weights element that already lives on the host (``(indices_input, indices_output, values)``):
+    what multi-slice builds return, so that device memory is bounded by one chunk of slices, not by their number."""
+
+    def __init__(self, ii: np.ndarray, io: np.ndarray, v: np.ndarray, n_in: int, n_out: int):
+        self.indices_input, self.indices_output, self.values = ii, io, v
+        self.n_in, self.n_out = int(n_in), int(n_out)
+
+    @property
+    def nnz(self) -> int:
+        return int(self.values.size)
+
+    def to_host(self):
+        return (self.indices_input, self.indices_output, self.values)
 
 
 # ---------------------------------------------------------------------------
@@ -680,6 +705,59 @@ def find_indices_2d(x: torch.Tensor, y: torch.Tensor, px: torch.Tensor, py: torc
 
 
 BOUNDS_MODES = {"extrapolate": 0, "nan": 1, "raise": 2}
+
+
+def multilinear1d_weights(x_in: torch.Tensor, x_out: torch.Tensor, weights_input: torch.Tensor | None = None,
+                          bounds: str = "extrapolate"):
+    """1D multilinear weights of D stacked grids (``rg_multilinear1d_weights``): ``(ii, io, v)`` of shape
+    ``(D, 2 m)``, every row sorted by (input, output) like ``weights()`` returns it, and the number of output points
+    outside their grid (only counted -- one host sync -- for ``bounds="raise"``)."""
+    L = _lib.load()
+    if bounds not in BOUNDS_MODES:
+        raise ValueError(f"Unrecognized {bounds=}, expected one of ('extrapolate', 'nan', 'raise').")
+    device = x_in.device
+    D, n = x_in.shape
+    m = x_out.shape[1]
+    ii = torch.empty((D, 2 * m), dtype=I64, device=device)
+    io = torch.empty((D, 2 * m), dtype=I64, device=device)
+    v = torch.empty((D, 2 * m), dtype=F64, device=device)
+    n_outside = 0
+    # at most 65535 grids and 2^31 triplets per call
+    per = max(1, min(65535, (2 ** 31 - 2) // max(2 * m, 1)))
+    with torch.cuda.device(device):
+        for d0 in range(0, D, per):
+            d1 = min(D, d0 + per)
+            nbytes = ctypes.c_size_t()
+            _lib.check(L.rg_multilinear1d_workspace_bytes(d1 - d0, m, ctypes.byref(nbytes)), "rg_multilinear1d_workspace_bytes")
+            ws = _workspace(nbytes.value, device)
+            cnt = ctypes.c_int64()
+            _lib.check(L.rg_multilinear1d_weights(device.index, _stream(device), d1 - d0, n, m, x_in[d0:d1].data_ptr(),
+                                                  x_out[d0:d1].data_ptr(),
+                                                  None if weights_input is None else weights_input[d0:d1].data_ptr(),
+                                                  BOUNDS_MODES[bounds], ii[d0:d1].data_ptr(), io[d0:d1].data_ptr(),
+                                                  v[d0:d1].data_ptr(), ctypes.byref(cnt) if bounds == "raise" else None,
+                                                  ws.data_ptr(), ws.numel()), "rg_multilinear1d_weights")
+            n_outside += int(cnt.value)
+    return ii, io, v, n_outside
+
+
+def sort_triplets(ii: torch.Tensor, io: torch.Tensor, v: torch.Tensor, n_in: int, n_out: int):
+    """Raw triplets of one element -> sorted by (input, output), stable (``rg_sort_triplets``: the ordering of
+    ``_coalesce``, _weights_arrays.py:54-59)."""
+    L = _lib.load()
+    device = v.device
+    n = int(v.numel())
+    oi, oo, ov = torch.empty_like(ii), torch.empty_like(io), torch.empty_like(v)
+    if n == 0:
+        return oi, oo, ov
+    with torch.cuda.device(device):
+        nbytes = ctypes.c_size_t()
+        _lib.check(L.rg_sort_triplets_workspace_bytes(n, ctypes.byref(nbytes)), "rg_sort_triplets_workspace_bytes")
+        ws = _workspace(nbytes.value, device)
+        _lib.check(L.rg_sort_triplets(device.index, _stream(device), n, int(n_in), int(n_out), ii.data_ptr(), io.data_ptr(),
+                                      v.data_ptr(), oi.data_ptr(), oo.data_ptr(), ov.data_ptr(), ws.data_ptr(), ws.numel()),
+                   "rg_sort_triplets")
+    return oi, oo, ov
 
 
 def multilinear2d_weights(x: torch.Tensor, y: torch.Tensor, px: torch.Tensor, py: torch.Tensor,

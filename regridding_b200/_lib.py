@@ -46,6 +46,10 @@ SIGNATURES: dict[str, list] = {
     "rg_find_indices_2d": [_int, _vp, _i64, _i64, _vp, _vp, _i64, _vp, _vp, _i64, _vp, _vp, _sz],
     "rg_multilinear2d_weights": [_int, _vp, _i64, _i64, _vp, _vp, _i64, _vp, _vp, _vp, _i64, _int, _vp, _vp, _vp],
     "rg_ell4_apply": [_int, _vp, _i64, _i64, _i64, _vp, _vp, _vp, _vp],
+    "rg_multilinear1d_workspace_bytes": [_i64, _i64, _p_sz],
+    "rg_multilinear1d_weights": [_int, _vp, _i64, _i64, _i64, _vp, _vp, _vp, _int, _vp, _vp, _vp, _p_i64, _vp, _sz],
+    "rg_sort_triplets_workspace_bytes": [_i64, _p_sz],
+    "rg_sort_triplets": [_int, _vp, _i64, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz],
     "rg_fill_gauss_seidel_2d": [_int, _vp, _vp, _i64, _i64, _i64, ctypes.POINTER(_vp), _p_i64, _i64],
     "rg_csr_workspace_bytes": [_i64, _i64, _p_sz],
     "rg_csr_from_coo": [_int, _vp, _i64, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz],

@@ -48,36 +48,11 @@ def weights_multilinear(coordinates_input, coordinates_output, axis_input, axis_
     if weights_input is not None:
         w_in = stack(np.broadcast_to(weights_input, shape_in), axis_in[0], n)
 
-    fill = np.iinfo(int).max
-    index = _device.find_indices_1d(x_in, x_out, fill, "searchsorted")
-    index_max = n - 2
-    outside = (index < 0) | (index > index_max)
-    if bounds == "raise" and bool(outside.any().item()):
-        raise ValueError(f"{int(outside.sum().item())} of the output points fall outside the input grid, and {bounds=}.")
-    below = x_out < x_in[:, :1]
-    i0 = torch.where(below, torch.zeros_like(index), index.clamp(0, index_max))  # wml.py:105-119
-    i1 = i0 + 1
-    x0 = torch.gather(x_in, 1, i0)
-    x1 = torch.gather(x_in, 1, i1)
-    w1 = (x_out - x0) / (x1 - x0)  # wml.py:185-186
-    w0 = 1 - w1
-    if w_in is not None:
-        w0 = w0 * torch.gather(w_in, 1, i0)
-        w1 = w1 * torch.gather(w_in, 1, i1)
-    if bounds == "nan":
-        nan = torch.full_like(w0, float("nan"))
-        w0 = torch.where(outside, nan, w0)
-        w1 = torch.where(outside, nan, w1)
-
-    i_out = torch.arange(m, device=device, dtype=torch.int64).expand(D, m)
-    ii = torch.stack((i0, i1), dim=2).reshape(D, 2 * m)
-    io = torch.stack((i_out, i_out), dim=2).reshape(D, 2 * m)
-    vv = torch.stack((w0, w1), dim=2).reshape(D, 2 * m)
-    # canonical layout (_weights_arrays.py:44-73): stable sort by (input, output); the pairs are unique
-    key = ii * m + io
-    order = torch.sort(key, dim=1, stable=True).indices
-    ii, io, vv = torch.gather(ii, 1, order), torch.gather(io, 1, order), torch.gather(vv, 1, order)
-
+    # location (searchsorted + the reference's fix-ups), weights and the saved-weights ordering in one C-ABI call
+    # (rg_multilinear1d_weights, csrc/rg_multilinear1d.cu)
+    ii, io, vv, n_outside = _device.multilinear1d_weights(x_in, x_out, w_in, bounds)
+    if bounds == "raise" and n_outside:
+        raise ValueError(f"{n_outside} of the output points fall outside the input grid, and {bounds=}.")
     elements = [_device.DeviceWeights(ii[d].contiguous(), io[d].contiguous(), vv[d].contiguous(), n, m)
                 for d in range(D)]
     return elements, tuple(shape_in), tuple(shape_out), tuple(shape_orth)
@@ -119,7 +94,6 @@ def _weights_multilinear_2d(coords_in, coords_out, axis_in, axis_out, shape_in, 
         if w_in is not None:
             vv = vv * _device.to_device(w_in[d].reshape(-1), device)[ii]
         # canonical layout (_weights_arrays.py:44-73): stable sort by (input, output); the pairs are unique
-        order = torch.sort(ii * P + io, stable=True).indices
-        elements.append(_device.DeviceWeights(ii[order].contiguous(), io[order].contiguous(), vv[order].contiguous(),
-                                              n_in, P))
+        ii, io, vv = _device.sort_triplets(ii.contiguous(), io.contiguous(), vv.contiguous(), n_in, P)
+        elements.append(_device.DeviceWeights(ii, io, vv, n_in, P))
     return elements, tuple(shape_in), tuple(shape_out), tuple(shape_orth)

@@ -171,6 +171,17 @@ def pack_elements(elements, shape_input, shape_output, shape_orthogonal) -> Pack
     if len(elements) == 0 or int(offsets[-1]) == 0:
         z = np.empty(0)
         return PackedWeights(offsets, z.astype(np.int64), z.astype(np.int64), z, shape_input, shape_output, shape_orthogonal)
+    if all(isinstance(e.values, np.ndarray) for e in elements):  # built in chunks and already on the host
+        ii = np.concatenate([e.indices_input for e in elements])
+        io = np.concatenate([e.indices_output for e in elements])
+        v = np.concatenate([e.values for e in elements])
+        return PackedWeights(offsets, ii, io, v, shape_input, shape_output, shape_orthogonal)
+    host = lambda t: t if isinstance(t, np.ndarray) else t.cpu().numpy()  # noqa: E731
+    if any(isinstance(e.values, np.ndarray) for e in elements):
+        ii = np.concatenate([host(e.indices_input) for e in elements])
+        io = np.concatenate([host(e.indices_output) for e in elements])
+        v = np.concatenate([host(e.values) for e in elements])
+        return PackedWeights(offsets, ii, io, v, shape_input, shape_output, shape_orthogonal)
     ii = torch.cat([e.indices_input for e in elements]).cpu().numpy()
     io = torch.cat([e.indices_output for e in elements]).cpu().numpy()
     v = torch.cat([e.values for e in elements]).cpu().numpy()

@@ -26,6 +26,8 @@ def _orthogonal_shape(shape: tuple[int, ...], axis: tuple[int, ...]) -> tuple[in
 def _device_weights_of(element, n_in: int, n_out: int, device) -> _device.DeviceWeights:
     if isinstance(element, _device.DeviceWeights):
         return element
+    if isinstance(element, _device.HostWeights):
+        element = element.to_host()
     indices_input, indices_output, values = element
     values = getattr(values, "value", values)  # unit-carrying values (rfw.py:134-141)
     key = (indices_input, indices_output, values)

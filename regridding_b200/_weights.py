@@ -56,7 +56,10 @@ def weights(
         triple = dw.to_host()
         if unit_weights is not None:
             triple = (triple[0], triple[1], triple[2] << unit_weights)
+        elif isinstance(dw, _device.HostWeights):
+            pass  # built in chunks and already downloaded: no device copy is kept
         else:
+            _cache.freeze(triple)  # in-place edits would leave the cached device copy behind: they raise instead
             _cache.remember(triple, dw)
         result[k] = triple
     return result.reshape(shape_orth), shape_in, shape_out
@@ -144,36 +147,63 @@ def _weights_conservative_device(
             w = None
             if weights_input is not None:
                 w = weights_input[index]  # wcons.py:125-126: orthogonal axes are assumed to lead
-            elements.append(_device.build_weights_2d(xi[k], yi[k], xo[k], yo[k], w, device=device))
+            dw = _device.build_weights_2d(xi[k], yi[k], xo[k], yo[k], w, device=device)
+            if n_slices > 1:
+                # per-slice grids (BASELINE config 4): every slice is downloaded before the next is built, so device
+                # memory does not grow with the number of slices
+                dw = _device.HostWeights(*dw.to_host(), dw.n_in, dw.n_out)
+            elements.append(dw)
     else:
         raise NotImplementedError("Regridding operations greater than 2D are not supported")  # wcons.py:141-144
     return elements, shape_cells_in, shape_cells_out, tuple(shape_orth)
 
 
-def _conservative_1d(x_in: np.ndarray, x_out: np.ndarray, w, device) -> list[_device.DeviceWeights]:
+_CHUNK_BYTES_1D = 1 << 30  # device memory of one chunk of stacked 1D builds (3 arrays of (S, n + m) 8-byte entries)
+
+
+def _conservative_1d(x_in: np.ndarray, x_out: np.ndarray, w, device) -> list:
     """1D conservative weights of S stacked spectra in the public layout (wcons.py:59-106 +
     warr.py:44-73).  The walk emits one triplet per overlap; for ascending grids that is
     already the (input, output)-sorted order, for descending ones the (negative,
-    complemented) indices are re-sorted per spectrum on the device."""
+    complemented) indices are re-sorted per spectrum on the device.
+
+    The spectra are built in chunks bounded by ``_CHUNK_BYTES_1D`` of device memory and every chunk is
+    downloaded (one copy per array) before the next is built: device memory does not grow with S, and there
+    are no per-spectrum device copies.  A single spectrum keeps its device copy (so that
+    ``regrid_from_weights(*weights(...))`` does not upload it again)."""
     S, n = x_in.shape
     m = x_out.shape[1]
-    xi = _device.to_device(x_in, device)
-    xo = _device.to_device(x_out, device)
-    wd = None if w is None else _device.to_device(w, device)
-    ii, io, v, counts = _device.cons1d_batched(xi, xo, wd)
-    counts_h = counts.cpu().numpy()
-    descending = bool(((xi[:, 0] >= xi[:, -1]) | (xo[:, 0] >= xo[:, -1])).any().item())
-    elements = []
-    for s in range(S):
-        c = int(counts_h[s])
-        a, b, val = ii[s, :c], io[s, :c], v[s, :c]
-        if descending and c > 1:
-            # _coalesce (warr.py:54-59): stable sort on (input - min) * span + (output - min)
-            key = (a - a.min()) * (b.max() - b.min() + 1) + (b - b.min())
-            order = torch.sort(key, stable=True).indices
-            a, b, val = a[order], b[order], val[order]
-        # the saved layout keeps the reference's (possibly negative) indices; the device copy used
-        # by the apply is wrapped to [0, n) like Numba's negative indexing does (rfw.py:179-182)
-        dw = _device.DeviceWeights(a.contiguous(), b.contiguous(), val.contiguous(), n - 1, m - 1)
-        elements.append(dw)
+    per = max(1, _CHUNK_BYTES_1D // (24 * (n + m)))
+    elements: list = []
+    for s0 in range(0, S, per):
+        s1 = min(S, s0 + per)
+        xi = _device.to_device(x_in[s0:s1], device)
+        xo = _device.to_device(x_out[s0:s1], device)
+        wd = None if w is None else _device.to_device(w[s0:s1], device)
+        ii, io, v, counts = _device.cons1d_batched(xi, xo, wd)
+        counts_h = counts.cpu().numpy()
+        desc = ((xi[:, 0] >= xi[:, -1]) | (xo[:, 0] >= xo[:, -1])).cpu().numpy()
+        if S == 1:
+            c = int(counts_h[0])
+            a, b, val = ii[0, :c], io[0, :c], v[0, :c]
+            if desc[0] and c > 1:
+                a, b, val = _sorted_1d(a, b, val)
+            elements.append(_device.DeviceWeights(a.contiguous(), b.contiguous(), val.contiguous(), n - 1, m - 1))
+            continue
+        for k in np.flatnonzero(desc):  # rare: _coalesce's stable sort (warr.py:54-59) on the complemented indices
+            c = int(counts_h[k])
+            if c > 1:
+                a, b, val = _sorted_1d(ii[k, :c], io[k, :c], v[k, :c])
+                ii[k, :c], io[k, :c], v[k, :c] = a, b, val
+        ii_h, io_h, v_h = ii.cpu().numpy(), io.cpu().numpy(), v.cpu().numpy()
+        for k in range(s1 - s0):
+            c = int(counts_h[k])
+            # the saved layout keeps the reference's (possibly negative) indices
+            elements.append(_device.HostWeights(ii_h[k, :c].copy(), io_h[k, :c].copy(), v_h[k, :c].copy(), n - 1, m - 1))
     return elements
+
+
+def _sorted_1d(a, b, val):
+    key = (a - a.min()) * (b.max() - b.min() + 1) + (b - b.min())
+    order = torch.sort(key, stable=True).indices
+    return a[order], b[order], val[order]

@@ -14,8 +14,11 @@ inputs (no cross-host determinism needed there).
 from __future__ import annotations
 
 import hashlib
+import pathlib
 
 import numpy as np
+
+ROOT_GOLDEN = pathlib.Path(__file__).resolve().parent / "golden"
 
 # cos(0.4), sin(0.4) as literals: no libm in the golden input path.
 COS04 = 0.9210609940028851
@@ -186,6 +189,24 @@ def cases_1d():
     out["partial_right"] = (np.linspace(0, 1, 9)[None], np.linspace(-0.71, 0.52, 6)[None], None)
     out["coincident"] = (np.linspace(0, 1, 9)[None], np.linspace(0, 1, 5)[None], None)
     out["out_inside_in"] = (np.linspace(0, 1, 6)[None], np.linspace(0.21, 0.83, 14)[None], None)
+    return out
+
+
+def cases_multilinear_1d():
+    """name -> (x_input, x_output, weights_input or None, bounds)."""
+    rng = np.random.default_rng(21)
+    out = {}
+    x = np.linspace(0.0, 1.0, 11)
+    out["single_sorted"] = (x, np.linspace(0.05, 0.95, 7), None, "extrapolate")
+    out["single_unsorted_outside_extrapolate"] = (x, np.array([0.31, -0.2, 1.3, 0.0, 1.0, 0.5, 0.31, 0.77]), None, "extrapolate")
+    out["single_unsorted_outside_nan"] = (x, np.array([0.31, -0.2, 1.3, 0.0, 1.0, 0.5, 0.31, 0.77]), None, "nan")
+    base = np.linspace(4000.0, 7000.0, 65)
+    S = 6
+    xin = base * (1 + 1e-4 * rng.standard_normal((S, 1))) + 0.3 * ((base / 500.0) % 1.0) * rng.random((S, 1))
+    xout = np.linspace(3990.0, 7010.0, 90) + 0.05 * rng.random((S, 1))
+    out["spectra_stack_nan"] = (xin, xout, None, "nan")
+    out["spectra_stack_extrapolate_w"] = (xin, rng.permuted(xout, axis=1), rng.random((S, 65)) + 0.5, "extrapolate")
+    out["nonuniform"] = (np.cumsum(rng.random(40) + 0.1), np.sort(rng.random(55) * 25.0), None, "extrapolate")
     return out
 
 

@@ -576,6 +576,47 @@ def test_multilinear_1d(rg):
     assert np.allclose(ext, 3 * np.array([-0.2, 1.3]) + 1)
 
 
+def test_multilinear_1d_vs_reference_goldens(rg):
+    """weights(method="multilinear") / regrid_from_weights / regrid against the reference's own output
+    (tests/golden/golden_v3.npz, make_golden_v3.py): indices, weights (bit for bit, NaNs included) and applied values."""
+    with np.load(cases.ROOT_GOLDEN / "golden_v3.npz") as z:
+        G = {k: z[k] for k in z.files}
+    for name, (x_in, x_out, w, bounds) in cases.cases_multilinear_1d().items():
+        kw = dict(axis_input=-1, axis_output=-1) if x_in.ndim > 1 else {}
+        W = rg.weights((x_in,), (x_out,), weights_input=w, method="multilinear", bounds=bounds, **kw)
+        assert [*W[1], *W[2]] == list(G[f"ml1d/{name}/shapes"])
+        flat = W[0].reshape(-1)
+        for d in range(flat.size):
+            ii, io, v = flat[d]
+            assert ii.dtype == np.int64 and io.dtype == np.int64 and v.dtype == np.float64
+            assert np.array_equal(ii, G[f"ml1d/{name}/{d}/ii"]), (name, d)
+            assert np.array_equal(io, G[f"ml1d/{name}/{d}/io"]), (name, d)
+            assert np.array_equal(v, G[f"ml1d/{name}/{d}/v"], equal_nan=True), (name, d)
+        vals = np.random.default_rng(3).random(W[1])
+        assert np.array_equal(rg.regrid_from_weights(*W, vals, **kw), G[f"ml1d/{name}/apply"], equal_nan=True), name
+        got = rg.regrid((x_in,), (x_out,), vals, method="multilinear", bounds=bounds, **kw)
+        assert np.array_equal(got, G[f"ml1d/{name}/regrid"], equal_nan=True), name
+    x = np.linspace(0, 1, 11)
+    with pytest.raises(ValueError, match="2 of the output points fall outside"):
+        rg.weights((x,), (np.array([-0.2, 0.5, 1.3]),), bounds="raise")
+
+
+def test_weights_1d_many_spectra_are_built_in_chunks(rg, oracle, monkeypatch):
+    """Stacked 1D conservative builds run in chunks bounded by a byte budget: same triplets as the oracle."""
+    from regridding_b200 import _weights
+
+    xin, xout, _ = cases.cases_1d()["spectra"]
+    monkeypatch.setattr(_weights, "_CHUNK_BYTES_1D", 24 * (xin.shape[1] + xout.shape[1]) * 7)  # 7 spectra per chunk
+    W = rg.weights((xin,), (xout,), axis_input=-1, axis_output=-1, method="conservative")
+    ref = oracle.weights_conservative_1d_batched(xin, xout)
+    for s in range(xin.shape[0]):
+        for a, b in zip(W[0][s], ref[s]):
+            assert np.array_equal(a, b)
+    vals = np.random.default_rng(0).random(W[1])
+    out = rg.regrid_from_weights(*W, vals, axis_input=-1, axis_output=-1)
+    assert np.array_equal(out, rg.regrid((xin,), (xout,), vals, axis_input=-1, axis_output=-1, method="conservative"))
+
+
 # ---------------------------------------------------------------------------
 # transposed weights (regridding/_weights/_weights_transposed)
 # ---------------------------------------------------------------------------

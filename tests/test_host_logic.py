@@ -95,12 +95,44 @@ def test_cache_is_identity_keyed():
     # transpose_weights re-uses the values array with the index arrays swapped: must not hit the forward matrix
     assert _cache.lookup((io, ii, v)) is None
     assert _cache.lookup((ii.copy(), io, v)) is None
+    # the transposed use gets its own entry and does not evict the forward one
+    token_t = object()
+    _cache.remember((io, ii, v), token_t)
+    assert _cache.lookup((io, ii, v)) is token_t and _cache.lookup((ii, io, v)) is token
+    # an in-place edit after the upload invalidates the entry (arrays handed out by weights() are read-only on top)
+    v[1] = 7.0
+    assert _cache.lookup((ii, io, v)) is None
+    _cache.freeze((ii, io, v))
+    with pytest.raises(ValueError):
+        v[0] = 1.0
     n = len(_cache._entries)
     del v
     import gc
 
     gc.collect()
     assert len(_cache._entries) == n - 1
+
+
+def test_cache_is_bounded_by_device_bytes(monkeypatch):
+    class Fake:
+        device = None
+
+        def __init__(self, nbytes):
+            self.nbytes = nbytes
+
+        def device_bytes(self):
+            return self.nbytes
+
+    _cache.clear()
+    monkeypatch.setenv("REGRID_B200_CACHE_BYTES", "1000")
+    keep = []
+    for k in range(4):
+        el = (np.arange(3) + k, np.arange(3), np.arange(3.0) + k)
+        keep.append(el)
+        _cache.remember(el, Fake(400))
+    assert _cache.lookup(keep[0]) is None and _cache.lookup(keep[1]) is None  # evicted, oldest first
+    assert _cache.lookup(keep[2]) is not None and _cache.lookup(keep[3]) is not None
+    _cache.clear()
 
 
 def test_shard_ranges_cover_exactly():
