@@ -131,7 +131,7 @@ def regrid_from_weights(
     weights_arr = np.broadcast_to(np.array(weights), shape_orth, subok=True)
     flat_weights = weights_arr.reshape(-1)
     unit_weights = getattr(flat_weights[0][2], "unit", None) if flat_weights.size and not isinstance(
-        flat_weights[0], _device.DeviceWeights) else None
+        flat_weights[0], (_device.DeviceWeights, _device.HostWeights)) else None
 
     cells_in = tuple(full_in[a] for a in axis_in)
     cells_out = tuple(full_out[a] for a in axis_out)
