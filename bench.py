@@ -64,10 +64,16 @@ def build_bytes(v_in: int, v_out: int, nnz: int) -> int:
 
 
 # dram__bytes_read.sum + dram__bytes_write.sum of one launch of the dominant kernel from the committed
-# `ncu --set full` capture, scaled to the launch the bench times; None until measured.
-# profiles/r1e_apply_ncu_summary.txt: 9.685 GB read + 8.535 GB written for a 256-frame launch at config 3
-# = 71.17 MB per frame (1.05x the algorithmic bytes); the weights part (slot arrays, ~0.19 GB) is inside.
-TRAFFIC_NCU: dict = {"apply_bytes_per_frame": (9.685029e9 + 8.534865e9) / 256}
+# `ncu --set full` capture of THIS kernel, scaled to the launch the bench times; None until measured.
+# profiles/r2_apply_ncu_summary.txt (k_apply_bulk, 256-frame launch at config 3): 9.579 GB read + 8.540 GB written
+# = 70.78 MB per frame (1.04x the algorithmic bytes; footprint halos that miss L2 + the slot arrays).
+TRAFFIC_NCU: dict = {"apply_bytes_per_frame": (9.578994e9 + 8.539667e9) / 256,
+                     "source": "ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum of one 256-frame launch of "
+                               "rg::k_apply_bulk, scaled to this launch's frames (profiles/r2_apply_ncu_summary.txt)"}
+# fp64-pipe utilisation of the build's walk kernels from the committed ncu capture (north_star: "fp64-pipe utilisation
+# for the build"): sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_elapsed, profiles/r2_build_ncu_summary.txt
+BUILD_NCU: dict = {"fp64_pipe_pct": {"k_walk_count": None, "k_walk_emit": None}, "source": None}
+FLOPS_PER_PIECE = 64  # 3 edge tests x 17 + 6 intersection point + 4 area + 2 weight divides + 1 negate
 
 
 # The reference's own Numba implementation (as shipped, warm JIT cache) measured in the build container
@@ -417,6 +423,21 @@ def run_ours(args):
                      "sample": f"{nb - 1}^2-cell grid of the same family (sweep {ts:.1f} s + coalesce {tc:.1f} s); "
                                "the CPU algorithm is super-linear in the grid size, so this flatters it"}
 
+    extras = None
+    if not args.no_extras:
+        torch.cuda.empty_cache()
+        extras = extra_configs(dev, rank, world, peak, barrier, max_over_ranks, with_cpu=(rank == 0 and world == 1 and not args.no_cpu))
+
+    # fp64 FMA-chain throughput of this device: the denominator of the build's fp64 roofline
+    import ctypes
+
+    from regridding_b200 import _lib
+
+    tf = ctypes.c_double()
+    _lib.check(_lib.load().rg_measure_fp64_peak(dev.index, torch.cuda.current_stream(dev).cuda_stream, ctypes.byref(tf)),
+               "rg_measure_fp64_peak")
+    fp64_peak = float(tf.value)
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -433,9 +454,8 @@ def run_ours(args):
                    "parallelism": f"frames x{world} (no collective)"},
         "roofline": {"bound": "hbm", "achieved": per_gpu, "peak": peak, "unit": "GB/s", "frac": per_gpu / peak,
                      "traffic": (TRAFFIC_NCU["apply_bytes_per_frame"] * F if n == 2049 else None),
-                     "traffic_source": "ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum of one 256-frame "
-                                       "launch, scaled to this launch's frames (profiles/r1e_apply_ncu_summary.txt)",
-                     "peak_source": peak_src, "kernel": "rg::k_apply_staged",
+                     "traffic_source": TRAFFIC_NCU["source"],
+                     "peak_source": peak_src, "kernel": "rg::k_apply_bulk",
                      "algorithmic_bytes_per_launch": abytes},
         "e2e": {"value": e2e_value, "unit": UNIT, "frames": Fe,
                 "h2d_bytes_per_step": 8 * Fe * n_in, "d2h_bytes_per_step": 8 * Fe * n_out,
@@ -453,6 +473,14 @@ def run_ours(args):
             "roofline": {"bound": "hbm", "achieved": bbytes / (build_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
                          "frac": bbytes / (build_ms * 1e-3) / 1e9 / peak, "algorithmic_bytes": bbytes,
                          "note": "the build is fp64-latency / divergence bound, not HBM bound; see DESIGN.md"},
+            "roofline_fp64": {
+                "bound": "fp64", "unit": "TFLOP/s", "peak": fp64_peak,
+                "peak_source": "rg_measure_fp64_peak: 8 independent DFMA chains per thread on all SMs, measured in this run",
+                "flops": FLOPS_PER_PIECE * (build_stats.get("fragments") or 0) // 2,
+                "flops_model": "64 fp64 flops per piece (SURVEY.md 8d), pieces = raw fragments / 2",
+                "achieved": FLOPS_PER_PIECE * ((build_stats.get("fragments") or 0) // 2) / (build_ms * 1e-3) / 1e12,
+                "frac": FLOPS_PER_PIECE * ((build_stats.get("fragments") or 0) // 2) / (build_ms * 1e-3) / 1e12 / fp64_peak,
+                "ncu_fp64_pipe_pct": BUILD_NCU["fp64_pipe_pct"], "ncu_source": BUILD_NCU["source"]},
             # config 4 (every orthogonal slice carries its own grid): slices shard across ranks with no collective,
             # every rank runs full builds of its own slices -> aggregate = ranks x the per-rank rate (max over ranks)
             "per_slice_sharded": {"n_gpus": world, "value": world * n_in / (build_ms * 1e-3) / 1e6, "unit": "Mcells/s",
@@ -473,6 +501,7 @@ def run_ours(args):
                     "api": "regridding_b200.weights(method='conservative') host coords -> host triplets"},
             "cpu_baseline": cpu_build,
         },
+        "configs": extras,
         "checksum": checksum,
         # SHA-256 of the public (ii, io, v): `--impl reference` prints the same key for the CPU oracle's triplets
         "weights_sha256": weights_sha,
@@ -481,6 +510,172 @@ def run_ours(args):
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+
+# ---------------------------------------------------------------------------
+# the other BASELINE.json configurations (1, 2, 4, 5): extra keys of the same JSON line
+# ---------------------------------------------------------------------------
+
+
+def extra_configs(dev, rank, world, peak, barrier, max_over_ranks, with_cpu):
+    """One measured object per BASELINE config besides config 3; every rank does the same amount of work (weak
+    scaling, aggregate = world x per-rank rate by the slowest rank) except config 4, whose 8 x world frames are
+    sharded over the ranks (each frame carries its own grid: no collective)."""
+    import torch
+
+    import regridding_b200 as rg
+    from regridding_b200 import _device
+    from tests import cases
+
+    out = {}
+
+    def timed(fn, reps=5, warm=2):
+        for _ in range(warm):
+            r = fn()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            r = fn()
+        e1.record()
+        torch.cuda.synchronize(dev)
+        return max_over_ranks(e0.elapsed_time(e1) / reps), r
+
+    def roof(bytes_, ms):
+        a = bytes_ / (ms * 1e-3) / 1e9
+        return {"bound": "hbm", "achieved": a, "peak": peak, "unit": "GB/s", "frac": a / peak, "algorithmic_bytes": bytes_}
+
+    T = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)  # noqa: E731
+
+    # ---- config 1: 100x100 vertices -> 120x80, one image -------------------------------------------------
+    gi, go, _ = cases.case_2d("fam100")
+    co = cases.perturb_like_reference(go, (-1, -2), 42)
+    t = [T(a) for a in (*gi, *co)]
+    ms_b, dw = timed(lambda: _device.build_weights_2d(*t, device=dev))
+    plan = dw.plan((99, 99), (119, 79))
+    x = torch.rand((1, dw.n_in), dtype=torch.float64, device=dev)
+    ms_a, _ = timed(lambda: _device.apply_planned(plan, x), reps=20)
+    vals1 = np.random.default_rng(0).random((99, 99))
+    rg.regrid(gi, go, vals1, method="conservative")
+    t0 = time.perf_counter()
+    rg.regrid(gi, go, vals1, method="conservative")
+    t_api = time.perf_counter() - t0
+    out["config1"] = {"workload": "100x100 vertices -> 120x80 vertices, one image", "build_ms": ms_b, "apply_ms_1_frame": ms_a,
+                      "nnz": dw.nnz, "staged_tiles": plan.n_tiles - plan.n_generic_tiles, "tiles": plan.n_tiles,
+                      "regrid_api_s_host_to_host": t_api, "build_Mcells_per_s": dw.n_in / ms_b / 1e3,
+                      "reference_numba_regrid_s": 0.0317}
+
+    # ---- config 2: S spectra x 4096 bins with per-spectrum grids, fused 1D conservative regrid -----------
+    S, n = 262144, 4097
+    g = torch.Generator(device=dev)
+    g.manual_seed(rank)
+    base = torch.linspace(4000.0, 7000.0, n, dtype=torch.float64, device=dev)
+    xin = base * (1 + 1e-4 * torch.randn((S, 1), dtype=torch.float64, device=dev, generator=g)) + \
+        0.3 * torch.sin(base / 500 + torch.rand((S, 1), dtype=torch.float64, device=dev, generator=g))
+    xout = torch.linspace(4001.0, 6999.0, n, dtype=torch.float64, device=dev) + \
+        0.05 * torch.rand((S, 1), dtype=torch.float64, device=dev, generator=g)
+    vals = torch.rand((S, n - 1), dtype=torch.float64, device=dev, generator=g)
+    res = torch.empty((S, n - 1), dtype=torch.float64, device=dev)
+    ms, _ = timed(lambda: _device.regrid1d_conservative(xin, xout, vals, out=res), reps=5)
+    byt = S * (8 * n + 8 * n + 8 * (n - 1) + 8 * (n - 1))
+    c2 = {"workload": f"{S} spectra per GPU x 4096 bins, per-spectrum wavelength grids, fused conservative regrid "
+                      "(inputs resident in HBM)",
+          "ms": ms, "spectra_per_s": world * S / ms * 1e3, "roofline": roof(byt, ms), "n_gpus": world,
+          "full_1M_spectra_s_extrapolated_per_gpu": ms * (1e6 / S) / 1e3,
+          "reference_numba_spectra_per_s_8_vcpu": 592}
+    if with_cpu:
+        from oracle import oracle
+
+        Sc = 2048
+        xi_h, xo_h, v_h = xin[:Sc].cpu().numpy(), xout[:Sc].cpu().numpy(), vals[:Sc].cpu().numpy()
+        t0 = time.perf_counter()
+        W1 = oracle.weights_conservative_1d_batched(xi_h, xo_h)
+        for k in range(Sc):
+            oracle.regrid_from_weights(*W1[k], v_h[k:k + 1], n - 1)
+        dt = time.perf_counter() - t0
+        c2["cpu_baseline"] = {"value": Sc / dt, "unit": "spectra/s", "cores": oracle.num_threads(), "kind": "port",
+                              "sample": f"{Sc} spectra: batched weights build + per-spectrum apply ({dt:.2f} s)"}
+        got = res[:4].cpu().numpy()
+        want = np.stack([oracle.regrid_from_weights(*W1[k], v_h[k:k + 1], n - 1)[0] for k in range(4)])
+        c2["equals_cpu_port_bitwise_on_4_spectra"] = bool(np.array_equal(got, want))
+    out["config2"] = c2
+    del xin, xout, vals, res
+    torch.cuda.empty_cache()
+
+    # ---- config 4: every frame carries its own grid; 8 frames per GPU, sharded with no collective ---------
+    n4, per_rank = 2049, 8
+    frames = [rank * per_rank + q for q in range(per_rank)]
+    grids, t_jit = [], 0.0
+    for f in frames:
+        gi4, go4 = cases.benchmark_family(n4, distorted=True, angle=0.4 + 0.002 * f, phase=float(f))
+        t0 = time.perf_counter()
+        co4 = cases.perturb_like_reference(go4, (-1, -2), 42)   # the reference's host jitter stream (NumPy)
+        t_jit += time.perf_counter() - t0
+        grids.append([torch.from_numpy(np.ascontiguousarray(a)).pin_memory() for a in (*gi4, *co4)])
+    _device.build_weights_2d(*[a.to(dev) for a in grids[0]], device=dev)  # warm-up
+    barrier()
+    t0 = time.perf_counter()
+    nnz4 = 0
+    copy_stream = torch.cuda.Stream(dev)
+    nxt = None
+    with torch.cuda.stream(copy_stream):
+        nxt = [a.to(dev, non_blocking=True) for a in grids[0]]
+        ev = torch.cuda.Event()
+        ev.record()
+    for q in range(per_rank):
+        torch.cuda.current_stream(dev).wait_event(ev)
+        cur = nxt
+        if q + 1 < per_rank:   # H2D of the next frame's coordinates overlaps this frame's build
+            with torch.cuda.stream(copy_stream):
+                nxt = [a.to(dev, non_blocking=True) for a in grids[q + 1]]
+                ev = torch.cuda.Event()
+                ev.record()
+        nnz4 += _device.build_weights_2d(*cur, device=dev).nnz
+    torch.cuda.synchronize(dev)
+    wall = max_over_ranks(time.perf_counter() - t0)
+    jit = max_over_ranks(t_jit)
+    cells4 = (n4 - 1) ** 2
+    out["config4"] = {"workload": f"{per_rank * world} frames x 2048^2, each with its own curvilinear grid; {per_rank} per GPU",
+                      "n_gpus": world, "frames": per_rank * world, "frames_per_gpu": per_rank,
+                      "device_wall_s": wall, "scope": "pinned host coordinates -> H2D (overlapped) -> build -> device-resident triplets",
+                      "Mcells_per_s": world * per_rank * cells4 / wall / 1e6, "ms_per_frame_per_gpu": wall / per_rank * 1e3,
+                      "host_jitter_s_per_gpu": jit,
+                      "note": "the reference's seeded jitter is a serial NumPy stream (0.14 s per 2049^2 grid): end to end it "
+                              "dominates the GPU build by ~30x on any number of GPUs; see DESIGN.md",
+                      "nnz_rank0": nnz4, "reference_numba_s_per_frame_8_vcpu": 72.0}
+    del grids, nxt, cur
+    torch.cuda.empty_cache()
+
+    # ---- config 5: cell location of 8192^2 output points in a 4096^2-vertex curvilinear grid -------------
+    gi5, _ = cases.benchmark_family(4096, distorted=True)
+    X, Y = T(gi5[0]), T(gi5[1])
+    m = 8192
+    c5 = {"workload": "find_indices of 8192^2 rectilinear output points in a 4096^2-vertex distorted curvilinear grid",
+          "points": m * m, "n_gpus": world}
+    for name, scale in (("inside_0.7_bbox", 0.7), ("full_bbox", 1.0)):
+        cx, cy = float(X.min() + X.max()) / 2, float(Y.min() + Y.max()) / 2
+        hx, hy = float(X.max() - X.min()) / 2 * scale, float(Y.max() - Y.min()) / 2 * scale
+        px = torch.linspace(cx - hx, cx + hx, m, dtype=torch.float64, device=dev)[:, None].expand(m, m).contiguous()
+        py = torch.linspace(cy - hy, cy + hy, m, dtype=torch.float64, device=dev)[None, :].expand(m, m).contiguous()
+        ms5, idx = timed(lambda: _device.find_indices_2d(X, Y, px, py, -1), reps=3, warm=1)
+        c5[name] = {"ms": ms5, "Mpoints_per_s": world * m * m / ms5 / 1e3, "fraction_inside": float((idx >= 0).double().mean()),
+                    "roofline": roof((16 + 8) * m * m, ms5)}
+        if with_cpu and name == "full_bbox":
+            from oracle import oracle
+
+            rng = np.random.default_rng(5)
+            a, b = rng.integers(0, m, 100000), rng.integers(0, m, 100000)
+            pxs, pys = px[a, b].cpu().numpy(), py[a, b].cpu().numpy()
+            t0 = time.perf_counter()
+            want = oracle.index_of_points(gi5[0], gi5[1], pxs, pys, -1, "secant")
+            dt = time.perf_counter() - t0
+            c5["cpu_baseline"] = {"value": 1e5 / dt / 1e6, "unit": "Mpoints/s", "cores": oracle.num_threads(), "kind": "port",
+                                  "sample": f"100000 of the points, index_of_point_secant ({dt:.2f} s)"}
+            c5["equals_cpu_port_on_sample"] = bool(np.array_equal(idx[a, b].cpu().numpy(), want))
+        del px, py, idx
+    out["config5"] = c5
+    return out
 
 
 def main():
@@ -496,6 +691,7 @@ def main():
     ap.add_argument("--cpu-build-n", type=int, default=1025)
     ap.add_argument("--ref-frames", type=int, default=32)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the extra lines for BASELINE configs 1, 2, 4, 5")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

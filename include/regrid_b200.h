@@ -37,6 +37,10 @@ extern "C" {
 #define RG_E_WORKSPACE (-3)  /* workspace too small */
 #define RG_E_WALK (-4)       /* a sweep walk did not terminate (degenerate / folded grid) */
 
+/* Measurement helper (bench.py): fp64 FMA-chain throughput of the device in TFLOP/s (2 flops per FMA), the
+ * denominator of the build's fp64 roofline; synchronises the stream. */
+int rg_measure_fp64_peak(int device, void* stream, double* tflops_host);
+
 const char* rg_last_error_string(void);
 int rg_version(void);
 

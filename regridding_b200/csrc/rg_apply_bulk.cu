@@ -67,8 +67,14 @@
 #ifndef RG_REGS_PRODUCER
 #define RG_REGS_PRODUCER 40
 #endif
-// the CTA's register pool is what the launch allocated (kBulkThreads x the launch-time count, 80): the two budgets must
+// the CTA's register pool is what the launch allocated (kBulkThreads x the launch-time count): the two budgets must
 // fit in it or the consumers' setmaxnreg.inc waits forever
+#ifndef RG_STORE_CS
+#define RG_STORE_CS 0   // results are written with streaming (evict-first) stores: they are never read again, the footprint
+#endif                  // halos the neighbouring tiles share should own the L2
+#ifndef RG_FAKE_STORE
+#define RG_FAKE_STORE 0   // ablation: full-width global stores of register values, no shared-memory staging (WRONG results)
+#endif
 #ifndef RG_DIRECT_STORE
 #define RG_DIRECT_STORE 0   // experiment: 8-byte stores straight from the accumulators (no shared-memory staging)
 #endif
@@ -107,7 +113,8 @@ constexpr int kPatch = RG_PATCH_COLS;      // tiles are issued in patches of kPa
 constexpr int kPatchRows = RG_PATCH_ROWS;  // CTAs) so that footprint halos are shared through L2
 static_assert((kCP / 2) % 2 == 1 && kCP % 2 == 0, "kCP/2 must be odd");
 static_assert(kT == 8, "lane & 7 = frame");
-static_assert(kCW * RG_REGS_CONSUMER + kPW * RG_REGS_PRODUCER <= (kCW + kPW) * 80, "setmaxnreg budgets exceed the CTA's pool");
+constexpr int kLaunchRegs = (65536 / ((kCW + kPW) * 32)) / 8 * 8;   // what __launch_bounds__(threads, 1) lets ptxas allocate
+static_assert(kCW * RG_REGS_CONSUMER + kPW * RG_REGS_PRODUCER <= (kCW + kPW) * kLaunchRegs, "setmaxnreg budgets exceed the CTA's pool");
 static_assert(kCW % 4 == 0 && kPW % 4 == 0, "setmaxnreg works on warpgroups (4 warps)");
 static_assert(kTW == 32 && kPadMax % 8 == 0, "layout");
 
@@ -550,7 +557,10 @@ k_apply_bulk(int64_t n_frames, int64_t n_in, int64_t cells_left, int64_t h_out, 
             for (int tr = 0; tr < th; tr++) {
                 const int64_t o = f * n_out + out_base + (int64_t)tr * w_out;
                 if (tw == kTW && out_aligned && (o & 1) == 0) {
-                    if (lane < 16) *reinterpret_cast<double2*>(vout + o + 2 * lane) = make_double2(0.0, 0.0);
+                    if (lane < 16) {
+                        if (RG_STORE_CS) __stcs(reinterpret_cast<double2*>(vout + o + 2 * lane), make_double2(0.0, 0.0));
+                        else *reinterpret_cast<double2*>(vout + o + 2 * lane) = make_double2(0.0, 0.0);
+                    }
                 } else if (lane < tw) {
                     vout[o + lane] = 0.0;
                 }
@@ -592,14 +602,18 @@ k_apply_bulk(int64_t n_frames, int64_t n_in, int64_t cells_left, int64_t h_out, 
             bulk_load(smem_u32(S.val), slot_val + base, (unsigned)nslots * 8u, &S.slots_ready);
             bulk_load(smem_u32(S.lidx), slot_lidx + base, (unsigned)nslots * 2u, &S.slots_ready);
         }
-        constexpr int RPL = kRMAX / 32;
-        static_assert(kT % kPW == 0, "every producer warp owns kT / kPW frames of a stage");
+        // kPW <= kT: a warp owns kT / kPW frames of a stage; kPW > kT: kPW / kT warps share one frame (rows dealt out)
+        constexpr int kFW = kPW > kT ? kT : kPW;     // frame groups
+        constexpr int kPartW = kPW / kFW;            // warps per frame
+        static_assert(kT % kFW == 0 && kPW % kFW == 0 && (kRMAX / 32) % kPartW == 0, "producer warps must tile frames x rows");
+        constexpr int RPL = kRMAX / 32 / kPartW;
+        const int fw = pw % kFW, part = pw / kFW;
         int32_t src[RPL];
         unsigned dst[RPL], len[RPL];
         unsigned row_bytes = 0;
 #pragma unroll
         for (int j = 0; j < RPL; j++) {
-            const int r = lane + 32 * j;
+            const int r = (lane + 32 * j) * kPartW + part;
             const int32_t a = tile_rows[(int64_t)tile * kRowInts + 2 * r];
             const unsigned dl = (r < nrows) ? (unsigned)tile_rows[(int64_t)tile * kRowInts + 2 * r + 1] : 0u;
             src[j] = a;
@@ -607,37 +621,37 @@ k_apply_bulk(int64_t n_frames, int64_t n_in, int64_t cells_left, int64_t h_out, 
             len[j] = (dl >> 16) * 8u;
             row_bytes += len[j];
         }
-        const unsigned frame_bytes = __reduce_add_sync(0xffffffffu, row_bytes);   // staged bytes of one frame
+        const unsigned frame_bytes = __reduce_add_sync(0xffffffffu, row_bytes);   // bytes this warp stages per frame
         // this lane's rows in the first frame of this producer warp; advanced by kT frames per sub-block
-        const double* p0 = vin + (f_begin + pw) * n_in;
+        const double* p0 = vin + (f_begin + fw) * n_in;
         const int64_t stage_step = (int64_t)kT * n_in;
         for (int s = 0; s < nsub; s++, p0 += stage_step) {
             const int st = s % kNST;
             if (s >= kNST) mbar_wait(&S.empty[st], (unsigned)((s / kNST - 1) & 1));
-            const unsigned sbase = smem_u32(S.in_s[st]) + pw * (kCP * 8);
-            const int64_t f0 = f_begin + (int64_t)s * kT + pw;
+            const unsigned sbase = smem_u32(S.in_s[st]) + fw * (kCP * 8);
+            const int64_t f0 = f_begin + (int64_t)s * kT + fw;
             if (!odd_in) {
                 // even n_in: every frame is 16-byte aligned and no span reaches beyond its frame
                 int nfr = 0;
 #pragma unroll
-                for (int i = 0; i < kT / kPW; i++) nfr += (f0 + i * kPW < f_end && !RG_SKIP_LOAD) ? 1 : 0;
+                for (int i = 0; i < kT / kFW; i++) nfr += (f0 + i * kFW < f_end && !RG_SKIP_LOAD) ? 1 : 0;
                 if (lane == 0) mbar_arrive_expect_tx(&S.full[st], frame_bytes * nfr);
                 __syncwarp();
 #pragma unroll
-                for (int i = 0; i < kT / kPW; i++) {
-                    if (f0 + i * kPW < f_end && !RG_SKIP_LOAD) {
-                        const double* pf = p0 + (int64_t)i * kPW * n_in;
+                for (int i = 0; i < kT / kFW; i++) {
+                    if (f0 + i * kFW < f_end && !RG_SKIP_LOAD) {
+                        const double* pf = p0 + (int64_t)i * kFW * n_in;
 #pragma unroll
                         for (int j = 0; j < RPL; j++)
-                            if (len[j]) bulk_load(sbase + i * kPW * (kCP * 8) + dst[j], pf + src[j], len[j], &S.full[st]);
+                            if (len[j]) bulk_load(sbase + i * kFW * (kCP * 8) + dst[j], pf + src[j], len[j], &S.full[st]);
                     }
                 }
             } else {
                 // odd n_in: odd frames are staged from one cell earlier; copies are clipped to the caller's buffer
                 unsigned mine = 0;
 #pragma unroll
-                for (int i = 0; i < kT / kPW; i++) {
-                    const int64_t f = f0 + i * kPW;
+                for (int i = 0; i < kT / kFW; i++) {
+                    const int64_t f = f0 + i * kFW;
                     if (f >= f_end || RG_SKIP_LOAD) continue;
                     const int64_t fs = f * n_in - (f & 1);   // first double of the (shifted) frame
 #pragma unroll
@@ -650,15 +664,15 @@ k_apply_bulk(int64_t n_frames, int64_t n_in, int64_t cells_left, int64_t h_out, 
                 if (lane == 0) mbar_arrive_expect_tx(&S.full[st], total);
                 __syncwarp();
 #pragma unroll
-                for (int i = 0; i < kT / kPW; i++) {
-                    const int64_t f = f0 + i * kPW;
+                for (int i = 0; i < kT / kFW; i++) {
+                    const int64_t f = f0 + i * kFW;
                     if (f >= f_end || RG_SKIP_LOAD) continue;
                     const int64_t fs = f * n_in - (f & 1);
 #pragma unroll
                     for (int j = 0; j < RPL; j++) {
                         const int64_t room = cells_left - (fs + src[j]);
                         const unsigned n = (unsigned)max((int64_t)0, min((int64_t)len[j], room * 8));
-                        if (n) bulk_load(sbase + i * kPW * (kCP * 8) + dst[j], vin + fs + src[j], n, &S.full[st]);
+                        if (n) bulk_load(sbase + i * kFW * (kCP * 8) + dst[j], vin + fs + src[j], n, &S.full[st]);
                     }
                 }
             }
@@ -790,7 +804,18 @@ k_apply_bulk(int64_t n_frames, int64_t n_in, int64_t cells_left, int64_t h_out, 
         if (lane == 0) mbar_arrive(&S.empty[st]);  // this warp is done with the stage: the producers may refill it
         // ---- write-out of the warp's tile row: 8 frames x 256 B, staged four frames at a time in the warp's
         // private slice; 16 B per lane, two frames per store instruction ----
-        if (RG_DIRECT_STORE) {
+        if (RG_FAKE_STORE) {
+            if (row_live) {
+                double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+                for (int k = 0; k < kQuadsRow; k += 2) { s0 += acc[k]; s1 += acc[k + 1]; }
+#pragma unroll
+                for (int i = 0; i < kT; i += 2) {
+                    const int64_t f = f0 + i + hf;
+                    if (f < f_end) *reinterpret_cast<double2*>(op + (int64_t)i * n_out) = make_double2(s0, s1);
+                }
+            }
+        } else if (RG_DIRECT_STORE) {
             if (row_live && !RG_SKIP_STORE && f0 + t < f_end) {
                 double* o = vout + (f0 + t) * n_out + row_off;
 #pragma unroll
@@ -814,7 +839,8 @@ k_apply_bulk(int64_t n_frames, int64_t n_in, int64_t cells_left, int64_t h_out, 
                         double* o = op + (int64_t)(4 * h + i) * n_out;
                         const double* si = outw + (i + hf) * kOS + (c2 ^ (2 * (i + hf)));
                         if (row_vec && (((f * n_out + row_off) & 1) == 0)) {
-                            *reinterpret_cast<double2*>(o) = *reinterpret_cast<const double2*>(si);
+                            if (RG_STORE_CS) __stcs(reinterpret_cast<double2*>(o), *reinterpret_cast<const double2*>(si));
+                            else *reinterpret_cast<double2*>(o) = *reinterpret_cast<const double2*>(si);
                         } else {
                             if (c2 < tw) o[0] = si[0];   // (a pair of cells is never split by the swizzle)
                             if (c2 + 1 < tw) o[1] = si[1];

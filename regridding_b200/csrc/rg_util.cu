@@ -195,5 +195,53 @@ extern "C" int rg_transpose_conservative(int device, void* stream, int64_t nnz, 
     return RG_OK;
 }
 
+// fp64 FMA-chain throughput of this device: the denominator of the build's fp64 roofline (the
+// vector fp64 peak is not in MEASURED_PEAKS.json).  8 independent DFMA chains per thread, all SMs full.
+namespace rg {
+__global__ void __launch_bounds__(256) k_fp64_fma_chain(int iters, double seed, double* __restrict__ sink)
+{
+    double a0 = seed + threadIdx.x, a1 = a0 + 1.0, a2 = a0 + 2.0, a3 = a0 + 3.0, a4 = a0 + 4.0, a5 = a0 + 5.0, a6 = a0 + 6.0,
+           a7 = a0 + 7.0;
+    const double m = 1.0 + 1e-9, c = 1e-9;
+#pragma unroll 4
+    for (int i = 0; i < iters; i++) {
+        a0 = __fma_rn(a0, m, c); a1 = __fma_rn(a1, m, c); a2 = __fma_rn(a2, m, c); a3 = __fma_rn(a3, m, c);
+        a4 = __fma_rn(a4, m, c); a5 = __fma_rn(a5, m, c); a6 = __fma_rn(a6, m, c); a7 = __fma_rn(a7, m, c);
+    }
+    const double r = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
+    if (r == 123.456) sink[0] = r;  // keeps the chains alive
+}
+}  // namespace rg
+
+extern "C" int rg_measure_fp64_peak(int device, void* stream, double* tflops_host)
+{
+    if (!tflops_host) return rg::fail(RG_E_ARG, "rg_measure_fp64_peak: null output");
+    RG_CUDA(cudaSetDevice(device));
+    cudaStream_t st = (cudaStream_t)stream;
+    double* sink = nullptr;
+    RG_CUDA(cudaMalloc(&sink, 8));
+    cudaEvent_t e0, e1;
+    RG_CUDA(cudaEventCreate(&e0));
+    RG_CUDA(cudaEventCreate(&e1));
+    const int iters = 8192, blocks = rg::kNumSM * 8, threads = 256;
+    rg::k_fp64_fma_chain<<<blocks, threads, 0, st>>>(256, 1.0, sink);  // warm-up
+    double best = 0.0;
+    for (int rep = 0; rep < 3; rep++) {
+        RG_CUDA(cudaEventRecord(e0, st));
+        rg::k_fp64_fma_chain<<<blocks, threads, 0, st>>>(iters, 1.0, sink);
+        RG_CUDA(cudaEventRecord(e1, st));
+        RG_CUDA(cudaEventSynchronize(e1));
+        float ms = 0.f;
+        RG_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+        const double tf = 2.0 * 8.0 * iters * (double)blocks * threads / (ms * 1e-3) / 1e12;
+        if (tf > best) best = tf;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(sink);
+    *tflops_host = best;
+    return RG_OK;
+}
+
 extern "C" const char* rg_last_error_string(void) { return rg::g_err; }
 extern "C" int rg_version(void) { return 100; }

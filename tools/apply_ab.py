@@ -28,7 +28,8 @@ if check:
                 break
         else:
             print(name, "ok", (n, mx, my), "generic tiles", plan.n_generic_tiles, "of", plan.n_tiles)
-n, F = 2049, 256
+import os
+n, F = 2049, int(os.environ.get('AB_FRAMES', '256'))
 dw, si, so = build(n, n, n)
 plan = dw.plan(si, so)
 vin = torch.rand((F, (n-1)**2), dtype=torch.float64, device=dev); out = torch.empty_like(vin)
@@ -42,7 +43,7 @@ for _ in range(10): _device.apply_planned(plan, vin, out)
 e1.record(); torch.cuda.synchronize()
 ms = e0.elapsed_time(e1) / 10
 byt = 8*F*2*(n-1)**2 + 12*dw.nnz + 4*((n-1)**2+1)
-print("%%s: %%.3f ms / 256 frames  %%.0f GB/s  frac %%.3f  slots/nnz %%.3f" %% (name, ms, byt/ms/1e6, byt/ms/1e6/6537.3, plan.slot_val.numel()/dw.nnz), flush=True)
+print("%%s: %%.3f ms / %%d frames  %%.0f GB/s  frac %%.3f  slots/nnz %%.3f" %% (name, ms, F, byt/ms/1e6, byt/ms/1e6/6537.3, plan.slot_val.numel()/dw.nnz), flush=True)
 ''' % ROOT
 libs = [ROOT / "regridding_b200" / "libregrid_b200.so"] + sorted((ROOT / "regridding_b200" / "variants").glob("lib_*.so"))
 for lib in libs:
