@@ -84,6 +84,21 @@ __device__ __forceinline__ bool cell_contains(const GridView& g, int i, int j, d
     return w != 0.0;
 }
 
+// the same predicate on corner coordinates the caller already holds (vertex order (i,j), (i+1,j), (i+1,j+1), (i,j+1))
+__device__ __forceinline__ bool quad_contains(double x00, double y00, double x10, double y10, double x11, double y11,
+                                              double x01, double y01, double px, double py)
+{
+    const double ax = dsub(x00, px), ay = dsub(y00, py);
+    const double bx = dsub(x10, px), by = dsub(y10, py);
+    const double cx = dsub(x11, px), cy = dsub(y11, py);
+    const double dx = dsub(x01, px), dy = dsub(y01, py);
+    double w = winding_edge(dx, dy, ax, ay);
+    w += winding_edge(ax, ay, bx, by);
+    w += winding_edge(bx, by, cx, cy);
+    w += winding_edge(cx, cy, dx, dy);
+    return w != 0.0;
+}
+
 // Lowest-index containing cell among the 3x3 neighbourhood of (i0, j0):
 // _index_of_point_local, _grids.py:286-349.  Returns the flat cell index or -1.
 __device__ inline int locate_local(const GridView& g, double px, double py, int i0, int j0)
