@@ -37,6 +37,19 @@ extern "C" {
 #define RG_E_WORKSPACE (-3)  /* workspace too small */
 #define RG_E_WALK (-4)       /* a sweep walk did not terminate (degenerate / folded grid) */
 
+/* ------------------------------------------------------------------------------
+ * ndarray_linear_interpolation
+ * replaces  _ndarray_linear_interpolation_1d / _2d and _linear_interpolation / _bilinear_interpolation,
+ *           regridding/_interp_ndarray.py:192-297 (cell index clamped to [0, n - 2]: linear extrapolation outside).
+ * D slices; slice d interpolates a + d * a_stride (n values, or (nx, ny) row-major) at its m (or P) fractional
+ * indices x + d * x_stride (and y likewise); a stride of 0 shares the array / the indices between the slices (the
+ * reference broadcasts them).  out is (D, m) / (D, P) contiguous. */
+int rg_interp_linear_1d(int device, void* stream, int64_t D, int64_t n, int64_t m,
+                        int64_t a_stride, int64_t x_stride, const double* a, const double* x, double* out);
+int rg_interp_bilinear_2d(int device, void* stream, int64_t D, int64_t nx, int64_t ny, int64_t P,
+                          int64_t a_stride, int64_t xy_stride,
+                          const double* a, const double* x, const double* y, double* out);
+
 /* Measurement helper (bench.py): fp64 FMA-chain throughput of the device in TFLOP/s (2 flops per FMA), the
  * denominator of the build's fp64 roofline; synchronises the stream. */
 int rg_measure_fp64_peak(int device, void* stream, double* tflops_host);

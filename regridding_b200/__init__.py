@@ -13,9 +13,10 @@ from ._regrid import regrid, regrid_from_weights
 from ._weights import weights, weights_packed
 from ._packed import PackedWeights
 from ._fill import fill
+from ._interp import ndarray_linear_interpolation
 from ._transposed import transpose_weights, transpose_weights_conservative
 from . import _device as device  # device-resident operators (torch CUDA tensors in / out)
 
 __all__ = ["regrid", "weights", "regrid_from_weights", "find_indices", "transpose_weights",
-           "transpose_weights_conservative", "weights_packed", "PackedWeights", "fill", "device"]
+           "transpose_weights_conservative", "weights_packed", "PackedWeights", "fill", "ndarray_linear_interpolation", "device"]
 __version__ = "0.1.0"

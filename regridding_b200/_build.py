@@ -14,7 +14,7 @@ HERE = pathlib.Path(__file__).resolve().parent
 CSRC = HERE / "csrc"
 LIB = HERE / "libregrid_b200.so"
 
-SOURCES = ["rg_util.cu", "rg_apply.cu", "rg_apply_bulk.cu", "rg_build2d.cu", "rg_locate.cu", "rg_cons1d.cu", "rg_multilinear2d.cu", "rg_multilinear1d.cu", "rg_fill.cu"]
+SOURCES = ["rg_util.cu", "rg_apply.cu", "rg_apply_bulk.cu", "rg_build2d.cu", "rg_locate.cu", "rg_cons1d.cu", "rg_multilinear2d.cu", "rg_multilinear1d.cu", "rg_interp.cu", "rg_fill.cu"]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

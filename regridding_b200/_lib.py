@@ -50,6 +50,8 @@ SIGNATURES: dict[str, list] = {
     "rg_multilinear1d_weights": [_int, _vp, _i64, _i64, _i64, _vp, _vp, _vp, _int, _vp, _vp, _vp, _p_i64, _vp, _sz],
     "rg_sort_triplets_workspace_bytes": [_i64, _p_sz],
     "rg_sort_triplets": [_int, _vp, _i64, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz],
+    "rg_interp_linear_1d": [_int, _vp, _i64, _i64, _i64, _i64, _i64, _vp, _vp, _vp],
+    "rg_interp_bilinear_2d": [_int, _vp, _i64, _i64, _i64, _i64, _i64, _i64, _vp, _vp, _vp, _vp],
     "rg_measure_fp64_peak": [_int, _vp, ctypes.POINTER(ctypes.c_double)],
     "rg_fill_gauss_seidel_2d": [_int, _vp, _vp, _i64, _i64, _i64, ctypes.POINTER(_vp), _p_i64, _i64],
     "rg_csr_workspace_bytes": [_i64, _i64, _p_sz],

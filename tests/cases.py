@@ -210,6 +210,29 @@ def cases_multilinear_1d():
     return out
 
 
+def cases_interp_ndarray():
+    """name -> (a, indices, kwargs) for ndarray_linear_interpolation (shapes of _tests/test_interp_ndarray.py:12-200)."""
+    rng = np.random.default_rng(31)
+    sz_t, sz_x, sz_y = 9, 10, 11
+    out = {}
+    a1 = rng.random(sz_x)
+    out["1d_inside"] = (a1, (np.linspace(0, sz_x - 1, 21),), {})
+    out["1d_extrapolate"] = (a1, (rng.random(40) * (sz_x + 3) - 2,), {"axis": -1})
+    a2 = rng.random((sz_x, sz_y))
+    x = np.linspace(0, sz_x - 1, 100)[:, None]
+    y = np.linspace(0, sz_y - 1, 5)[None, :]
+    out["2d_grid"] = (a2, tuple(np.broadcast_arrays(x, y)), {"axis": (0, ~0)})
+    out["2d_scattered_extrapolate"] = (a2, (rng.random(500) * (sz_x + 2) - 1.5, rng.random(500) * (sz_y + 2) - 1.5), {})
+    a3 = rng.random((sz_t, sz_x, sz_y))
+    out["3d_axis12_shared_indices"] = (a3, (rng.random((1, 30)) * (sz_x - 1), rng.random((1, 30)) * (sz_y - 1)),
+                                       {"axis": (1, 2), "axis_indices": (1,)})
+    out["3d_axis12_per_slice_indices"] = (a3, (rng.random((sz_t, 7, 4)) * (sz_x - 1), rng.random((sz_t, 7, 4)) * (sz_y - 1)),
+                                          {"axis": (1, 2), "axis_indices": (1, 2)})
+    out["3d_axis0_1d"] = (a3, (rng.random((13, sz_x, sz_y)) * (sz_t - 1),), {"axis": 0, "axis_indices": 0})
+    out["big_2d"] = (rng.random((200, 300)), (rng.random(20000) * 205 - 3, rng.random(20000) * 305 - 3), {})
+    return out
+
+
 def cases_find_indices():
     rng = np.random.default_rng(5)
     D, n, m = 7, 33, 41

@@ -47,7 +47,13 @@ def multilinear_1d():
         put(f"ml1d/{name}/regrid", regridding.regrid((x_in,), (x_out,), vals, method="multilinear", bounds=bounds, **kw))
 
 
+def interp_ndarray():
+    for name, (a, indices, kw) in cases.cases_interp_ndarray().items():
+        put(f"interp/{name}", regridding.ndarray_linear_interpolation(a, indices, **kw))
+
+
 if __name__ == "__main__":
     multilinear_1d()
+    interp_ndarray()
     np.savez_compressed(HERE / "golden_v3.npz", **G)
     print("wrote", len(G), "arrays")

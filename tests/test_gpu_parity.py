@@ -601,6 +601,29 @@ def test_multilinear_1d_vs_reference_goldens(rg):
         rg.weights((x,), (np.array([-0.2, 0.5, 1.3]),), bounds="raise")
 
 
+def test_ndarray_linear_interpolation_vs_reference_goldens(rg):
+    """regridding.ndarray_linear_interpolation (regridding/_interp_ndarray.py:11-297) on the device against the
+    reference's own output, bit for bit (1D plain IEEE; 2D the fastmath contraction the reference's JIT emits), for
+    every axis / axis_indices combination the reference's tests use, incl. extrapolation; plus its error behaviour."""
+    with np.load(cases.ROOT_GOLDEN / "golden_v3.npz") as z:
+        G = {k: z[k] for k in z.files}
+    for name, (a, indices, kw) in cases.cases_interp_ndarray().items():
+        got = rg.ndarray_linear_interpolation(a, indices, **kw)
+        want = G[f"interp/{name}"]
+        assert got.shape == want.shape and got.dtype == np.float64, name
+        assert np.array_equal(got, want), (name, float(np.max(np.abs(got - want))))
+    with pytest.raises(ValueError, match="must match the number of elements in axis"):
+        rg.ndarray_linear_interpolation(np.zeros((3, 4)), (np.zeros(2),))
+    with pytest.raises(NotImplementedError):
+        rg.ndarray_linear_interpolation(np.zeros((3, 4, 5)), (np.zeros(2), np.zeros(2), np.zeros(2)))
+    # regridding/_tests/test_interp_ndarray.py:12-88: agrees with scipy.ndimage.map_coordinates inside the array
+    scipy_ndimage = pytest.importorskip("scipy.ndimage")
+    a = np.random.default_rng(0).random((10, 11))
+    x, y = np.broadcast_arrays(np.linspace(0, 9, 100)[:, None], np.linspace(0, 10, 5)[None, :])
+    got = rg.ndarray_linear_interpolation(a, (x, y), axis=(0, 1))
+    assert np.allclose(got, scipy_ndimage.map_coordinates(a, np.stack([x, y]), order=1))
+
+
 def test_weights_1d_many_spectra_are_built_in_chunks(rg, oracle, monkeypatch):
     """Stacked 1D conservative builds run in chunks bounded by a byte budget: same triplets as the oracle."""
     from regridding_b200 import _weights
