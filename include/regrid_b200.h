@@ -239,6 +239,20 @@ int rg_multilinear2d_weights(int device, void* stream, int64_t nx, int64_t ny,
 int rg_ell4_apply(int device, void* stream, int64_t n_frames, int64_t n_in, int64_t n_points,
                   const int64_t* idx4, const double* w4, const double* values_in, double* values_out);
 
+/* Per-slice builds: n_slices grid pairs of one shape (BASELINE config 4: every frame carries its own grid; the
+ * reference loops over the orthogonal slices in Python, _weights_conservative.py:110-139), enqueued back to back
+ * without any host synchronisation.  Arrays of n_slices device pointers (host arrays of pointers); workspace and
+ * `frags` are shared and reused slice after slice; counts_dev is [n_slices][8] with the layout of rg_build2d_band. */
+int rg_build2d_batched(int device, void* stream, int64_t n_slices,
+                       int64_t nx_in, int64_t ny_in, int64_t nx_out, int64_t ny_out,
+                       const double* const* x_in, const double* const* y_in,
+                       const double* const* x_out, const double* const* y_out,
+                       const double* const* weights_input_or_null,
+                       void* workspace, size_t workspace_bytes,
+                       void* frags, int64_t frag_capacity,
+                       int64_t* const* indices_input, int64_t* const* indices_output, double* const* values,
+                       int64_t nnz_capacity, int64_t* counts_dev);
+
 /* ------------------------------------------------------------------------------
  * 1D multilinear weights (weights()'s default method) and the saved-weights ordering of raw triplets
  * replaces  _weights_multilinear / _weights_from_indices_multilinear(_1d)

@@ -272,7 +272,10 @@ class BandBuild:
         if c[self.MISMATCH]:
             return None, "mismatch"
         _band_caps[self.key] = (int(nfrag * 1.02) + 1024, int(nnz * 1.02) + 1024)
-        dw = DeviceWeights(self.ii[:nnz], self.io[:nnz], self.v[:nnz], self.n_in, self.n_out)
+        ii, io, v = self.ii[:nnz], self.io[:nnz], self.v[:nnz]
+        if self.nnz_capacity > 1.5 * nnz + 4096:   # first build of a shape: do not keep the over-sized estimate alive
+            ii, io, v = ii.clone(), io.clone(), v.clone()
+        dw = DeviceWeights(ii, io, v, self.n_in, self.n_out)
         dw.stats = {"fragments": nfrag, "nnz": nnz, "repaired_segments": 0, "unknown_guesses": int(c[4])}
         return dw, "ok"
 
@@ -342,6 +345,61 @@ def build_weights_2d_band(x_in, y_in, x_out, y_out, weights_input=None, row_band
             break
     return build_weights_2d(x_in, y_in, x_out, y_out, weights_input, cell_band=(lo * (nyi - 1), hi * (nyi - 1)),
                             device=device)
+
+
+def build_weights_2d_batched(slices, weights_input=None, device=None) -> list:
+    """Per-slice builds (every slice its own grid pair, all of one shape): ``slices`` is a sequence of
+    ``(x_in, y_in, x_out, y_out)`` on the device; the builds are enqueued back to back with no host synchronisation
+    (``rg_build2d_batched``) and the counts are read once at the end.  Returns one ``DeviceWeights`` per slice; a
+    slice whose buffers were too small or whose walk states did not verify is rebuilt by ``build_weights_2d``."""
+    L = _lib.load()
+    slices = list(slices)
+    if not slices:
+        return []
+    device = cuda_device(device if device is not None else slices[0][0].device)
+    S = len(slices)
+    t = [[to_device(a, device) for a in sl] for sl in slices]
+    nxi, nyi = t[0][0].shape
+    nxo, nyo = t[0][2].shape
+    for sl in t:
+        if sl[0].shape != (nxi, nyi) or sl[1].shape != (nxi, nyi) or sl[2].shape != (nxo, nyo) or sl[3].shape != (nxo, nyo):
+            raise ValueError("all slices of a batched build must share one input and one output grid shape")
+    n_in, n_out = (nxi - 1) * (nyi - 1), (nxo - 1) * (nyo - 1)
+    w = None
+    if weights_input is not None:
+        w = [to_device(wi, device) for wi in weights_input]
+    key = (nxi, nyi, nxo, nyo, 0, nxi - 1)
+    if key in _band_caps:
+        fcap, ncap = _band_caps[key]
+    else:
+        fcap = int(10 * (n_in + n_out)) + 4096
+        ncap = fcap // 2
+    arr = lambda ptrs: (ctypes.c_void_p * S)(*ptrs)  # noqa: E731
+    with torch.cuda.device(device):
+        st = _stream(device)
+        ws = _workspace(build2d_workspace_bytes(nxi, nyi, nxo, nyo), device)
+        frags = frags_empty(fcap, device)
+        ii = [torch.empty(ncap, dtype=I64, device=device) for _ in range(S)]
+        io = [torch.empty(ncap, dtype=I64, device=device) for _ in range(S)]
+        v = [torch.empty(ncap, dtype=F64, device=device) for _ in range(S)]
+        counts = torch.empty((S, 8), dtype=I64, device=device)
+        _lib.check(L.rg_build2d_batched(device.index, st, S, nxi, nyi, nxo, nyo,
+                                        arr([sl[0].data_ptr() for sl in t]), arr([sl[1].data_ptr() for sl in t]),
+                                        arr([sl[2].data_ptr() for sl in t]), arr([sl[3].data_ptr() for sl in t]),
+                                        None if w is None else arr([wi.data_ptr() for wi in w]),
+                                        ws.data_ptr(), ws.numel(), frags.data_ptr(), fcap,
+                                        arr([a.data_ptr() for a in ii]), arr([a.data_ptr() for a in io]),
+                                        arr([a.data_ptr() for a in v]), ncap, counts.data_ptr()),
+                   "rg_build2d_batched")
+        host = counts.cpu()  # the one synchronisation
+    out = []
+    for s in range(S):
+        bb = BandBuild(ii[s], io[s], v[s], counts[s], fcap, ncap, n_in, n_out, key, ())
+        dw, status = bb.finish(host[s])
+        if status != "ok":
+            dw = build_weights_2d(*t[s], None if w is None else w[s], device=device)
+        out.append(dw)
+    return out
 
 
 @dataclasses.dataclass

@@ -30,6 +30,9 @@ SIGNATURES: dict[str, list] = {
                         _vp, _i64, _p_i64],
     "rg_build2d_emit": [_int, _vp, _i64, _i64, _i64, _i64, _i64, _i64, _vp, _sz, _vp, _i64,
                         _vp, _vp, _vp, _i64],
+    "rg_build2d_batched": [_int, _vp, _i64, _i64, _i64, _i64, _i64, ctypes.POINTER(_vp), ctypes.POINTER(_vp),
+                           ctypes.POINTER(_vp), ctypes.POINTER(_vp), ctypes.POINTER(_vp), _vp, _sz, _vp, _i64,
+                           ctypes.POINTER(_vp), ctypes.POINTER(_vp), ctypes.POINTER(_vp), _i64, _vp],
     "rg_build2d_part_count": [_int, _vp, _i64, _i64, _i64, _i64, _vp, _vp, _vp, _vp, _int, _int, _vp, _sz, _p_i64,
                               _int, _p_i64, _p_i64, _p_sz, _vp],
     "rg_build2d_part_fill": [_int, _vp, _i64, _i64, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _int, _int, _vp, _sz,

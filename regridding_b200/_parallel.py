@@ -21,6 +21,7 @@ is walked twice, and the result is still bit-identical to the single-GPU build.
 
 from __future__ import annotations
 
+import numpy as _np
 import torch
 import torch.distributed as dist
 
@@ -103,6 +104,46 @@ def build_weights_2d_banded(x_in, y_in, x_out, y_out, weights_input=None, replic
     ii, io, v = allgather_concat([dw.indices_input, dw.indices_output, dw.values], group)
     out = _device.DeviceWeights(ii, io, v, dw.n_in, dw.n_out)
     out.stats = dw.stats
+    return out
+
+
+def build_weights_2d_slices(slices_host, weights_input=None, group=None, device=None, chunk: int = 4) -> dict:
+    """Per-slice grids (BASELINE config 4; the reference's Python loop, _weights_conservative.py:110-139) sharded over
+    the ranks with NO collective: rank r builds the contiguous share ``shard_range(n_slices, r, W)``.
+
+    ``slices_host`` is a sequence of ``(x_in, y_in, x_out, y_out)`` host arrays (output coordinates already perturbed
+    -- the seeded jitter is one serial NumPy stream by the reference's definition: draw it once, e.g. on rank 0, and
+    hand every rank its slices).  The rank's slices go through pinned staging buffers; the H2D copy of chunk k + 1
+    overlaps the builds of chunk k (``rg_build2d_batched``: no host synchronisation inside a chunk).
+    Returns ``{slice index: DeviceWeights}`` of this rank's slices."""
+    rank, W = world(group)
+    dev = _device.cuda_device(device)
+    n = len(slices_host)
+    lo, hi = shard_range(n, rank, W)
+    mine = list(range(lo, hi))
+    out: dict = {}
+    if not mine:
+        return out
+    copy_stream = torch.cuda.Stream(dev)
+
+    def upload(ks):
+        with torch.cuda.stream(copy_stream):
+            t = [[torch.from_numpy(_np.ascontiguousarray(a, dtype=_np.float64)).pin_memory().to(dev, non_blocking=True)
+                  for a in slices_host[k]] for k in ks]
+            ev = torch.cuda.Event()
+            ev.record()
+        return t, ev
+
+    chunks = [mine[c:c + chunk] for c in range(0, len(mine), chunk)]
+    nxt = upload(chunks[0])
+    for c, ks in enumerate(chunks):
+        t, ev = nxt
+        torch.cuda.current_stream(dev).wait_event(ev)
+        if c + 1 < len(chunks):
+            nxt = upload(chunks[c + 1])
+        ws_in = None if weights_input is None else [weights_input[k] for k in ks]
+        for k, dw in zip(ks, _device.build_weights_2d_batched(t, ws_in, device=dev)):
+            out[k] = dw
     return out
 
 

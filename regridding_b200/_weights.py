@@ -143,21 +143,27 @@ def _weights_conservative_device(
         xi, yi = (stacked(c, axis_in) for c in coords_in)
         xo, yo = (stacked(c, axis_out) for c in coords_out)
         elements = []
-        for k, index in enumerate(np.ndindex(*shape_orth)):
-            w = None
-            if weights_input is not None:
-                w = weights_input[index]  # wcons.py:125-126: orthogonal axes are assumed to lead
-            dw = _device.build_weights_2d(xi[k], yi[k], xo[k], yo[k], w, device=device)
-            if n_slices > 1:
-                # per-slice grids (BASELINE config 4): every slice is downloaded before the next is built, so device
-                # memory does not grow with the number of slices
-                dw = _device.HostWeights(*dw.to_host(), dw.n_in, dw.n_out)
-            elements.append(dw)
+        indices = list(np.ndindex(*shape_orth))
+        if n_slices == 1:
+            w = None if weights_input is None else weights_input[indices[0]]  # wcons.py:125-126: orthogonal axes lead
+            elements.append(_device.build_weights_2d(xi[0], yi[0], xo[0], yo[0], w, device=device))
+        else:
+            # per-slice grids (BASELINE config 4): chunks of slices are uploaded, built back to back without host
+            # synchronisation (rg_build2d_batched) and downloaded before the next chunk, so device memory does not
+            # grow with the number of slices
+            per = _SLICES_PER_CHUNK_2D
+            for k0 in range(0, n_slices, per):
+                ks = range(k0, min(n_slices, k0 + per))
+                sl = [tuple(_device.to_device(a[k], device) for a in (xi, yi, xo, yo)) for k in ks]
+                ws_in = None if weights_input is None else [weights_input[indices[k]] for k in ks]
+                for dw in _device.build_weights_2d_batched(sl, ws_in, device=device):
+                    elements.append(_device.HostWeights(*dw.to_host(), dw.n_in, dw.n_out))
     else:
         raise NotImplementedError("Regridding operations greater than 2D are not supported")  # wcons.py:141-144
     return elements, shape_cells_in, shape_cells_out, tuple(shape_orth)
 
 
+_SLICES_PER_CHUNK_2D = 4    # 2D slices built per batched call (each keeps its triplets on the device until downloaded)
 _CHUNK_BYTES_1D = 1 << 30  # device memory of one chunk of stacked 1D builds (3 arrays of (S, n + m) 8-byte entries)
 
 

@@ -1582,6 +1582,16 @@ __global__ void k_band_relevance(GridView gout, const uint8_t* __restrict__ rast
 
 // after the bounding boxes: extents reset, raster scales (ONE evaluation shared by the kernels that mark and that
 // look up, so that overlapping intervals always map to overlapping index ranges)
+// the band is the whole grid: every segment of the output passes is relevant
+__global__ void k_band_info_full(BandInfo* info, int nx_out, int ny_out)
+{
+    if (threadIdx.x != 0) return;
+    // pass 0 (axis 0): line = j, segment = i; pass 1 (axis 1): line = i, segment = j
+    info->ext[0][0] = 0; info->ext[0][1] = ny_out - 1; info->ext[0][2] = 0; info->ext[0][3] = nx_out - 2;
+    info->ext[1][0] = 0; info->ext[1][1] = nx_out - 1; info->ext[1][2] = 0; info->ext[1][3] = ny_out - 2;
+    info->sx = info->sy = 0.0;
+}
+
 __global__ void k_band_info_init(BandInfo* info, const double* __restrict__ bbox_in)
 {
     if (threadIdx.x < 8) info->ext[threadIdx.x >> 2][threadIdx.x & 3] = (threadIdx.x & 1) ? -1 : INT32_MAX;
@@ -1846,7 +1856,7 @@ extern "C" int rg_build2d_band(int device, void* stream,
     RG_CUDA(cudaMemsetAsync(l.flags, 0, sizeof(int32_t) * 8, st));
     RG_CUDA(cudaMemsetAsync(l.hist + cell_lo, 0, sizeof(int32_t) * (size_t)(nb + 1), st));
     RG_CUDA(cudaMemsetAsync(l.cursor + cell_lo, 0, sizeof(int32_t) * (size_t)(nb + 1), st));
-    RG_CUDA(cudaMemsetAsync(l.raster, 0, (size_t)kRasterN * kRasterN, st));
+    if (!(row_lo == 0 && row_hi == nxi - 1)) RG_CUDA(cudaMemsetAsync(l.raster, 0, (size_t)kRasterN * kRasterN, st));
     RG_CUDA(cudaMemsetAsync(counts_dev, 0, sizeof(int64_t) * 8, st));
     // areas of the band's cells (k_cell_area works on the rows [row_lo, row_hi) of the grid: a view of those rows would
     // move the peeled first-edge pattern of grid_volume, so the full-grid kernel runs on the band's cell range)
@@ -1866,11 +1876,18 @@ extern "C" int rg_build2d_band(int device, void* stream,
     B.row_lo = (int)row_lo; B.row_hi = (int)row_hi;
     B.rel[0] = l.rel[0]; B.rel[1] = l.rel[1];
     B.info = l.info;
-    k_band_info_init<<<1, 32, 0, st>>>(l.info, l.bbox);
-    k_band_raster<<<(unsigned)ceil_div(nb, T), T, 0, st>>>(gin, (int)row_lo, (int)row_hi, l.bbox, l.info, l.raster);
-    RG_LAUNCH_CHECK("k_band_raster");
-    k_band_relevance<<<(unsigned)ceil_div(l.Vo, T), T, 0, st>>>(gout, l.raster, l.bbox, l.rel[0], l.rel[1], l.info);
-    RG_LAUNCH_CHECK("k_band_relevance");
+    if (row_lo == 0 && row_hi == nxi - 1) {
+        // the band is the whole grid (per-slice builds without host synchronisation): everything is relevant
+        RG_CUDA(cudaMemsetAsync(l.rel[0], 1, (size_t)l.Vo, st));
+        RG_CUDA(cudaMemsetAsync(l.rel[1], 1, (size_t)l.Vo, st));
+        k_band_info_full<<<1, 32, 0, st>>>(l.info, (int)nxo, (int)nyo);
+    } else {
+        k_band_info_init<<<1, 32, 0, st>>>(l.info, l.bbox);
+        k_band_raster<<<(unsigned)ceil_div(nb, T), T, 0, st>>>(gin, (int)row_lo, (int)row_hi, l.bbox, l.info, l.raster);
+        RG_LAUNCH_CHECK("k_band_raster");
+        k_band_relevance<<<(unsigned)ceil_div(l.Vo, T), T, 0, st>>>(gout, l.raster, l.bbox, l.rel[0], l.rel[1], l.info);
+        RG_LAUNCH_CHECK("k_band_relevance");
+    }
     {
         // input vertices of rows row_lo - 1 .. row_hi + 1: every start / end vertex of a walked segment of passes 2, 3
         const int64_t r0 = row_lo > 0 ? row_lo - 1 : 0, r1 = (row_hi + 2 < nxi ? row_hi + 2 : nxi);
@@ -1907,5 +1924,30 @@ extern "C" int rg_build2d_band(int device, void* stream,
     RG_LAUNCH_CHECK("k_bucket_emit");
     k_band_counts<<<1, 32, 0, st>>>(2, nullptr, 0, counts_dev, l.flags);
     RG_LAUNCH_CHECK("k_band_counts");
+    return RG_OK;
+}
+
+// Per-slice builds (every orthogonal slice carries its own grid pair: the Python loop of
+// regridding/_weights/_weights_conservative.py:110-139) enqueued back to back with NO host synchronisation:
+// slice s is the whole-grid case of rg_build2d_band.  Workspace and fragment buffer are reused slice after slice
+// (stream order); every slice has its own output arrays and its own 8 counters.
+extern "C" int rg_build2d_batched(int device, void* stream, int64_t n_slices,
+                                  int64_t nxi, int64_t nyi, int64_t nxo, int64_t nyo,
+                                  const double* const* xin, const double* const* yin,
+                                  const double* const* xout, const double* const* yout,
+                                  const double* const* w_in_or_null,
+                                  void* workspace, size_t workspace_bytes,
+                                  void* frags, int64_t frag_capacity,
+                                  int64_t* const* ii, int64_t* const* io, double* const* v, int64_t nnz_capacity,
+                                  int64_t* counts_dev /* [n_slices][8] */)
+{
+    if (n_slices < 0 || !xin || !yin || !xout || !yout || !ii || !io || !v || !counts_dev)
+        return fail(RG_E_ARG, "rg_build2d_batched: bad argument");
+    for (int64_t s = 0; s < n_slices; s++) {
+        const int rc = rg_build2d_band(device, stream, nxi, nyi, nxo, nyo, xin[s], yin[s], xout[s], yout[s],
+                                       w_in_or_null ? w_in_or_null[s] : nullptr, 0, nxi - 1, workspace, workspace_bytes,
+                                       frags, frag_capacity, ii[s], io[s], v[s], nnz_capacity, counts_dev + 8 * s);
+        if (rc) return rc;
+    }
     return RG_OK;
 }

@@ -601,6 +601,28 @@ def test_multilinear_1d_vs_reference_goldens(rg):
         rg.weights((x,), (np.array([-0.2, 0.5, 1.3]),), bounds="raise")
 
 
+def test_build2d_batched_equals_single_builds(rg, dev):
+    """rg_build2d_batched (per-slice grids enqueued back to back, no host sync; BASELINE config 4's inner loop) gives
+    the same triplets as one rg_build2d_* build per slice; also through the single-process form of the sharded entry."""
+    from regridding_b200 import _parallel
+
+    slices = []
+    for f in range(5):
+        gi, go = cases.benchmark_family(97, 90, 101, distorted=True, angle=0.4 + 0.01 * f, phase=float(f))
+        co = cases.perturb_like_reference(go, (-1, -2), 42)
+        slices.append((gi[0], gi[1], co[0], co[1]))
+    want = [rg.device.build_weights_2d(*sl, device=dev) for sl in slices]
+    for attempt in range(2):   # first call: estimated buffer sizes; second: learned ones
+        got = rg.device.build_weights_2d_batched([tuple(T(a, dev) for a in sl) for sl in slices], device=dev)
+        for a, b in zip(got, want):
+            assert torch.equal(a.indices_input, b.indices_input) and torch.equal(a.indices_output, b.indices_output)
+            assert torch.equal(a.values, b.values)
+    sharded = _parallel.build_weights_2d_slices(slices, device=dev, chunk=2)
+    assert sorted(sharded) == list(range(5))
+    for k, b in enumerate(want):
+        assert torch.equal(sharded[k].values, b.values) and torch.equal(sharded[k].indices_output, b.indices_output)
+
+
 def test_ndarray_linear_interpolation_vs_reference_goldens(rg):
     """regridding.ndarray_linear_interpolation (regridding/_interp_ndarray.py:11-297) on the device against the
     reference's own output, bit for bit (1D plain IEEE; 2D the fastmath contraction the reference's JIT emits), for
