@@ -228,7 +228,7 @@ def regrid(
     if method == "multilinear" and n_coordinates == 2 and all(
             np.ndim(c) == 2 for c in (*coordinates_input, *coordinates_output)):
         return _regrid_multilinear_2d_fused(coordinates_input, coordinates_output, values_input, values_output,
-                                            axis_input, axis_output, bounds)
+                                            axis_input, axis_output, bounds, perturb, seed)
     if method == "conservative":
         elements, shape_in, shape_out, shape_orth = _weights_conservative_device(
             coordinates_input, coordinates_output, axis_input, axis_output, None, perturb, seed)
@@ -309,7 +309,7 @@ def _regrid_conservative_1d_fused(coordinates_input, coordinates_output, values_
 
 
 def _regrid_multilinear_2d_fused(coordinates_input, coordinates_output, values_input, values_output,
-                                 axis_input, axis_output, bounds):
+                                 axis_input, axis_output, bounds, perturb=None, seed=_util.SEED_DEFAULT):
     """``regrid(method="multilinear")`` between two 2D grids shared by every orthogonal slice of the values
     (BASELINE config 5): cell location, bilinear weights and the four-point gather all stay on the GPU and no
     triplets are materialised (``rg_find_indices_2d`` -> ``rg_multilinear2d_weights`` -> ``rg_ell4_apply``).
@@ -320,7 +320,8 @@ def _regrid_multilinear_2d_fused(coordinates_input, coordinates_output, values_i
     if unit is not None:
         values_input = values_input.value
     (coords_in, coords_out, axis_in, axis_out, shape_in, shape_out, _orth) = \
-        _util.normalize_input_output_coordinates(coordinates_input, coordinates_output, axis_input, axis_output)
+        _util.normalize_input_output_coordinates(coordinates_input, coordinates_output, axis_input, axis_output,
+                                                 perturb=bool(perturb), seed=seed)  # wml.py:58-59: None means False
     device = _device.cuda_device()
     x, y = (_device.to_device(np.asarray(getattr(c, "value", c), dtype=np.float64), device) for c in coords_in)
     px, py = (_device.to_device(np.asarray(getattr(c, "value", c), dtype=np.float64), device) for c in coords_out)
@@ -328,8 +329,11 @@ def _regrid_multilinear_2d_fused(coordinates_input, coordinates_output, values_i
     on_device = isinstance(values_input, torch.Tensor) and values_input.is_cuda
     vals = values_input if on_device else np.asarray(values_input, dtype=np.float64)
     nd = vals.ndim
-    a_in = tuple(sorted(a % nd for a in (axis_input if axis_input is not None else (-2, -1))))
-    a_out = tuple(sorted(a % nd for a in (axis_output if axis_output is not None else (-2, -1))))
+    # the axes returned by the normalisation are negative and relative to the COORDINATE arrays, exactly as
+    # regrid_from_weights takes them against the weights' shapes (rfw.py:64-68): with bare 2D grids the resampled
+    # axes of the values are always their last two, whatever positive axis numbers the caller wrote
+    a_in = tuple(sorted(a % nd for a in axis_in))
+    a_out = tuple(sorted(a % nd for a in axis_out))
     if tuple(vals.shape[a] for a in a_in) != grid_in:
         raise ValueError(f"values_input has shape {tuple(vals.shape)} along {a_in=}, expected the vertex grid {grid_in}")
     idx4, w4, n_outside = _device.multilinear2d_weights(x, y, px, py, bounds)

@@ -85,11 +85,11 @@ def transpose_weights_conservative(
     for d in range(flat.size):
         indices_input, indices_output, values = flat[d]
         dw = _cache.lookup((indices_input, indices_output, values), device)
-        if dw is None:
-            dw = _device.DeviceWeights(_device.to_device(indices_input, device, _device.I64),
-                                       _device.to_device(indices_output, device, _device.I64),
-                                       _device.to_device(np.asarray(values, dtype=np.float64), device),
-                                       vol_in.shape[1], vol_out.shape[1])
+        if dw is None or dw.n_in != vol_in.shape[1] or dw.n_out != vol_out.shape[1]:
+            # range-checked upload (weights built for other grid shapes raise IndexError instead of reading out
+            # of bounds on the device); the transposed values are computed from the wrapped indices
+            dw = _device.DeviceWeights.from_host(indices_input, indices_output, values, vol_in.shape[1],
+                                                 vol_out.shape[1], device)
         v_t = _device.transpose_conservative(dw, vol_in[d], vol_out[d], None if w is None else w[d])
         result[d] = (indices_output, indices_input, v_t.cpu().numpy())
     return result.reshape(shape), shape_output, shape_input
