@@ -1534,22 +1534,33 @@ __global__ void k_band_raster(GridView g, int row_lo, int row_hi, const double* 
         for (int iy = iy0; iy <= iy1; iy++) raster[ix * kRasterN + iy] = 1;
 }
 
-// Thread per OUTPUT vertex (i, j): relevance of the two segments that start there (pass 1: to (i, j+1); pass 0: to
-// (i+1, j)) and the extent of the relevant segments in (line, segment) space.
-__global__ void k_band_relevance(GridView gout, const uint8_t* __restrict__ raster,
-                                 const double* __restrict__ bbox_in, uint8_t* __restrict__ rel0, uint8_t* __restrict__ rel1,
-                                 BandInfo* __restrict__ info)
+// raster cell (ix | iy << 16) of every output vertex: one streaming pass over the output grid
+__global__ void k_band_vertex_cells(GridView gout, const double* __restrict__ bbox_in, const BandInfo* __restrict__ info,
+                                    uint32_t* __restrict__ vcell)
 {
     const int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const int64_t nv = (int64_t)gout.nx * gout.ny;
+    if (v >= (int64_t)gout.nx * gout.ny) return;
+    const unsigned ix = (unsigned)raster_index(gout.x[v], bbox_in[0], info->sx);
+    const unsigned iy = (unsigned)raster_index(gout.y[v], bbox_in[1], info->sy);
+    vcell[v] = ix | (iy << 16);
+}
+
+// Thread per OUTPUT vertex (i, j): relevance of the two segments that start there (pass 1: to (i, j+1); pass 0: to
+// (i+1, j)) and the extent of the relevant segments in (line, segment) space.  A segment is relevant iff a raster
+// cell under its bounding box is marked (indices are clamped to the raster: segments beyond the input grid's bbox can
+// only over-report).
+__global__ void k_band_relevance(int nx, int ny, const uint8_t* __restrict__ raster, const uint32_t* __restrict__ vcell,
+                                 uint8_t* __restrict__ rel0, uint8_t* __restrict__ rel1, BandInfo* __restrict__ info)
+{
+    const int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t nv = (int64_t)nx * ny;
     int ext[8] = { INT32_MAX, -1, INT32_MAX, -1, INT32_MAX, -1, INT32_MAX, -1 };  // pass 0: Lmin Lmax kmin kmax; pass 1
     if (v < nv) {
-        const int i = (int)(v / gout.ny), j = (int)(v % gout.ny);
-        // raster cell of the vertex and of its two successors; a segment is relevant iff a raster cell under its bounding
-        // box is marked (indices are clamped to the raster: segments beyond the input grid's bbox can only over-report)
-        const double sx = info->sx, sy = info->sy, x0 = bbox_in[0], y0 = bbox_in[1];
-        const int ix = raster_index(gout.x[v], x0, sx), iy = raster_index(gout.y[v], y0, sy);
-        auto marked = [&](int ixb, int iyb) {
+        const int i = (int)(v / ny), j = (int)(v % ny);
+        const uint32_t c = vcell[v];
+        const int ix = (int)(c & 0xffffu), iy = (int)(c >> 16);
+        auto marked = [&](uint32_t cb) {
+            const int ixb = (int)(cb & 0xffffu), iyb = (int)(cb >> 16);
             const int xa = min(ix, ixb), xb = max(ix, ixb), ya = min(iy, iyb), yb = max(iy, iyb);
             for (int a = xa; a <= xb; a++)
                 for (int b = ya; b <= yb; b++)
@@ -1557,8 +1568,8 @@ __global__ void k_band_relevance(GridView gout, const uint8_t* __restrict__ rast
             return false;
         };
         bool r1 = false, r0 = false;
-        if (j + 1 < gout.ny) r1 = marked(raster_index(gout.x[v + 1], x0, sx), raster_index(gout.y[v + 1], y0, sy));
-        if (i + 1 < gout.nx) r0 = marked(raster_index(gout.x[v + gout.ny], x0, sx), raster_index(gout.y[v + gout.ny], y0, sy));
+        if (j + 1 < ny) r1 = marked(vcell[v + 1]);
+        if (i + 1 < nx) r0 = marked(vcell[v + ny]);
         rel0[v] = r0;
         rel1[v] = r1;
         if (r0) { ext[0] = ext[1] = j; ext[2] = ext[3] = i; }   // pass 0 (axis 0): line = j, segment = i
@@ -1580,8 +1591,6 @@ __global__ void k_band_relevance(GridView gout, const uint8_t* __restrict__ rast
     }
 }
 
-// after the bounding boxes: extents reset, raster scales (ONE evaluation shared by the kernels that mark and that
-// look up, so that overlapping intervals always map to overlapping index ranges)
 // the band is the whole grid: every segment of the output passes is relevant
 __global__ void k_band_info_full(BandInfo* info, int nx_out, int ny_out)
 {
@@ -1885,7 +1894,10 @@ extern "C" int rg_build2d_band(int device, void* stream,
         k_band_info_init<<<1, 32, 0, st>>>(l.info, l.bbox);
         k_band_raster<<<(unsigned)ceil_div(nb, T), T, 0, st>>>(gin, (int)row_lo, (int)row_hi, l.bbox, l.info, l.raster);
         RG_LAUNCH_CHECK("k_band_raster");
-        k_band_relevance<<<(unsigned)ceil_div(l.Vo, T), T, 0, st>>>(gout, l.raster, l.bbox, l.rel[0], l.rel[1], l.info);
+        // (seg_start of pass 0 is free until the count walk: scratch for the vertices' raster cells)
+        uint32_t* vcell = reinterpret_cast<uint32_t*>(l.seg_start[0]);
+        k_band_vertex_cells<<<(unsigned)ceil_div(l.Vo, T), T, 0, st>>>(gout, l.bbox, l.info, vcell);
+        k_band_relevance<<<(unsigned)ceil_div(l.Vo, T), T, 0, st>>>((int)nxo, (int)nyo, l.raster, vcell, l.rel[0], l.rel[1], l.info);
         RG_LAUNCH_CHECK("k_band_relevance");
     }
     {
