@@ -374,14 +374,21 @@ __device__ inline void line_start_body(const PassParams& P, int L, const double*
     int state = kStateOutside;
     if (in_box) {
         // point_is_inside_polygon over grid_boundary (_grids.py:167-215): counter-clockwise in index space;
-        // the scan-order edges of the i = 0 face and of the j = ny-1 face run the other way round.
+        // the scan-order edges of the i = 0 face and of the j = ny-1 face run the other way round.  Only edges whose
+        // y-range contains py contribute (every other edge adds exactly 0), so the two bounding-box levels cull whole
+        // groups; the threads of the CTA take the level-1 groups (32 edges each) in turn.
         const Boundary& b = P.bnd;
         double w = 0.0;
-        for (int s = threadIdx.x; s < b.n_edges; s += 256) {
-            double x0 = dsub(b.x3[s], px), y0 = dsub(b.y3[s], py);
-            double x1 = dsub(b.x4[s], px), y1 = dsub(b.y4[s], py);
-            const bool reversed = (s < b.ne_a0) || (s >= 2 * b.ne_a0 + b.ne_a1);
-            w += reversed ? winding_edge(x1, y1, x0, y0) : winding_edge(x0, y0, x1, y1);
+        for (int g1 = threadIdx.x; g1 < b.n_g1; g1 += 256) {
+            const BBox B1 = b.bb1[g1];
+            if (!(B1.ylo <= py && py <= B1.yhi)) continue;
+            const int se = min(b.n_edges, (g1 + 1) * 32);
+            for (int s = g1 * 32; s < se; s++) {
+                const double x0 = dsub(b.x3[s], px), y0 = dsub(b.y3[s], py);
+                const double x1 = dsub(b.x4[s], px), y1 = dsub(b.y4[s], py);
+                const bool reversed = (s < b.ne_a0) || (s >= 2 * b.ne_a0 + b.ne_a1);
+                w += reversed ? winding_edge(x1, y1, x0, y0) : winding_edge(x0, y0, x1, y1);
+            }
         }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) w += __shfl_xor_sync(0xffffffffu, w, o);  // halves: exact in any order

@@ -186,36 +186,42 @@ __device__ inline int locate_guess(const GridView& g, double px, double py)
     const double det0 = ax * by - bx * ay;
     double i = 0.5 * g.nx, j = 0.5 * g.ny;
     if (det0 != 0.0 && det0 == det0) {
-        i = ((px - x00) * by - (py - y00) * bx) / det0;
-        j = ((py - y00) * ax - (px - x00) * ay) / det0;
+        const double r0 = 1.0 / det0;
+        i = ((px - x00) * by - (py - y00) * bx) * r0;
+        j = ((py - y00) * ax - (px - x00) * ay) * r0;
         i = fmin(fmax(i, -1.0), (double)ncx + 1.0);
         j = fmin(fmax(j, -1.0), (double)ncy + 1.0);
     }
+    // Newton on the bilinear map of the current cell, written for instruction count (a whole warp runs as long as its
+    // slowest lane): fused arithmetic and an approximate reciprocal refined once -- the iteration corrects itself, and
+    // a guess is verified by the chain check anyway
+#pragma unroll 1
     for (int it = 0; it < 12; it++) {
-        int i0 = (int)floor(i), j0 = (int)floor(j);
-        i0 = min(max(i0, 0), ncx - 1);
-        j0 = min(max(j0, 0), ncy - 1);
-        const int64_t a = (int64_t)i0 * g.ny + j0;
-        const double x00c = g.x[a], x01 = g.x[a + 1], x10 = g.x[a + g.ny], x11 = g.x[a + g.ny + 1];
-        const double y00c = g.y[a], y01 = g.y[a + 1], y10 = g.y[a + g.ny], y11 = g.y[a + g.ny + 1];
-        const double u = i - i0, v = j - j0;
-        const double X = (x00c * (1 - u) + x10 * u) * (1 - v) + (x01 * (1 - u) + x11 * u) * v;
-        const double Y = (y00c * (1 - u) + y10 * u) * (1 - v) + (y01 * (1 - u) + y11 * u) * v;
-        const double ex = X - px, ey = Y - py;
-        const double dxdi = (x10 - x00c) * (1 - v) + (x11 - x01) * v;
-        const double dxdj = (x01 - x00c) * (1 - u) + (x11 - x10) * u;
-        const double dydi = (y10 - y00c) * (1 - v) + (y11 - y01) * v;
-        const double dydj = (y01 - y00c) * (1 - u) + (y11 - y10) * u;
-        const double det = dxdi * dydj - dxdj * dydi;
-        if (det == 0.0 || !(det == det)) break;
-        double di = (dydj * ex - dxdj * ey) / det;
-        double dj = (-dydi * ex + dxdi * ey) / det;
-        di = fmin(fmax(di, -(double)g.nx), (double)g.nx);
-        dj = fmin(fmax(dj, -(double)g.ny), (double)g.ny);
+        const int i0 = min(max(__double2int_rd(i), 0), ncx - 1), j0 = min(max(__double2int_rd(j), 0), ncy - 1);
+        const double* gx = g.x + ((int64_t)i0 * g.ny + j0);
+        const double* gy = g.y + ((int64_t)i0 * g.ny + j0);
+        const double x00c = gx[0], x01 = gx[1], x10 = gx[g.ny], x11 = gx[g.ny + 1];
+        const double y00c = gy[0], y01 = gy[1], y10 = gy[g.ny], y11 = gy[g.ny + 1];
+        const double u = i - i0, v = j - j0, u1 = 1.0 - u, v1 = 1.0 - v;
+        const double xa = dfma(x10, u, x00c * u1), xb = dfma(x11, u, x01 * u1);
+        const double ya = dfma(y10, u, y00c * u1), yb = dfma(y11, u, y01 * u1);
+        const double ex = dfma(xb, v, xa * v1) - px, ey = dfma(yb, v, ya * v1) - py;
+        const double dxdi = dfma(x11 - x01, v, (x10 - x00c) * v1);
+        const double dxdj = dfma(x11 - x10, u, (x01 - x00c) * u1);
+        const double dydi = dfma(y11 - y01, v, (y10 - y00c) * v1);
+        const double dydj = dfma(y11 - y10, u, (y01 - y00c) * u1);
+        const double det = dfma(dxdi, dydj, -(dxdj * dydi));
+        double rr;
+        asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(rr) : "d"(det));
+        const double rdet = dfma(rr, dfma(-det, rr, 1.0), rr);
+        const double di = dfma(dydj, ex, -(dxdj * ey)) * rdet;
+        const double dj = dfma(dxdi, ey, -(dydi * ex)) * rdet;
+        const double big = fmax(fabs(di), fabs(dj));
+        if (!(big < 4.0 * (g.nx + g.ny))) break;   // diverging or NaN (degenerate cell): the careful path decides
         i -= di;
         j -= dj;
-        if (fabs(di) < 1e-4 && fabs(dj) < 1e-4) {
-            const int ic = (int)floor(i), jc = (int)floor(j);
+        if (big < 1e-4) {
+            const int ic = __double2int_rd(i), jc = __double2int_rd(j);
             if (ic >= 0 && jc >= 0 && ic < ncx && jc < ncy) {
                 const double fu = i - ic, fv = j - jc;
                 // (no exact containment test here: with the step below 1e-4 the solution is ~1e-8 cells from the
