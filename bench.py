@@ -108,6 +108,8 @@ class ClockSampler:
         self.active = False
 
     def start(self):
+        if os.environ.get("BENCH_NO_SAMPLER"):   # development: rule the sampler out as a disturbance
+            return
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
                                           "-lms", "50", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)

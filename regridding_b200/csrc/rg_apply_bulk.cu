@@ -26,6 +26,7 @@
 // copies start one cell earlier (spans carry 2 spare cells for that) and the frame's lanes add 8 bytes to their
 // gather addresses -- no fallback to the generic kernel for odd widths.
 #include "rg_common.cuh"
+#include "rg_async.cuh"
 
 // development switches (ablations for profiles/r2_apply_tuning.md); all 0 in the product build
 #ifndef RG_SKIP_COMPUTE
@@ -489,42 +490,6 @@ k_plan_slots(int64_t h_out, int64_t w_out, int tiles_x, const int32_t* __restric
 // ---------------------------------------------------------------------------
 // bulk-copy staged apply
 // ---------------------------------------------------------------------------
-__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned count)
-{
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar)
-{
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, unsigned bytes)
-{
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-// try_wait suspends the warp in hardware until the phase completes or the hint (ns) expires: no issue slots are
-// burnt by polling while the other warps of the SM compute
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity)
-{
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "WAIT_%=:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n"
-        "@p bra DONE_%=;\n"
-        "bra WAIT_%=;\n"
-        "DONE_%=:\n"
-        "}\n" ::"r"(smem_u32(bar)), "r"(parity), "r"(20000u) : "memory");
-}
-// global -> shared bulk copy (TMA engine, SASS UBLKCP.S.G); bytes land on the mbarrier's transaction count
-__device__ __forceinline__ void bulk_load(unsigned smem_dst, const void* gmem_src, unsigned bytes, uint64_t* bar)
-{
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(smem_dst),
-                 "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
-                 : "memory");
-}
-
 // vin must be 16-byte aligned.  `cells_left` = doubles from vin to the end of the caller's values_in buffer: copies
 // are clipped to it (only the spare cells of the very last rows can reach beyond).
 __global__ void __launch_bounds__(kBulkThreads, 1)

@@ -5,6 +5,7 @@
 //  regridding/_weights/_weights_conservative.py:59-106).  Not fastmath in the reference
 // (c1d.py:59), so plain IEEE subtraction / division reproduces it bit for bit.
 #include "rg_common.cuh"
+#include "rg_async.cuh"
 
 namespace rg {
 
@@ -157,6 +158,206 @@ k_regrid1d(int64_t S, int64_t n, int64_t m,
 }
 
 // ---------------------------------------------------------------------------
+// fused regrid, streamed (the config-2 path: 1M spectra x 4096 bins, no input weights).
+//
+// One persistent CTA per SM, two stages of shared memory.  Thread 0 brings the three rows of the NEXT spectrum (sweep
+// edges, static edges, values: 98 KB at 4096 bins = the algorithmic minimum of HBM traffic) with three bulk copies
+// (cp.async.bulk, the TMA engine; completion on an mbarrier with expect-tx) while all warps compute the CURRENT one,
+// so loads stay in flight during the whole compute phase and no thread spends instructions on staging.  Rows of odd
+// length start 8 bytes off every other spectrum: the copy then starts one double earlier ("skew") and the readers
+// add the skew; the first / last spectrum of a call, whose over-read could leave the caller's buffers, are staged by
+// plain loads instead.
+//
+// k_regrid1d_staged (below) was issue bound (ncu: 71 % of the issue slots, 41 k warp instructions per spectrum:
+// 35 % searches, 40 % pieces, 15 % staging).  Here a warp owns 128 consecutive static cells; the sweep cell of a
+// static edge comes from a linear-interpolation guess corrected by at most two neighbour steps and VERIFIED
+// (K = first cell whose right edge lies beyond the edge; any lane that does not verify sends the warp to the plain
+// binary search), and the piece loop carries the right edge over as the next left edge.  Same pieces, same
+// operations in the same order as k_regrid1d: bit-identical.
+// ---------------------------------------------------------------------------
+constexpr int kStreamThreads = 1024;
+
+struct Stream1DStage {
+    double* sw;   // staged rows: element q of the row lives at [skew + q]
+    double* st;
+    double* vi;
+};
+
+template <bool GEN>
+__device__ __forceinline__ void regrid1d_stream_cells(const double* __restrict__ sw_raw, const double* __restrict__ st_raw,
+                                                      const double* __restrict__ vi, int n, int m, bool rev_sw, bool rev_st,
+                                                      double* __restrict__ vo, int iters)
+{
+    // ascending views (c1d.py:100-110); GEN = false: both rows ascend, the views are the rows
+    auto SW = [&](int k) -> double { return GEN ? sw_raw[rev_sw ? n - 1 - k : k] : sw_raw[k]; };
+    auto ST = [&](int e) -> double { return GEN ? st_raw[rev_st ? m - 1 - e : e] : st_raw[e]; };
+    const int ncell = n - 1;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+    const int C = ((m - 1 + 32 * nwarps - 1) / (32 * nwarps)) * 32;   // static cells per warp (multiple of 32)
+    const int c0 = warp * C;
+    if (c0 >= m - 1) return;
+    const double sw0 = SW(0);
+    const float scale = (float)((double)(n - 1) / (SW(n - 1) - sw0));
+    // K(a) = first sweep cell in [0, n-1] whose right edge is beyond a (n-1: none)
+    auto locate = [&](double a) -> int {
+        int c = __float2int_rd(fminf(fmaxf((float)(a - sw0) * scale, 0.0f), (float)(n - 1)));
+        bool ok = false;
+#pragma unroll
+        for (int t = 0; t < 3; t++) {
+            const bool up = (c < n - 1) && (SW(min(c + 1, n - 1)) <= a);
+            const bool dn = (c > 0) && (SW(c) > a);
+            ok = !(up || dn);
+            if (t < 2) c += (int)up - (int)dn;
+        }
+        if (__any_sync(0xffffffffu, !ok)) {   // far from uniform spacing (or NaN edges): the plain binary search
+            int lo = 0, hi = n - 1;
+            for (int it = 0; it < iters; it++) {
+                const int mid = (lo + hi) >> 1;
+                const bool cgt = SW(min(mid + 1, n - 1)) > a;
+                if (lo < hi) { if (cgt) hi = mid; else lo = mid + 1; }
+            }
+            if (!ok) c = lo;
+        }
+        return c;
+    };
+    int e = min(c0 + lane, m - 1);
+    double a = ST(e);
+    int K = locate(a);
+    for (int r = 0; r < C; r += 32) {
+        if (c0 + r >= m - 1) break;
+        const int e_n = min(c0 + r + 32 + lane, m - 1);
+        const double a_n = ST(e_n);
+        const int K_n = locate(a_n);
+        // right edge of my cell: the next lane's edge (lane 31: lane 0 of the next round)
+        double b = __shfl_down_sync(0xffffffffu, a, 1);
+        int Kb = __shfl_down_sync(0xffffffffu, K, 1);
+        const double bw = __shfl_sync(0xffffffffu, a_n, 0);
+        const int Kw = __shfl_sync(0xffffffffu, K_n, 0);
+        if (lane == 31) { b = bw; Kb = Kw; }
+        const int cell = c0 + r + lane;
+        if (cell < m - 1) {
+            double acc = 0.0;
+            if (!GEN) {
+                const int kend = min(Kb, n - 2);   // (a cell that only touches b is rejected by p1 < p2)
+                double l = sw_raw[K];
+#pragma unroll 1
+                for (int k = K; k <= kend; k++) {
+                    const double rr = sw_raw[k + 1];
+                    const double v = vi[k];
+                    const double p1 = l > a ? l : a;
+                    const double p2 = rr < b ? rr : b;
+                    if (p1 < p2) {
+                        const double ratio = ddiv(dsub(p2, p1), dsub(rr, l));
+                        acc = dadd(acc, dmul(ratio, v));
+                    }
+                    l = rr;
+                }
+                vo[cell] = acc;
+            } else {
+                const int k0 = K;
+                const int k1 = min(Kb - (SW(Kb) == b ? 1 : 0), n - 2);
+                const int cnt = k1 - k0 + 1;
+                for (int q = 0; q < cnt; q++) {
+                    const int k = rev_sw ? (k1 - q) : (k0 + q);  // ascending wrapped input index
+                    const double l = SW(k), rr = SW(k + 1);
+                    const double p1 = l > a ? l : a;
+                    const double p2 = rr < b ? rr : b;
+                    if (!(p1 < p2)) continue;
+                    const int li = rev_sw ? (ncell - 1 - k) : k;  // wrapped index (= the reference's ~k + ncell)
+                    const double length = dsub(SW(li + 1), SW(li));   // c1d.py:118, 305-307 (indexed in the view)
+                    const double ratio = ddiv(dsub(p2, p1), length);
+                    acc = dadd(acc, dmul(ratio, vi[li]));
+                }
+                vo[rev_st ? (m - 2 - cell) : cell] = acc;
+            }
+        }
+        a = a_n;
+        K = K_n;
+    }
+}
+
+__global__ void __launch_bounds__(kStreamThreads, 1)
+k_regrid1d_stream(int64_t S, int n, int m, int cap_n, int cap_m,
+                  const double* __restrict__ x_in, const double* __restrict__ x_out,
+                  const double* __restrict__ vin, double* __restrict__ vout)
+{
+    extern __shared__ __align__(16) double smem_d[];
+    __shared__ __align__(8) uint64_t full[2];
+    // stage layout: [cap_n] sweep edges, [cap_m] static edges, [cap_n] values (capacities even, >= length + 2)
+    const int stage_doubles = 2 * cap_n + cap_m;
+    auto stage = [&](int s) -> Stream1DStage {
+        double* b = smem_d + (size_t)s * stage_doubles;
+        return Stream1DStage{ b, b + cap_n, b + cap_n + cap_m };
+    };
+    auto skew_of = [](const double* p) -> int { return (int)(((uintptr_t)p >> 3) & 1); };
+    // a spectrum may be bulk-copied when the 16-byte aligned copies stay inside the caller's buffers
+    auto bulk_ok = [&](int64_t sp) -> bool {
+        const double* r0 = x_in + sp * n;
+        const double* r1 = x_out + sp * m;
+        const double* r2 = vin + sp * (n - 1);
+        const int s0 = skew_of(r0), s1 = skew_of(r1), s2 = skew_of(r2);
+        const bool front = sp > 0 || (s0 | s1 | s2) == 0;
+        const bool back = sp < S - 1 || (((s0 + n) | (s1 + m) | (s2 + n - 1)) & 1) == 0;
+        return front && back;
+    };
+    auto issue = [&](int64_t sp, int s) {   // thread 0 only
+        const Stream1DStage g = stage(s);
+        const double* r0 = x_in + sp * n;
+        const double* r1 = x_out + sp * m;
+        const double* r2 = vin + sp * (n - 1);
+        const int s0 = skew_of(r0), s1 = skew_of(r1), s2 = skew_of(r2);
+        const unsigned b0 = (unsigned)(((s0 + n) * 8 + 15) & ~15), b1 = (unsigned)(((s1 + m) * 8 + 15) & ~15),
+                       b2 = (unsigned)(((s2 + n - 1) * 8 + 15) & ~15);
+        asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");   // the stage was last touched by ordinary loads / stores
+        mbar_arrive_expect_tx(&full[s], b0 + b1 + b2);
+        bulk_load(smem_u32(g.sw), r0 - s0, b0, &full[s]);
+        bulk_load(smem_u32(g.st), r1 - s1, b1, &full[s]);
+        bulk_load(smem_u32(g.vi), r2 - s2, b2, &full[s]);
+    };
+    if (threadIdx.x == 0) {
+        mbar_init(&full[0], 1);
+        mbar_init(&full[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    }
+    __syncthreads();
+    int iters = 0;
+    while ((1 << iters) < n) iters++;
+    unsigned phase[2] = { 0u, 0u };
+    int64_t sp = blockIdx.x;
+    if (threadIdx.x == 0 && sp < S && bulk_ok(sp)) issue(sp, 0);
+    for (int it = 0; sp < S; sp += gridDim.x, it++) {
+        const int s = it & 1;
+        const int64_t nxt = sp + gridDim.x;
+        // (stage s^1 was released by the __syncthreads that ended the previous iteration)
+        if (threadIdx.x == 0 && nxt < S && bulk_ok(nxt)) issue(nxt, s ^ 1);
+        const Stream1DStage g = stage(s);
+        const double* r0 = x_in + sp * n;
+        const double* r1 = x_out + sp * m;
+        const double* r2 = vin + sp * (n - 1);
+        int s0 = skew_of(r0), s1 = skew_of(r1), s2 = skew_of(r2);
+        if (bulk_ok(sp)) {
+            mbar_wait(&full[s], phase[s]);
+            phase[s] ^= 1u;
+        } else {   // first / last spectrum of the call
+            s0 = s1 = s2 = 0;
+            for (int q = threadIdx.x; q < n; q += blockDim.x) g.sw[q] = r0[q];
+            for (int q = threadIdx.x; q < m; q += blockDim.x) g.st[q] = r1[q];
+            for (int q = threadIdx.x; q < n - 1; q += blockDim.x) g.vi[q] = r2[q];
+            __syncthreads();
+        }
+        const double* sw = g.sw + s0;
+        const double* st = g.st + s1;
+        const double* vi = g.vi + s2;
+        const bool rev_sw = !(sw[0] < sw[n - 1]);  // c1d.py:100-110
+        const bool rev_st = !(st[0] < st[m - 1]);
+        double* vo = vout + sp * (m - 1);
+        if (!rev_sw && !rev_st) regrid1d_stream_cells<false>(sw, st, vi, n, m, false, false, vo, iters);
+        else regrid1d_stream_cells<true>(sw, st, vi, n, m, rev_sw, rev_st, vo, iters);
+        __syncthreads();   // every warp is done with stage s before it is refilled
+    }
+}
+
+// ---------------------------------------------------------------------------
 // fused regrid, shared-memory staged (the config-2 path: 1M spectra x 4096 bins).
 // One CTA per spectrum: the ascending views of both edge arrays and the spectrum's values are
 // staged in shared memory with coalesced loads (131 kB of HBM traffic per spectrum = the
@@ -295,6 +496,18 @@ extern "C" int rg_regrid1d_conservative(int device, void* stream, int64_t S, int
     cudaStream_t st = (cudaStream_t)stream;
     const int T = 256;
     // shared-memory staged kernel whenever one spectrum (both edge arrays + values [+ weights]) fits on chip
+    // streamed kernel (persistent CTAs, two stages filled by bulk copies) when two spectra fit on chip
+    if (!w_in && n < (1 << 24) && m < (1 << 24)) {
+        const int cap_n = (int)((n + 2 + 1) & ~(int64_t)1), cap_m = (int)((m + 2 + 1) & ~(int64_t)1);
+        const size_t smem2 = (size_t)2 * (2 * cap_n + cap_m) * sizeof(double);
+        if (smem2 <= 227 * 1024 && !getenv("RG_NO_STREAM1D")) {
+            RG_CUDA(cudaFuncSetAttribute(k_regrid1d_stream, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+            const unsigned grid = (unsigned)(S < kNumSM ? S : kNumSM);
+            k_regrid1d_stream<<<grid, kStreamThreads, smem2, st>>>(S, (int)n, (int)m, cap_n, cap_m, x_in, x_out, values_in, values_out);
+            RG_LAUNCH_CHECK("k_regrid1d_stream");
+            return RG_OK;
+        }
+    }
     const size_t smem = (size_t)(n + m + (n - 1) + (w_in ? n - 1 : 0)) * sizeof(double);
     if (smem <= 200 * 1024 && n < (1 << 30) && m < (1 << 30)) {
         auto kern = w_in ? k_regrid1d_staged<true> : k_regrid1d_staged<false>;

@@ -488,6 +488,41 @@ def test_conservative_1d_fused_paths_agree(rg, dev, oracle):
                 assert np.array_equal(fused[s_], ref), (n, m, s_, ww is None)
 
 
+def test_conservative_1d_streamed_kernel_equals_staged_and_oracle(rg, dev, oracle, monkeypatch):
+    """The streamed kernel (persistent CTAs, two stages filled by bulk copies) against the staged one and the oracle:
+    more spectra than CTAs (several iterations per CTA, both stages), odd and even row lengths (rows of odd length
+    start 8 bytes off every other spectrum: skewed copies), mis-aligned base pointers (first / last spectrum staged by
+    plain loads), descending and far-from-uniform grids (search fall-back), output cells beyond the input range."""
+    rng = np.random.default_rng(11)
+    for n, m, S in ((4097, 4097, 301), (1000, 1201, 310), (513, 64, 5), (2, 2, 3), (3, 700, 2)):
+        xin = np.sort(rng.uniform(0.0, 100.0, (S, n)), axis=1)
+        xin[::7] = np.linspace(0.0, 100.0, n) + 0.3 * np.sin(np.linspace(0, 20, n))      # smooth grids: guesses verify
+        xin[1] = xin[1, ::-1].copy()                                                     # descending input grid
+        xin[S - 1] = np.cumsum(rng.exponential(1.0, n)) ** 2                             # strongly non-uniform
+        xout = np.sort(rng.uniform(-5.0, 105.0, (S, m)), axis=1)
+        xout[2 % S] = xout[2 % S, ::-1].copy()                                           # descending output grid
+        vals = rng.random((S, n - 1))
+        import torch
+
+        for shift in (0, 1):   # 1: every buffer starts 8 bytes off a 16-byte boundary
+            def dev_of(a):
+                flat = torch.empty(a.size + 2, dtype=torch.float64, device=dev)
+                view = flat[shift:shift + a.size].view(a.shape)
+                view.copy_(torch.from_numpy(a))
+                return view
+            a, b, c = dev_of(xin), dev_of(xout), dev_of(vals)
+            monkeypatch.delenv("RG_NO_STREAM1D", raising=False)
+            streamed = rg.device.regrid1d_conservative(a, b, c).cpu().numpy()
+            monkeypatch.setenv("RG_NO_STREAM1D", "1")
+            staged = rg.device.regrid1d_conservative(a, b, c).cpu().numpy()
+            monkeypatch.delenv("RG_NO_STREAM1D", raising=False)
+            assert np.array_equal(streamed, staged), (n, m, S, shift)
+        for s_ in sorted({0, 1, 2 % S, 7 % S, S // 2, S - 1}):
+            tri = oracle.coalesce(*oracle.weights_conservative_1d(xin[s_], xout[s_]))
+            ref = oracle.regrid_from_weights(tri[0] % (n - 1), tri[1] % (m - 1), tri[2], vals[s_:s_ + 1], m - 1)[0]
+            assert np.array_equal(streamed[s_], ref), (n, m, s_)
+
+
 def test_regrid_1d_fused_fast_path_equals_weights_path(rg):
     """regrid(method="conservative") along one axis takes the fused kernel (no weights materialised);
     it must return what weights() + regrid_from_weights() return, for any axis position, broadcast
