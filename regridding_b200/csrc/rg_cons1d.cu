@@ -169,11 +169,11 @@ k_regrid1d(int64_t S, int64_t n, int64_t m,
 // plain loads instead.
 //
 // k_regrid1d_staged (below) was issue bound (ncu: 71 % of the issue slots, 41 k warp instructions per spectrum:
-// 35 % searches, 40 % pieces, 15 % staging).  Here a warp owns 128 consecutive static cells; the sweep cell of a
-// static edge comes from a linear-interpolation guess corrected by at most two neighbour steps and VERIFIED
-// (K = first cell whose right edge lies beyond the edge; any lane that does not verify sends the warp to the plain
-// binary search), and the piece loop carries the right edge over as the next left edge.  Same pieces, same
-// operations in the same order as k_regrid1d: bit-identical.
+// 35 % searches, 40 % pieces, 15 % staging).  Here a thread takes one static cell: the sweep cell of its left edge
+// comes from a linear-interpolation guess corrected by neighbour steps whose exit conditions DEFINE the cell (lanes
+// that run out of steps take the plain binary search); the right edge needs no search at all, the piece loop runs
+// while the sweep cell's left edge is below it and carries every right edge over as the next left edge.  Same
+// pieces, same operations in the same order as k_regrid1d: bit-identical.
 // ---------------------------------------------------------------------------
 constexpr int kStreamThreads = 1024;
 
@@ -192,87 +192,68 @@ __device__ __forceinline__ void regrid1d_stream_cells(const double* __restrict__
     auto SW = [&](int k) -> double { return GEN ? sw_raw[rev_sw ? n - 1 - k : k] : sw_raw[k]; };
     auto ST = [&](int e) -> double { return GEN ? st_raw[rev_st ? m - 1 - e : e] : st_raw[e]; };
     const int ncell = n - 1;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
-    const int C = ((m - 1 + 32 * nwarps - 1) / (32 * nwarps)) * 32;   // static cells per warp (multiple of 32)
-    const int c0 = warp * C;
-    if (c0 >= m - 1) return;
     const double sw0 = SW(0);
     const float scale = (float)((double)(n - 1) / (SW(n - 1) - sw0));
-    // K(a) = first sweep cell in [0, n-1] whose right edge is beyond a (n-1: none)
+    // K(a) = first sweep cell in [0, n-1] whose right edge is beyond a (n-1: none): a linear-interpolation guess moved
+    // down while the cell's left edge is beyond a, then up while its right edge is not; a loop that ends by its
+    // condition leaves (K == 0 || SW(K) <= a) && (K == n-1 || SW(K+1) > a), which defines K for sorted edges.  Lanes
+    // that run out of steps (grids far from uniform) take the plain binary search.
     auto locate = [&](double a) -> int {
         int c = __float2int_rd(fminf(fmaxf((float)(a - sw0) * scale, 0.0f), (float)(n - 1)));
-        bool ok = false;
-#pragma unroll
-        for (int t = 0; t < 3; t++) {
-            const bool up = (c < n - 1) && (SW(min(c + 1, n - 1)) <= a);
-            const bool dn = (c > 0) && (SW(c) > a);
-            ok = !(up || dn);
-            if (t < 2) c += (int)up - (int)dn;
-        }
-        if (__any_sync(0xffffffffu, !ok)) {   // far from uniform spacing (or NaN edges): the plain binary search
+        int t = 0;
+#pragma unroll 1
+        for (; t < 4 && c > 0 && SW(c) > a; t++) c--;
+        bool ok = t < 4;
+#pragma unroll 1
+        for (t = 0; t < 4 && c < n - 1 && SW(c + 1) <= a; t++) c++;
+        ok = ok && t < 4;
+        if (!ok) {
             int lo = 0, hi = n - 1;
-            for (int it = 0; it < iters; it++) {
+            for (int it = 0; it < iters && lo < hi; it++) {
                 const int mid = (lo + hi) >> 1;
-                const bool cgt = SW(min(mid + 1, n - 1)) > a;
-                if (lo < hi) { if (cgt) hi = mid; else lo = mid + 1; }
+                if (SW(mid + 1) > a) hi = mid; else lo = mid + 1;
             }
-            if (!ok) c = lo;
+            c = lo;
         }
         return c;
     };
-    int e = min(c0 + lane, m - 1);
-    double a = ST(e);
-    int K = locate(a);
-    for (int r = 0; r < C; r += 32) {
-        if (c0 + r >= m - 1) break;
-        const int e_n = min(c0 + r + 32 + lane, m - 1);
-        const double a_n = ST(e_n);
-        const int K_n = locate(a_n);
-        // right edge of my cell: the next lane's edge (lane 31: lane 0 of the next round)
-        double b = __shfl_down_sync(0xffffffffu, a, 1);
-        int Kb = __shfl_down_sync(0xffffffffu, K, 1);
-        const double bw = __shfl_sync(0xffffffffu, a_n, 0);
-        const int Kw = __shfl_sync(0xffffffffu, K_n, 0);
-        if (lane == 31) { b = bw; Kb = Kw; }
-        const int cell = c0 + r + lane;
-        if (cell < m - 1) {
-            double acc = 0.0;
-            if (!GEN) {
-                const int kend = min(Kb, n - 2);   // (a cell that only touches b is rejected by p1 < p2)
-                double l = sw_raw[K];
+    for (int cell = threadIdx.x; cell < m - 1; cell += blockDim.x) {
+        const double a = ST(cell), b = ST(cell + 1);
+        const int K = locate(a);
+        double acc = 0.0;
+        if (!GEN) {
+            // cells K, K+1, ... while their left edge is below b (a cell that only touches b has no piece)
+            double l = sw_raw[K];
 #pragma unroll 1
-                for (int k = K; k <= kend; k++) {
-                    const double rr = sw_raw[k + 1];
-                    const double v = vi[k];
-                    const double p1 = l > a ? l : a;
-                    const double p2 = rr < b ? rr : b;
-                    if (p1 < p2) {
-                        const double ratio = ddiv(dsub(p2, p1), dsub(rr, l));
-                        acc = dadd(acc, dmul(ratio, v));
-                    }
-                    l = rr;
+            for (int k = K; k <= n - 2 && l < b; k++) {
+                const double rr = sw_raw[k + 1];
+                const double p1 = l > a ? l : a;
+                const double p2 = rr < b ? rr : b;
+                if (p1 < p2) {
+                    const double ratio = ddiv(dsub(p2, p1), dsub(rr, l));
+                    acc = dadd(acc, dmul(ratio, vi[k]));
                 }
-                vo[cell] = acc;
-            } else {
-                const int k0 = K;
-                const int k1 = min(Kb - (SW(Kb) == b ? 1 : 0), n - 2);
-                const int cnt = k1 - k0 + 1;
-                for (int q = 0; q < cnt; q++) {
-                    const int k = rev_sw ? (k1 - q) : (k0 + q);  // ascending wrapped input index
-                    const double l = SW(k), rr = SW(k + 1);
-                    const double p1 = l > a ? l : a;
-                    const double p2 = rr < b ? rr : b;
-                    if (!(p1 < p2)) continue;
-                    const int li = rev_sw ? (ncell - 1 - k) : k;  // wrapped index (= the reference's ~k + ncell)
-                    const double length = dsub(SW(li + 1), SW(li));   // c1d.py:118, 305-307 (indexed in the view)
-                    const double ratio = ddiv(dsub(p2, p1), length);
-                    acc = dadd(acc, dmul(ratio, vi[li]));
-                }
-                vo[rev_st ? (m - 2 - cell) : cell] = acc;
+                l = rr;
             }
+            vo[cell] = acc;
+        } else {
+            const int Kb = locate(b);
+            const int k0 = K;
+            const int k1 = min(Kb - (SW(Kb) == b ? 1 : 0), n - 2);
+            const int cnt = k1 - k0 + 1;
+            for (int q = 0; q < cnt; q++) {
+                const int k = rev_sw ? (k1 - q) : (k0 + q);  // ascending wrapped input index
+                const double l = SW(k), rr = SW(k + 1);
+                const double p1 = l > a ? l : a;
+                const double p2 = rr < b ? rr : b;
+                if (!(p1 < p2)) continue;
+                const int li = rev_sw ? (ncell - 1 - k) : k;  // wrapped index (= the reference's ~k + ncell)
+                const double length = dsub(SW(li + 1), SW(li));   // c1d.py:118, 305-307 (indexed in the view)
+                const double ratio = ddiv(dsub(p2, p1), length);
+                acc = dadd(acc, dmul(ratio, vi[li]));
+            }
+            vo[rev_st ? (m - 2 - cell) : cell] = acc;
         }
-        a = a_n;
-        K = K_n;
     }
 }
 
