@@ -98,7 +98,20 @@ static __global__ void k_bbox(const __grid_constant__ BoundarySet S)
     double* bbox = S.bbox[blockIdx.y];  // xlo, ylo, xhi, yhi
     const int64_t n = (int64_t)g.nx * g.ny;
     double xlo = INFINITY, ylo = INFINITY, xhi = -INFINITY, yhi = -INFINITY;
-    for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < n; q += (int64_t)gridDim.x * blockDim.x) {
+    // four independent loads of each array in flight per thread (the scan is latency bound otherwise)
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    for (; q + 3 * stride < n; q += 4 * stride) {
+        double x[4], y[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) { x[u] = g.x[q + u * stride]; y[u] = g.y[q + u * stride]; }
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            xlo = fmin(xlo, x[u]); xhi = fmax(xhi, x[u]);
+            ylo = fmin(ylo, y[u]); yhi = fmax(yhi, y[u]);
+        }
+    }
+    for (; q < n; q += stride) {
         const double x = g.x[q], y = g.y[q];
         xlo = fmin(xlo, x); xhi = fmax(xhi, x);
         ylo = fmin(ylo, y); yhi = fmax(yhi, y);
@@ -254,8 +267,11 @@ static void carve_boundary(Carver& c, Boundary& b, int64_t nx, int64_t ny)
 
 
 // builds the boundary structures and the bboxes (xlo, ylo, xhi, yhi) of one or two grids: 4 launches
-static inline int build_boundaries(cudaStream_t st, int n, const GridView* g, const Boundary* b, double* const* bbox)
+// (`n_bbox` < n: the bboxes of the grids n_bbox .. n-1 are only initialised; the caller reduces them elsewhere)
+static inline int build_boundaries(cudaStream_t st, int n, const GridView* g, const Boundary* b, double* const* bbox,
+                                   int n_bbox = -1)
 {
+    if (n_bbox < 0) n_bbox = n;
     const int T = 256;
     BoundarySet S;
     memset(&S, 0, sizeof(S));
@@ -267,7 +283,7 @@ static inline int build_boundaries(cudaStream_t st, int n, const GridView* g, co
         g2max = b[q].n_g2 > g2max ? b[q].n_g2 : g2max;
     }
     k_bbox_init<<<1, 32, 0, st>>>(S);
-    k_bbox<<<dim3(kNumSM * 2, n), T, 0, st>>>(S);
+    if (n_bbox > 0) k_bbox<<<dim3(kNumSM * 4, n_bbox), T, 0, st>>>(S);
     RG_LAUNCH_CHECK("k_bbox");
     k_boundary_edges_bb1<<<dim3((unsigned)ceil_div((int64_t)g1max * 32, T), n), T, 0, st>>>(S);
     k_boundary_bb2<<<dim3((unsigned)ceil_div((int64_t)g2max * 32, T), n), T, 0, st>>>(S);

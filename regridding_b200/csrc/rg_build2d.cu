@@ -959,7 +959,8 @@ struct Layout {
     int64_t* scan_scratch;
     int32_t* flags;
     // band builds (rg_build2d_band)
-    uint8_t* raster;         // [kRasterN^2] does a cell of the band touch this cell of the raster over the input bbox?
+    uint8_t* raster8;        // [kRasterN^2] byte marks (plain stores), packed into `raster`
+    uint32_t* raster;        // [kRasterN][kRasterN / 32] bitmap: does a cell of the band touch this cell of the raster over the input bbox?
     uint8_t* rel[2];         // [output vertices] can the pass-0 / pass-1 segment starting here have a piece in the band?
     struct BandInfo* info;
     size_t bytes;
@@ -970,7 +971,7 @@ struct BandInfo {            // device memory, written by k_band_finalize
     int32_t rect[4][4];      // per pass: first line, lines, first segment, segments of the rectangle that is walked
     int64_t tstart[5];       // first thread of every pass in the per-segment launches (multiples of 256)
     int32_t ext[2][4];       // scratch: per OUTPUT pass the extent (Lmin, Lmax, kmin, kmax) of its relevant segments
-    double sx, sy;           // raster cells per unit length over the input grid's bbox
+    float sx, sy;            // raster cells per unit length over the input grid's bbox
 };
 
 static Layout make_layout(void* ws, int64_t nxi, int64_t nyi, int64_t nxo, int64_t nyo)
@@ -1007,7 +1008,8 @@ static Layout make_layout(void* ws, int64_t nxi, int64_t nyi, int64_t nxo, int64
     l.colptr = c.take<int64_t>(l.Ci + 1);
     l.scan_scratch = c.take<int64_t>(scan_scratch_elems(l.Ci));
     l.flags = c.take<int32_t>(8);
-    l.raster = c.take<uint8_t>((size_t)kRasterN * kRasterN);
+    l.raster8 = c.take<uint8_t>((size_t)kRasterN * kRasterN);
+    l.raster = c.take<uint32_t>((size_t)kRasterN * kRasterN / 32);
     l.rel[0] = c.take<uint8_t>(l.Vo);
     l.rel[1] = c.take<uint8_t>(l.Vo);
     l.info = c.take<BandInfo>(1);
@@ -1515,15 +1517,24 @@ struct BandParams {
     const BandInfo* info;
 };
 
-__device__ __forceinline__ int raster_index(double x, double lo, double scale)
+__device__ __forceinline__ int raster_index(double x, double lo, float scale)
 {
-    const double t = floor((x - lo) * scale);   // monotone in x: overlapping intervals give overlapping index ranges
-    return (int)fmin(fmax(t, 0.0), (double)(kRasterN - 1));
+    // any NON-DECREASING function of x does (overlapping intervals then give overlapping index ranges), as long as
+    // marking and testing use the same one: the difference is rounded to fp32 (monotone), scaled and floored
+    const int t = __float2int_rd(__fmul_rn((float)(x - lo), scale));
+    return min(max(t, 0), kRasterN - 1);
+}
+
+// bits iy0 .. iy1 of a raster row that fall into its 32-bit word w
+__device__ __forceinline__ uint32_t raster_row_mask(int iy0, int iy1, int w)
+{
+    const int lo = max(iy0 - 32 * w, 0), hi = min(iy1 - 32 * w, 31);
+    return (0xffffffffu >> (31 - hi)) & (0xffffffffu << lo);
 }
 
 // every cell of the band marks the raster cells its bounding box touches
 __global__ void k_band_raster(GridView g, int row_lo, int row_hi, const double* __restrict__ bbox,
-                              const BandInfo* __restrict__ info, uint8_t* __restrict__ raster)
+                              const BandInfo* __restrict__ info, uint8_t* __restrict__ raster8)
 {
     const int ncy = g.ny - 1;
     const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -1532,69 +1543,134 @@ __global__ void k_band_raster(GridView g, int row_lo, int row_hi, const double* 
     const int64_t v = (int64_t)a * g.ny + b;
     const double x0 = g.x[v], x1 = g.x[v + 1], x2 = g.x[v + g.ny], x3 = g.x[v + g.ny + 1];
     const double y0 = g.y[v], y1 = g.y[v + 1], y2 = g.y[v + g.ny], y3 = g.y[v + g.ny + 1];
-    const double sx = info->sx, sy = info->sy;
+    const float sx = info->sx, sy = info->sy;
     const int ix0 = raster_index(fmin(fmin(x0, x1), fmin(x2, x3)), bbox[0], sx);
     const int ix1 = raster_index(fmax(fmax(x0, x1), fmax(x2, x3)), bbox[0], sx);
     const int iy0 = raster_index(fmin(fmin(y0, y1), fmin(y2, y3)), bbox[1], sy);
     const int iy1 = raster_index(fmax(fmax(y0, y1), fmax(y2, y3)), bbox[1], sy);
     for (int ix = ix0; ix <= ix1; ix++)
-        for (int iy = iy0; iy <= iy1; iy++) raster[ix * kRasterN + iy] = 1;
+        for (int iy = iy0; iy <= iy1; iy++) raster8[ix * kRasterN + iy] = 1;   // plain stores: no ordering needed
 }
 
-// raster cell (ix | iy << 16) of every output vertex: one streaming pass over the output grid
-__global__ void k_band_vertex_cells(GridView gout, const double* __restrict__ bbox_in, const BandInfo* __restrict__ info,
-                                    uint32_t* __restrict__ vcell)
+// byte marks -> bitmap (bit iy & 31 of word [ix][iy >> 5]): 32 KB, read by every warp of k_band_relevance
+__global__ void k_band_raster_pack(const uint8_t* __restrict__ raster8, uint32_t* __restrict__ raster)
 {
-    const int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (v >= (int64_t)gout.nx * gout.ny) return;
-    const unsigned ix = (unsigned)raster_index(gout.x[v], bbox_in[0], info->sx);
-    const unsigned iy = (unsigned)raster_index(gout.y[v], bbox_in[1], info->sy);
-    vcell[v] = ix | (iy << 16);
-}
-
-// Thread per OUTPUT vertex (i, j): relevance of the two segments that start there (pass 1: to (i, j+1); pass 0: to
-// (i+1, j)) and the extent of the relevant segments in (line, segment) space.  A segment is relevant iff a raster
-// cell under its bounding box is marked (indices are clamped to the raster: segments beyond the input grid's bbox can
-// only over-report).
-__global__ void k_band_relevance(int nx, int ny, const uint8_t* __restrict__ raster, const uint32_t* __restrict__ vcell,
-                                 uint8_t* __restrict__ rel0, uint8_t* __restrict__ rel1, BandInfo* __restrict__ info)
-{
-    const int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const int64_t nv = (int64_t)nx * ny;
-    int ext[8] = { INT32_MAX, -1, INT32_MAX, -1, INT32_MAX, -1, INT32_MAX, -1 };  // pass 0: Lmin Lmax kmin kmax; pass 1
-    if (v < nv) {
-        const int i = (int)(v / ny), j = (int)(v % ny);
-        const uint32_t c = vcell[v];
-        const int ix = (int)(c & 0xffffu), iy = (int)(c >> 16);
-        auto marked = [&](uint32_t cb) {
-            const int ixb = (int)(cb & 0xffffu), iyb = (int)(cb >> 16);
-            const int xa = min(ix, ixb), xb = max(ix, ixb), ya = min(iy, iyb), yb = max(iy, iyb);
-            for (int a = xa; a <= xb; a++)
-                for (int b = ya; b <= yb; b++)
-                    if (raster[a * kRasterN + b]) return true;
-            return false;
-        };
-        bool r1 = false, r0 = false;
-        if (j + 1 < ny) r1 = marked(vcell[v + 1]);
-        if (i + 1 < nx) r0 = marked(vcell[v + ny]);
-        rel0[v] = r0;
-        rel1[v] = r1;
-        if (r0) { ext[0] = ext[1] = j; ext[2] = ext[3] = i; }   // pass 0 (axis 0): line = j, segment = i
-        if (r1) { ext[4] = ext[5] = i; ext[6] = ext[7] = j; }   // pass 1 (axis 1): line = i, segment = j
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= kRasterN * (kRasterN / 32)) return;
+    const uint4* src = reinterpret_cast<const uint4*>(raster8 + (size_t)q * 32);
+    uint32_t m = 0;
+#pragma unroll
+    for (int h = 0; h < 2; h++) {
+        const uint4 u = src[h];
+        const uint32_t wds[4] = { u.x, u.y, u.z, u.w };
+#pragma unroll
+        for (int t = 0; t < 4; t++)
+#pragma unroll
+            for (int bq = 0; bq < 4; bq++)
+                if ((wds[t] >> (8 * bq)) & 0xffu) m |= 1u << (h * 16 + t * 4 + bq);
     }
-    if (!__any_sync(0xffffffffu, ext[1] >= 0 || ext[5] >= 0)) return;  // nothing relevant in this warp (the common case)
-#pragma unroll
-    for (int q = 0; q < 8; q++) {
-        int e = ext[q];
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            const int other = __shfl_xor_sync(0xffffffffu, e, o);
-            e = (q & 1) ? max(e, other) : min(e, other);
+    raster[q] = m;
+}
+
+// Relevance of the two sweep segments that start at every OUTPUT vertex (i, j) (pass 1: to (i, j+1); pass 0: to
+// (i+1, j)), the extent of the relevant segments in (line, segment) space and the bounding box of the output grid:
+// ONE streaming pass over the output grid.  A segment is relevant iff a raster cell under its bounding box is marked
+// (indices are clamped to the raster: segments beyond the input grid's bbox can only over-report).  The raster
+// bitmap (32 KB) stays in L1; a warp takes 32 consecutive vertices of a row: the raster cell of the right neighbour
+// comes from the next lane, the one of the lower neighbour from its coordinates (that row is in L2 by the time it is
+// reached again).  Extents and bbox are reduced in registers over the grid-stride loop, then per CTA (a few atomics
+// per CTA).  The kernel is instruction bound (ncu): fp32 raster indices, 32-bit index arithmetic, one-word test when
+// both ends of a segment fall into one raster cell.
+constexpr int kRelThreads = 256;
+__global__ void __launch_bounds__(kRelThreads, 6) k_band_relevance(GridView gout, const double* __restrict__ bbox_in,
+                                                                   const uint32_t* __restrict__ raster,
+                                                                   uint8_t* __restrict__ rel0, uint8_t* __restrict__ rel1,
+                                                                   BandInfo* __restrict__ info, double* __restrict__ bbox_out)
+{
+    __shared__ int s_ext[kRelThreads / 32][8];
+    __shared__ double s_bb[kRelThreads / 32][4];
+    const uint32_t* __restrict__ s_raster = raster;   // 32 KB: stays in L1
+    const int nx = gout.nx, ny = gout.ny;
+    const double x_lo = bbox_in[0], y_lo = bbox_in[1];
+    const float sx = info->sx, sy = info->sy;
+    const int lane = threadIdx.x & 31;
+    int ext[8] = { INT32_MAX, -1, INT32_MAX, -1, INT32_MAX, -1, INT32_MAX, -1 };  // pass 0: Lmin Lmax kmin kmax; pass 1
+    double bxlo = INFINITY, bylo = INFINITY, bxhi = -INFINITY, byhi = -INFINITY;
+    auto cell_of = [&](double x, double y) -> uint32_t {
+        return (unsigned)raster_index(x, x_lo, sx) | ((unsigned)raster_index(y, y_lo, sy) << 16);
+    };
+    auto marked = [&](uint32_t ca, uint32_t cb) -> bool {
+        const int ixa = (int)(ca & 0xffffu), iya = (int)(ca >> 16);
+        if (ca == cb) return (s_raster[ixa * (kRasterN / 32) + (iya >> 5)] >> (iya & 31)) & 1u;   // the common case
+        const int ixb = (int)(cb & 0xffffu), iyb = (int)(cb >> 16);
+        const int xa = min(ixa, ixb), xb = max(ixa, ixb), ya = min(iya, iyb), yb = max(iya, iyb);
+        for (int a = xa; a <= xb; a++)
+            for (int w = ya >> 5; w <= (yb >> 5); w++)
+                if (s_raster[a * (kRasterN / 32) + w] & raster_row_mask(ya, yb, w)) return true;
+        return false;
+    };
+    // a chunk = 32 consecutive vertices of ONE row (the last chunk of a row is partial)
+    const unsigned cpr = (unsigned)(ny + 31) / 32u;
+    const unsigned nchunk = cpr * (unsigned)nx;
+    const unsigned wstride = gridDim.x * (blockDim.x >> 5);
+    unsigned w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    for (; w < nchunk; w += wstride) {
+        const int i = (int)(w / cpr), j = (int)(w - (unsigned)i * cpr) * 32 + lane;
+        const bool in = j < ny;
+        const bool has_r = in && j + 1 < ny, has_d = in && i + 1 < nx;
+        const int64_t v = (int64_t)i * ny + j;
+        double x = 0.0, y = 0.0, xd = 0.0, yd = 0.0;
+        if (in) { x = gout.x[v]; y = gout.y[v]; }
+        if (has_d) { xd = gout.x[v + ny]; yd = gout.y[v + ny]; }
+        const uint32_t c = cell_of(x, y);
+        uint32_t cr = __shfl_down_sync(0xffffffffu, c, 1);
+        if (lane == 31 && has_r) cr = cell_of(gout.x[v + 1], gout.y[v + 1]);
+        const uint32_t cd = cell_of(xd, yd);
+        const bool r1 = has_r && marked(c, cr);
+        const bool r0 = has_d && marked(c, cd);
+        if (in) {
+            rel0[v] = r0;
+            rel1[v] = r1;
+            bxlo = x < bxlo ? x : bxlo; bxhi = x > bxhi ? x : bxhi;
+            bylo = y < bylo ? y : bylo; byhi = y > byhi ? y : byhi;
         }
-        if ((threadIdx.x & 31) == 0 && e != ((q & 1) ? -1 : INT32_MAX)) {
+        if (r0) { ext[0] = min(ext[0], j); ext[1] = max(ext[1], j); ext[2] = min(ext[2], i); ext[3] = max(ext[3], i); }  // pass 0: line = j, segment = i
+        if (r1) { ext[4] = min(ext[4], i); ext[5] = max(ext[5], i); ext[6] = min(ext[6], j); ext[7] = max(ext[7], j); }  // pass 1: line = i, segment = j
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+        for (int q = 0; q < 8; q++) {
+            const int other = __shfl_xor_sync(0xffffffffu, ext[q], o);
+            ext[q] = (q & 1) ? max(ext[q], other) : min(ext[q], other);
+        }
+        bxlo = fmin(bxlo, __shfl_xor_sync(0xffffffffu, bxlo, o));
+        bylo = fmin(bylo, __shfl_xor_sync(0xffffffffu, bylo, o));
+        bxhi = fmax(bxhi, __shfl_xor_sync(0xffffffffu, bxhi, o));
+        byhi = fmax(byhi, __shfl_xor_sync(0xffffffffu, byhi, o));
+    }
+    if (lane == 0) {
+#pragma unroll
+        for (int q = 0; q < 8; q++) s_ext[threadIdx.x >> 5][q] = ext[q];
+        s_bb[threadIdx.x >> 5][0] = bxlo; s_bb[threadIdx.x >> 5][1] = bylo;
+        s_bb[threadIdx.x >> 5][2] = bxhi; s_bb[threadIdx.x >> 5][3] = byhi;
+    }
+    __syncthreads();
+    const int nw = (int)(blockDim.x >> 5);
+    if (threadIdx.x < 8) {
+        const int q = threadIdx.x;
+        int e = s_ext[0][q];
+        for (int u = 1; u < nw; u++) e = (q & 1) ? max(e, s_ext[u][q]) : min(e, s_ext[u][q]);
+        if (e != ((q & 1) ? -1 : INT32_MAX)) {
             if (q & 1) atomicMax(&info->ext[q >> 2][q & 3], e);
             else atomicMin(&info->ext[q >> 2][q & 3], e);
         }
+    } else if (threadIdx.x >= 32 && threadIdx.x < 36) {
+        const int q = threadIdx.x - 32;
+        double e = s_bb[0][q];
+        for (int u = 1; u < nw; u++) e = q < 2 ? fmin(e, s_bb[u][q]) : fmax(e, s_bb[u][q]);
+        if (q < 2) atomic_min_double(&bbox_out[q], e);
+        else atomic_max_double(&bbox_out[q], e);
     }
 }
 
@@ -1605,15 +1681,15 @@ __global__ void k_band_info_full(BandInfo* info, int nx_out, int ny_out)
     // pass 0 (axis 0): line = j, segment = i; pass 1 (axis 1): line = i, segment = j
     info->ext[0][0] = 0; info->ext[0][1] = ny_out - 1; info->ext[0][2] = 0; info->ext[0][3] = nx_out - 2;
     info->ext[1][0] = 0; info->ext[1][1] = nx_out - 1; info->ext[1][2] = 0; info->ext[1][3] = ny_out - 2;
-    info->sx = info->sy = 0.0;
+    info->sx = info->sy = 0.0f;
 }
 
 __global__ void k_band_info_init(BandInfo* info, const double* __restrict__ bbox_in)
 {
     if (threadIdx.x < 8) info->ext[threadIdx.x >> 2][threadIdx.x & 3] = (threadIdx.x & 1) ? -1 : INT32_MAX;
     if (threadIdx.x == 0) {
-        info->sx = kRasterN / (bbox_in[2] - bbox_in[0]);
-        info->sy = kRasterN / (bbox_in[3] - bbox_in[1]);
+        info->sx = (float)(kRasterN / (bbox_in[2] - bbox_in[0]));
+        info->sy = (float)(kRasterN / (bbox_in[3] - bbox_in[1]));
     }
 }
 
@@ -1760,24 +1836,21 @@ __global__ void __launch_bounds__(128, 8) k_band_walk_count(const __grid_constan
     }
 }
 
-__global__ void k_band_chain_check(const __grid_constant__ Pass4 Q, const BandParams B, int32_t* __restrict__ flags)
+// Chain check of one walked segment (folded into the emit walk, which visits the same rectangle): the end state of
+// a walked predecessor must equal the start state this segment used, and the end state of a relevant segment whose
+// successor is not walked must equal the located state of the next vertex.
+// (the predecessor of a RELEVANT segment is always walked; a halo segment's own start is verified by the rank whose
+// band its predecessor touches, or is "outside" by geometry)
+__device__ __forceinline__ bool band_chain_bad(const PassParams& P, const BandParams& B, int L, int k, int64_t v,
+                                               bool relevant, bool next_relevant)
 {
-    const BandInfo& I = *B.info;
-    const int64_t total = I.tstart[4];
-    for (int64_t gtid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; gtid < total; gtid += (int64_t)gridDim.x * blockDim.x) {
-        int p, L, k;
-        if (!band_segment(Q, I, gtid, p, L, k)) continue;
-        const PassParams& P = Q.p[p];
-        const int64_t step = vertex_step(P), v = vertex_of(P, L, k);
-        if (!band_walked(P, B, L, k, v)) continue;
-        bool bad = false;
-        // (the predecessor of a RELEVANT segment is always walked; a halo segment's own start is verified by the rank
-        // whose band its predecessor touches, or is "outside" by geometry)
-        if (k >= 1 && band_walked(P, B, L, k - 1, v - step)) bad = P.seg_end[v - step] != P.seg_start[v];
-        if (band_relevant(P, B, L, k, v) && k + 1 < P.nseg && !band_walked(P, B, L, k + 1, v + step))
-            bad = bad || (P.seg_end[v] != P.guess[v + step]);
-        if (bad) atomicOr(&flags[kFlagBandMismatch], 1);
-    }
+    const int64_t step = vertex_step(P);
+    bool bad = false;
+    if (k >= 1 && (relevant || band_relevant(P, B, L, k - 1, v - step))) bad = P.seg_end[v - step] != P.seg_start[v];
+    if (relevant && k + 1 < P.nseg && !next_relevant &&
+        !(k + 2 < P.nseg && band_relevant(P, B, L, k + 2, v + 2 * step)))
+        bad = bad || (P.seg_end[v] != P.guess[v + step]);
+    return bad;
 }
 
 __global__ void __launch_bounds__(128, 8)
@@ -1793,7 +1866,11 @@ k_band_walk_emit(const __grid_constant__ Pass4 Q, const BandParams B, const int6
         if (!band_segment(Q, I, gtid, p, L, k)) continue;
         const PassParams& P = Q.p[p];
         const int64_t v = vertex_of(P, L, k), v2 = v + vertex_step(P);
-        if (!band_relevant(P, B, L, k, v) || !P.seg_hit[v]) continue;
+        const bool relevant = band_relevant(P, B, L, k, v);
+        const bool next_relevant = k + 1 < P.nseg && band_relevant(P, B, L, k + 1, v2);
+        if (!relevant && !next_relevant) continue;   // not walked
+        if (band_chain_bad(P, B, L, k, v, relevant, next_relevant)) atomicOr(&flags[kFlagBandMismatch], 1);
+        if (!relevant || !P.seg_hit[v]) continue;
         EmitSink sink{ boff, cursor, frag, area_in, w_in, flags, L, k, frag_capacity };
         const int nc = P.pc_n[v];
         if (nc != kPieceNone) {
@@ -1872,7 +1949,6 @@ extern "C" int rg_build2d_band(int device, void* stream,
     RG_CUDA(cudaMemsetAsync(l.flags, 0, sizeof(int32_t) * 8, st));
     RG_CUDA(cudaMemsetAsync(l.hist + cell_lo, 0, sizeof(int32_t) * (size_t)(nb + 1), st));
     RG_CUDA(cudaMemsetAsync(l.cursor + cell_lo, 0, sizeof(int32_t) * (size_t)(nb + 1), st));
-    if (!(row_lo == 0 && row_hi == nxi - 1)) RG_CUDA(cudaMemsetAsync(l.raster, 0, (size_t)kRasterN * kRasterN, st));
     RG_CUDA(cudaMemsetAsync(counts_dev, 0, sizeof(int64_t) * 8, st));
     // areas of the band's cells (k_cell_area works on the rows [row_lo, row_hi) of the grid: a view of those rows would
     // move the peeled first-edge pattern of grid_volume, so the full-grid kernel runs on the band's cell range)
@@ -1884,7 +1960,8 @@ extern "C" int rg_build2d_band(int device, void* stream,
     {
         const GridView gv[2] = { gin, gout };
         double* const bb[2] = { l.bbox, l.bbox + 4 };
-        rc = build_boundaries(st, 2, gv, l.bnd, bb);
+        // (a partial band streams the output grid in k_band_relevance anyway: its bbox is reduced there)
+        rc = build_boundaries(st, 2, gv, l.bnd, bb, (row_lo == 0 && row_hi == nxi - 1) ? 2 : 1);
         if (rc) return rc;
     }
     const Pass4 Q = make_pass4(l, xin, yin, xout, yout, cell_lo, cell_hi, 0, 1);
@@ -1899,12 +1976,12 @@ extern "C" int rg_build2d_band(int device, void* stream,
         k_band_info_full<<<1, 32, 0, st>>>(l.info, (int)nxo, (int)nyo);
     } else {
         k_band_info_init<<<1, 32, 0, st>>>(l.info, l.bbox);
-        k_band_raster<<<(unsigned)ceil_div(nb, T), T, 0, st>>>(gin, (int)row_lo, (int)row_hi, l.bbox, l.info, l.raster);
+        uint8_t* raster8 = l.raster8;
+        RG_CUDA(cudaMemsetAsync(raster8, 0, (size_t)kRasterN * kRasterN, st));
+        k_band_raster<<<(unsigned)ceil_div(nb, T), T, 0, st>>>(gin, (int)row_lo, (int)row_hi, l.bbox, l.info, raster8);
         RG_LAUNCH_CHECK("k_band_raster");
-        // (seg_start of pass 0 is free until the count walk: scratch for the vertices' raster cells)
-        uint32_t* vcell = reinterpret_cast<uint32_t*>(l.seg_start[0]);
-        k_band_vertex_cells<<<(unsigned)ceil_div(l.Vo, T), T, 0, st>>>(gout, l.bbox, l.info, vcell);
-        k_band_relevance<<<(unsigned)ceil_div(l.Vo, T), T, 0, st>>>((int)nxo, (int)nyo, l.raster, vcell, l.rel[0], l.rel[1], l.info);
+        k_band_raster_pack<<<kRasterN * (kRasterN / 32) / 256, 256, 0, st>>>(raster8, l.raster);
+        k_band_relevance<<<kNumSM * 8, kRelThreads, 0, st>>>(gout, l.bbox, l.raster, l.rel[0], l.rel[1], l.info, l.bbox + 4);
         RG_LAUNCH_CHECK("k_band_relevance");
     }
     {
@@ -1922,8 +1999,6 @@ extern "C" int rg_build2d_band(int device, void* stream,
     const unsigned walk_grid = kNumSM * 16;   // grid-stride: the amount of work is only known on the device
     k_band_walk_count<<<walk_grid, 128, 0, st>>>(Q, B, l.hist, l.flags);
     RG_LAUNCH_CHECK("k_band_walk_count");
-    k_band_chain_check<<<kNumSM * 8, T, 0, st>>>(Q, B, l.flags);
-    RG_LAUNCH_CHECK("k_band_chain_check");
     rc = exclusive_scan_i32_i64(st, l.hist + cell_lo, l.boff + cell_lo, nb, l.scan_scratch);
     if (rc) return rc;
     k_band_counts<<<1, 32, 0, st>>>(0, l.boff + cell_hi, frag_capacity, counts_dev, l.flags);
