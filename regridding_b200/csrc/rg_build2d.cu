@@ -960,7 +960,7 @@ struct Layout {
     int32_t* flags;
     // band builds (rg_build2d_band)
     uint8_t* raster8;        // [kRasterN^2] byte marks (plain stores), packed into `raster`
-    uint32_t* raster;        // [kRasterN][kRasterN / 32] bitmap: does a cell of the band touch this cell of the raster over the input bbox?
+    uint32_t* raster;        // [kRasterN^2 / 8] 4 bits per raster cell (k_band_raster_pack): does a cell of the band touch it / its 2x1, 1x2, 2x2 block?
     uint8_t* rel[2];         // [output vertices] can the pass-0 / pass-1 segment starting here have a piece in the band?
     struct BandInfo* info;
     size_t bytes;
@@ -972,6 +972,7 @@ struct BandInfo {            // device memory, written by k_band_finalize
     int64_t tstart[5];       // first thread of every pass in the per-segment launches (multiples of 256)
     int32_t ext[2][4];       // scratch: per OUTPUT pass the extent (Lmin, Lmax, kmin, kmax) of its relevant segments
     float sx, sy;            // raster cells per unit length over the input grid's bbox
+    unsigned long long work[2];   // dynamic work distribution of the count / emit walks: next unclaimed rectangle position
 };
 
 static Layout make_layout(void* ws, int64_t nxi, int64_t nyi, int64_t nxo, int64_t nyo)
@@ -1009,7 +1010,7 @@ static Layout make_layout(void* ws, int64_t nxi, int64_t nyi, int64_t nxo, int64
     l.scan_scratch = c.take<int64_t>(scan_scratch_elems(l.Ci));
     l.flags = c.take<int32_t>(8);
     l.raster8 = c.take<uint8_t>((size_t)kRasterN * kRasterN);
-    l.raster = c.take<uint32_t>((size_t)kRasterN * kRasterN / 32);
+    l.raster = c.take<uint32_t>((size_t)kRasterN * kRasterN / 8);
     l.rel[0] = c.take<uint8_t>(l.Vo);
     l.rel[1] = c.take<uint8_t>(l.Vo);
     l.info = c.take<BandInfo>(1);
@@ -1525,13 +1526,6 @@ __device__ __forceinline__ int raster_index(double x, double lo, float scale)
     return min(max(t, 0), kRasterN - 1);
 }
 
-// bits iy0 .. iy1 of a raster row that fall into its 32-bit word w
-__device__ __forceinline__ uint32_t raster_row_mask(int iy0, int iy1, int w)
-{
-    const int lo = max(iy0 - 32 * w, 0), hi = min(iy1 - 32 * w, 31);
-    return (0xffffffffu >> (31 - hi)) & (0xffffffffu << lo);
-}
-
 // every cell of the band marks the raster cells its bounding box touches
 __global__ void k_band_raster(GridView g, int row_lo, int row_hi, const double* __restrict__ bbox,
                               const BandInfo* __restrict__ info, uint8_t* __restrict__ raster8)
@@ -1552,31 +1546,38 @@ __global__ void k_band_raster(GridView g, int row_lo, int row_hi, const double* 
         for (int iy = iy0; iy <= iy1; iy++) raster8[ix * kRasterN + iy] = 1;   // plain stores: no ordering needed
 }
 
-// byte marks -> bitmap (bit iy & 31 of word [ix][iy >> 5]): 32 KB, read by every warp of k_band_relevance
+// byte marks -> 4 bits per raster cell (x, y), 8 cells per 32-bit word: bit 0 = the cell itself, bit 1 = the cell or
+// (x, y+1), bit 2 = the cell or (x+1, y), bit 3 = any cell of the 2x2 block at (x, y).  A segment whose ends lie in
+// the same or in neighbouring raster cells (every segment of a grid finer than the raster) is then tested EXACTLY
+// with one load: bit (dx << 1 | dy) of the nibble at the lower corner of its raster bounding box.
 __global__ void k_band_raster_pack(const uint8_t* __restrict__ raster8, uint32_t* __restrict__ raster)
 {
-    const int q = blockIdx.x * blockDim.x + threadIdx.x;
-    if (q >= kRasterN * (kRasterN / 32)) return;
-    const uint4* src = reinterpret_cast<const uint4*>(raster8 + (size_t)q * 32);
-    uint32_t m = 0;
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;   // word q holds cells 8q .. 8q+7 of the flattened raster
+    if (q >= kRasterN * kRasterN / 8) return;
+    const int x = (q * 8) / kRasterN, y0 = (q * 8) % kRasterN;
+    const bool has_x1 = x + 1 < kRasterN;
+    uint32_t word = 0;
+    bool r_prev = raster8[x * kRasterN + y0] != 0;
+    bool d_prev = has_x1 && raster8[(x + 1) * kRasterN + y0] != 0;
 #pragma unroll
-    for (int h = 0; h < 2; h++) {
-        const uint4 u = src[h];
-        const uint32_t wds[4] = { u.x, u.y, u.z, u.w };
-#pragma unroll
-        for (int t = 0; t < 4; t++)
-#pragma unroll
-            for (int bq = 0; bq < 4; bq++)
-                if ((wds[t] >> (8 * bq)) & 0xffu) m |= 1u << (h * 16 + t * 4 + bq);
+    for (int t = 0; t < 8; t++) {
+        const int y1 = y0 + t + 1;
+        const bool r_next = y1 < kRasterN && raster8[x * kRasterN + y1] != 0;
+        const bool d_next = has_x1 && y1 < kRasterN && raster8[(x + 1) * kRasterN + y1] != 0;
+        const uint32_t nib = (uint32_t)r_prev | ((uint32_t)(r_prev || r_next) << 1) | ((uint32_t)(r_prev || d_prev) << 2) |
+                             ((uint32_t)(r_prev || r_next || d_prev || d_next) << 3);
+        word |= nib << (4 * t);
+        r_prev = r_next;
+        d_prev = d_next;
     }
-    raster[q] = m;
+    raster[q] = word;
 }
 
 // Relevance of the two sweep segments that start at every OUTPUT vertex (i, j) (pass 1: to (i, j+1); pass 0: to
 // (i+1, j)), the extent of the relevant segments in (line, segment) space and the bounding box of the output grid:
 // ONE streaming pass over the output grid.  A segment is relevant iff a raster cell under its bounding box is marked
-// (indices are clamped to the raster: segments beyond the input grid's bbox can only over-report).  The raster
-// bitmap (32 KB) stays in L1; a warp takes 32 consecutive vertices of a row: the raster cell of the right neighbour
+// (indices are clamped to the raster: segments beyond the input grid's bbox can only over-report).  The packed
+// raster is served by L1; a warp takes 32 consecutive vertices of a row: the raster cell of the right neighbour
 // comes from the next lane, the one of the lower neighbour from its coordinates (that row is in L2 by the time it is
 // reached again).  Extents and bbox are reduced in registers over the grid-stride loop, then per CTA (a few atomics
 // per CTA).  The kernel is instruction bound (ncu): fp32 raster indices, 32-bit index arithmetic, one-word test when
@@ -1589,7 +1590,7 @@ __global__ void __launch_bounds__(kRelThreads, 6) k_band_relevance(GridView gout
 {
     __shared__ int s_ext[kRelThreads / 32][8];
     __shared__ double s_bb[kRelThreads / 32][4];
-    const uint32_t* __restrict__ s_raster = raster;   // 32 KB: stays in L1
+    const uint32_t* __restrict__ s_raster = raster;   // 128 KB, a warp touches one or two sectors of it: served by L1
     const int nx = gout.nx, ny = gout.ny;
     const double x_lo = bbox_in[0], y_lo = bbox_in[1];
     const float sx = info->sx, sy = info->sy;
@@ -1600,13 +1601,18 @@ __global__ void __launch_bounds__(kRelThreads, 6) k_band_relevance(GridView gout
         return (unsigned)raster_index(x, x_lo, sx) | ((unsigned)raster_index(y, y_lo, sy) << 16);
     };
     auto marked = [&](uint32_t ca, uint32_t cb) -> bool {
-        const int ixa = (int)(ca & 0xffffu), iya = (int)(ca >> 16);
-        if (ca == cb) return (s_raster[ixa * (kRasterN / 32) + (iya >> 5)] >> (iya & 31)) & 1u;   // the common case
-        const int ixb = (int)(cb & 0xffffu), iyb = (int)(cb >> 16);
+        const int ixa = (int)(ca & 0xffffu), iya = (int)(ca >> 16), ixb = (int)(cb & 0xffffu), iyb = (int)(cb >> 16);
         const int xa = min(ixa, ixb), xb = max(ixa, ixb), ya = min(iya, iyb), yb = max(iya, iyb);
+        const int dx = xb - xa, dy = yb - ya;
+        if ((dx | dy) <= 1) {   // one load: nibble of the lower corner, bit by the shape of the bounding box
+            const int cell = xa * kRasterN + ya;
+            return (s_raster[cell >> 3] >> (4 * (cell & 7) + ((dx << 1) | dy))) & 1u;
+        }
         for (int a = xa; a <= xb; a++)
-            for (int w = ya >> 5; w <= (yb >> 5); w++)
-                if (s_raster[a * (kRasterN / 32) + w] & raster_row_mask(ya, yb, w)) return true;
+            for (int b = ya; b <= yb; b++) {
+                const int cell = a * kRasterN + b;
+                if ((s_raster[cell >> 3] >> (4 * (cell & 7))) & 1u) return true;
+            }
         return false;
     };
     // a chunk = 32 consecutive vertices of ONE row (the last chunk of a row is partial)
@@ -1682,12 +1688,14 @@ __global__ void k_band_info_full(BandInfo* info, int nx_out, int ny_out)
     info->ext[0][0] = 0; info->ext[0][1] = ny_out - 1; info->ext[0][2] = 0; info->ext[0][3] = nx_out - 2;
     info->ext[1][0] = 0; info->ext[1][1] = nx_out - 1; info->ext[1][2] = 0; info->ext[1][3] = ny_out - 2;
     info->sx = info->sy = 0.0f;
+    info->work[0] = info->work[1] = 0ull;
 }
 
 __global__ void k_band_info_init(BandInfo* info, const double* __restrict__ bbox_in)
 {
     if (threadIdx.x < 8) info->ext[threadIdx.x >> 2][threadIdx.x & 3] = (threadIdx.x & 1) ? -1 : INT32_MAX;
     if (threadIdx.x == 0) {
+        info->work[0] = info->work[1] = 0ull;
         info->sx = (float)(kRasterN / (bbox_in[2] - bbox_in[0]));
         info->sy = (float)(kRasterN / (bbox_in[3] - bbox_in[1]));
     }
@@ -1807,14 +1815,33 @@ __global__ void __launch_bounds__(256) k_band_line_starts(const __grid_constant_
     line_start_body(P, L, bbox2, s_w);
 }
 
+// The walks visit the (line, segment) rectangles of the four passes, of which only the band's stripe is walked: a
+// static assignment leaves some warps with many long walks and others with none, so in the count walk every WARP
+// claims kClaim consecutive positions at a time from a global counter until the rectangles are exhausted (the emit
+// walk replays cached pieces: short, uniform work, for which the static grid-stride loop measured faster).
+constexpr int kClaim = 128;   // positions per claim (one hot counter: ~1 ns per atomic, 4 M positions at config 3)
+__device__ __forceinline__ int64_t band_claim(BandInfo* info, int which)
+{
+    unsigned long long base = 0;
+    if ((threadIdx.x & 31) == 0) base = atomicAdd(&info->work[which], (unsigned long long)kClaim);
+    return (int64_t)__shfl_sync(0xffffffffu, base, 0);
+}
+
 __global__ void __launch_bounds__(128, 8) k_band_walk_count(const __grid_constant__ Pass4 Q, const BandParams B,
                                                             int32_t* __restrict__ hist, int32_t* __restrict__ flags)
 {
     const BandInfo& I = *B.info;
     const int64_t total = I.tstart[4];
-    for (int64_t gtid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; gtid < total; gtid += (int64_t)gridDim.x * blockDim.x) {
+    int64_t claim = 0;
+    for (int sub = kClaim;; sub += 32) {
+        if (sub >= kClaim) {
+            claim = band_claim(const_cast<BandInfo*>(B.info), 0);
+            sub = 0;
+        }
+        if (claim >= total) break;
+        const int64_t gtid = claim + sub + (threadIdx.x & 31);
         int p, L, k;
-        if (!band_segment(Q, I, gtid, p, L, k)) continue;
+        if (gtid >= total || !band_segment(Q, I, gtid, p, L, k)) continue;
         const PassParams& P = Q.p[p];
         const int64_t v = vertex_of(P, L, k), v2 = v + vertex_step(P);
         const bool relevant = band_relevant(P, B, L, k, v);
@@ -1980,7 +2007,7 @@ extern "C" int rg_build2d_band(int device, void* stream,
         RG_CUDA(cudaMemsetAsync(raster8, 0, (size_t)kRasterN * kRasterN, st));
         k_band_raster<<<(unsigned)ceil_div(nb, T), T, 0, st>>>(gin, (int)row_lo, (int)row_hi, l.bbox, l.info, raster8);
         RG_LAUNCH_CHECK("k_band_raster");
-        k_band_raster_pack<<<kRasterN * (kRasterN / 32) / 256, 256, 0, st>>>(raster8, l.raster);
+        k_band_raster_pack<<<kRasterN * kRasterN / 8 / 256, 256, 0, st>>>(raster8, l.raster);
         k_band_relevance<<<kNumSM * 8, kRelThreads, 0, st>>>(gout, l.bbox, l.raster, l.rel[0], l.rel[1], l.info, l.bbox + 4);
         RG_LAUNCH_CHECK("k_band_relevance");
     }
