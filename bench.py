@@ -72,7 +72,10 @@ TRAFFIC_NCU: dict = {"apply_bytes_per_frame": (9.578994e9 + 8.539667e9) / 256,
                                "rg::k_apply_bulk, scaled to this launch's frames (profiles/r2_apply_ncu_summary.txt)"}
 # fp64-pipe utilisation of the build's walk kernels from the committed ncu capture (north_star: "fp64-pipe utilisation
 # for the build"): sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_elapsed, profiles/r2_build_ncu_summary.txt
-BUILD_NCU: dict = {"fp64_pipe_pct": {"k_walk_count": None, "k_walk_emit": None}, "source": None}
+BUILD_NCU: dict = {"fp64_pipe_pct": {"k_walk_count": 18.78, "k_walk_emit": 4.90, "k_vertex_guess": 43.79},
+                   "issue_slots_pct": {"k_walk_count": 70.7, "k_walk_emit": 35.0, "k_bucket_sort": 82.6, "k_bucket_emit": 24.6},
+                   "dram_bytes": {"k_walk_count": 1.989e9, "k_walk_emit": 2.817e9, "k_bucket_sort": 1.919e9, "k_bucket_emit": 1.477e9},
+                   "source": "profiles/r2_build_ncu_summary.txt (ncu --set full of one config-3 build)"}
 FLOPS_PER_PIECE = 64  # 3 edge tests x 17 + 6 intersection point + 4 area + 2 weight divides + 1 negate
 
 
@@ -482,7 +485,8 @@ def run_ours(args):
                 "flops_model": "64 fp64 flops per piece (SURVEY.md 8d), pieces = raw fragments / 2",
                 "achieved": FLOPS_PER_PIECE * ((build_stats.get("fragments") or 0) // 2) / (build_ms * 1e-3) / 1e12,
                 "frac": FLOPS_PER_PIECE * ((build_stats.get("fragments") or 0) // 2) / (build_ms * 1e-3) / 1e12 / fp64_peak,
-                "ncu_fp64_pipe_pct": BUILD_NCU["fp64_pipe_pct"], "ncu_source": BUILD_NCU["source"]},
+                "ncu_fp64_pipe_pct": BUILD_NCU["fp64_pipe_pct"], "ncu_issue_slots_pct": BUILD_NCU["issue_slots_pct"],
+                "ncu_dram_bytes": BUILD_NCU["dram_bytes"], "ncu_source": BUILD_NCU["source"]},
             # config 4 (every orthogonal slice carries its own grid): slices shard across ranks with no collective,
             # every rank runs full builds of its own slices -> aggregate = ranks x the per-rank rate (max over ranks)
             "per_slice_sharded": {"n_gpus": world, "value": world * n_in / (build_ms * 1e-3) / 1e6, "unit": "Mcells/s",
@@ -625,7 +629,8 @@ def extra_configs(dev, rank, world, peak, barrier, max_over_ranks, with_cpu):
         def __getitem__(self, k):
             return tuple(a.numpy() for a in grids[k - rank * per_rank])
 
-    _parallel.build_weights_2d_slices(_Share(), device=dev)  # warm-up (learns the buffer sizes of this shape)
+    for _ in range(2):  # warm-up (the first call learns the buffer sizes of this shape, the second allocates them)
+        _parallel.build_weights_2d_slices(_Share(), device=dev)
     barrier()
     t0 = time.perf_counter()
     built = _parallel.build_weights_2d_slices(_Share(), device=dev)

@@ -144,6 +144,39 @@ def test_build2d_band_build_equals_full(rg, dev, name, world_size):
     assert torch.equal(one.values, parts[-1].values) and torch.equal(one.indices_output, parts[-1].indices_output)
 
 
+def test_build2d_band_replayed_from_graph_with_grids_updated_in_place(rg, dev, monkeypatch):
+    """rg_build2d_band_replay: the identical call (same buffers) is launched directly, then captured, then replayed
+    from a CUDA graph.  The output grid is rewritten IN PLACE between the calls (the per-frame grids of
+    _weights_conservative.py:110-139): every replay must equal a fresh single-GPU build of the current coordinates."""
+    from regridding_b200 import _parallel
+
+    monkeypatch.delenv("RG_NO_BAND_GRAPH", raising=False)
+    n = 161
+    gi, _ = cases.benchmark_family(n, distorted=True)
+    xi, yi = T(gi[0], dev), T(gi[1], dev)
+    xo = torch.empty((n, n), dtype=torch.float64, device=dev)
+    yo = torch.empty((n, n), dtype=torch.float64, device=dev)
+    lo, hi = _parallel.shard_range(n - 1, 1, 3)
+    ncy = n - 1
+    kept = None   # the previous result stays alive for one round, as in `dw = build(...)` loops: two buffer sets alternate
+    for f in range(8):
+        _, go = cases.benchmark_family(n, distorted=True, angle=0.4 + 0.01 * (f // 2), phase=float(f // 2))
+        co = cases.perturb_like_reference(go, (-1, -2), 42)
+        xo.copy_(torch.from_numpy(co[0]))
+        yo.copy_(torch.from_numpy(co[1]))
+        dw, status = rg.device.build2d_band_enqueue(xi, yi, xo, yo, None, lo, hi, device=dev).finish()
+        if status == "capacity":
+            dw, status = rg.device.build2d_band_enqueue(xi, yi, xo, yo, None, lo, hi, device=dev).finish()
+        assert status == "ok", (f, status)
+        full = rg.device.build_weights_2d(xi, yi, xo, yo, device=dev)
+        sel = (full.indices_input >= lo * ncy) & (full.indices_input < hi * ncy)
+        assert torch.equal(dw.indices_input, full.indices_input[sel]), f
+        assert torch.equal(dw.indices_output, full.indices_output[sel]), f
+        assert torch.equal(dw.values, full.values[sel]), f
+        kept = dw
+    assert kept is not None
+
+
 @pytest.mark.parametrize("name,world_size", [("dist129", 2), ("dist129", 3), ("dist129", 8), ("fam100", 5)])
 def test_build2d_line_sharded_equals_full(rg, dev, name, world_size):
     """Line-sharded build (every rank walks 1/W of the sweep lines, fragments exchanged to the band owners,
