@@ -133,18 +133,6 @@ int rg_build2d_band(int device, void* stream,
                     int64_t* indices_input, int64_t* indices_output, double* values, int64_t nnz_capacity,
                     int64_t* counts_dev);
 
-/* rg_build2d_band with the enqueue replayed from a CUDA graph when the SAME call (every size, pointer and capacity)
- * repeats -- grids updated in place and rebuilt (the per-frame grids of _weights_conservative.py:110-139), benchmark
- * loops.  First sighting of a call: plain launches; second: captured; afterwards: one graph launch.  Same arguments,
- * same results, same stream order.  RG_NO_BAND_GRAPH=1 in the environment forces plain launches. */
-int rg_build2d_band_replay(int device, void* stream,
-                    int64_t nx_in, int64_t ny_in, int64_t nx_out, int64_t ny_out,
-                    const double* x_in, const double* y_in, const double* x_out, const double* y_out,
-                    const double* weights_input_or_null, int64_t row_lo, int64_t row_hi,
-                    void* workspace, size_t workspace_bytes,
-                    void* frags, int64_t frag_capacity,
-                    int64_t* indices_input, int64_t* indices_output, double* values, int64_t nnz_capacity,
-                    int64_t* counts_dev);
 
 /* ------------------------------------------------------------------------------
  * Line-sharded 2D build (strong scaling of ONE large build over W ranks).

@@ -318,12 +318,11 @@ def build2d_band_enqueue(x_in, y_in, x_out, y_out, weights_input, row_lo: int, r
         io = torch.empty(ncap, dtype=I64, device=device)
         v = torch.empty(ncap, dtype=F64, device=device)
         counts = torch.empty(8, dtype=I64, device=device)
-        # (replayed from a CUDA graph from the third identical call on: grids rebuilt in place, benchmark loops)
-        _lib.check(L.rg_build2d_band_replay(device.index, st, nxi, nyi, nxo, nyo, xi.data_ptr(), yi.data_ptr(),
-                                            xo.data_ptr(), yo.data_ptr(), _lib.ptr(w), int(row_lo), int(row_hi),
-                                            ws.data_ptr(), ws.numel(), frags.data_ptr(), fcap,
-                                            ii.data_ptr(), io.data_ptr(), v.data_ptr(), ncap, counts.data_ptr()),
-                   "rg_build2d_band_replay")
+        _lib.check(L.rg_build2d_band(device.index, st, nxi, nyi, nxo, nyo, xi.data_ptr(), yi.data_ptr(),
+                                     xo.data_ptr(), yo.data_ptr(), _lib.ptr(w), int(row_lo), int(row_hi),
+                                     ws.data_ptr(), ws.numel(), frags.data_ptr(), fcap,
+                                     ii.data_ptr(), io.data_ptr(), v.data_ptr(), ncap, counts.data_ptr()),
+                   "rg_build2d_band")
     return BandBuild(ii, io, v, counts, fcap, ncap, n_in, n_out, key, (ws, frags, xi, yi, xo, yo, w))
 
 

@@ -2072,106 +2072,3 @@ extern "C" int rg_build2d_batched(int device, void* stream, int64_t n_slices,
     }
     return RG_OK;
 }
-
-// ---------------------------------------------------------------------------
-// rg_build2d_band_replay: the same enqueue as rg_build2d_band, replayed from a CUDA graph when the SAME call (every
-// size, pointer and capacity equal) repeats: grids updated in place and rebuilt frame after frame, benchmark loops.
-// The band build is ~30 short launches and 5 memsets with no host synchronisation between them; replayed as a graph
-// the launches keep their order but lose the per-launch submission and most of the dependency latency between
-// them.  A key is launched directly the first time it is seen (a one-off build pays nothing), captured on its
-// second sighting, replayed afterwards.  The cache holds the last 16 keys.
-// ---------------------------------------------------------------------------
-#include <mutex>
-#include <vector>
-#include <cstring>
-
-namespace {
-
-struct BandKey {
-    int64_t v[24];
-    bool operator==(const BandKey& o) const { return std::memcmp(v, o.v, sizeof(v)) == 0; }
-};
-struct BandGraph {
-    BandKey key;
-    cudaGraphExec_t exec;   // nullptr: seen once, not captured yet
-    uint64_t stamp;
-};
-std::mutex g_band_mutex;
-std::vector<BandGraph> g_band_graphs;
-uint64_t g_band_clock = 0;
-bool g_band_graphs_off = false;
-
-}  // namespace
-
-extern "C" int rg_build2d_band_replay(int device, void* stream,
-                                      int64_t nxi, int64_t nyi, int64_t nxo, int64_t nyo,
-                                      const double* xin, const double* yin, const double* xout, const double* yout,
-                                      const double* w_in, int64_t row_lo, int64_t row_hi,
-                                      void* workspace, size_t workspace_bytes,
-                                      void* frags, int64_t frag_capacity,
-                                      int64_t* ii, int64_t* io, double* v, int64_t nnz_capacity,
-                                      int64_t* counts_dev /* [8] */)
-{
-    auto direct = [&]() {
-        return rg_build2d_band(device, stream, nxi, nyi, nxo, nyo, xin, yin, xout, yout, w_in, row_lo, row_hi, workspace,
-                               workspace_bytes, frags, frag_capacity, ii, io, v, nnz_capacity, counts_dev);
-    };
-    if (g_band_graphs_off || getenv("RG_NO_BAND_GRAPH")) return direct();
-    BandKey key;
-    std::memset(&key, 0, sizeof(key));
-    const int64_t fields[] = { device, (int64_t)(intptr_t)stream, nxi, nyi, nxo, nyo, (int64_t)(intptr_t)xin,
-                               (int64_t)(intptr_t)yin, (int64_t)(intptr_t)xout, (int64_t)(intptr_t)yout,
-                               (int64_t)(intptr_t)w_in, row_lo, row_hi, (int64_t)(intptr_t)workspace,
-                               (int64_t)workspace_bytes, (int64_t)(intptr_t)frags, frag_capacity, (int64_t)(intptr_t)ii,
-                               (int64_t)(intptr_t)io, (int64_t)(intptr_t)v, nnz_capacity, (int64_t)(intptr_t)counts_dev };
-    static_assert(sizeof(fields) <= sizeof(key.v), "key too small");
-    std::memcpy(key.v, fields, sizeof(fields));
-
-    std::lock_guard<std::mutex> lock(g_band_mutex);
-    BandGraph* hit = nullptr;
-    for (auto& g : g_band_graphs)
-        if (g.key == key) { hit = &g; break; }
-    if (!hit) {   // first sighting: remember the key, launch directly
-        if (g_band_graphs.size() >= 16) {
-            size_t oldest = 0;
-            for (size_t q = 1; q < g_band_graphs.size(); q++)
-                if (g_band_graphs[q].stamp < g_band_graphs[oldest].stamp) oldest = q;
-            if (g_band_graphs[oldest].exec) cudaGraphExecDestroy(g_band_graphs[oldest].exec);
-            g_band_graphs.erase(g_band_graphs.begin() + (long)oldest);
-        }
-        g_band_graphs.push_back(BandGraph{ key, nullptr, ++g_band_clock });
-        return direct();
-    }
-    hit->stamp = ++g_band_clock;
-    RG_CUDA(cudaSetDevice(device));
-    cudaStream_t st = (cudaStream_t)stream;
-    if (!hit->exec) {   // second sighting: capture
-        int rc = sort_smem_opt_in(device);   // (attribute calls stay outside the capture)
-        if (rc) return rc;
-        if (cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
-            cudaGetLastError();
-            g_band_graphs_off = true;
-            return direct();
-        }
-        rc = direct();
-        cudaGraph_t graph = nullptr;
-        const cudaError_t e_end = cudaStreamEndCapture(st, &graph);
-        if (rc != RG_OK || e_end != cudaSuccess || !graph) {
-            if (graph) cudaGraphDestroy(graph);
-            cudaGetLastError();
-            g_band_graphs_off = true;   // capture is not available here: plain launches from now on
-            return direct();
-        }
-        cudaGraphExec_t exec = nullptr;
-        const cudaError_t e_inst = cudaGraphInstantiate(&exec, graph, 0);
-        cudaGraphDestroy(graph);
-        if (e_inst != cudaSuccess || !exec) {
-            cudaGetLastError();
-            g_band_graphs_off = true;
-            return direct();
-        }
-        hit->exec = exec;
-    }
-    RG_CUDA(cudaGraphLaunch(hit->exec, st));
-    return RG_OK;
-}

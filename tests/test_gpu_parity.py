@@ -144,13 +144,12 @@ def test_build2d_band_build_equals_full(rg, dev, name, world_size):
     assert torch.equal(one.values, parts[-1].values) and torch.equal(one.indices_output, parts[-1].indices_output)
 
 
-def test_build2d_band_replayed_from_graph_with_grids_updated_in_place(rg, dev, monkeypatch):
-    """rg_build2d_band_replay: the identical call (same buffers) is launched directly, then captured, then replayed
-    from a CUDA graph.  The output grid is rewritten IN PLACE between the calls (the per-frame grids of
-    _weights_conservative.py:110-139): every replay must equal a fresh single-GPU build of the current coordinates."""
+def test_build2d_band_rebuilt_with_grids_updated_in_place(rg, dev):
+    """The band build re-run on the SAME buffers (scratch, learned capacities) while the output grid is rewritten in
+    place between the calls (the per-frame grids of _weights_conservative.py:110-139): every rebuild must equal a fresh
+    single-GPU build of the current coordinates -- nothing of a previous build may leak through the reused workspace."""
     from regridding_b200 import _parallel
 
-    monkeypatch.delenv("RG_NO_BAND_GRAPH", raising=False)
     n = 161
     gi, _ = cases.benchmark_family(n, distorted=True)
     xi, yi = T(gi[0], dev), T(gi[1], dev)
