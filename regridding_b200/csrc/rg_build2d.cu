@@ -33,6 +33,14 @@
 #include "rg_geom.cuh"
 #include "rg_boundary.cuh"
 
+// resident CTAs of 128 threads per SM the walk kernels are compiled for (8 -> 64 registers per thread)
+#ifndef RG_COUNT_MINB
+#define RG_COUNT_MINB 8
+#endif
+#ifndef RG_EMIT_MINB
+#define RG_EMIT_MINB 8
+#endif
+
 namespace rg {
 
 // ---------------------------------------------------------------------------
@@ -475,7 +483,7 @@ __global__ void k_vertex_guess_part(const __grid_constant__ Pass4 Q, int32_t* fl
     if (r == kLocUnknown) atomicAdd(&flags[kFlagUnknown], 1);
 }
 
-__global__ void __launch_bounds__(128, 8) k_walk_count(const __grid_constant__ Pass4 Q, int32_t* __restrict__ hist)
+__global__ void __launch_bounds__(128, RG_COUNT_MINB) k_walk_count(const __grid_constant__ Pass4 Q, int32_t* __restrict__ hist)
 {
     const int64_t gtid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (gtid >= Q.tstart[4]) return;
@@ -560,7 +568,7 @@ __global__ void k_repair(const __grid_constant__ Pass4 Q, int32_t* __restrict__ 
     }
 }
 
-__global__ void __launch_bounds__(128, 8)
+__global__ void __launch_bounds__(128, RG_EMIT_MINB)
 k_walk_emit(const __grid_constant__ Pass4 Q, const int64_t* __restrict__ boff, int32_t* __restrict__ cursor,
             Frag* __restrict__ frag,
             const double* __restrict__ area_in, const double* __restrict__ w_in, int32_t* __restrict__ flags)
@@ -1827,7 +1835,7 @@ __device__ __forceinline__ int64_t band_claim(BandInfo* info, int which)
     return (int64_t)__shfl_sync(0xffffffffu, base, 0);
 }
 
-__global__ void __launch_bounds__(128, 8) k_band_walk_count(const __grid_constant__ Pass4 Q, const BandParams B,
+__global__ void __launch_bounds__(128, RG_COUNT_MINB) k_band_walk_count(const __grid_constant__ Pass4 Q, const BandParams B,
                                                             int32_t* __restrict__ hist, int32_t* __restrict__ flags)
 {
     const BandInfo& I = *B.info;
@@ -1880,7 +1888,7 @@ __device__ __forceinline__ bool band_chain_bad(const PassParams& P, const BandPa
     return bad;
 }
 
-__global__ void __launch_bounds__(128, 8)
+__global__ void __launch_bounds__(128, RG_EMIT_MINB)
 k_band_walk_emit(const __grid_constant__ Pass4 Q, const BandParams B, const int64_t* __restrict__ boff,
                  int32_t* __restrict__ cursor, Frag* __restrict__ frag, int64_t frag_capacity,
                  const double* __restrict__ area_in, const double* __restrict__ w_in, int32_t* __restrict__ flags)
