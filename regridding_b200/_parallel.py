@@ -2,21 +2,17 @@
 Multi-GPU sharding (one process per GPU, ``torch.distributed`` over NCCL/NVLink).
 
 The path shards without any data-path collective:
-  * independent orthogonal slices (spectra of config 2, frames of configs 3/4) are split
-    into contiguous rank ranges (``shard_range``);
-  * one large 2D build is split into contiguous INPUT-ROW bands: the public layout is
-    sorted by input cell first (regridding/_weights/_weights_arrays.py:54-59), so the
-    per-rank results concatenate in rank order with no re-sort.
-The only collective is the optional all-gather of the band triplets when the caller
-wants the full matrix replicated on every rank (e.g. before a frame-sharded apply).
-A banded build still verifies every sweep line end to end (that is what keeps it
-bit-identical to the full build), but the emit walk, the bucket sort and the merge only
-touch the segments / fragments of the rank's own band.
-
-``build_weights_2d_sharded`` is the strong-scaling build: the sweep LINES are dealt out across
-the ranks (every rank walks 1/W of all four passes), the fragments travel to the owner of their
-input-row band in one all-to-all over NVLink, and the owner sorts and merges its band.  Nothing
-is walked twice, and the result is still bit-identical to the single-GPU build.
+  * independent orthogonal slices (spectra of config 2, frames of configs 3/4, the per-slice grids of config 4:
+    ``build_weights_2d_slices``) are split into contiguous rank ranges (``shard_range``);
+  * ONE large 2D build (``build_weights_2d_sharded``) is split into contiguous INPUT-ROW bands: the public layout is
+    sorted by input cell first (regridding/_weights/_weights_arrays.py:54-59), so the per-rank results concatenate
+    in rank order with no re-sort.  ``exchange="band"`` (default): a rank walks only the sweep segments that can
+    reach its band (``rg_build2d_band``) -- no fragment is exchanged, the only collective is a 16-byte all-reduce of
+    status flags.  ``"p2p"`` / ``"nccl"``: the older line-sharded build (sweep lines dealt out across the ranks,
+    fragments read by the band owners over NVLink peer memory or sent by all-to-all).  ``build_weights_2d_banded``:
+    every rank walks everything and keeps its band.
+All of them are bit-identical to the single-GPU build.  The optional all-gather of the band triplets
+(``replicate=True``) is for callers who want the full matrix on every rank (e.g. before a frame-sharded apply).
 """
 
 from __future__ import annotations
@@ -47,11 +43,15 @@ def band_cells(ncx: int, ncy: int, rank: int, world_size: int) -> tuple[int, int
     return r0 * ncy, r1 * ncy
 
 
+_ALLGATHER_CHOICE: dict = {}
+
+
 def allgather_concat(tensors, group=None):
     """Variable-length all-gather along dim 0 of one tensor or of a list of 1-D 8-byte tensors that share their
-    length: every rank gets ``cat([t_0, ..., t_{W-1}])`` of each.  One small collective for the lengths, then
-    ONE all-gather of the tensors packed side by side and padded to the longest band, then one compaction
-    per tensor; works under gloo on CPU too."""
+    length: every rank gets ``cat([t_0, ..., t_{W-1}])`` of each.  One small collective for the lengths, then either
+    ONE all-gather of the tensors packed side by side and padded to the longest band + one compaction per tensor
+    (also the gloo / CPU path), or NCCL broadcasts straight into views of the result; on CUDA the first call times
+    both and later calls take the faster one."""
     single = isinstance(tensors, torch.Tensor)
     ts = [tensors] if single else list(tensors)
     rank, W = world(group)
@@ -68,17 +68,53 @@ def allgather_concat(tensors, group=None):
     if most == 0:
         return tensors
     k = len(ts)
-    if dev.type == "cuda":
-        # NCCL gathers uneven shares straight into views of the result (one grouped broadcast per rank): no padding,
-        # no compaction pass
+    offs = [0]
+    for c in counts_h:
+        offs.append(offs[-1] + c)
+
+    def by_broadcasts():
+        # NCCL gathers uneven shares straight into views of the result (one grouped broadcast per rank and tensor):
+        # no padding, no compaction pass
         outs = []
-        offs = [0]
-        for c in counts_h:
-            offs.append(offs[-1] + c)
         for t in ts:
             full = torch.empty(offs[-1], dtype=t.dtype, device=dev)
             dist.all_gather([full[offs[r]:offs[r + 1]] for r in range(W)], t.contiguous(), group=group)
             outs.append(full)
+        return outs
+
+    def by_padded_allgather():
+        # ONE all_gather_into_tensor (NCCL's own all-gather: rings / NVLS) of the tensors packed side by side and
+        # padded to the longest share, then one compaction (torch.cat of W views) per tensor
+        packed = torch.empty((k, most), dtype=torch.int64, device=dev)
+        for q, t in enumerate(ts):
+            packed[q, :t.shape[0]] = t.contiguous().view(torch.int64)
+        flat = torch.empty(W * k * most, dtype=torch.int64, device=dev)
+        dist.all_gather_into_tensor(flat, packed.view(-1), group=group)
+        gathered = flat.view(W, k, most)
+        return [torch.cat([gathered[r, q, :counts_h[r]] for r in range(W)]).view(t.dtype) for q, t in enumerate(ts)]
+
+    if dev.type == "cuda":
+        # Which of the two is faster depends on the box (NVLS, the NCCL version, message sizes: measured 0.8 and 2.5 ms
+        # for the broadcasts on two 8 x B200 boxes): the first call of a (group size, tensor count, size class) times
+        # both on the device, the ranks agree on the maximum, later calls take the winner.
+        key = (W, k, int(most).bit_length(), dev.index)
+        mode = _ALLGATHER_CHOICE.get(key)
+        if mode is None:
+            times, outs = [], None
+            for fn in (by_broadcasts, by_padded_allgather):
+                fn()  # warm-up (communicator set-up, allocator)
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                outs = fn()
+                e1.record()
+                torch.cuda.synchronize(dev)
+                times.append(e0.elapsed_time(e1))
+            t = torch.tensor(times, dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
+            tb, tp = t.tolist()
+            _ALLGATHER_CHOICE[key] = "broadcasts" if tb <= tp else "padded"
+            return outs[0] if single else outs
+        outs = by_broadcasts() if mode == "broadcasts" else by_padded_allgather()
         return outs[0] if single else outs
     packed = torch.empty((k, most), dtype=torch.int64, device=dev)
     for q, t in enumerate(ts):
