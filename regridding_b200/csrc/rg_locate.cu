@@ -126,35 +126,134 @@ __device__ inline int locate_seeded(const GridView& g, double px, double py, dou
     return r;
 }
 
-// Pass 1: a warp owns a strip of 32 x kLocRun consecutive points; lane k takes the points k, k + 32, ... of the strip
-// (coalesced loads and stores; neighbouring lanes work in neighbouring cells, so the grid loads of a warp share
-// cache lines).  Every point is seeded with the affine map through three corners of the grid PLUS the error that
-// map made at the lane's previous point (32 points earlier: the correction varies slowly), which lands within a
-// fraction of a cell on regular point sets.  A point the iteration cannot place in a cell is classified EXACTLY:
-// outside the vertex bounding box, in an unmarked cell of the occupancy raster, or boundary winding number 0 (the
-// reference's own line-start test, c2d.py:308-317) => `fill`; otherwise it is queued for the exhaustive pass 2.
-__global__ void __launch_bounds__(128)
-k_locate_walk(GridView g, Boundary bnd, const double* __restrict__ bbox, const double* __restrict__ scales,
-              const uint8_t* __restrict__ raster, int64_t n, const double* __restrict__ px, const double* __restrict__ py,
-              int64_t fill, int64_t* __restrict__ out, uint8_t* __restrict__ pending, int32_t* __restrict__ n_pending)
+// Cell walk: from the seed cell, the signs of the four edge cross products either accept the cell or say which edge
+// to cross (1-2 cell tests per point on regular point sets; 24 fp64 operations per test against ~60 for a Newton
+// step with its acceptance test).  With A = c0 + c1 + c2 + c3 (twice the signed area of the quad, whatever the
+// point) and d_k = c_k / A:
+//   * all d_k > 1e-5: the point is strictly inside the intersection of the four inner half-planes (the kernel of the
+//     quad, inside it also for a concave cell), at least ~1e-5 cells from every edge -- eight orders of magnitude
+//     above the rounding error of the products.  The reference's containment predicate (point_is_inside_polygon,
+//     geometry.py:737-829) cannot disagree there, and in a mesh without overlapping cells no lower-index cell
+//     contains an interior point: the cell is the answer;
+//   * some d_k < -1e-5: the point is beyond that edge: step into the neighbour across it;
+//   * anything else (on or within ~1e-5 cells of an edge line, a degenerate cell, a step off the grid, more than
+//     kWalkSteps steps) returns -1 and the point goes to the slow pass (locate_seeded -> locate_newton: exact).
+// (fi, fj) come back as the estimate d3 / (d3 + d1), d0 / (d0 + d2) of the point's index coordinates (exact in a
+// parallelogram): the seed correction for the lane's next point.
+constexpr int kWalkSteps = 6;
+__device__ __forceinline__ int locate_cellwalk(const GridView& g, double px, double py, double& fi, double& fj)
+{
+    const int ncx = g.nx - 1, ncy = g.ny - 1;
+    int i0 = min(max(__double2int_rd(fi), 0), ncx - 1), j0 = min(max(__double2int_rd(fj), 0), ncy - 1);
+#pragma unroll 1
+    for (int it = 0; it < kWalkSteps; it++) {
+        const double* gx = g.x + (i0 * g.ny + j0);
+        const double* gy = g.y + (i0 * g.ny + j0);
+        const double x00 = gx[0], x01 = gx[1], x10 = gx[g.ny], x11 = gx[g.ny + 1];
+        const double y00 = gy[0], y01 = gy[1], y10 = gy[g.ny], y11 = gy[g.ny + 1];
+        // edges in the order (i0,j0)->(i0+1,j0) [side j = j0], ->(i0+1,j0+1) [side i = i0+1], ->(i0,j0+1) [side j = j0+1],
+        // ->(i0,j0) [side i = i0]
+        const double c0 = dfma(x10 - x00, py - y00, -((y10 - y00) * (px - x00)));
+        const double c1 = dfma(x11 - x10, py - y10, -((y11 - y10) * (px - x10)));
+        const double c2 = dfma(x01 - x11, py - y11, -((y01 - y11) * (px - x11)));
+        const double c3 = dfma(x00 - x01, py - y01, -((y00 - y01) * (px - x01)));
+        const double A = (c0 + c1) + (c2 + c3);
+        if (!(fabs(A) > 0.0)) return -1;   // degenerate cell or NaN
+        const double tol = 1e-5 * fabs(A);
+        const double s = A > 0.0 ? 1.0 : -1.0;
+        const double d0 = s * c0, d1 = s * c1, d2 = s * c2, d3 = s * c3;
+        if (d0 > tol && d1 > tol && d2 > tol && d3 > tol) {
+            double r0, r1;
+            const double si = d3 + d1, sj = d0 + d2;
+            asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r0) : "d"(si));
+            asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r1) : "d"(sj));
+            fi = (double)i0 + d3 * r0;
+            fj = (double)j0 + d0 * r1;
+            return i0 * ncy + j0;
+        }
+        int di = 0, dj = 0;
+        if (d1 < -tol) di = 1; else if (d3 < -tol) di = -1;
+        if (d2 < -tol) dj = 1; else if (d0 < -tol) dj = -1;
+        if (di == 0 && dj == 0) return -1;       // within the tolerance of an edge line: slow pass
+        i0 += di;
+        j0 += dj;
+        if (i0 < 0 || j0 < 0 || i0 >= ncx || j0 >= ncy) return -1;   // off the grid: the slow pass classifies the point
+    }
+    return -1;
+}
+
+// affine map (x, y) -> (i, j) through the corners (0, 0), (ncx, 0), (0, ncy) of the grid: rows (m00 m01), (m10 m11)
+struct LocAffine {
+    double x00, y00, m00, m01, m10, m11;
+};
+__device__ __forceinline__ LocAffine loc_affine(const GridView& g)
+{
+    const int ncx = g.nx - 1, ncy = g.ny - 1;
+    LocAffine a = { g.x[0], g.y[0], 0.0, 0.0, 0.0, 0.0 };
+    const double ax = (g.x[(int64_t)ncx * g.ny] - a.x00) / ncx, ay = (g.y[(int64_t)ncx * g.ny] - a.y00) / ncx;
+    const double bx = (g.x[ncy] - a.x00) / ncy, by = (g.y[ncy] - a.y00) / ncy;
+    const double det0 = ax * by - bx * ay;
+    if (det0 != 0.0 && det0 == det0) {
+        a.m00 = by / det0; a.m01 = -bx / det0;
+        a.m10 = -ay / det0; a.m11 = ax / det0;
+    }
+    return a;
+}
+
+// Seed table: the affine map misses the true index coordinates by the grid's distortion (tens of cells); the miss
+// varies slowly, so it is tabulated at a kSeedTab^2 lattice of grid vertices.  A lane's FIRST point has no
+// predecessor to take a correction from: it looks the miss up at its affine index and once more at the corrected
+// one, which leaves an error of a cell or two for the walk.
+constexpr int kSeedTab = 256;
+__global__ void k_locate_seed_table(GridView g, double2* __restrict__ tab)
+{
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= kSeedTab * kSeedTab) return;
+    const int ncx = g.nx - 1, ncy = g.ny - 1;
+    const int a = q / kSeedTab, b = q % kSeedTab;
+    const int i = (int)(((int64_t)a * ncx + (kSeedTab - 1) / 2) / (kSeedTab - 1)), j = (int)(((int64_t)b * ncy + (kSeedTab - 1) / 2) / (kSeedTab - 1));
+    const LocAffine M = loc_affine(g);
+    const double x = g.x[(int64_t)i * g.ny + j], y = g.y[(int64_t)i * g.ny + j];
+    const double ai = M.m00 * (x - M.x00) + M.m01 * (y - M.y00), aj = M.m10 * (x - M.x00) + M.m11 * (y - M.y00);
+    double2 c = make_double2((double)i - ai, (double)j - aj);
+    if (!(c.x == c.x) || !(c.y == c.y)) c = make_double2(0.0, 0.0);
+    tab[q] = c;
+}
+__device__ __forceinline__ double2 loc_seed_lookup(const double2* __restrict__ tab, double i, double j, double si, double sj)
+{
+    const int a = min(max(__double2int_rn(i * si), 0), kSeedTab - 1), b = min(max(__double2int_rn(j * sj), 0), kSeedTab - 1);
+    return tab[a * kSeedTab + b];
+}
+
+constexpr uint8_t kPendSlow = 2;    // pending[]: the cell walk did not settle the point -> k_locate_slow
+constexpr uint8_t kPendBrute = 1;   //            inside the boundary polygon but not placed -> k_locate_brute
+
+// Pass 1 (FAST): a warp owns a strip of 32 x kLocRun consecutive points; lane k takes the points k, k + 32, ... of
+// the strip (coalesced loads and stores; neighbouring lanes work in neighbouring cells, so the grid loads of a warp
+// share cache lines).  Every point is seeded with the affine map through three corners of the grid PLUS the error
+// that map made at the lane's previous point (32 points earlier: the correction varies slowly), which lands within
+// a cell or two on regular point sets, and located by the cell walk.  A point outside the vertex bounding box or in
+// an unmarked cell of the occupancy raster lies in no cell => `fill`.  Whatever the walk does not settle is only
+// FLAGGED: the Newton iteration, the exact predicate and the boundary winding number live in k_locate_slow, so that
+// this kernel -- latency bound on its dependent loads -- needs few registers and runs at full occupancy.
+#ifndef RG_LOC_MINB
+#define RG_LOC_MINB 10
+#endif
+__global__ void __launch_bounds__(128, RG_LOC_MINB)
+k_locate_fast(GridView g, const double* __restrict__ bbox, const double* __restrict__ scales,
+              const uint8_t* __restrict__ raster, const double2* __restrict__ seed_tab, int64_t n,
+              const double* __restrict__ px, const double* __restrict__ py,
+              int64_t fill, int64_t* __restrict__ out, uint8_t* __restrict__ pending, int32_t* __restrict__ counter,
+              uint32_t* __restrict__ queue, int64_t queue_cap)
 {
     const int lane = threadIdx.x & 31;
     const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int64_t p0 = warp * (32 * kLocRun) + lane;
     if (p0 >= n) return;
     const int ncx = g.nx - 1, ncy = g.ny - 1;
-    // affine map (x, y) -> (i, j) through the corners (0, 0), (ncx, 0), (0, ncy)
-    double m00 = 0.0, m01 = 0.0, m10 = 0.0, m11 = 0.0;
-    const double x00 = g.x[0], y00 = g.y[0];
-    {
-        const double ax = (g.x[(int64_t)ncx * g.ny] - x00) / ncx, ay = (g.y[(int64_t)ncx * g.ny] - y00) / ncx;
-        const double bx = (g.x[ncy] - x00) / ncy, by = (g.y[ncy] - y00) / ncy;
-        const double det0 = ax * by - bx * ay;
-        if (det0 != 0.0 && det0 == det0) {
-            m00 = by / det0; m01 = -bx / det0;
-            m10 = -ay / det0; m11 = ax / det0;
-        }
-    }
+    const LocAffine M = loc_affine(g);
+    const double tsi = (double)(kSeedTab - 1) / ncx, tsj = (double)(kSeedTab - 1) / ncy;
+    bool have_c = false;   // does (ci, cj) come from a located predecessor?
     const double bx0 = bbox[0], by0 = bbox[1], bx1 = bbox[2], by1 = bbox[3], sx = scales[0], sy = scales[1];
     double ci = 0.0, cj = 0.0;   // what the affine map missed at the previous point
 #pragma unroll 1
@@ -162,28 +261,77 @@ k_locate_walk(GridView g, Boundary bnd, const double* __restrict__ bbox, const d
         const int64_t p = p0 + 32 * q;
         if (p >= n) break;
         const double x = px[p], y = py[p];
-        const double ai = m00 * (x - x00) + m01 * (y - y00), aj = m10 * (x - x00) + m11 * (y - y00);
-        double i = fmin(fmax(ai + ci, -1.0), (double)ncx + 1.0), j = fmin(fmax(aj + cj, -1.0), (double)ncy + 1.0);
-        if (m00 == 0.0 && m01 == 0.0) { i = 0.5 * g.nx; j = 0.5 * g.ny; }
-        // a point outside the vertex bounding box or in an unmarked cell of the occupancy raster lies in no cell
         const bool maybe = bx0 <= x && x <= bx1 && by0 <= y && y <= by1 &&
                            raster[loc_raster_index(x, bx0, sx) * kLocRaster + loc_raster_index(y, by0, sy)];
         uint8_t pend = 0;
         int64_t res = fill;
         if (maybe) {
-            const int r = locate_seeded(g, x, y, i, j);
-            ci = i - ai;
-            cj = j - aj;
+            const double ai = M.m00 * (x - M.x00) + M.m01 * (y - M.y00), aj = M.m10 * (x - M.x00) + M.m11 * (y - M.y00);
+            if (!have_c) {
+                const double2 c1 = loc_seed_lookup(seed_tab, ai, aj, tsi, tsj);
+                const double2 c2 = loc_seed_lookup(seed_tab, ai + c1.x, aj + c1.y, tsi, tsj);
+                ci = c2.x;
+                cj = c2.y;
+            }
+            double i = fmin(fmax(ai + ci, -1.0), (double)ncx + 1.0), j = fmin(fmax(aj + cj, -1.0), (double)ncy + 1.0);
+            if (M.m00 == 0.0 && M.m01 == 0.0) { i = 0.5 * g.nx; j = 0.5 * g.ny; }
+            const int r = locate_cellwalk(g, x, y, i, j);
             if (r >= 0) {
                 res = r;
-            } else if (boundary_winding(bnd, x, y) != 0.0) {
-                pend = 1;
-                atomicAdd(n_pending, 1);
+                ci = i - ai;
+                cj = j - aj;
+                have_c = true;
+            } else {
+                pend = kPendSlow;
+                const int at = atomicAdd(&counter[1], 1);
+                if (at < queue_cap) queue[at] = (uint32_t)p;
             }
         }
         out[p] = res;
         pending[p] = pend;
     }
+}
+
+// Pass 1b (SLOW): the points the cell walk flagged (0.1-0.3 % at config 5: the band around the grid's boundary and
+// points within ~1e-5 cells of an edge), taken from the queue the fast pass filled -- or, if they did not fit, found
+// by scanning the flags with one thread per point: Newton from the table seed + exact predicate / 3x3 lowest-index resolve
+// (locate_seeded -> locate_newton); a point no cell is found for is classified EXACTLY by the boundary winding
+// number (the reference's own line-start test, c2d.py:308-317): 0 => `fill`, otherwise it is queued for the
+// exhaustive pass 2.
+__global__ void __launch_bounds__(128)
+k_locate_slow(GridView g, Boundary bnd, const double2* __restrict__ seed_tab, int64_t n,
+              const double* __restrict__ px, const double* __restrict__ py,
+              int64_t fill, int64_t* __restrict__ out, uint8_t* __restrict__ pending, int32_t* __restrict__ n_pending,
+              const uint32_t* __restrict__ queue, int64_t n_queue)
+{
+    // queue != nullptr: thread per queued point (dense warps); else thread per point, unflagged threads leave at once
+    int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (queue) {
+        if (p >= n_queue) return;
+        p = queue[p];
+    }
+    if (p >= n || pending[p] != kPendSlow) return;
+    const int ncx = g.nx - 1, ncy = g.ny - 1;
+    const double tsi = (double)(kSeedTab - 1) / ncx, tsj = (double)(kSeedTab - 1) / ncy;
+    const LocAffine M = loc_affine(g);
+    const double x = px[p], y = py[p];
+    const double ai = M.m00 * (x - M.x00) + M.m01 * (y - M.y00), aj = M.m10 * (x - M.x00) + M.m11 * (y - M.y00);
+    const double2 c1 = loc_seed_lookup(seed_tab, ai, aj, tsi, tsj);
+    const double2 c2 = loc_seed_lookup(seed_tab, ai + c1.x, aj + c1.y, tsi, tsj);
+    double i = fmin(fmax(ai + c2.x, -1.0), (double)ncx + 1.0);
+    double j = fmin(fmax(aj + c2.y, -1.0), (double)ncy + 1.0);
+    if (M.m00 == 0.0 && M.m01 == 0.0) { i = 0.5 * g.nx; j = 0.5 * g.ny; }
+    const int r = locate_seeded(g, x, y, i, j);
+    uint8_t pend = 0;
+    int64_t res = fill;
+    if (r >= 0) {
+        res = r;
+    } else if (boundary_winding(bnd, x, y) != 0.0) {
+        pend = kPendBrute;
+        atomicAdd(n_pending, 1);
+    }
+    out[p] = res;
+    pending[p] = pend;
 }
 
 // Pass 2: exhaustive and exact (index_of_point_brute).  One warp per pending point scans
@@ -218,6 +366,9 @@ struct LocateLayout {
     int32_t* counter;
     uint8_t* raster;
     double* scales;
+    double2* seed_tab;   // [kSeedTab^2] what the affine map misses at a coarse lattice of grid vertices
+    uint32_t* queue;     // [queue_cap] points the cell walk did not settle (when they fit and n_points < 2^32)
+    int64_t queue_cap;
     size_t bytes;
 };
 
@@ -231,6 +382,9 @@ static LocateLayout locate_layout(void* ws, int64_t nx, int64_t ny, int64_t n_po
     l.counter = c.take<int32_t>(4);
     l.raster = c.take<uint8_t>((size_t)kLocRaster * kLocRaster);
     l.scales = c.take<double>(2);
+    l.seed_tab = c.take<double2>((size_t)kSeedTab * kSeedTab);
+    l.queue_cap = n_points / 16 + 1024;
+    l.queue = c.take<uint32_t>((size_t)l.queue_cap);
     l.bytes = c.total();
     return l;
 }
@@ -309,12 +463,26 @@ extern "C" int rg_find_indices_2d(int device, void* stream, int64_t nx, int64_t 
     k_locate_raster<<<(unsigned)ceil_div(ceil_div(nx - 1, kLocBlock) * ceil_div(ny - 1, kLocBlock), 256), 256, 0, st>>>(
         g, l.bbox, l.scales, l.raster);
     RG_LAUNCH_CHECK("k_locate_raster");
-    k_locate_walk<<<(unsigned)ceil_div(ceil_div(n_points, 32 * kLocRun) * 32, 128), 128, 0, st>>>(
-        g, l.bnd, l.bbox, l.scales, l.raster, n_points, px, py, fill, cell_flat, l.pending, l.counter);
-    RG_LAUNCH_CHECK("k_locate_walk");
-    int32_t n_pending = 0;
-    RG_CUDA(cudaMemcpyAsync(&n_pending, l.counter, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    k_locate_seed_table<<<kSeedTab * kSeedTab / 256, 256, 0, st>>>(g, l.seed_tab);
+    k_locate_fast<<<(unsigned)ceil_div(ceil_div(n_points, 32 * kLocRun) * 32, 128), 128, 0, st>>>(
+        g, l.bbox, l.scales, l.raster, l.seed_tab, n_points, px, py, fill, cell_flat, l.pending, l.counter, l.queue, l.queue_cap);
+    RG_LAUNCH_CHECK("k_locate_fast");
+    int32_t counters[2] = { 0, 0 };   // [0] points queued for the exhaustive pass, [1] points the cell walk did not settle
+    RG_CUDA(cudaMemcpyAsync(counters, l.counter, sizeof(counters), cudaMemcpyDeviceToHost, st));
     RG_CUDA(cudaStreamSynchronize(st));
+    const int64_t n_slow = counters[1];
+    if (n_slow != 0) {   // (a wrapped 32-bit count is negative: the flags are scanned then)
+        const bool queued = n_slow > 0 && n_slow <= l.queue_cap && n_points < ((int64_t)1 << 31);
+        const int64_t threads = queued ? n_slow : n_points;
+        k_locate_slow<<<(unsigned)ceil_div(threads, 128), 128, 0, st>>>(g, l.bnd, l.seed_tab, n_points, px, py, fill, cell_flat,
+                                                                       l.pending, l.counter, queued ? l.queue : nullptr, n_slow);
+        RG_LAUNCH_CHECK("k_locate_slow");
+        RG_CUDA(cudaMemcpyAsync(counters, l.counter, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+        RG_CUDA(cudaStreamSynchronize(st));
+    }
+    const int32_t n_pending = counters[0];
+    if (getenv("RG_LOC_DEBUG")) fprintf(stderr, "rg_find_indices_2d: %lld points, %d to the slow pass, %d to the exhaustive pass\n",
+                                        (long long)n_points, counters[1], n_pending);
     if (n_pending > 0) {
         int64_t warps = n_points < 148 * 64 ? n_points : 148 * 64;
         k_locate_brute<<<(unsigned)ceil_div(warps * 32, 256), 256, 0, st>>>(g, n_points, px, py, fill, cell_flat, l.pending);
