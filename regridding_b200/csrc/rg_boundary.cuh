@@ -225,6 +225,22 @@ __device__ inline int boundary_entry(const Boundary& b, double px, double py, do
 // point_is_inside_polygon, geometry.py:737-829) around (px, py), evaluated only on the
 // edges whose y-range contains py: every other edge contributes exactly 0, and the
 // contributions are multiples of 1/2, so the sum is exact in any order.
+// contribution of the 32 edges of group g1
+__device__ __forceinline__ double boundary_winding_group(const Boundary& b, int g1, double px, double py)
+{
+    double w = 0.0;
+    const int se = min(b.n_edges, (g1 + 1) * 32);
+    for (int s = g1 * 32; s < se; s++) {
+        const double x0 = dsub(b.x3[s], px), y0 = dsub(b.y3[s], py);
+        const double x1 = dsub(b.x4[s], px), y1 = dsub(b.y4[s], py);
+        // the polygon runs counter-clockwise in index space; the scan-order edges of the
+        // i = 0 face and of the j = ny-1 face run the other way round
+        const bool reversed = (s < b.ne_a0) || (s >= 2 * b.ne_a0 + b.ne_a1);
+        w += reversed ? winding_edge(x1, y1, x0, y0) : winding_edge(x0, y0, x1, y1);
+    }
+    return w;
+}
+
 __device__ inline double boundary_winding(const Boundary& b, double px, double py)
 {
     double w = 0.0;
@@ -235,15 +251,7 @@ __device__ inline double boundary_winding(const Boundary& b, double px, double p
         for (int g1 = g2 * 32; g1 < g1e; g1++) {
             const BBox B1 = b.bb1[g1];
             if (!(B1.ylo <= py && py <= B1.yhi)) continue;
-            const int se = min(b.n_edges, (g1 + 1) * 32);
-            for (int s = g1 * 32; s < se; s++) {
-                const double x0 = dsub(b.x3[s], px), y0 = dsub(b.y3[s], py);
-                const double x1 = dsub(b.x4[s], px), y1 = dsub(b.y4[s], py);
-                // the polygon runs counter-clockwise in index space; the scan-order edges of the
-                // i = 0 face and of the j = ny-1 face run the other way round
-                const bool reversed = (s < b.ne_a0) || (s >= 2 * b.ne_a0 + b.ne_a1);
-                w += reversed ? winding_edge(x1, y1, x0, y0) : winding_edge(x0, y0, x1, y1);
-            }
+            w += boundary_winding_group(b, g1, px, py);
         }
     }
     return w;

@@ -627,6 +627,41 @@ def test_find_indices_2d_matches_reference_locators(rg, dev, oracle, golden):
     assert 0 < n_out < P
 
 
+def test_find_indices_2d_slow_pass_fallbacks(rg, dev, oracle, monkeypatch):
+    """The paths config 5 never takes: the marks do not fit the queue (the slow pass scans the output for its
+    sentinels), no raster-row index of the boundary (box walk), a `fill` equal to the first sentinel value, points on
+    vertices / edges / outside next to the boundary."""
+    g = cases.curvilinear(70, 55, distort=0.01)
+    rng = np.random.default_rng(11)
+    P = 4000
+    px = rng.uniform(g[0].min() - 0.05, g[0].max() + 0.05, P)
+    py = rng.uniform(g[1].min() - 0.05, g[1].max() + 0.05, P)
+    # on vertices, on edge midpoints (tolerance zone of the cell walk) and non-finite
+    k = rng.integers(0, 69, 300), rng.integers(0, 54, 300)
+    px[:300], py[:300] = g[0][k], g[1][k]
+    px[300:600] = 0.5 * (g[0][k] + g[0][k[0] + 1, k[1]])
+    py[300:600] = 0.5 * (g[1][k] + g[1][k[0] + 1, k[1]])
+    px[600], py[601], px[602] = np.nan, np.inf, -np.inf
+    big = np.iinfo(np.int64).max
+    want = np.empty(P, np.int64)
+    for q in range(P):
+        i, j = oracle.index_of_point(g[0], g[1], px[q], py[q], "brute")
+        want[q] = -1 if i == big else i * (g[0].shape[1] - 1) + j
+    args = (T(g[0], dev), T(g[1], dev), T(px, dev), T(py, dev))
+    base = rg.device.find_indices_2d(*args, -1).cpu().numpy()
+    assert np.array_equal(base, want)
+    lo = np.iinfo(np.int64).min
+    got = rg.device.find_indices_2d(*args, lo).cpu().numpy()
+    assert np.array_equal(got, np.where(want < 0, lo, want))
+    monkeypatch.setenv("RG_LOC_QUEUE_CAP", "7")
+    assert np.array_equal(rg.device.find_indices_2d(*args, -1).cpu().numpy(), want)
+    assert np.array_equal(rg.device.find_indices_2d(*args, lo + 1).cpu().numpy(), np.where(want < 0, lo + 1, want))
+    monkeypatch.setenv("RG_LOC_NO_ROWMASK", "1")
+    assert np.array_equal(rg.device.find_indices_2d(*args, -1).cpu().numpy(), want)
+    monkeypatch.delenv("RG_LOC_QUEUE_CAP")
+    assert np.array_equal(rg.device.find_indices_2d(*args, -1).cpu().numpy(), want)
+
+
 def test_multilinear_1d(rg):
     """regridding/_weights/_weights_multilinear_test.py: linear functions are reproduced exactly."""
     x = np.linspace(0, 1, 11)
