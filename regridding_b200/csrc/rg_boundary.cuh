@@ -98,20 +98,33 @@ static __global__ void k_bbox(const __grid_constant__ BoundarySet S)
     double* bbox = S.bbox[blockIdx.y];  // xlo, ylo, xhi, yhi
     const int64_t n = (int64_t)g.nx * g.ny;
     double xlo = INFINITY, ylo = INFINITY, xhi = -INFINITY, yhi = -INFINITY;
-    // four independent loads of each array in flight per thread (the scan is latency bound otherwise)
+    // four independent 16-byte loads of each array in flight per thread (the scan is latency bound otherwise)
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    for (; q + 3 * stride < n; q += 4 * stride) {
-        double x[4], y[4];
+    int64_t done = 0;   // elements covered by the vector loop
+    if (((reinterpret_cast<uintptr_t>(g.x) | reinterpret_cast<uintptr_t>(g.y)) & 15) == 0) {
+        const double2* x2 = reinterpret_cast<const double2*>(g.x);
+        const double2* y2 = reinterpret_cast<const double2*>(g.y);
+        const int64_t n2 = n / 2;
+        int64_t r = q;
+        for (; r + 3 * stride < n2; r += 4 * stride) {
+            double2 x[4], y[4];
 #pragma unroll
-        for (int u = 0; u < 4; u++) { x[u] = g.x[q + u * stride]; y[u] = g.y[q + u * stride]; }
+            for (int u = 0; u < 4; u++) { x[u] = x2[r + u * stride]; y[u] = y2[r + u * stride]; }
 #pragma unroll
-        for (int u = 0; u < 4; u++) {
-            xlo = fmin(xlo, x[u]); xhi = fmax(xhi, x[u]);
-            ylo = fmin(ylo, y[u]); yhi = fmax(yhi, y[u]);
+            for (int u = 0; u < 4; u++) {
+                xlo = fmin(xlo, fmin(x[u].x, x[u].y)); xhi = fmax(xhi, fmax(x[u].x, x[u].y));
+                ylo = fmin(ylo, fmin(y[u].x, y[u].y)); yhi = fmax(yhi, fmax(y[u].x, y[u].y));
+            }
         }
+        for (; r < n2; r += stride) {
+            const double2 x = x2[r], y = y2[r];
+            xlo = fmin(xlo, fmin(x.x, x.y)); xhi = fmax(xhi, fmax(x.x, x.y));
+            ylo = fmin(ylo, fmin(y.x, y.y)); yhi = fmax(yhi, fmax(y.x, y.y));
+        }
+        done = 2 * n2;
     }
-    for (; q < n; q += stride) {
+    for (q += done; q < n; q += stride) {
         const double x = g.x[q], y = g.y[q];
         xlo = fmin(xlo, x); xhi = fmax(xhi, x);
         ylo = fmin(ylo, y); yhi = fmax(yhi, y);

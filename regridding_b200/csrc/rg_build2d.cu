@@ -32,6 +32,7 @@
 #include "rg_common.cuh"
 #include "rg_geom.cuh"
 #include "rg_boundary.cuh"
+#include <mutex>
 
 // resident CTAs of 128 threads per SM the walk kernels are compiled for (8 -> 64 registers per thread)
 #ifndef RG_COUNT_MINB
@@ -965,6 +966,7 @@ struct Layout {
     int32_t* nuniq;
     int64_t* colptr;
     int64_t* scan_scratch;
+    unsigned long long* scan_status[2];   // band build: status words of its two single-launch scans
     int32_t* flags;
     // band builds (rg_build2d_band)
     uint8_t* raster8;        // [kRasterN^2] byte marks (plain stores), packed into `raster`
@@ -1016,6 +1018,8 @@ static Layout make_layout(void* ws, int64_t nxi, int64_t nyi, int64_t nxo, int64
     l.nuniq = c.take<int32_t>(l.Ci + 1);
     l.colptr = c.take<int64_t>(l.Ci + 1);
     l.scan_scratch = c.take<int64_t>(scan_scratch_elems(l.Ci));
+    l.scan_status[0] = c.take<unsigned long long>(2 * scan_status_elems(l.Ci));
+    l.scan_status[1] = l.scan_status[0] + scan_status_elems(l.Ci);
     l.flags = c.take<int32_t>(8);
     l.raster8 = c.take<uint8_t>((size_t)kRasterN * kRasterN);
     l.raster = c.take<uint32_t>((size_t)kRasterN * kRasterN / 8);
@@ -1526,6 +1530,13 @@ struct BandParams {
     const BandInfo* info;
 };
 
+// raster cells per unit length along x (axis 0) / y (axis 1) over the input grid's bbox: ONE expression for the kernel
+// that marks and the kernel that tests
+__device__ __forceinline__ float band_raster_scale(const double* __restrict__ bbox, int axis)
+{
+    return (float)(kRasterN / (bbox[2 + axis] - bbox[axis]));
+}
+
 __device__ __forceinline__ int raster_index(double x, double lo, float scale)
 {
     // any NON-DECREASING function of x does (overlapping intervals then give overlapping index ranges), as long as
@@ -1545,7 +1556,7 @@ __global__ void k_band_raster(GridView g, int row_lo, int row_hi, const double* 
     const int64_t v = (int64_t)a * g.ny + b;
     const double x0 = g.x[v], x1 = g.x[v + 1], x2 = g.x[v + g.ny], x3 = g.x[v + g.ny + 1];
     const double y0 = g.y[v], y1 = g.y[v + 1], y2 = g.y[v + g.ny], y3 = g.y[v + g.ny + 1];
-    const float sx = info->sx, sy = info->sy;
+    const float sx = band_raster_scale(bbox, 0), sy = band_raster_scale(bbox, 1);
     const int ix0 = raster_index(fmin(fmin(x0, x1), fmin(x2, x3)), bbox[0], sx);
     const int ix1 = raster_index(fmax(fmax(x0, x1), fmax(x2, x3)), bbox[0], sx);
     const int iy0 = raster_index(fmin(fmin(y0, y1), fmin(y2, y3)), bbox[1], sy);
@@ -1594,17 +1605,15 @@ constexpr int kRelThreads = 256;
 __global__ void __launch_bounds__(kRelThreads, 6) k_band_relevance(GridView gout, const double* __restrict__ bbox_in,
                                                                    const uint32_t* __restrict__ raster,
                                                                    uint8_t* __restrict__ rel0, uint8_t* __restrict__ rel1,
-                                                                   BandInfo* __restrict__ info, double* __restrict__ bbox_out)
+                                                                   BandInfo* __restrict__ info)
 {
     __shared__ int s_ext[kRelThreads / 32][8];
-    __shared__ double s_bb[kRelThreads / 32][4];
     const uint32_t* __restrict__ s_raster = raster;   // 128 KB, a warp touches one or two sectors of it: served by L1
     const int nx = gout.nx, ny = gout.ny;
     const double x_lo = bbox_in[0], y_lo = bbox_in[1];
-    const float sx = info->sx, sy = info->sy;
+    const float sx = band_raster_scale(bbox_in, 0), sy = band_raster_scale(bbox_in, 1);
     const int lane = threadIdx.x & 31;
     int ext[8] = { INT32_MAX, -1, INT32_MAX, -1, INT32_MAX, -1, INT32_MAX, -1 };  // pass 0: Lmin Lmax kmin kmax; pass 1
-    double bxlo = INFINITY, bylo = INFINITY, bxhi = -INFINITY, byhi = -INFINITY;
     auto cell_of = [&](double x, double y) -> uint32_t {
         return (unsigned)raster_index(x, x_lo, sx) | ((unsigned)raster_index(y, y_lo, sy) << 16);
     };
@@ -1645,8 +1654,6 @@ __global__ void __launch_bounds__(kRelThreads, 6) k_band_relevance(GridView gout
         if (in) {
             rel0[v] = r0;
             rel1[v] = r1;
-            bxlo = x < bxlo ? x : bxlo; bxhi = x > bxhi ? x : bxhi;
-            bylo = y < bylo ? y : bylo; byhi = y > byhi ? y : byhi;
         }
         if (r0) { ext[0] = min(ext[0], j); ext[1] = max(ext[1], j); ext[2] = min(ext[2], i); ext[3] = max(ext[3], i); }  // pass 0: line = j, segment = i
         if (r1) { ext[4] = min(ext[4], i); ext[5] = max(ext[5], i); ext[6] = min(ext[6], j); ext[7] = max(ext[7], j); }  // pass 1: line = i, segment = j
@@ -1658,16 +1665,10 @@ __global__ void __launch_bounds__(kRelThreads, 6) k_band_relevance(GridView gout
             const int other = __shfl_xor_sync(0xffffffffu, ext[q], o);
             ext[q] = (q & 1) ? max(ext[q], other) : min(ext[q], other);
         }
-        bxlo = fmin(bxlo, __shfl_xor_sync(0xffffffffu, bxlo, o));
-        bylo = fmin(bylo, __shfl_xor_sync(0xffffffffu, bylo, o));
-        bxhi = fmax(bxhi, __shfl_xor_sync(0xffffffffu, bxhi, o));
-        byhi = fmax(byhi, __shfl_xor_sync(0xffffffffu, byhi, o));
     }
     if (lane == 0) {
 #pragma unroll
         for (int q = 0; q < 8; q++) s_ext[threadIdx.x >> 5][q] = ext[q];
-        s_bb[threadIdx.x >> 5][0] = bxlo; s_bb[threadIdx.x >> 5][1] = bylo;
-        s_bb[threadIdx.x >> 5][2] = bxhi; s_bb[threadIdx.x >> 5][3] = byhi;
     }
     __syncthreads();
     const int nw = (int)(blockDim.x >> 5);
@@ -1679,33 +1680,43 @@ __global__ void __launch_bounds__(kRelThreads, 6) k_band_relevance(GridView gout
             if (q & 1) atomicMax(&info->ext[q >> 2][q & 3], e);
             else atomicMin(&info->ext[q >> 2][q & 3], e);
         }
-    } else if (threadIdx.x >= 32 && threadIdx.x < 36) {
-        const int q = threadIdx.x - 32;
-        double e = s_bb[0][q];
-        for (int u = 1; u < nw; u++) e = q < 2 ? fmin(e, s_bb[u][q]) : fmax(e, s_bb[u][q]);
-        if (q < 2) atomic_min_double(&bbox_out[q], e);
-        else atomic_max_double(&bbox_out[q], e);
     }
 }
 
-// the band is the whole grid: every segment of the output passes is relevant
-__global__ void k_band_info_full(BandInfo* info, int nx_out, int ny_out)
+// First launch of a band build: status flags and counters cleared, bounding boxes initialised for their reductions,
+// the extents of the relevant output segments reset (or set to everything when the band is the whole grid), and the
+// rectangles of the INPUT-line passes, which are known in closed form: the lines / segments bounding the band's cells.
+__global__ void k_band_begin(const __grid_constant__ Pass4 Q, int row_lo, int row_hi, int full, int nx_out, int ny_out,
+                             int32_t* __restrict__ flags, int64_t* __restrict__ counts, double* __restrict__ bbox2,
+                             BandInfo* __restrict__ info)
 {
-    if (threadIdx.x != 0) return;
-    // pass 0 (axis 0): line = j, segment = i; pass 1 (axis 1): line = i, segment = j
-    info->ext[0][0] = 0; info->ext[0][1] = ny_out - 1; info->ext[0][2] = 0; info->ext[0][3] = nx_out - 2;
-    info->ext[1][0] = 0; info->ext[1][1] = nx_out - 1; info->ext[1][2] = 0; info->ext[1][3] = ny_out - 2;
-    info->sx = info->sy = 0.0f;
+    const int t = threadIdx.x;
+    if (t < 8) {
+        flags[t] = 0;
+        counts[t] = 0;
+        bbox2[t] = ((t & 3) < 2) ? INFINITY : -INFINITY;
+        info->ext[t >> 2][t & 3] = (t & 1) ? -1 : INT32_MAX;
+    }
+    __syncthreads();
+    if (t != 0) return;
     info->work[0] = info->work[1] = 0ull;
-}
-
-__global__ void k_band_info_init(BandInfo* info, const double* __restrict__ bbox_in)
-{
-    if (threadIdx.x < 8) info->ext[threadIdx.x >> 2][threadIdx.x & 3] = (threadIdx.x & 1) ? -1 : INT32_MAX;
-    if (threadIdx.x == 0) {
-        info->work[0] = info->work[1] = 0ull;
-        info->sx = (float)(kRasterN / (bbox_in[2] - bbox_in[0]));
-        info->sy = (float)(kRasterN / (bbox_in[3] - bbox_in[1]));
+    info->sx = info->sy = 0.0f;
+    if (full) {
+        // pass 0 (axis 0): line = j, segment = i; pass 1 (axis 1): line = i, segment = j
+        info->ext[0][0] = 0; info->ext[0][1] = ny_out - 1; info->ext[0][2] = 0; info->ext[0][3] = nx_out - 2;
+        info->ext[1][0] = 0; info->ext[1][1] = nx_out - 1; info->ext[1][2] = 0; info->ext[1][3] = ny_out - 2;
+    }
+    for (int p = 0; p < 4; p++) {
+        const PassParams& P = Q.p[p];
+        if (!P.sweep_input) continue;
+        int L0, nL, k0, nK;
+        if (P.axis) {   // line = input vertex row; lines row_lo .. row_hi bound the band's cells
+            L0 = row_lo; nL = min(row_hi, P.nlines - 1) - row_lo + 1; k0 = 0; nK = P.nseg;
+        } else {        // segment = input row
+            L0 = 0; nL = P.nlines; k0 = max(row_lo - 1, 0); nK = row_hi - k0;
+        }
+        if (nL <= 0 || nK <= 0) { nL = 0; nK = 0; }
+        info->rect[p][0] = L0; info->rect[p][1] = nL; info->rect[p][2] = k0; info->rect[p][3] = nK;
     }
 }
 
@@ -1755,26 +1766,21 @@ __global__ void k_band_guess_in(GridView gin, GridView gout, int64_t v_lo, int64
     if (r == kLocUnknown) atomicAdd(&flags[kFlagUnknown], 1);
 }
 
-// rectangles in (line, segment) space that the per-segment kernels cover, per pass
-__global__ void k_band_finalize(const __grid_constant__ Pass4 Q, int row_lo, int row_hi, BandInfo* info)
+// rectangles in (line, segment) space that the per-segment kernels cover: the OUTPUT-line passes, from the extents
+// of their relevant segments (the input-line passes: k_band_begin), and the first thread of every pass
+__global__ void k_band_finalize(const __grid_constant__ Pass4 Q, BandInfo* info)
 {
     if (threadIdx.x != 0) return;
     for (int p = 0; p < 4; p++) {
         const PassParams& P = Q.p[p];
+        if (P.sweep_input) continue;
         int L0 = 0, nL = 0, k0 = 0, nK = 0;
-        if (!P.sweep_input) {
-            const int* e = info->ext[P.axis];  // ext[0]: pass 0 (axis 0), ext[1]: pass 1 (axis 1)
-            if (e[1] >= e[0] && e[3] >= e[2]) {
-                L0 = e[0]; nL = e[1] - e[0] + 1;
-                k0 = max(e[2] - 1, 0);            // halo: the predecessor of the first relevant segment
-                nK = e[3] - k0 + 1;
-            }
-        } else if (P.axis) {   // pass 3: line = input vertex row; lines row_lo .. row_hi bound the band's cells
-            L0 = row_lo; nL = min(row_hi, P.nlines - 1) - row_lo + 1; k0 = 0; nK = P.nseg;
-        } else {               // pass 2: segment = input row
-            L0 = 0; nL = P.nlines; k0 = max(row_lo - 1, 0); nK = row_hi - k0;
+        const int* e = info->ext[P.axis];  // ext[0]: pass 0 (axis 0), ext[1]: pass 1 (axis 1)
+        if (e[1] >= e[0] && e[3] >= e[2]) {
+            L0 = e[0]; nL = e[1] - e[0] + 1;
+            k0 = max(e[2] - 1, 0);            // halo: the predecessor of the first relevant segment
+            nK = e[3] - k0 + 1;
         }
-        if (nL <= 0 || nK <= 0) { nL = 0; nK = 0; }
         info->rect[p][0] = L0; info->rect[p][1] = nL; info->rect[p][2] = k0; info->rect[p][3] = nK;
     }
     info->tstart[0] = 0;
@@ -1808,12 +1814,14 @@ __device__ __forceinline__ bool band_segment(const Pass4& Q, const BandInfo& I, 
 }
 
 // exact start state of the lines whose first segment is walked (CTA per line of every pass)
+// (`which`: 0 = the output-line passes only, 1 = the input-line passes only, 2 = all four)
 __global__ void __launch_bounds__(256) k_band_line_starts(const __grid_constant__ Pass4 Q, const BandParams B,
-                                                          const double* __restrict__ bbox2)
+                                                          const double* __restrict__ bbox2, int which)
 {
     __shared__ double s_w[8];
     const int p = pass_of_slot(Q, (int)blockIdx.x);
     const PassParams& P = Q.p[p];
+    if (which != 2 && (int)(P.sweep_input != 0) != which) return;
     const int L = (int)blockIdx.x - Q.lstart[p];
     if (L >= P.nlines) return;
     if (P.sweep_input && (P.axis ? (L < B.row_lo || L > B.row_hi) : (B.row_lo > 1))) return;  // known without the rectangle
@@ -1956,6 +1964,32 @@ __global__ void k_band_counts(int stage, const int64_t* __restrict__ total, int6
 
 }  // namespace rg
 
+// side stream + events of the band build's two-stream preparation: one set per device, created on first use
+namespace rg {
+struct BandSide {
+    cudaStream_t stream;
+    cudaEvent_t fork, join;
+};
+static BandSide* band_side(int device)
+{
+    static std::mutex mu;
+    static BandSide* table[64] = { nullptr };
+    if (device < 0 || device >= 64) return nullptr;
+    std::lock_guard<std::mutex> lock(mu);
+    if (!table[device]) {
+        BandSide* b = new BandSide();
+        if (cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking) != cudaSuccess ||
+            cudaEventCreateWithFlags(&b->fork, cudaEventDisableTiming) != cudaSuccess ||
+            cudaEventCreateWithFlags(&b->join, cudaEventDisableTiming) != cudaSuccess) {
+            delete b;
+            return nullptr;
+        }
+        table[device] = b;
+    }
+    return table[device];
+}
+}  // namespace rg
+
 extern "C" int rg_build2d_band(int device, void* stream,
                                int64_t nxi, int64_t nyi, int64_t nxo, int64_t nyo,
                                const double* xin, const double* yin, const double* xout, const double* yout,
@@ -1981,56 +2015,95 @@ extern "C" int rg_build2d_band(int device, void* stream,
     const int64_t ncy = nyi - 1;
     const int64_t cell_lo = row_lo * ncy, cell_hi = row_hi * ncy, nb = cell_hi - cell_lo;
 
-    RG_CUDA(cudaMemsetAsync(l.flags, 0, sizeof(int32_t) * 8, st));
-    RG_CUDA(cudaMemsetAsync(l.hist + cell_lo, 0, sizeof(int32_t) * (size_t)(nb + 1), st));
-    RG_CUDA(cudaMemsetAsync(l.cursor + cell_lo, 0, sizeof(int32_t) * (size_t)(nb + 1), st));
-    RG_CUDA(cudaMemsetAsync(counts_dev, 0, sizeof(int64_t) * 8, st));
-    // areas of the band's cells (k_cell_area works on the rows [row_lo, row_hi) of the grid: a view of those rows would
-    // move the peeled first-edge pattern of grid_volume, so the full-grid kernel runs on the band's cell range)
-    {
-        GridView gb = gin;
-        k_cell_area_range<<<(unsigned)ceil_div(nb, T), T, 0, st>>>(gb, cell_lo, cell_hi, l.area_in);
-        RG_LAUNCH_CHECK("k_cell_area_range");
-    }
-    {
-        const GridView gv[2] = { gin, gout };
-        double* const bb[2] = { l.bbox, l.bbox + 4 };
-        // (a partial band streams the output grid in k_band_relevance anyway: its bbox is reduced there)
-        rc = build_boundaries(st, 2, gv, l.bnd, bb, (row_lo == 0 && row_hi == nxi - 1) ? 2 : 1);
-        if (rc) return rc;
-    }
+    const bool full = row_lo == 0 && row_hi == nxi - 1;
+    BandSide* side = band_side(device);
+    if (!side) return fail((int)cudaErrorUnknown, "rg_build2d_band: cannot create the side stream");
+    cudaStream_t ss = side->stream;
     const Pass4 Q = make_pass4(l, xin, yin, xout, yout, cell_lo, cell_hi, 0, 1);
     BandParams B;
     B.row_lo = (int)row_lo; B.row_hi = (int)row_hi;
     B.rel[0] = l.rel[0]; B.rel[1] = l.rel[1];
     B.info = l.info;
-    if (row_lo == 0 && row_hi == nxi - 1) {
-        // the band is the whole grid (per-slice builds without host synchronisation): everything is relevant
-        RG_CUDA(cudaMemsetAsync(l.rel[0], 1, (size_t)l.Vo, st));
-        RG_CUDA(cudaMemsetAsync(l.rel[1], 1, (size_t)l.Vo, st));
-        k_band_info_full<<<1, 32, 0, st>>>(l.info, (int)nxo, (int)nyo);
-    } else {
-        k_band_info_init<<<1, 32, 0, st>>>(l.info, l.bbox);
-        uint8_t* raster8 = l.raster8;
-        RG_CUDA(cudaMemsetAsync(raster8, 0, (size_t)kRasterN * kRasterN, st));
-        k_band_raster<<<(unsigned)ceil_div(nb, T), T, 0, st>>>(gin, (int)row_lo, (int)row_hi, l.bbox, l.info, raster8);
+    BoundarySet S, S_out;   // both grids / the output grid alone
+    memset(&S, 0, sizeof(S));
+    S.n = 2;
+    S.g[0] = gin; S.g[1] = gout; S.b[0] = l.bnd[0]; S.b[1] = l.bnd[1]; S.bbox[0] = l.bbox; S.bbox[1] = l.bbox + 4;
+    memset(&S_out, 0, sizeof(S_out));
+    S_out.n = 1;
+    S_out.g[0] = gout; S_out.b[0] = l.bnd[1]; S_out.bbox[0] = l.bbox + 4;
+    const int g1max = l.bnd[0].n_g1 > l.bnd[1].n_g1 ? l.bnd[0].n_g1 : l.bnd[1].n_g1;
+    const int g2max = l.bnd[0].n_g2 > l.bnd[1].n_g2 ? l.bnd[0].n_g2 : l.bnd[1].n_g2;
+
+    // The preparation runs on TWO streams.  Everything that leads to the relevant output segments is a chain of short
+    // dependent launches (bbox of the input grid -> raster of the band -> relevance of the output segments -> extents ->
+    // located states of the output vertices); everything else the walks need -- cleared histograms, cell areas, the
+    // bbox of the output grid, the located states of the input vertices around the band and the start states of the
+    // input lines -- does not depend on it and runs beside it on a side stream.
+    k_band_begin<<<1, 32, 0, st>>>(Q, (int)row_lo, (int)row_hi, full ? 1 : 0, (int)nxo, (int)nyo, l.flags, counts_dev, l.bbox, l.info);
+    RG_LAUNCH_CHECK("k_band_begin");
+    k_boundary_edges_bb1<<<dim3((unsigned)ceil_div((int64_t)g1max * 32, T), 2), T, 0, st>>>(S);
+    k_boundary_bb2<<<dim3((unsigned)ceil_div((int64_t)g2max * 32, T), 2), T, 0, st>>>(S);
+    RG_LAUNCH_CHECK("k_boundary");
+    RG_CUDA(cudaEventRecord(side->fork, st));
+    // ---- main stream first (the host enqueues ~20 operations here: the chain the walks wait for goes out first, the
+    // side stream's work is submitted while the GPU already runs it)
+    if (!full) {
+        RG_CUDA(cudaMemsetAsync(l.raster8, 0, (size_t)kRasterN * kRasterN, st));
+        k_bbox<<<dim3(kNumSM * 4, 1), T, 0, st>>>(S);
+        RG_LAUNCH_CHECK("k_bbox");
+        k_band_raster<<<(unsigned)ceil_div(nb, T), T, 0, st>>>(gin, (int)row_lo, (int)row_hi, l.bbox, l.info, l.raster8);
         RG_LAUNCH_CHECK("k_band_raster");
-        k_band_raster_pack<<<kRasterN * kRasterN / 8 / 256, 256, 0, st>>>(raster8, l.raster);
-        k_band_relevance<<<kNumSM * 8, kRelThreads, 0, st>>>(gout, l.bbox, l.raster, l.rel[0], l.rel[1], l.info, l.bbox + 4);
+        k_band_raster_pack<<<kRasterN * kRasterN / 8 / 256, 256, 0, st>>>(l.raster8, l.raster);
+        k_band_relevance<<<kNumSM * 8, kRelThreads, 0, st>>>(gout, l.bbox, l.raster, l.rel[0], l.rel[1], l.info);
         RG_LAUNCH_CHECK("k_band_relevance");
+        k_band_finalize<<<1, 32, 0, st>>>(Q, l.info);
+        k_band_guess_out<<<kNumSM * 8, T, 0, st>>>(gout, gin, l.rel[0], l.rel[1], l.info, l.guess[0], l.flags);
+        RG_LAUNCH_CHECK("k_band_guess_out");
+        k_band_line_starts<<<(unsigned)Q.lstart[4], 256, 0, st>>>(Q, B, l.bbox, 0);
+        RG_LAUNCH_CHECK("k_band_line_starts");
+    } else {
+        k_bbox<<<dim3(kNumSM * 4, 2), T, 0, st>>>(S);
+        RG_LAUNCH_CHECK("k_bbox");
     }
+    // ---- side stream
+    RG_CUDA(cudaStreamWaitEvent(ss, side->fork, 0));
+    if (!full) {
+        k_bbox<<<dim3(kNumSM * 4, 1), T, 0, ss>>>(S_out);
+        RG_LAUNCH_CHECK("k_bbox");
+    }
+    if (full) {
+        // the band is the whole grid (per-slice builds without host synchronisation): everything is relevant
+        RG_CUDA(cudaMemsetAsync(l.rel[0], 1, (size_t)l.Vo, ss));
+        RG_CUDA(cudaMemsetAsync(l.rel[1], 1, (size_t)l.Vo, ss));
+    }
+    RG_CUDA(cudaMemsetAsync(l.scan_status[0], 0, sizeof(unsigned long long) * 2 * scan_status_elems(l.Ci), ss));
+    RG_CUDA(cudaMemsetAsync(l.hist + cell_lo, 0, sizeof(int32_t) * (size_t)(nb + 1), ss));
+    RG_CUDA(cudaMemsetAsync(l.cursor + cell_lo, 0, sizeof(int32_t) * (size_t)(nb + 1), ss));
+    // areas of the band's cells (k_cell_area works on the rows [row_lo, row_hi) of the grid: a view of those rows would
+    // move the peeled first-edge pattern of grid_volume, so the full-grid kernel runs on the band's cell range)
+    k_cell_area_range<<<(unsigned)ceil_div(nb, T), T, 0, ss>>>(gin, cell_lo, cell_hi, l.area_in);
+    RG_LAUNCH_CHECK("k_cell_area_range");
     {
         // input vertices of rows row_lo - 1 .. row_hi + 1: every start / end vertex of a walked segment of passes 2, 3
         const int64_t r0 = row_lo > 0 ? row_lo - 1 : 0, r1 = (row_hi + 2 < nxi ? row_hi + 2 : nxi);
         const int64_t v_lo = r0 * nyi, v_hi = r1 * nyi;
-        k_band_guess_in<<<(unsigned)ceil_div(v_hi - v_lo, T), T, 0, st>>>(gin, gout, v_lo, v_hi, l.guess[1], l.flags);
+        k_band_guess_in<<<(unsigned)ceil_div(v_hi - v_lo, T), T, 0, ss>>>(gin, gout, v_lo, v_hi, l.guess[1], l.flags);
         RG_LAUNCH_CHECK("k_band_guess_in");
     }
-    k_band_finalize<<<1, 32, 0, st>>>(Q, (int)row_lo, (int)row_hi, l.info);
-    k_band_guess_out<<<kNumSM * 8, T, 0, st>>>(gout, gin, l.rel[0], l.rel[1], l.info, l.guess[0], l.flags);
-    RG_LAUNCH_CHECK("k_band_guess_out");
-    k_band_line_starts<<<(unsigned)Q.lstart[4], 256, 0, st>>>(Q, B, l.bbox);
-    RG_LAUNCH_CHECK("k_band_line_starts");
+    if (!full) {
+        k_band_line_starts<<<(unsigned)Q.lstart[4], 256, 0, ss>>>(Q, B, l.bbox, 1);
+        RG_LAUNCH_CHECK("k_band_line_starts");
+    }
+    RG_CUDA(cudaEventRecord(side->join, ss));
+    // ---- join
+    RG_CUDA(cudaStreamWaitEvent(st, side->join, 0));
+    if (full) {
+        k_band_finalize<<<1, 32, 0, st>>>(Q, l.info);
+        k_band_guess_out<<<kNumSM * 8, T, 0, st>>>(gout, gin, l.rel[0], l.rel[1], l.info, l.guess[0], l.flags);
+        RG_LAUNCH_CHECK("k_band_guess_out");
+        k_band_line_starts<<<(unsigned)Q.lstart[4], 256, 0, st>>>(Q, B, l.bbox, 2);
+        RG_LAUNCH_CHECK("k_band_line_starts");
+    }
     // grid-stride: the amount of work of a partial band is only known on the device.  The whole-grid band (per-slice
     // builds) has one position per segment of the four passes: one thread each for the emit, whose scattered stores
     // and cursor atomics want neighbouring segments close in TIME (1.15 ms against 1.97 ms for the persistent loop).
@@ -2044,9 +2117,10 @@ extern "C" int rg_build2d_band(int device, void* stream,
     }
     k_band_walk_count<<<walk_grid, 128, 0, st>>>(Q, B, l.hist, l.flags);
     RG_LAUNCH_CHECK("k_band_walk_count");
-    rc = exclusive_scan_i32_i64(st, l.hist + cell_lo, l.boff + cell_lo, nb, l.scan_scratch);
+    // (single-launch scans; the total goes to counts[0] / counts[1] with the capacity check)
+    rc = exclusive_scan_i32_i64_single(st, l.hist + cell_lo, l.boff + cell_lo, nb, l.scan_status[0], frag_capacity, counts_dev,
+                                       l.flags + kFlagCapacity);
     if (rc) return rc;
-    k_band_counts<<<1, 32, 0, st>>>(0, l.boff + cell_hi, frag_capacity, counts_dev, l.flags);
     // boff of the band starts at 0: cells index it globally (boff[cell]), fragments locally
     k_band_walk_emit<<<emit_grid, 128, 0, st>>>(Q, B, l.boff, l.cursor, (Frag*)frags, frag_capacity, l.area_in, w_in, l.flags);
     RG_LAUNCH_CHECK("k_band_walk_emit");
@@ -2055,9 +2129,9 @@ extern "C" int rg_build2d_band(int device, void* stream,
     k_bucket_sort<<<(unsigned)ceil_div(nb, kSortCells), kSortThreads, sizeof(SortSmem), st>>>(
         l.boff + cell_lo, nb, (Frag*)frags, l.nuniq + cell_lo, l.flags + kFlagCapacity);
     RG_LAUNCH_CHECK("k_bucket_sort");
-    rc = exclusive_scan_i32_i64(st, l.nuniq + cell_lo, l.colptr + cell_lo, nb, l.scan_scratch);
+    rc = exclusive_scan_i32_i64_single(st, l.nuniq + cell_lo, l.colptr + cell_lo, nb, l.scan_status[1], nnz_capacity, counts_dev + 1,
+                                       l.flags + kFlagCapacity);
     if (rc) return rc;
-    k_band_counts<<<1, 32, 0, st>>>(1, l.colptr + cell_hi, nnz_capacity, counts_dev, l.flags);
     k_bucket_emit<<<(unsigned)ceil_div(nb, 256), 256, 0, st>>>(l.boff + cell_lo, 1, cell_lo, l.colptr + cell_lo, nb,
                                                               (const Frag*)frags, ii, io, v, l.flags + kFlagCapacity);
     RG_LAUNCH_CHECK("k_bucket_emit");

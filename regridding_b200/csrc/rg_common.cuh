@@ -66,6 +66,11 @@ constexpr int kScanTile = 2048;
 int exclusive_scan_i32_i64(cudaStream_t st, const int32_t* in, int64_t* out, int64_t n, int64_t* block_sums);
 int exclusive_scan_i32_i32(cudaStream_t st, const int32_t* in, int32_t* out, int64_t n, int64_t* block_sums);
 inline size_t scan_scratch_elems(int64_t n) { return (size_t)ceil_div(n, kScanTile) + 2; }
+// one launch (decoupled look-back); `status_zeroed`: scan_status_elems(n) words, ZERO at entry; optional report of the
+// total with a capacity check (see rg_util.cu)
+int exclusive_scan_i32_i64_single(cudaStream_t st, const int32_t* in, int64_t* out, int64_t n, unsigned long long* status_zeroed,
+                                  int64_t capacity, int64_t* report, int32_t* cap_flag);
+inline size_t scan_status_elems(int64_t n) { return (size_t)ceil_div(n, kScanTile) + 1; }
 
 // ---------------------------------------------------------------------------
 // device arithmetic: every fused multiply-add is explicit (compile with -fmad=false)

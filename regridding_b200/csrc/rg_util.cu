@@ -121,6 +121,102 @@ static int scan_impl(cudaStream_t st, const int32_t* in, OutT* out, int64_t n, i
     return RG_OK;
 }
 
+// ---------------------------------------------------------------------------
+// Single-launch exclusive scan (int32 -> int64) with decoupled look-back: a tile publishes its aggregate, then its
+// inclusive prefix, in one 64-bit status word (2 state bits + 62 value bits); warp 0 of a tile looks back over 32
+// predecessors at a time until it meets an inclusive prefix.  Tiles are numbered by a ticket counter, so a tile's
+// predecessors always started before it.  `status` (scan_status_elems(n) words, the ticket in the last one) must be
+// ZERO at entry.  The last tile also stores the grand total at out[n] and, when `report` is given, at report[0],
+// raising *cap_flag when it exceeds `capacity` (or the int32 range the fragment offsets are kept in).
+// ---------------------------------------------------------------------------
+constexpr unsigned long long kScanAgg = 1ull << 62, kScanInc = 2ull << 62, kScanMask = (1ull << 62) - 1;
+
+template <int THREADS, int ITEMS>
+__global__ void __launch_bounds__(THREADS) k_scan_lookback(const int32_t* __restrict__ in, int64_t* __restrict__ out, int64_t n,
+                                                           unsigned long long* status, int64_t ntiles, int64_t capacity,
+                                                           int64_t* __restrict__ report, int32_t* __restrict__ cap_flag)
+{
+    __shared__ int64_t warp_tot[THREADS / 32];
+    __shared__ int64_t s_prefix;
+    __shared__ unsigned s_tile;
+    if (threadIdx.x == 0) s_tile = atomicAdd((unsigned*)(status + ntiles), 1u);
+    __syncthreads();
+    const int64_t tile = s_tile;
+    const int64_t base = tile * (THREADS * ITEMS) + (int64_t)threadIdx.x * ITEMS;
+    int32_t v[ITEMS];
+    int64_t tsum = 0;
+#pragma unroll
+    for (int q = 0; q < ITEMS; q++) {
+        v[q] = (base + q < n) ? in[base + q] : 0;
+        tsum += v[q];
+    }
+    int64_t inc = tsum;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        int64_t t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += t;
+    }
+    if (lane == 31) warp_tot[wid] = inc;
+    __syncthreads();
+    int64_t woff = 0, total = 0;
+#pragma unroll
+    for (int w = 0; w < THREADS / 32; w++) {
+        if (w < wid) woff += warp_tot[w];
+        total += warp_tot[w];
+    }
+    if (wid == 0) {
+        volatile unsigned long long* vs = status;
+        if (lane == 0) vs[tile] = (tile == 0 ? kScanInc : kScanAgg) | (unsigned long long)total;
+        int64_t prefix = 0;
+        if (tile > 0) {
+            for (int64_t j = tile - 1 - lane;; j -= 32) {   // (tiles before the first count as inclusive 0)
+                unsigned long long sv = kScanInc;
+                if (j >= 0) {
+                    do { sv = vs[j]; } while ((sv >> 62) == 0ull);
+                }
+                const unsigned inc_mask = __ballot_sync(0xffffffffu, (sv >> 62) == 2ull);
+                const int first = inc_mask ? __ffs(inc_mask) - 1 : 32;
+                int64_t val = lane <= first ? (int64_t)(sv & kScanMask) : 0;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) val += __shfl_xor_sync(0xffffffffu, val, o);
+                prefix += val;
+                if (inc_mask) break;
+            }
+            if (lane == 0) vs[tile] = kScanInc | (unsigned long long)(prefix + total);
+        }
+        if (lane == 0) {
+            s_prefix = prefix;
+            if (tile == ntiles - 1) {
+                const int64_t grand = prefix + total;
+                out[n] = grand;
+                if (report) {
+                    report[0] = grand;
+                    if (grand > capacity || grand >= INT32_MAX) *cap_flag = 1;
+                }
+            }
+        }
+    }
+    __syncthreads();
+    int64_t run = s_prefix + woff + (inc - tsum);
+#pragma unroll
+    for (int q = 0; q < ITEMS; q++) {
+        if (base + q < n) out[base + q] = run;
+        run += v[q];
+    }
+}
+
+int exclusive_scan_i32_i64_single(cudaStream_t st, const int32_t* in, int64_t* out, int64_t n, unsigned long long* status_zeroed,
+                                  int64_t capacity, int64_t* report, int32_t* cap_flag)
+{
+    constexpr int THREADS = 256, ITEMS = kScanTile / THREADS;
+    if (n <= 0) return RG_E_ARG;
+    const int64_t ntiles = ceil_div(n, kScanTile);
+    k_scan_lookback<THREADS, ITEMS><<<(unsigned)ntiles, THREADS, 0, st>>>(in, out, n, status_zeroed, ntiles, capacity, report, cap_flag);
+    RG_LAUNCH_CHECK("k_scan_lookback");
+    return RG_OK;
+}
+
 int exclusive_scan_i32_i64(cudaStream_t st, const int32_t* in, int64_t* out, int64_t n, int64_t* block_sums)
 {
     return scan_impl<int64_t>(st, in, out, n, block_sums);
