@@ -17,9 +17,9 @@ measured in the same run and reported in the "build" object of the same JSON lin
 
 Multi-GPU: frames are independent units, so every rank applies the shared weights to its
 own F frames with NO data-path collective ("scaling": "weak"); the 2D build is additionally
-timed as ONE build sharded over the ranks (strong scaling, "build.sharded": every rank walks 1/N of
-the sweep lines, the band owners read the other ranks' fragments over NVLink peer memory and merge
-their band of the weights; "replicated_ms" adds the all-gather that leaves the full matrix on every rank).
+timed as ONE build sharded over the ranks (strong scaling, "build.sharded": rank r builds the band of input
+rows it owns and walks only the sweep segments that can reach it -- no fragments are exchanged, one 16-byte
+all-reduce of status flags; "replicated_ms" adds the all-gather that leaves the full matrix on every rank).
 
 --impl reference: the CPU oracle (a C port of the reference's algorithm, OpenMP over the
 reference's own prange loops) on this box's host cores, same metric / config, bounded sample.
@@ -663,7 +663,7 @@ def extra_configs(dev, rank, world, peak, barrier, max_over_ranks, with_cpu):
         hx, hy = float(X.max() - X.min()) / 2 * scale, float(Y.max() - Y.min()) / 2 * scale
         px = torch.linspace(cx - hx, cx + hx, m, dtype=torch.float64, device=dev)[:, None].expand(m, m).contiguous()
         py = torch.linspace(cy - hy, cy + hy, m, dtype=torch.float64, device=dev)[None, :].expand(m, m).contiguous()
-        ms5, idx = timed(lambda: _device.find_indices_2d(X, Y, px, py, -1), reps=3, warm=1)
+        ms5, idx = timed(lambda: _device.find_indices_2d(X, Y, px, py, -1), reps=5, warm=3)  # (warm: both result buffers allocated)
         c5[name] = {"ms": ms5, "Mpoints_per_s": world * m * m / ms5 / 1e3, "fraction_inside": float((idx >= 0).double().mean()),
                     "roofline": roof((16 + 8) * m * m, ms5)}
         if with_cpu and name == "full_bbox":
