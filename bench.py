@@ -18,8 +18,7 @@ measured in the same run and reported in the "build" object of the same JSON lin
 Multi-GPU: frames are independent units, so every rank applies the shared weights to its
 own F frames with NO data-path collective ("scaling": "weak"); the 2D build is additionally
 timed as ONE build sharded over the ranks (strong scaling, "build.sharded": rank r builds the band of input
-rows it owns and walks only the sweep segments that can reach it -- no fragments are exchanged, one 16-byte
-all-reduce of status flags; "replicated_ms" adds the all-gather that leaves the full matrix on every rank).
+rows it owns and walks only the sweep segments that can reach it -- no fragments are exchanged, no collective; "replicated_ms" adds the all-gather that leaves the full matrix on every rank).
 
 --impl reference: the CPU oracle (a C port of the reference's algorithm, OpenMP over the
 reference's own prange loops) on this box's host cores, same metric / config, bounded sample.
@@ -498,8 +497,8 @@ def run_ours(args):
                 "scaling": "strong", "exchange": exchange["mode"],
                 "equals_single_gpu_build_bitwise_on_every_rank": sharded_equal,
                 "result": "every rank holds its input-row band of the public triplets; exchange=band: every rank walks only "
-                          "the sweep segments that can reach its band, no fragments are exchanged (one 16-byte all-reduce of "
-                          "status flags)",
+                          "the sweep segments that can reach its band and verifies its own walk states: no fragments are "
+                          "exchanged, no collective",
                 "replicated_ms": replicated_ms,
                 "replicated_collective": "all-gather of the band triplets (full matrix on every rank)"},
             "e2e": {"value": n_in / e2e_build_s / 1e6, "unit": "Mcells/s", "seconds": e2e_build_s,

@@ -121,9 +121,12 @@ int rg_build2d_stats(int device, void* stream, int64_t nx_in, int64_t ny_in, int
  * triplets; it walks only the sweep segments whose bounding box meets a cell of the band (exact, see
  * rg_build2d.cu).  Stream-ordered, NO host synchronisation: `frags` (16-byte records) and ii / io / v are sized
  * by the caller's estimate; counts_dev[0] = fragments, [1] = triplets, [2..7] = status flags
- * (2 walk overflow, 3 repairs, 4 unknown guesses, 5 rank overflow, 6 CHAIN MISMATCH -> the caller must OR this
- * over the ranks and, if set anywhere, rebuild with rg_build2d_count/_fill/_emit on the same band,
- * 7 CAPACITY -> buffers too small: reallocate from counts_dev[0..1] and call again). */
+ * (2 walk overflow, 3 repairs, 4 unknown guesses, 5 rank overflow, 6 CHAIN MISMATCH -> a walk state of THIS band
+ * could not be verified (every state a band uses is verified by the band itself: no agreement with other ranks is
+ * needed): rebuild this band with rg_build2d_count/_fill/_emit,
+ * 7 CAPACITY -> buffers too small: reallocate from counts_dev[0..1] and call again).
+ * The preparation runs on the caller's stream and on a library-owned side stream (per device) that is forked from
+ * and joined back into the caller's stream inside the call: the call is stream-ordered for the caller. */
 int rg_build2d_band(int device, void* stream,
                     int64_t nx_in, int64_t ny_in, int64_t nx_out, int64_t ny_out,
                     const double* x_in, const double* y_in, const double* x_out, const double* y_out,

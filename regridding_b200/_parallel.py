@@ -7,8 +7,8 @@ The path shards without any data-path collective:
   * ONE large 2D build (``build_weights_2d_sharded``) is split into contiguous INPUT-ROW bands: the public layout is
     sorted by input cell first (regridding/_weights/_weights_arrays.py:54-59), so the per-rank results concatenate
     in rank order with no re-sort.  ``exchange="band"`` (default): a rank walks only the sweep segments that can
-    reach its band (``rg_build2d_band``) -- no fragment is exchanged, the only collective is a 16-byte all-reduce of
-    status flags.  ``"p2p"`` / ``"nccl"``: the older line-sharded build (sweep lines dealt out across the ranks,
+    reach its band (``rg_build2d_band``) -- no fragment is exchanged and there is no collective at all: every walk
+    state a rank uses is verified by the rank itself.  ``"p2p"`` / ``"nccl"``: the older line-sharded build (sweep lines dealt out across the ranks,
     fragments read by the band owners over NVLink peer memory or sent by all-to-all).  ``build_weights_2d_banded``:
     every rank walks everything and keeps its band.
 All of them are bit-identical to the single-GPU build.  The optional all-gather of the band triplets
@@ -304,23 +304,21 @@ def _sharded_build_nccl(x_in, y_in, x_out, y_out, weights_input, rank, W, bounds
 
 def _sharded_build_band(x_in, y_in, x_out, y_out, weights_input, rank, W, group, device, mark):
     """Exchange-free band build: rank r builds the band of input rows ``shard_range(ncx, r, W)`` by walking only the
-    sweep segments that can reach it (``rg_build2d_band``).  The only collective is an 16-byte all-reduce (MAX) of the
-    status flags: a chain of walk states that does not verify on ANY rank sends every rank to the sequentially
-    verified banded build, a too-small buffer anywhere repeats the build with the learned sizes."""
+    sweep segments that can reach it (``rg_build2d_band``).  NO collective: every walk state a rank uses is verified by
+    the rank itself (chain of walked segments + exact check of every run's first state), so a band that does not
+    verify, or whose buffers were too small, is rebuilt by its own rank without involving the others."""
     nxi, nyi = x_in.shape
     lo, hi = shard_range(nxi - 1, rank, W)
     dev = _device.cuda_device(device if device is not None else (x_in.device if isinstance(x_in, torch.Tensor) else None))
-    status = "mismatch"
-    dw = None
+    if hi <= lo:
+        mark("band")
+        e = torch.empty(0, dtype=torch.int64, device=dev)
+        return _device.DeviceWeights(e, e.clone(), torch.empty(0, dtype=torch.float64, device=dev),
+                                     (nxi - 1) * (nyi - 1), (x_out.shape[0] - 1) * (x_out.shape[1] - 1))
+    status, dw = "mismatch", None
     for _ in range(4):
-        bb = _device.build2d_band_enqueue(x_in, y_in, x_out, y_out, weights_input, lo, hi, device=dev) if hi > lo else None
-        counts = bb.counts if bb is not None else torch.zeros(8, dtype=torch.int64, device=dev)
-        dist.all_reduce(counts[6:8], op=dist.ReduceOp.MAX, group=group)  # mismatch / capacity flags, in place
-        host = counts.cpu()  # the one host synchronisation of the build
-        if bb is None:
-            status = "mismatch" if host[6] else ("capacity" if host[7] else "ok")
-        else:
-            dw, status = bb.finish(host)
+        # (finish(): the one host synchronisation of the build)
+        dw, status = _device.build2d_band_enqueue(x_in, y_in, x_out, y_out, weights_input, lo, hi, device=dev).finish()
         if status != "capacity":
             break
     mark("band")
@@ -328,10 +326,6 @@ def _sharded_build_band(x_in, y_in, x_out, y_out, weights_input, rank, W, group,
         ncy = nyi - 1
         dw = _device.build_weights_2d(x_in, y_in, x_out, y_out, weights_input, cell_band=(lo * ncy, hi * ncy), device=dev)
         mark("fallback")
-    elif dw is None:
-        e = torch.empty(0, dtype=torch.int64, device=dev)
-        dw = _device.DeviceWeights(e, e.clone(), torch.empty(0, dtype=torch.float64, device=dev),
-                                   (nxi - 1) * (nyi - 1), (x_out.shape[0] - 1) * (x_out.shape[1] - 1))
     return dw
 
 

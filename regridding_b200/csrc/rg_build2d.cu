@@ -973,6 +973,8 @@ struct Layout {
     uint32_t* raster;        // [kRasterN^2 / 8] 4 bits per raster cell (k_band_raster_pack): does a cell of the band touch it / its 2x1, 1x2, 2x2 block?
     uint8_t* rel[2];         // [output vertices] can the pass-0 / pass-1 segment starting here have a piece in the band?
     struct BandInfo* info;
+    unsigned long long* vq;  // [vq_cap] pass << 40 | sweep vertex of the run starts located "outside"
+    int64_t vq_cap;
     size_t bytes;
 };
 
@@ -983,6 +985,7 @@ struct BandInfo {            // device memory, written by k_band_finalize
     int32_t ext[2][4];       // scratch: per OUTPUT pass the extent (Lmin, Lmax, kmin, kmax) of its relevant segments
     float sx, sy;            // raster cells per unit length over the input grid's bbox
     unsigned long long work[2];   // dynamic work distribution of the count / emit walks: next unclaimed rectangle position
+    unsigned int vq_n;            // run starts located "outside" that wait for their exact check (k_band_verify_outside)
 };
 
 static Layout make_layout(void* ws, int64_t nxi, int64_t nyi, int64_t nxo, int64_t nyo)
@@ -1026,6 +1029,8 @@ static Layout make_layout(void* ws, int64_t nxi, int64_t nyi, int64_t nxo, int64
     l.rel[0] = c.take<uint8_t>(l.Vo);
     l.rel[1] = c.take<uint8_t>(l.Vo);
     l.info = c.take<BandInfo>(1);
+    l.vq_cap = 8 * (nxo + nyo) + 1024;
+    l.vq = c.take<unsigned long long>((size_t)l.vq_cap);
     l.bytes = c.total();
     return l;
 }
@@ -1512,12 +1517,13 @@ extern "C" int rg_build2d_merge_emit(int device, void* stream, int64_t n_cells, 
 //     segment is RELEVANT iff the raster cells under its own bbox contain a mark: exact and conservative.
 // Exactness of the walk states: the reference walks a line sequentially (c2d.py:324-387); here every walked
 // segment starts from the located cell of its first vertex, and the chain "end state of k-1 == start state of k"
-// is verified for every walked pair -- the predecessor of a relevant segment is always walked too (halo), and
-// the end state of a relevant segment is compared with the located state of the next vertex.  Every pair of a
-// line with a possible piece is therefore verified by the rank(s) that own one of the two; pairs nobody
-// walks lie outside every cell bbox of the static grid (state "outside" on both sides by geometry).  Any
-// mismatch (never observed: it needs a vertex exactly on a cell edge) raises kFlagBandMismatch; the caller
-// ORs the flag over the ranks and falls back to the sequentially verified banded build (rg_build2d_count/_fill).
+// is verified for every walked pair -- the predecessor of a relevant segment is always walked too (halo).  The FIRST
+// segment of a run of walked segments has no walked predecessor: its start state is verified EXACTLY instead
+// (band_start_exact: strictly inside the located cell beyond rounding error, or boundary winding number 0; the first
+// segment of a LINE starts from the exact line-start state).  Every state a rank uses is thus verified by the rank
+// itself -- a band needs no agreement with the other ranks, hence no collective.  Any failure (never observed: it
+// needs a vertex within rounding error of a cell edge) raises kFlagBandMismatch and the caller rebuilds that band
+// with the sequentially verified banded build (rg_build2d_count/_fill), on its own.
 //
 // No host synchronisation inside: buffers are sized by the caller's estimate, overflow raises kFlagCapacity
 // and the counts come back in `counts_dev` (the caller reads them once, after everything was enqueued).
@@ -1528,6 +1534,8 @@ struct BandParams {
     int row_lo, row_hi;        // band of input rows
     const uint8_t* rel[2];     // relevance of the pass-0 / pass-1 segment starting at each output vertex
     const BandInfo* info;
+    unsigned long long* vq;    // run starts located "outside" (filled by the emit walk, checked by k_band_verify_outside)
+    int64_t vq_cap;
 };
 
 // raster cells per unit length along x (axis 0) / y (axis 1) over the input grid's bbox: ONE expression for the kernel
@@ -1701,6 +1709,7 @@ __global__ void k_band_begin(const __grid_constant__ Pass4 Q, int row_lo, int ro
     if (t != 0) return;
     info->work[0] = info->work[1] = 0ull;
     info->sx = info->sy = 0.0f;
+    info->vq_n = 0u;
     if (full) {
         // pass 0 (axis 0): line = j, segment = i; pass 1 (axis 1): line = i, segment = j
         info->ext[0][0] = 0; info->ext[0][1] = ny_out - 1; info->ext[0][2] = 0; info->ext[0][3] = nx_out - 2;
@@ -1879,17 +1888,79 @@ __global__ void __launch_bounds__(128, RG_COUNT_MINB) k_band_walk_count(const __
     }
 }
 
+// EXACT check of the located state of a sweep vertex: the start state of the first segment of a run of walked
+// segments, which no walked predecessor verifies.  "In cell c" holds when the vertex lies strictly inside the
+// intersection of the four inner half-planes of c's edges, by more than the rounding error of the cross products
+// (each is one fused multiply-add of two differences: |error| <= 4 eps (|ex Py| + |ey Px|); the margin asked for is
+// 45 eps) -- in a mesh without overlapping cells the sequential walk of the reference can then only be in c.
+// "Outside" holds when the winding number of the static grid's boundary polygon around the vertex is exactly 0: the
+// reference's own line-start test (c2d.py:308-317).  Anything else (a vertex within rounding error of a cell edge,
+// an unknown state) is not verified: the caller raises the mismatch flag and the band is rebuilt sequentially.
+// (returns 1: verified, 0: not verified, 2: located "outside" -- the caller evaluates the winding number with its
+// whole warp, band_winding_warp)
+__device__ __noinline__ int band_start_exact(const PassParams& P, int64_t v)
+{
+    const int s = P.guess[v];
+    const double px = P.sweep.x[v], py = P.sweep.y[v];
+    if (s == kStateOutside) return 2;
+    if (s < 0) return 0;
+    const GridView& g = P.stat;
+    const int i0 = s / P.ncy_st, j0 = s - i0 * P.ncy_st;
+    const double* gx = g.x + ((int64_t)i0 * g.ny + j0);
+    const double* gy = g.y + ((int64_t)i0 * g.ny + j0);
+    const double x00 = gx[0], x01 = gx[1], x10 = gx[g.ny], x11 = gx[g.ny + 1];
+    const double y00 = gy[0], y01 = gy[1], y10 = gy[g.ny], y11 = gy[g.ny + 1];
+    // edges (i0,j0)->(i0+1,j0)->(i0+1,j0+1)->(i0,j0+1)->(i0,j0): cross product of the edge with (vertex -> point)
+    int pos = 0, neg = 0;
+    auto edge = [&](double ax, double ay, double bx, double by) {
+        const double ex = bx - ax, ey = by - ay, qx = px - ax, qy = py - ay;
+        const double t = ey * qx;
+        const double c = dfma(ex, qy, -t);
+        const double margin = 1e-14 * (fabs(ex * qy) + fabs(t));
+        pos += c > margin;
+        neg += c < -margin;
+    };
+    edge(x00, y00, x10, y10);
+    edge(x10, y10, x11, y11);
+    edge(x11, y11, x01, y01);
+    edge(x01, y01, x00, y00);
+    return (pos == 4 || neg == 4) ? 1 : 0;
+}
+
+// boundary winding number around (px, py), the 32 lanes of the warp sharing the edge groups (all lanes call with the
+// same point; contributions are multiples of 1/2: the partial sums add up exactly in any order)
+__device__ __forceinline__ double band_winding_warp(const Boundary& b, double px, double py)
+{
+    double w = 0.0;
+    for (int g1 = threadIdx.x & 31; g1 < b.n_g1; g1 += 32) {
+        const BBox B1 = b.bb1[g1];
+        if (B1.ylo <= py && py <= B1.yhi) w += boundary_winding_group(b, g1, px, py);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) w += __shfl_xor_sync(0xffffffffu, w, o);
+    return w;
+}
+
 // Chain check of one walked segment (folded into the emit walk, which visits the same rectangle): the end state of
-// a walked predecessor must equal the start state this segment used, and the end state of a relevant segment whose
-// successor is not walked must equal the located state of the next vertex.
-// (the predecessor of a RELEVANT segment is always walked; a halo segment's own start is verified by the rank whose
-// band its predecessor touches, or is "outside" by geometry)
+// a walked predecessor must equal the start state this segment used; the first segment of a run (its predecessor is
+// not walked) must start from an EXACTLY verified state; and the end state of a relevant segment whose successor is
+// not walked must equal the located state of the next vertex.  Every state a rank uses is therefore verified by the
+// rank itself: a band needs no agreement with the other ranks.
+// (`need_winding`: the run starts from a located "outside" -- the caller's warp evaluates the winding number)
 __device__ __forceinline__ bool band_chain_bad(const PassParams& P, const BandParams& B, int L, int k, int64_t v,
-                                               bool relevant, bool next_relevant)
+                                               bool relevant, bool next_relevant, bool& need_winding)
 {
     const int64_t step = vertex_step(P);
     bool bad = false;
-    if (k >= 1 && (relevant || band_relevant(P, B, L, k - 1, v - step))) bad = P.seg_end[v - step] != P.seg_start[v];
+    if (k >= 1) {
+        if (relevant || band_relevant(P, B, L, k - 1, v - step)) {
+            bad = P.seg_end[v - step] != P.seg_start[v];
+        } else {
+            const int e = band_start_exact(P, v);
+            bad = e == 0;
+            need_winding = e == 2;
+        }
+    }
     if (relevant && k + 1 < P.nseg && !next_relevant &&
         !(k + 2 < P.nseg && band_relevant(P, B, L, k + 2, v + 2 * step)))
         bad = bad || (P.seg_end[v] != P.guess[v + step]);
@@ -1905,15 +1976,28 @@ k_band_walk_emit(const __grid_constant__ Pass4 Q, const BandParams B, const int6
     const BandInfo& I = *B.info;
     const int64_t total = I.tstart[4];
     for (int64_t gtid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; gtid < total; gtid += (int64_t)gridDim.x * blockDim.x) {
-        int p, L, k;
-        if (!band_segment(Q, I, gtid, p, L, k)) continue;
+        int p, L = 0, k = 0;
+        const bool seg = band_segment(Q, I, gtid, p, L, k);
         const PassParams& P = Q.p[p];
-        const int64_t v = vertex_of(P, L, k), v2 = v + vertex_step(P);
-        const bool relevant = band_relevant(P, B, L, k, v);
-        const bool next_relevant = k + 1 < P.nseg && band_relevant(P, B, L, k + 1, v2);
-        if (!relevant && !next_relevant) continue;   // not walked
-        if (band_chain_bad(P, B, L, k, v, relevant, next_relevant)) atomicOr(&flags[kFlagBandMismatch], 1);
-        if (!relevant || !P.seg_hit[v]) continue;
+        int64_t v = 0, v2 = 0;
+        bool relevant = false, walked = false, bad = false, need_winding = false;
+        if (seg) {
+            v = vertex_of(P, L, k);
+            v2 = v + vertex_step(P);
+            relevant = band_relevant(P, B, L, k, v);
+            const bool next_relevant = k + 1 < P.nseg && band_relevant(P, B, L, k + 1, v2);
+            walked = relevant || next_relevant;
+            if (walked) bad = band_chain_bad(P, B, L, k, v, relevant, next_relevant, need_winding);
+        }
+        if (need_winding) {
+            // run start located "outside": exact when the boundary winding number is 0.  The starts of neighbouring
+            // lines sit in neighbouring lanes, so they are queued and shared out warp by warp (k_band_verify_outside)
+            const unsigned at = atomicAdd(&const_cast<BandInfo*>(B.info)->vq_n, 1u);
+            if ((int64_t)at < B.vq_cap) B.vq[at] = ((unsigned long long)p << 40) | (unsigned long long)v;
+            else bad = true;
+        }
+        if (bad) atomicOr(&flags[kFlagBandMismatch], 1);
+        if (!walked || !relevant || !P.seg_hit[v]) continue;
         EmitSink sink{ boff, cursor, frag, area_in, w_in, flags, L, k, frag_capacity };
         const int nc = P.pc_n[v];
         if (nc != kPieceNone) {
@@ -1948,6 +2032,22 @@ k_band_walk_emit(const __grid_constant__ Pass4 Q, const BandParams B, const int6
     }
 }
 
+// exact check of the queued run starts that were located "outside": one warp per vertex, the lanes share the boundary
+// edge groups; a non-zero winding number (the vertex is inside the boundary polygon, or on it) is a mismatch
+__global__ void __launch_bounds__(128) k_band_verify_outside(const __grid_constant__ Pass4 Q, const BandParams B,
+                                                             int32_t* __restrict__ flags)
+{
+    const int64_t n = min((int64_t)B.info->vq_n, B.vq_cap);
+    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t t = warp; t < n; t += nwarps) {
+        const unsigned long long e = B.vq[t];
+        const PassParams& P = Q.p[(int)(e >> 40)];
+        const int64_t v = (int64_t)(e & ((1ull << 40) - 1));
+        const double w = band_winding_warp(P.bnd, P.sweep.x[v], P.sweep.y[v]);
+        if ((threadIdx.x & 31) == 0 && w != 0.0) atomicOr(&flags[kFlagBandMismatch], 1);
+    }
+}
+
 // counts[0] = fragments of the band, counts[1] = triplets; capacity flags (stage 0: after the count scan, 1: after the
 // unique-pair scan, 2: final report of all flags)
 __global__ void k_band_counts(int stage, const int64_t* __restrict__ total, int64_t capacity, int64_t* __restrict__ counts,
@@ -1959,6 +2059,7 @@ __global__ void k_band_counts(int stage, const int64_t* __restrict__ total, int6
         if (*total > capacity || *total >= INT32_MAX) flags[kFlagCapacity] = 1;
     } else {
         for (int q = 0; q < 6; q++) counts[2 + q] = flags[q];
+        if (stage == 3) counts[2 + kFlagBandMismatch] = 1;
     }
 }
 
@@ -1968,7 +2069,7 @@ __global__ void k_band_counts(int stage, const int64_t* __restrict__ total, int6
 namespace rg {
 struct BandSide {
     cudaStream_t stream;
-    cudaEvent_t fork, join;
+    cudaEvent_t fork, join, emitted, verified;
 };
 static BandSide* band_side(int device)
 {
@@ -1980,7 +2081,9 @@ static BandSide* band_side(int device)
         BandSide* b = new BandSide();
         if (cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking) != cudaSuccess ||
             cudaEventCreateWithFlags(&b->fork, cudaEventDisableTiming) != cudaSuccess ||
-            cudaEventCreateWithFlags(&b->join, cudaEventDisableTiming) != cudaSuccess) {
+            cudaEventCreateWithFlags(&b->join, cudaEventDisableTiming) != cudaSuccess ||
+            cudaEventCreateWithFlags(&b->emitted, cudaEventDisableTiming) != cudaSuccess ||
+            cudaEventCreateWithFlags(&b->verified, cudaEventDisableTiming) != cudaSuccess) {
             delete b;
             return nullptr;
         }
@@ -2024,6 +2127,7 @@ extern "C" int rg_build2d_band(int device, void* stream,
     B.row_lo = (int)row_lo; B.row_hi = (int)row_hi;
     B.rel[0] = l.rel[0]; B.rel[1] = l.rel[1];
     B.info = l.info;
+    B.vq = l.vq; B.vq_cap = l.vq_cap;
     BoundarySet S, S_out;   // both grids / the output grid alone
     memset(&S, 0, sizeof(S));
     S.n = 2;
@@ -2124,6 +2228,12 @@ extern "C" int rg_build2d_band(int device, void* stream,
     // boff of the band starts at 0: cells index it globally (boff[cell]), fragments locally
     k_band_walk_emit<<<emit_grid, 128, 0, st>>>(Q, B, l.boff, l.cursor, (Frag*)frags, frag_capacity, l.area_in, w_in, l.flags);
     RG_LAUNCH_CHECK("k_band_walk_emit");
+    // the exact check of the run starts located "outside" runs beside the sort / merge
+    RG_CUDA(cudaEventRecord(side->emitted, st));
+    RG_CUDA(cudaStreamWaitEvent(ss, side->emitted, 0));
+    k_band_verify_outside<<<kNumSM * 4, 128, 0, ss>>>(Q, B, l.flags);
+    RG_LAUNCH_CHECK("k_band_verify_outside");
+    RG_CUDA(cudaEventRecord(side->verified, ss));
     rc = sort_smem_opt_in(device);
     if (rc) return rc;
     k_bucket_sort<<<(unsigned)ceil_div(nb, kSortCells), kSortThreads, sizeof(SortSmem), st>>>(
@@ -2135,7 +2245,9 @@ extern "C" int rg_build2d_band(int device, void* stream,
     k_bucket_emit<<<(unsigned)ceil_div(nb, 256), 256, 0, st>>>(l.boff + cell_lo, 1, cell_lo, l.colptr + cell_lo, nb,
                                                               (const Frag*)frags, ii, io, v, l.flags + kFlagCapacity);
     RG_LAUNCH_CHECK("k_bucket_emit");
-    k_band_counts<<<1, 32, 0, st>>>(2, nullptr, 0, counts_dev, l.flags);
+    RG_CUDA(cudaStreamWaitEvent(st, side->verified, 0));
+    // (stage 3: test hook, reports a chain mismatch whatever the walks found)
+    k_band_counts<<<1, 32, 0, st>>>(getenv("RG_BAND_FORCE_MISMATCH") ? 3 : 2, nullptr, 0, counts_dev, l.flags);
     RG_LAUNCH_CHECK("k_band_counts");
     return RG_OK;
 }

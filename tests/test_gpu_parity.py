@@ -144,6 +144,45 @@ def test_build2d_band_build_equals_full(rg, dev, name, world_size):
     assert torch.equal(one.values, parts[-1].values) and torch.equal(one.indices_output, parts[-1].indices_output)
 
 
+def test_build2d_band_unverifiable_states_fall_back(rg, dev, monkeypatch):
+    """A band whose walk states do not all verify must say so ("mismatch") and the wrapper must then rebuild THAT band
+    with the sequentially verified banded build, on its own (no other rank is involved).  Forced through the test hook
+    RG_BAND_FORCE_MISMATCH: grids with sweep vertices within rounding error of a static cell edge -- what the exact check
+    of a run's first state rejects -- are outside the domain of the sweep itself (no walk terminates on them, here as in
+    the reference, which perturbs its output grid for that reason)."""
+    from regridding_b200 import _parallel
+
+    gi, go, _ = cases.case_2d("dist129")
+    co = cases.perturb_like_reference(go, (-1, -2), 42)
+    ncx, ncy = gi[0].shape[0] - 1, gi[0].shape[1] - 1
+
+    def check(xo, yo, world_size, expect=None):
+        full = rg.device.build_weights_2d(gi[0], gi[1], xo, yo, device=dev)
+        seen = []
+        for r in range(world_size):
+            lo, hi = _parallel.shard_range(ncx, r, world_size)
+            t = [T(a, dev) for a in (gi[0], gi[1], xo, yo)]
+            dw, status = rg.device.build2d_band_enqueue(*t, None, lo, hi, device=dev).finish()
+            if status == "capacity":
+                dw, status = rg.device.build2d_band_enqueue(*t, None, lo, hi, device=dev).finish()
+            seen.append(status)
+            sel = (full.indices_input >= lo * ncy) & (full.indices_input < hi * ncy)
+            if status == "ok":
+                assert torch.equal(dw.indices_output, full.indices_output[sel]) and torch.equal(dw.values, full.values[sel]), r
+            one = rg.device.build_weights_2d_band(gi[0], gi[1], xo, yo, None, row_band=(lo, hi), device=dev)
+            assert torch.equal(one.indices_input, full.indices_input[sel]), r
+            assert torch.equal(one.indices_output, full.indices_output[sel]), r
+            assert torch.equal(one.values, full.values[sel]), r
+        if expect is not None:
+            assert all(s == expect for s in seen), seen
+        return seen
+
+    monkeypatch.setenv("RG_BAND_FORCE_MISMATCH", "1")
+    check(co[0], co[1], 3, expect="mismatch")
+    monkeypatch.delenv("RG_BAND_FORCE_MISMATCH")
+    check(co[0], co[1], 3, expect="ok")
+
+
 def test_build2d_band_rebuilt_with_grids_updated_in_place(rg, dev):
     """The band build re-run on the SAME buffers (scratch, learned capacities) while the output grid is rewritten in
     place between the calls (the per-frame grids of _weights_conservative.py:110-139): every rebuild must equal a fresh
