@@ -121,7 +121,7 @@ int rg_build2d_stats(int device, void* stream, int64_t nx_in, int64_t ny_in, int
  * triplets; it walks only the sweep segments whose bounding box meets a cell of the band (exact, see
  * rg_build2d.cu).  Stream-ordered, NO host synchronisation: `frags` (16-byte records) and ii / io / v are sized
  * by the caller's estimate; counts_dev[0] = fragments, [1] = triplets, [2..7] = status flags
- * (2 walk overflow, 3 repairs, 4 unknown guesses, 5 rank overflow, 6 CHAIN MISMATCH -> a walk state of THIS band
+ * (2 walk overflow, 3 longest bucket (fragments of one input cell), 4 unknown guesses, 5 rank overflow, 6 CHAIN MISMATCH -> a walk state of THIS band
  * could not be verified (every state a band uses is verified by the band itself: no agreement with other ranks is
  * needed): rebuild this band with rg_build2d_count/_fill/_emit,
  * 7 CAPACITY -> buffers too small: reallocate from counts_dev[0..1] and call again).
@@ -135,6 +135,19 @@ int rg_build2d_band(int device, void* stream,
                     void* frags, int64_t frag_capacity,
                     int64_t* indices_input, int64_t* indices_output, double* values, int64_t nnz_capacity,
                     int64_t* counts_dev);
+/* The same band in ONE walk (no count walk, no replay): every input cell of the band owns `bucket_capacity` slots of
+ * `frags_strided` ((row_hi - row_lo) * (ny_in - 1) * bucket_capacity records of 16 bytes); the sort gathers the
+ * buckets from there into `frags`.  rg_build2d_band reports the longest bucket of a build in counts_dev[3]: size
+ * bucket_capacity from it (a little above) when the same shape is built again.  A bucket that overflows raises the
+ * CAPACITY flag (counts_dev[7]): build with rg_build2d_band instead.  Results are identical to rg_build2d_band's. */
+int rg_build2d_band_onewalk(int device, void* stream,
+                            int64_t nx_in, int64_t ny_in, int64_t nx_out, int64_t ny_out,
+                            const double* x_in, const double* y_in, const double* x_out, const double* y_out,
+                            const double* weights_input_or_null, int64_t row_lo, int64_t row_hi,
+                            void* workspace, size_t workspace_bytes,
+                            void* frags, int64_t frag_capacity,
+                            int64_t* indices_input, int64_t* indices_output, double* values, int64_t nnz_capacity,
+                            int64_t* counts_dev, void* frags_strided, int64_t bucket_capacity);
 
 
 /* ------------------------------------------------------------------------------

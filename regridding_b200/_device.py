@@ -10,6 +10,7 @@ from __future__ import annotations
 
 import ctypes
 import dataclasses
+import os
 import warnings
 
 import numpy as np
@@ -236,6 +237,8 @@ def build_weights_2d(x_in, y_in, x_out, y_out, weights_input=None, cell_band: tu
 
 # learned buffer sizes of band builds: (shape, band) -> (fragments, triplets) of the previous build
 _band_caps: dict = {}
+_band_buckets: dict = {}          # (device, stream, band cells, bucket capacity) -> strided fragment buckets
+_band_onewalk_failed: set = set()   # shapes whose one-walk build overflowed its buckets: two walks from then on
 # scratch of the last band build shape: (workspace, fragment buffer); stream-ordered reuse on the current stream
 _band_scratch: dict = {}
 
@@ -255,6 +258,7 @@ class BandBuild:
     n_out: int
     key: tuple
     keep: tuple  # buffers the enqueued kernels still use
+    bucket_capacity: int = 0   # > 0: this is a one-walk build (rg_build2d_band_onewalk)
 
     MISMATCH, CAPACITY = 6, 7
 
@@ -266,12 +270,21 @@ class BandBuild:
         if c[2] or c[5]:
             raise _lib.RegridB200Error("rg_build2d_band: a sweep walk did not terminate (degenerate or folded grid)")
         if c[self.CAPACITY]:
+            # (a one-walk build whose buckets overflowed is repeated as a two-walk build, and so are all later
+            # builds of the shape)
+            if self.bucket_capacity > 0:
+                _band_onewalk_failed.add(self.key)
             _band_caps[self.key] = (max(int(nfrag * 1.05) + 1024, self.frag_capacity),
-                                    max(int(nfrag * 0.55) + 1024, self.nnz_capacity))
+                                    max(int(nfrag * 0.55) + 1024, self.nnz_capacity), 0)
             return None, "capacity"
         if c[self.MISMATCH]:
             return None, "mismatch"
-        _band_caps[self.key] = (int(nfrag * 1.02) + 1024, int(nnz * 1.02) + 1024)
+        # the longest bucket sizes the fixed-capacity buckets of the one-walk rebuilds of this shape (even: 32-byte rows)
+        longest = int(c[3])
+        bcap = 0 if longest <= 0 else (longest + max(4, longest // 4) + 1) // 2 * 2
+        if self.key in _band_onewalk_failed:
+            bcap = 0
+        _band_caps[self.key] = (int(nfrag * 1.02) + 1024, int(nnz * 1.02) + 1024, bcap)
         ii, io, v = self.ii[:nnz], self.io[:nnz], self.v[:nnz]
         if self.nnz_capacity > 1.5 * nnz + 4096:   # first build of a shape: do not keep the over-sized estimate alive
             ii, io, v = ii.clone(), io.clone(), v.clone()
@@ -298,12 +311,15 @@ def build2d_band_enqueue(x_in, y_in, x_out, y_out, weights_input, row_lo: int, r
             raise ValueError(f"weights_input must have the input cell shape {(nxi - 1, nyi - 1)}, got {tuple(w.shape)}")
     key = (nxi, nyi, nxo, nyo, int(row_lo), int(row_hi))
     nb = (int(row_hi) - int(row_lo)) * (nyi - 1)
+    bcap = 0   # (0: two walks -- no build of this shape has reported its longest bucket yet, or a one-walk build overflowed)
     if key in _band_caps:
-        fcap, ncap = _band_caps[key]
+        fcap, ncap, bcap = _band_caps[key]
     else:
         share = nb / max(n_in, 1)
         fcap = int(10 * (nb + n_out * share)) + 4096
         ncap = fcap // 2
+    if os.environ.get("REGRID_B200_BAND_TWO_WALKS") or nb * bcap * 16 > (8 << 30):
+        bcap = 0
     with torch.cuda.device(device):
         st = _stream(device)
         # workspace and fragment buffer are scratch: kept per (device, shape) so that repeated builds allocate nothing
@@ -318,12 +334,27 @@ def build2d_band_enqueue(x_in, y_in, x_out, y_out, weights_input, row_lo: int, r
         io = torch.empty(ncap, dtype=I64, device=device)
         v = torch.empty(ncap, dtype=F64, device=device)
         counts = torch.empty(8, dtype=I64, device=device)
-        _lib.check(L.rg_build2d_band(device.index, st, nxi, nyi, nxo, nyo, xi.data_ptr(), yi.data_ptr(),
-                                     xo.data_ptr(), yo.data_ptr(), _lib.ptr(w), int(row_lo), int(row_hi),
-                                     ws.data_ptr(), ws.numel(), frags.data_ptr(), fcap,
-                                     ii.data_ptr(), io.data_ptr(), v.data_ptr(), ncap, counts.data_ptr()),
-                   "rg_build2d_band")
-    return BandBuild(ii, io, v, counts, fcap, ncap, n_in, n_out, key, (ws, frags, xi, yi, xo, yo, w))
+        strided = None
+        if bcap > 0:
+            # ONE walk into fixed-capacity buckets (capacity learned from an earlier build of this shape)
+            bkey = (device.index, st, nb, bcap)
+            strided = _band_buckets.get(bkey)
+            if strided is None:
+                _band_buckets.clear()
+                strided = frags_empty(nb * bcap, device)
+                _band_buckets[bkey] = strided
+            _lib.check(L.rg_build2d_band_onewalk(device.index, st, nxi, nyi, nxo, nyo, xi.data_ptr(), yi.data_ptr(),
+                                                 xo.data_ptr(), yo.data_ptr(), _lib.ptr(w), int(row_lo), int(row_hi),
+                                                 ws.data_ptr(), ws.numel(), frags.data_ptr(), fcap,
+                                                 ii.data_ptr(), io.data_ptr(), v.data_ptr(), ncap, counts.data_ptr(),
+                                                 strided.data_ptr(), bcap), "rg_build2d_band_onewalk")
+        else:
+            _lib.check(L.rg_build2d_band(device.index, st, nxi, nyi, nxo, nyo, xi.data_ptr(), yi.data_ptr(),
+                                         xo.data_ptr(), yo.data_ptr(), _lib.ptr(w), int(row_lo), int(row_hi),
+                                         ws.data_ptr(), ws.numel(), frags.data_ptr(), fcap,
+                                         ii.data_ptr(), io.data_ptr(), v.data_ptr(), ncap, counts.data_ptr()),
+                       "rg_build2d_band")
+    return BandBuild(ii, io, v, counts, fcap, ncap, n_in, n_out, key, (ws, frags, xi, yi, xo, yo, w, strided), bcap)
 
 
 def build_weights_2d_band(x_in, y_in, x_out, y_out, weights_input=None, row_band: tuple[int, int] | None = None,
@@ -370,7 +401,7 @@ def build_weights_2d_batched(slices, weights_input=None, device=None) -> list:
         w = [to_device(wi, device) for wi in weights_input]
     key = (nxi, nyi, nxo, nyo, 0, nxi - 1)
     if key in _band_caps:
-        fcap, ncap = _band_caps[key]
+        fcap, ncap = _band_caps[key][:2]
     else:
         fcap = int(10 * (n_in + n_out)) + 4096
         ncap = fcap // 2

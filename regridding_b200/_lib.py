@@ -44,6 +44,8 @@ SIGNATURES: dict[str, list] = {
     "rg_build2d_stats": [_int, _vp, _i64, _i64, _i64, _i64, _vp, _p_i32],
     "rg_build2d_band": [_int, _vp, _i64, _i64, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _vp, _sz,
                         _vp, _i64, _vp, _vp, _vp, _i64, _vp],
+    "rg_build2d_band_onewalk": [_int, _vp, _i64, _i64, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _vp, _sz,
+                                _vp, _i64, _vp, _vp, _vp, _i64, _vp, _vp, _i64],
     "rg_grid_area": [_int, _vp, _i64, _i64, _vp, _vp, _vp],
     "rg_find_indices_2d_workspace_bytes": [_i64, _i64, _i64, _p_sz],
     "rg_find_indices_2d": [_int, _vp, _i64, _i64, _vp, _vp, _i64, _vp, _vp, _i64, _vp, _vp, _sz],

@@ -325,6 +325,9 @@ struct EmitSink {
     int32_t* flags;
     int L, k;
     int64_t cap = INT64_MAX;  // records the fragment buffer holds (band builds size it by estimate)
+    // one-walk band builds: no offsets yet -- every input cell of the band owns `bucket_cap` slots of `frag`
+    int bucket_cap = 0;
+    int64_t cell_base = 0;
     __device__ __forceinline__ void piece(const PassParams& P, double x1, double y1, double x2, double y2,
                                           int ci, int cj, int piece_idx)
     {
@@ -341,13 +344,13 @@ struct EmitSink {
         const int64_t in0 = pc.in[0], in1 = pc.in[two ? 1 : 0];
         const double vol0 = area_in[in0];
         const double vol1 = area_in[in1];
-        const int64_t base0 = boff[in0];
-        const int64_t base1 = boff[in1];
+        const int64_t base0 = bucket_cap ? (in0 - cell_base) * bucket_cap : boff[in0];
+        const int64_t base1 = bucket_cap ? (in1 - cell_base) * bucket_cap : boff[in1];
         double wi0 = 1.0, wi1 = 1.0;
         if (w_in) { wi0 = w_in[in0]; wi1 = w_in[in1]; }
         const int old0 = atomicAdd(&cursor[in0], 1);
         const int old1 = two ? atomicAdd(&cursor[in1], 1) : 0;
-        if (base0 + old0 >= cap || base1 + old1 >= cap) {
+        if (bucket_cap ? (old0 >= bucket_cap || old1 >= bucket_cap) : (base0 + old0 >= cap || base1 + old1 >= cap)) {
             atomicOr(&flags[kFlagCapacity], 1);
             return;
         }
@@ -740,8 +743,11 @@ struct SortSmem {
 // read the same keys: shared-memory broadcasts), and the sorted records go straight to global memory.
 __global__ void __launch_bounds__(kSortThreads)
 k_bucket_sort(const int64_t* __restrict__ boff, int64_t n_cells, Frag* __restrict__ frag, int32_t* __restrict__ nuniq,
-              const int32_t* __restrict__ abort_flag = nullptr)
+              const int32_t* __restrict__ abort_flag = nullptr, const Frag* __restrict__ strided = nullptr, int bucket_cap = 0,
+              int32_t* __restrict__ max_bucket = nullptr)
 {
+    // `strided` (one-walk band builds): bucket c was written to strided[c * bucket_cap ...]; it is gathered from there
+    // and leaves, sorted, at the dense offsets `boff` like in the two-walk pipeline.  `max_bucket`: longest bucket seen.
     extern __shared__ __align__(16) unsigned char smem_raw[];
     SortSmem& S = *reinterpret_cast<SortSmem*>(smem_raw);
     if (abort_flag && *abort_flag) return;  // band builds: the fragment buffer was too small, nothing valid to sort
@@ -758,16 +764,28 @@ k_bucket_sort(const int64_t* __restrict__ boff, int64_t n_cells, Frag* __restric
     if (threadIdx.x == 0) S.is_long = 0;
     __syncthreads();
     if (len > 64) S.is_long = 1;
+    if (max_bucket && owner) {
+        const int m = __reduce_max_sync(0xffffffffu, (int)min(len, (int64_t)INT32_MAX));   // owners fill whole warps
+        if ((threadIdx.x & 31) == 0 && m > 0) atomicMax(max_bucket, m);
+    }
     __syncthreads();
     if (hi - lo <= kSortCap && !S.is_long) {
         const int n = (int)(hi - lo);
-        for (int e = threadIdx.x; e < n; e += kSortThreads) cp_async_frag(&S.frag[e], frag + lo + e);
+        if (!strided)
+            for (int e = threadIdx.x; e < n; e += kSortThreads) cp_async_frag(&S.frag[e], frag + lo + e);
         if (owner) {
             const int b = (int)(beg - lo), n_mine = (int)len;
             S.beg[threadIdx.x] = b;
             S.len[threadIdx.x] = n_mine;
             S.uniq[threadIdx.x] = 0;
             for (int e = b; e < b + n_mine; e++) S.cell[e] = (uint16_t)threadIdx.x;
+        }
+        if (strided) {
+            __syncthreads();
+            for (int e = threadIdx.x; e < n; e += kSortThreads) {
+                const int cl = S.cell[e];
+                cp_async_frag(&S.frag[e], strided + (c0 + cl) * bucket_cap + (e - S.beg[cl]));
+            }
         }
         cp_async_wait_all();
         __syncthreads();
@@ -789,7 +807,13 @@ k_bucket_sort(const int64_t* __restrict__ boff, int64_t n_cells, Frag* __restric
         if (owner && c < n_cells) nuniq[c] = S.uniq[threadIdx.x];
         return;
     }
-    if (owner) sort_buckets_global(frag, beg, end, c < n_cells, nuniq, c);  // warps 0..3 are complete
+    if (owner) {
+        if (strided) {   // the global-memory sort works in place on the dense layout
+            for (int64_t e = 0; e < len; e++) frag[beg + e] = strided[c * bucket_cap + e];
+            __syncwarp();
+        }
+        sort_buckets_global(frag, beg, end, c < n_cells, nuniq, c);  // warps 0..3 are complete
+    }
 }
 
 // Sharded builds: gather the band's buckets from the W source chunks and rank-sort them.  Every source's share
@@ -2032,6 +2056,72 @@ k_band_walk_emit(const __grid_constant__ Pass4 Q, const BandParams B, const int6
     }
 }
 
+// ONE-WALK band build: the count walk and the emit walk in one -- a segment is walked once and its fragments go
+// straight into fixed-capacity buckets (`bucket_cap` slots per input cell of the band, the capacity learned from an
+// earlier build of the same shape; a bucket that overflows raises kFlagCapacity and the caller falls back to the
+// two-walk build).  No histogram, no piece cache, no replay; the per-cell counts are the cursors, scanned AFTER the walk
+// for the dense offsets the sort writes to.  The chain check, which needs the end states of all segments, runs as its
+// own kernel beside the sort (k_band_chain_check).
+__global__ void __launch_bounds__(128, RG_COUNT_MINB)
+k_band_walk_once(const __grid_constant__ Pass4 Q, const BandParams B, int32_t* __restrict__ cursor, Frag* __restrict__ frag_strided,
+                 int bucket_cap, int64_t cell_base, const double* __restrict__ area_in, const double* __restrict__ w_in,
+                 int32_t* __restrict__ flags)
+{
+    const BandInfo& I = *B.info;
+    const int64_t total = I.tstart[4];
+    int64_t claim = 0;
+    for (int sub = kClaim;; sub += 32) {
+        if (sub >= kClaim) {
+            claim = band_claim(const_cast<BandInfo*>(B.info), 0);
+            sub = 0;
+        }
+        if (claim >= total) break;
+        const int64_t gtid = claim + sub + (threadIdx.x & 31);
+        int p, L, k;
+        if (gtid >= total || !band_segment(Q, I, gtid, p, L, k)) continue;
+        const PassParams& P = Q.p[p];
+        const int64_t v = vertex_of(P, L, k), v2 = v + vertex_step(P);
+        const bool relevant = band_relevant(P, B, L, k, v);
+        if (!relevant && !(k + 1 < P.nseg && band_relevant(P, B, L, k + 1, v2))) continue;
+        const int start = (k == 0) ? P.line_start[L] : P.guess[v];
+        P.seg_start[v] = start;
+        if (start <= kStateUnknown) {   // unknown or never located: the sequentially verified build decides
+            P.seg_end[v] = kStateInvalid;
+            atomicOr(&flags[kFlagBandMismatch], 1);
+            continue;
+        }
+        EmitSink sink{ nullptr, cursor, frag_strided, area_in, w_in, flags, L, k, INT64_MAX, bucket_cap, cell_base };
+        bool overflow = false;
+        P.seg_end[v] = walk_segment(P, P.sweep.x[v], P.sweep.y[v], P.sweep.x[v2], P.sweep.y[v2], start, sink, overflow);
+        if (overflow) atomicOr(&flags[kFlagOverflow], 1);
+    }
+}
+
+// chain check of every walked segment (one-walk builds; the two-walk build folds it into its emit walk)
+__global__ void __launch_bounds__(256) k_band_chain_check(const __grid_constant__ Pass4 Q, const BandParams B,
+                                                          int32_t* __restrict__ flags)
+{
+    const BandInfo& I = *B.info;
+    const int64_t total = I.tstart[4];
+    for (int64_t gtid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; gtid < total; gtid += (int64_t)gridDim.x * blockDim.x) {
+        int p, L, k;
+        if (!band_segment(Q, I, gtid, p, L, k)) continue;
+        const PassParams& P = Q.p[p];
+        const int64_t v = vertex_of(P, L, k), v2 = v + vertex_step(P);
+        const bool relevant = band_relevant(P, B, L, k, v);
+        const bool next_relevant = k + 1 < P.nseg && band_relevant(P, B, L, k + 1, v2);
+        if (!relevant && !next_relevant) continue;
+        bool need_winding = false;
+        bool bad = band_chain_bad(P, B, L, k, v, relevant, next_relevant, need_winding);
+        if (need_winding) {
+            const unsigned at = atomicAdd(&const_cast<BandInfo*>(B.info)->vq_n, 1u);
+            if ((int64_t)at < B.vq_cap) B.vq[at] = ((unsigned long long)p << 40) | (unsigned long long)v;
+            else bad = true;
+        }
+        if (bad) atomicOr(&flags[kFlagBandMismatch], 1);
+    }
+}
+
 // exact check of the queued run starts that were located "outside": one warp per vertex, the lanes share the boundary
 // edge groups; a non-zero winding number (the vertex is inside the boundary polygon, or on it) is a mismatch
 __global__ void __launch_bounds__(128) k_band_verify_outside(const __grid_constant__ Pass4 Q, const BandParams B,
@@ -2093,14 +2183,14 @@ static BandSide* band_side(int device)
 }
 }  // namespace rg
 
-extern "C" int rg_build2d_band(int device, void* stream,
-                               int64_t nxi, int64_t nyi, int64_t nxo, int64_t nyo,
-                               const double* xin, const double* yin, const double* xout, const double* yout,
-                               const double* w_in, int64_t row_lo, int64_t row_hi,
-                               void* workspace, size_t workspace_bytes,
-                               void* frags, int64_t frag_capacity,
-                               int64_t* ii, int64_t* io, double* v, int64_t nnz_capacity,
-                               int64_t* counts_dev /* [8] */)
+static int band_impl(int device, void* stream,
+                     int64_t nxi, int64_t nyi, int64_t nxo, int64_t nyo,
+                     const double* xin, const double* yin, const double* xout, const double* yout,
+                     const double* w_in, int64_t row_lo, int64_t row_hi,
+                     void* workspace, size_t workspace_bytes,
+                     void* frags, int64_t frag_capacity,
+                     int64_t* ii, int64_t* io, double* v, int64_t nnz_capacity,
+                     int64_t* counts_dev /* [8] */, void* frags_strided, int64_t bucket_cap)
 {
     int rc = check_sizes(nxi, nyi, nxo, nyo);
     if (rc) return rc;
@@ -2219,26 +2309,48 @@ extern "C" int rg_build2d_band(int device, void* stream,
         for (int p = 0; p < 4; p++) total += ceil_div(nl[p] * nk[p], 256) * 256;
         emit_grid = (unsigned)ceil_div(total, 128);
     }
-    k_band_walk_count<<<walk_grid, 128, 0, st>>>(Q, B, l.hist, l.flags);
-    RG_LAUNCH_CHECK("k_band_walk_count");
-    // (single-launch scans; the total goes to counts[0] / counts[1] with the capacity check)
-    rc = exclusive_scan_i32_i64_single(st, l.hist + cell_lo, l.boff + cell_lo, nb, l.scan_status[0], frag_capacity, counts_dev,
-                                       l.flags + kFlagCapacity);
-    if (rc) return rc;
-    // boff of the band starts at 0: cells index it globally (boff[cell]), fragments locally
-    k_band_walk_emit<<<emit_grid, 128, 0, st>>>(Q, B, l.boff, l.cursor, (Frag*)frags, frag_capacity, l.area_in, w_in, l.flags);
-    RG_LAUNCH_CHECK("k_band_walk_emit");
-    // the exact check of the run starts located "outside" runs beside the sort / merge
-    RG_CUDA(cudaEventRecord(side->emitted, st));
-    RG_CUDA(cudaStreamWaitEvent(ss, side->emitted, 0));
-    k_band_verify_outside<<<kNumSM * 4, 128, 0, ss>>>(Q, B, l.flags);
-    RG_LAUNCH_CHECK("k_band_verify_outside");
-    RG_CUDA(cudaEventRecord(side->verified, ss));
     rc = sort_smem_opt_in(device);
     if (rc) return rc;
-    k_bucket_sort<<<(unsigned)ceil_div(nb, kSortCells), kSortThreads, sizeof(SortSmem), st>>>(
-        l.boff + cell_lo, nb, (Frag*)frags, l.nuniq + cell_lo, l.flags + kFlagCapacity);
-    RG_LAUNCH_CHECK("k_bucket_sort");
+    if (bucket_cap > 0) {
+        // ONE walk: fragments go straight into fixed-capacity buckets; the cursors are the counts
+        k_band_walk_once<<<walk_grid, 128, 0, st>>>(Q, B, l.cursor, (Frag*)frags_strided, (int)bucket_cap, cell_lo, l.area_in, w_in,
+                                                    l.flags);
+        RG_LAUNCH_CHECK("k_band_walk_once");
+        // chain check + exact check of the run starts located "outside": beside the scan / sort / merge
+        RG_CUDA(cudaEventRecord(side->emitted, st));
+        RG_CUDA(cudaStreamWaitEvent(ss, side->emitted, 0));
+        k_band_chain_check<<<kNumSM * 8, 256, 0, ss>>>(Q, B, l.flags);
+        k_band_verify_outside<<<kNumSM * 4, 128, 0, ss>>>(Q, B, l.flags);
+        RG_LAUNCH_CHECK("k_band_verify_outside");
+        RG_CUDA(cudaEventRecord(side->verified, ss));
+        rc = exclusive_scan_i32_i64_single(st, l.cursor + cell_lo, l.boff + cell_lo, nb, l.scan_status[0], frag_capacity, counts_dev,
+                                           l.flags + kFlagCapacity);
+        if (rc) return rc;
+        k_bucket_sort<<<(unsigned)ceil_div(nb, kSortCells), kSortThreads, sizeof(SortSmem), st>>>(
+            l.boff + cell_lo, nb, (Frag*)frags, l.nuniq + cell_lo, l.flags + kFlagCapacity, (const Frag*)frags_strided, (int)bucket_cap,
+            l.flags + kFlagRepairs);
+        RG_LAUNCH_CHECK("k_bucket_sort");
+    } else {
+        k_band_walk_count<<<walk_grid, 128, 0, st>>>(Q, B, l.hist, l.flags);
+        RG_LAUNCH_CHECK("k_band_walk_count");
+        // (single-launch scans; the total goes to counts[0] / counts[1] with the capacity check)
+        rc = exclusive_scan_i32_i64_single(st, l.hist + cell_lo, l.boff + cell_lo, nb, l.scan_status[0], frag_capacity, counts_dev,
+                                           l.flags + kFlagCapacity);
+        if (rc) return rc;
+        // boff of the band starts at 0: cells index it globally (boff[cell]), fragments locally
+        k_band_walk_emit<<<emit_grid, 128, 0, st>>>(Q, B, l.boff, l.cursor, (Frag*)frags, frag_capacity, l.area_in, w_in, l.flags);
+        RG_LAUNCH_CHECK("k_band_walk_emit");
+        // the exact check of the run starts located "outside" runs beside the sort / merge
+        RG_CUDA(cudaEventRecord(side->emitted, st));
+        RG_CUDA(cudaStreamWaitEvent(ss, side->emitted, 0));
+        k_band_verify_outside<<<kNumSM * 4, 128, 0, ss>>>(Q, B, l.flags);
+        RG_LAUNCH_CHECK("k_band_verify_outside");
+        RG_CUDA(cudaEventRecord(side->verified, ss));
+        // (the longest bucket goes to the otherwise unused "repairs" counter: the capacity a one-walk rebuild needs)
+        k_bucket_sort<<<(unsigned)ceil_div(nb, kSortCells), kSortThreads, sizeof(SortSmem), st>>>(
+            l.boff + cell_lo, nb, (Frag*)frags, l.nuniq + cell_lo, l.flags + kFlagCapacity, nullptr, 0, l.flags + kFlagRepairs);
+        RG_LAUNCH_CHECK("k_bucket_sort");
+    }
     rc = exclusive_scan_i32_i64_single(st, l.nuniq + cell_lo, l.colptr + cell_lo, nb, l.scan_status[1], nnz_capacity, counts_dev + 1,
                                        l.flags + kFlagCapacity);
     if (rc) return rc;
@@ -2250,6 +2362,34 @@ extern "C" int rg_build2d_band(int device, void* stream,
     k_band_counts<<<1, 32, 0, st>>>(getenv("RG_BAND_FORCE_MISMATCH") ? 3 : 2, nullptr, 0, counts_dev, l.flags);
     RG_LAUNCH_CHECK("k_band_counts");
     return RG_OK;
+}
+
+extern "C" int rg_build2d_band(int device, void* stream,
+                               int64_t nxi, int64_t nyi, int64_t nxo, int64_t nyo,
+                               const double* xin, const double* yin, const double* xout, const double* yout,
+                               const double* w_in, int64_t row_lo, int64_t row_hi,
+                               void* workspace, size_t workspace_bytes,
+                               void* frags, int64_t frag_capacity,
+                               int64_t* ii, int64_t* io, double* v, int64_t nnz_capacity,
+                               int64_t* counts_dev /* [8] */)
+{
+    return band_impl(device, stream, nxi, nyi, nxo, nyo, xin, yin, xout, yout, w_in, row_lo, row_hi, workspace, workspace_bytes,
+                     frags, frag_capacity, ii, io, v, nnz_capacity, counts_dev, nullptr, 0);
+}
+
+extern "C" int rg_build2d_band_onewalk(int device, void* stream,
+                                       int64_t nxi, int64_t nyi, int64_t nxo, int64_t nyo,
+                                       const double* xin, const double* yin, const double* xout, const double* yout,
+                                       const double* w_in, int64_t row_lo, int64_t row_hi,
+                                       void* workspace, size_t workspace_bytes,
+                                       void* frags, int64_t frag_capacity,
+                                       int64_t* ii, int64_t* io, double* v, int64_t nnz_capacity,
+                                       int64_t* counts_dev /* [8] */, void* frags_strided, int64_t bucket_capacity)
+{
+    if (!frags_strided || bucket_capacity < 1 || bucket_capacity > 65535)
+        return fail(RG_E_ARG, "rg_build2d_band_onewalk: bad bucket buffer");
+    return band_impl(device, stream, nxi, nyi, nxo, nyo, xin, yin, xout, yout, w_in, row_lo, row_hi, workspace, workspace_bytes,
+                     frags, frag_capacity, ii, io, v, nnz_capacity, counts_dev, frags_strided, bucket_capacity);
 }
 
 // Per-slice builds (every orthogonal slice carries its own grid pair: the Python loop of

@@ -134,6 +134,15 @@ def test_build2d_band_build_equals_full(rg, dev, name, world_size):
         assert status == "ok", (name, world_size, r, status)
         parts.append(dw)
         nfrag += dw.stats["fragments"]
+        # the second build of a shape knows the longest bucket and walks ONCE (rg_build2d_band_onewalk): same band
+        again = rg.device.build2d_band_enqueue(T(gi[0], dev), T(gi[1], dev), T(co[0], dev), T(co[1], dev),
+                                               None if w is None else T(w, dev), lo, hi, device=dev)
+        assert again.bucket_capacity > 0, (name, r)
+        dw2, status2 = again.finish()
+        assert status2 == "ok", (name, world_size, r, status2)
+        assert torch.equal(dw2.indices_input, dw.indices_input) and torch.equal(dw2.indices_output, dw.indices_output)
+        assert torch.equal(dw2.values, dw.values)
+        assert dw2.stats["fragments"] == dw.stats["fragments"]
     assert nfrag == full.stats["fragments"]
     assert torch.equal(torch.cat([p.indices_input for p in parts]), full.indices_input)
     assert torch.equal(torch.cat([p.indices_output for p in parts]), full.indices_output)
@@ -142,6 +151,40 @@ def test_build2d_band_build_equals_full(rg, dev, name, world_size):
     lo, hi = _parallel.shard_range(ncx, world_size - 1, world_size)
     one = rg.device.build_weights_2d_band(gi[0], gi[1], co[0], co[1], w, row_band=(lo, hi), device=dev)
     assert torch.equal(one.values, parts[-1].values) and torch.equal(one.indices_output, parts[-1].indices_output)
+
+
+def test_build2d_band_onewalk_bucket_overflow_falls_back(rg, dev):
+    """One-walk band build whose fixed-capacity buckets are too small (capacity learned on other coordinates): it must
+    report "capacity", the repeat must take two walks and be right, and the shape must stay with two walks."""
+    from regridding_b200 import _parallel, _device
+
+    gi, go, _ = cases.case_2d("dist129")
+    co = cases.perturb_like_reference(go, (-1, -2), 42)
+    ncx, ncy = gi[0].shape[0] - 1, gi[0].shape[1] - 1
+    lo, hi = _parallel.shard_range(ncx, 1, 3)
+    t = [T(a, dev) for a in (gi[0], gi[1], co[0], co[1])]
+    full = rg.device.build_weights_2d(*t, device=dev)
+    sel = (full.indices_input >= lo * ncy) & (full.indices_input < hi * ncy)
+    dw, status = rg.device.build2d_band_enqueue(*t, None, lo, hi, device=dev).finish()
+    if status == "capacity":
+        dw, status = rg.device.build2d_band_enqueue(*t, None, lo, hi, device=dev).finish()
+    assert status == "ok"
+    key = (*gi[0].shape, *co[0].shape, lo, hi)
+    _device._band_onewalk_failed.discard(key)
+    fcap, ncap, bcap = _device._band_caps[key]
+    assert bcap > 0
+    _device._band_caps[key] = (fcap, ncap, 2)   # far too small
+    bb = rg.device.build2d_band_enqueue(*t, None, lo, hi, device=dev)
+    assert bb.bucket_capacity == 2
+    none, status = bb.finish()
+    assert none is None and status == "capacity"
+    bb = rg.device.build2d_band_enqueue(*t, None, lo, hi, device=dev)
+    assert bb.bucket_capacity == 0
+    dw2, status = bb.finish()
+    assert status == "ok"
+    assert torch.equal(dw2.indices_output, full.indices_output[sel]) and torch.equal(dw2.values, full.values[sel])
+    assert rg.device.build2d_band_enqueue(*t, None, lo, hi, device=dev).bucket_capacity == 0   # stays with two walks
+    _device._band_onewalk_failed.discard(key)
 
 
 def test_build2d_band_unverifiable_states_fall_back(rg, dev, monkeypatch):
