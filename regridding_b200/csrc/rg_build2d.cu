@@ -412,7 +412,13 @@ __device__ inline void line_start_body(const PassParams& P, int L, const double*
         for (int q = 0; q < 8; q++) w += s_w[q];
         if (w != 0.0) {
             int found = kLocUnknown;
-            if (lane == 0) found = locate_newton(P.stat, px, py, 0.5 * P.stat.nx, 0.5 * P.stat.ny);
+            // (the result does not depend on the seed -- see locate_newton; the affine map through three corners of
+            // the grid saves most of the iterations the grid centre needs)
+            if (lane == 0) {
+                double si, sj;
+                affine_seed(P.stat, px, py, si, sj);
+                found = locate_newton(P.stat, px, py, si, sj);
+            }
             found = __shfl_sync(0xffffffffu, found, 0);
             if (found < 0) {
                 // index_of_point_brute (_grids.py:223-279): lowest row-major containing cell
@@ -1846,24 +1852,6 @@ __device__ __forceinline__ bool band_segment(const Pass4& Q, const BandInfo& I, 
     return true;
 }
 
-// exact start state of the lines whose first segment is walked (CTA per line of every pass)
-// (`which`: 0 = the output-line passes only, 1 = the input-line passes only, 2 = all four)
-__global__ void __launch_bounds__(256) k_band_line_starts(const __grid_constant__ Pass4 Q, const BandParams B,
-                                                          const double* __restrict__ bbox2, int which)
-{
-    __shared__ double s_w[8];
-    const int p = pass_of_slot(Q, (int)blockIdx.x);
-    const PassParams& P = Q.p[p];
-    if (which != 2 && (int)(P.sweep_input != 0) != which) return;
-    const int L = (int)blockIdx.x - Q.lstart[p];
-    if (L >= P.nlines) return;
-    if (P.sweep_input && (P.axis ? (L < B.row_lo || L > B.row_hi) : (B.row_lo > 1))) return;  // known without the rectangle
-    const int* r = B.info->rect[p];
-    if (L < r[0] || L >= r[0] + r[1] || r[2] != 0 || r[3] <= 0) return;
-    if (!band_walked(P, B, L, 0, vertex_of(P, L, 0))) return;
-    line_start_body(P, L, bbox2, s_w);
-}
-
 // The walks visit the (line, segment) rectangles of the four passes, of which only the band's stripe is walked: a
 // static assignment leaves some warps with many long walks and others with none, so in the count walk every WARP
 // claims kClaim consecutive positions at a time from a global counter until the rectangles are exhausted (the emit
@@ -1895,7 +1883,7 @@ __global__ void __launch_bounds__(128, RG_COUNT_MINB) k_band_walk_count(const __
         const int64_t v = vertex_of(P, L, k), v2 = v + vertex_step(P);
         const bool relevant = band_relevant(P, B, L, k, v);
         if (!relevant && !(k + 1 < P.nseg && band_relevant(P, B, L, k + 1, v2))) continue;
-        const int start = (k == 0) ? P.line_start[L] : P.guess[v];
+        const int start = P.guess[v];   // (verified by the chain check: exactly, when no walked predecessor ends here)
         P.seg_start[v] = start;
         if (start <= kStateUnknown) {   // unknown or never located: the sequentially verified build decides
             P.seg_end[v] = kStateInvalid;
@@ -1976,14 +1964,12 @@ __device__ __forceinline__ bool band_chain_bad(const PassParams& P, const BandPa
 {
     const int64_t step = vertex_step(P);
     bool bad = false;
-    if (k >= 1) {
-        if (relevant || band_relevant(P, B, L, k - 1, v - step)) {
-            bad = P.seg_end[v - step] != P.seg_start[v];
-        } else {
-            const int e = band_start_exact(P, v);
-            bad = e == 0;
-            need_winding = e == 2;
-        }
+    if (k >= 1 && (relevant || band_relevant(P, B, L, k - 1, v - step))) {
+        bad = P.seg_end[v - step] != P.seg_start[v];
+    } else {   // first segment of a run (or of the line): no walked predecessor
+        const int e = band_start_exact(P, v);
+        bad = e == 0;
+        need_winding = e == 2;
     }
     if (relevant && k + 1 < P.nseg && !next_relevant &&
         !(k + 2 < P.nseg && band_relevant(P, B, L, k + 2, v + 2 * step)))
@@ -2083,7 +2069,7 @@ k_band_walk_once(const __grid_constant__ Pass4 Q, const BandParams B, int32_t* _
         const int64_t v = vertex_of(P, L, k), v2 = v + vertex_step(P);
         const bool relevant = band_relevant(P, B, L, k, v);
         if (!relevant && !(k + 1 < P.nseg && band_relevant(P, B, L, k + 1, v2))) continue;
-        const int start = (k == 0) ? P.line_start[L] : P.guess[v];
+        const int start = P.guess[v];   // (verified by the chain check: exactly, when no walked predecessor ends here)
         P.seg_start[v] = start;
         if (start <= kStateUnknown) {   // unknown or never located: the sequentially verified build decides
             P.seg_end[v] = kStateInvalid;
@@ -2218,29 +2204,28 @@ static int band_impl(int device, void* stream,
     B.rel[0] = l.rel[0]; B.rel[1] = l.rel[1];
     B.info = l.info;
     B.vq = l.vq; B.vq_cap = l.vq_cap;
-    BoundarySet S, S_out;   // both grids / the output grid alone
+    BoundarySet S;   // both grids
     memset(&S, 0, sizeof(S));
     S.n = 2;
     S.g[0] = gin; S.g[1] = gout; S.b[0] = l.bnd[0]; S.b[1] = l.bnd[1]; S.bbox[0] = l.bbox; S.bbox[1] = l.bbox + 4;
-    memset(&S_out, 0, sizeof(S_out));
-    S_out.n = 1;
-    S_out.g[0] = gout; S_out.b[0] = l.bnd[1]; S_out.bbox[0] = l.bbox + 4;
     const int g1max = l.bnd[0].n_g1 > l.bnd[1].n_g1 ? l.bnd[0].n_g1 : l.bnd[1].n_g1;
     const int g2max = l.bnd[0].n_g2 > l.bnd[1].n_g2 ? l.bnd[0].n_g2 : l.bnd[1].n_g2;
 
     // The preparation runs on TWO streams.  Everything that leads to the relevant output segments is a chain of short
     // dependent launches (bbox of the input grid -> raster of the band -> relevance of the output segments -> extents ->
     // located states of the output vertices); everything else the walks need -- cleared histograms, cell areas, the
-    // bbox of the output grid, the located states of the input vertices around the band and the start states of the
-    // input lines -- does not depend on it and runs beside it on a side stream.
+    // located states of the input vertices around the band -- does not depend on it and runs beside it on a side stream.
+    // (No exact line starts: the first segment of a line starts from the located state of its vertex like the first
+    // segment of any run, and the chain check verifies that state exactly.)
     k_band_begin<<<1, 32, 0, st>>>(Q, (int)row_lo, (int)row_hi, full ? 1 : 0, (int)nxo, (int)nyo, l.flags, counts_dev, l.bbox, l.info);
     RG_LAUNCH_CHECK("k_band_begin");
     k_boundary_edges_bb1<<<dim3((unsigned)ceil_div((int64_t)g1max * 32, T), 2), T, 0, st>>>(S);
     k_boundary_bb2<<<dim3((unsigned)ceil_div((int64_t)g2max * 32, T), 2), T, 0, st>>>(S);
     RG_LAUNCH_CHECK("k_boundary");
     RG_CUDA(cudaEventRecord(side->fork, st));
-    // ---- main stream first (the host enqueues ~20 operations here: the chain the walks wait for goes out first, the
-    // side stream's work is submitted while the GPU already runs it)
+    // The host enqueues ~25 operations here, ~3 us each, which is what the start of the build is bound by: the head of
+    // the main chain goes out first (the GPU then has ~100 us of work), the side stream's work next (it starts at once,
+    // beside it), the tail of the main chain last.
     if (!full) {
         RG_CUDA(cudaMemsetAsync(l.raster8, 0, (size_t)kRasterN * kRasterN, st));
         k_bbox<<<dim3(kNumSM * 4, 1), T, 0, st>>>(S);
@@ -2250,33 +2235,17 @@ static int band_impl(int device, void* stream,
         k_band_raster_pack<<<kRasterN * kRasterN / 8 / 256, 256, 0, st>>>(l.raster8, l.raster);
         k_band_relevance<<<kNumSM * 8, kRelThreads, 0, st>>>(gout, l.bbox, l.raster, l.rel[0], l.rel[1], l.info);
         RG_LAUNCH_CHECK("k_band_relevance");
-        k_band_finalize<<<1, 32, 0, st>>>(Q, l.info);
-        k_band_guess_out<<<kNumSM * 8, T, 0, st>>>(gout, gin, l.rel[0], l.rel[1], l.info, l.guess[0], l.flags);
-        RG_LAUNCH_CHECK("k_band_guess_out");
-        k_band_line_starts<<<(unsigned)Q.lstart[4], 256, 0, st>>>(Q, B, l.bbox, 0);
-        RG_LAUNCH_CHECK("k_band_line_starts");
     } else {
         k_bbox<<<dim3(kNumSM * 4, 2), T, 0, st>>>(S);
         RG_LAUNCH_CHECK("k_bbox");
     }
     // ---- side stream
     RG_CUDA(cudaStreamWaitEvent(ss, side->fork, 0));
-    if (!full) {
-        k_bbox<<<dim3(kNumSM * 4, 1), T, 0, ss>>>(S_out);
-        RG_LAUNCH_CHECK("k_bbox");
-    }
     if (full) {
         // the band is the whole grid (per-slice builds without host synchronisation): everything is relevant
         RG_CUDA(cudaMemsetAsync(l.rel[0], 1, (size_t)l.Vo, ss));
         RG_CUDA(cudaMemsetAsync(l.rel[1], 1, (size_t)l.Vo, ss));
     }
-    RG_CUDA(cudaMemsetAsync(l.scan_status[0], 0, sizeof(unsigned long long) * 2 * scan_status_elems(l.Ci), ss));
-    RG_CUDA(cudaMemsetAsync(l.hist + cell_lo, 0, sizeof(int32_t) * (size_t)(nb + 1), ss));
-    RG_CUDA(cudaMemsetAsync(l.cursor + cell_lo, 0, sizeof(int32_t) * (size_t)(nb + 1), ss));
-    // areas of the band's cells (k_cell_area works on the rows [row_lo, row_hi) of the grid: a view of those rows would
-    // move the peeled first-edge pattern of grid_volume, so the full-grid kernel runs on the band's cell range)
-    k_cell_area_range<<<(unsigned)ceil_div(nb, T), T, 0, ss>>>(gin, cell_lo, cell_hi, l.area_in);
-    RG_LAUNCH_CHECK("k_cell_area_range");
     {
         // input vertices of rows row_lo - 1 .. row_hi + 1: every start / end vertex of a walked segment of passes 2, 3
         const int64_t r0 = row_lo > 0 ? row_lo - 1 : 0, r1 = (row_hi + 2 < nxi ? row_hi + 2 : nxi);
@@ -2284,19 +2253,26 @@ static int band_impl(int device, void* stream,
         k_band_guess_in<<<(unsigned)ceil_div(v_hi - v_lo, T), T, 0, ss>>>(gin, gout, v_lo, v_hi, l.guess[1], l.flags);
         RG_LAUNCH_CHECK("k_band_guess_in");
     }
-    if (!full) {
-        k_band_line_starts<<<(unsigned)Q.lstart[4], 256, 0, ss>>>(Q, B, l.bbox, 1);
-        RG_LAUNCH_CHECK("k_band_line_starts");
-    }
+    RG_CUDA(cudaMemsetAsync(l.scan_status[0], 0, sizeof(unsigned long long) * 2 * scan_status_elems(l.Ci), ss));
+    if (bucket_cap <= 0) RG_CUDA(cudaMemsetAsync(l.hist + cell_lo, 0, sizeof(int32_t) * (size_t)(nb + 1), ss));
+    RG_CUDA(cudaMemsetAsync(l.cursor + cell_lo, 0, sizeof(int32_t) * (size_t)(nb + 1), ss));
+    // areas of the band's cells (k_cell_area works on the rows [row_lo, row_hi) of the grid: a view of those rows would
+    // move the peeled first-edge pattern of grid_volume, so the full-grid kernel runs on the band's cell range)
+    k_cell_area_range<<<(unsigned)ceil_div(nb, T), T, 0, ss>>>(gin, cell_lo, cell_hi, l.area_in);
+    RG_LAUNCH_CHECK("k_cell_area_range");
     RG_CUDA(cudaEventRecord(side->join, ss));
+    // ---- main stream, tail of the chain
+    if (!full) {
+        k_band_finalize<<<1, 32, 0, st>>>(Q, l.info);
+        k_band_guess_out<<<kNumSM * 8, T, 0, st>>>(gout, gin, l.rel[0], l.rel[1], l.info, l.guess[0], l.flags);
+        RG_LAUNCH_CHECK("k_band_guess_out");
+    }
     // ---- join
     RG_CUDA(cudaStreamWaitEvent(st, side->join, 0));
     if (full) {
         k_band_finalize<<<1, 32, 0, st>>>(Q, l.info);
         k_band_guess_out<<<kNumSM * 8, T, 0, st>>>(gout, gin, l.rel[0], l.rel[1], l.info, l.guess[0], l.flags);
         RG_LAUNCH_CHECK("k_band_guess_out");
-        k_band_line_starts<<<(unsigned)Q.lstart[4], 256, 0, st>>>(Q, B, l.bbox, 2);
-        RG_LAUNCH_CHECK("k_band_line_starts");
     }
     // grid-stride: the amount of work of a partial band is only known on the device.  The whole-grid band (per-slice
     // builds) has one position per segment of the four passes: one thread each for the emit, whose scattered stores

@@ -172,6 +172,27 @@ __device__ inline int locate_newton(const GridView& g, double px, double py, dou
     return kLocUnknown;
 }
 
+// index-space estimate of (px, py) by the affine map through the corners (0, 0), (ncx, 0), (0, ncy) of the grid
+// (clamped to one cell beyond the grid; the grid centre for a degenerate map)
+__device__ __forceinline__ void affine_seed(const GridView& g, double px, double py, double& i, double& j)
+{
+    const int ncx = g.nx - 1, ncy = g.ny - 1;
+    const double x00 = g.x[0], y00 = g.y[0];
+    const double ax = (g.x[(int64_t)ncx * g.ny] - x00) / ncx, ay = (g.y[(int64_t)ncx * g.ny] - y00) / ncx;
+    const double bx = (g.x[ncy] - x00) / ncy, by = (g.y[ncy] - y00) / ncy;
+    const double det0 = ax * by - bx * ay;
+    i = 0.5 * g.nx;
+    j = 0.5 * g.ny;
+    if (det0 != 0.0 && det0 == det0) {
+        const double r0 = 1.0 / det0;
+        const double ti = ((px - x00) * by - (py - y00) * bx) * r0, tj = ((py - y00) * ax - (px - x00) * ay) * r0;
+        if (ti == ti && tj == tj) {
+            i = fmin(fmax(ti, -1.0), (double)ncx + 1.0);
+            j = fmin(fmax(tj, -1.0), (double)ncy + 1.0);
+        }
+    }
+}
+
 // Cheap variant for the walk-state GUESSES of the 2D build (k_vertex_guess*): wrong guesses only cost a repair,
 // so the iteration starts from the affine map through three corners of the grid, stops as soon as the Newton step
 // is below 1e-4 cells and accepts the cell when the point is 1e-3 cells away from its edges (or "outside" when it
