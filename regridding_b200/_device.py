@@ -50,6 +50,8 @@ def _stream(device: torch.device) -> int:
 def to_device(a, device: torch.device, dtype=F64) -> torch.Tensor:
     """numpy array or tensor -> contiguous tensor on `device`."""
     if isinstance(a, torch.Tensor):
+        if a.device == device and a.dtype == dtype and a.is_contiguous():
+            return a
         return a.to(device=device, dtype=dtype).contiguous()
     a = np.ascontiguousarray(a, dtype={F64: np.float64, I64: np.int64, I32: np.int32}[dtype])
     with warnings.catch_warnings():
@@ -243,6 +245,19 @@ _band_onewalk_failed: set = set()   # shapes whose one-walk build overflowed its
 _band_scratch: dict = {}
 
 
+_pinned: dict = {}
+
+
+def _pinned_counts() -> torch.Tensor:
+    """pinned int64[8] the status counters of a band build are copied into (one per process: the copy is consumed
+    before the next build is finished)"""
+    t = _pinned.get("counts")
+    if t is None:
+        t = torch.empty(8, dtype=I64).pin_memory()
+        _pinned["counts"] = t
+    return t
+
+
 @dataclasses.dataclass
 class BandBuild:
     """One enqueued ``rg_build2d_band``: nothing has been synchronised yet.  ``counts`` (device int64[8]) holds
@@ -265,7 +280,13 @@ class BandBuild:
     def finish(self, counts_host=None):
         """-> (DeviceWeights | None, status): status is "ok", "mismatch" (use the sequentially verified build) or
         "capacity" (buffers were too small: the learned sizes are updated, build again)."""
-        c = (self.counts.cpu() if counts_host is None else counts_host).tolist()
+        if counts_host is None:
+            pin = _pinned_counts()
+            pin.copy_(self.counts, non_blocking=True)
+            torch.cuda.current_stream(self.counts.device).synchronize()
+            c = pin.tolist()
+        else:
+            c = counts_host.tolist()
         nfrag, nnz = int(c[0]), int(c[1])
         if c[2] or c[5]:
             raise _lib.RegridB200Error("rg_build2d_band: a sweep walk did not terminate (degenerate or folded grid)")
@@ -330,10 +351,12 @@ def build2d_band_enqueue(x_in, y_in, x_out, y_out, weights_input, row_lo: int, r
             scratch = (_workspace(build2d_workspace_bytes(nxi, nyi, nxo, nyo), device), frags_empty(fcap, device))
             _band_scratch[skey] = scratch
         ws, frags = scratch
-        ii = torch.empty(ncap, dtype=I64, device=device)
-        io = torch.empty(ncap, dtype=I64, device=device)
-        v = torch.empty(ncap, dtype=F64, device=device)
-        counts = torch.empty(8, dtype=I64, device=device)
+        # one allocation: counts[8] | indices_input | indices_output | values (views; 8-byte elements)
+        # (every array starts on a 256-byte boundary, like separate allocations would)
+        pad = (ncap + 31) // 32 * 32
+        buf = torch.empty(32 + 3 * pad, dtype=I64, device=device)
+        counts, ii, io = buf[:8], buf[32:32 + ncap], buf[32 + pad:32 + pad + ncap]
+        v = buf[32 + 2 * pad:32 + 2 * pad + ncap].view(F64)
         strided = None
         if bcap > 0:
             # ONE walk into fixed-capacity buckets (capacity learned from an earlier build of this shape)

@@ -98,7 +98,7 @@ static __global__ void k_bbox(const __grid_constant__ BoundarySet S)
     double* bbox = S.bbox[blockIdx.y];  // xlo, ylo, xhi, yhi
     const int64_t n = (int64_t)g.nx * g.ny;
     double xlo = INFINITY, ylo = INFINITY, xhi = -INFINITY, yhi = -INFINITY;
-    // four independent 16-byte loads of each array in flight per thread (the scan is latency bound otherwise)
+    // eight (then four) independent 16-byte loads of each array in flight per thread (the scan is latency bound otherwise)
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     int64_t done = 0;   // elements covered by the vector loop
@@ -107,6 +107,16 @@ static __global__ void k_bbox(const __grid_constant__ BoundarySet S)
         const double2* y2 = reinterpret_cast<const double2*>(g.y);
         const int64_t n2 = n / 2;
         int64_t r = q;
+        for (; r + 7 * stride < n2; r += 8 * stride) {
+            double2 x[8], y[8];
+#pragma unroll
+            for (int u = 0; u < 8; u++) { x[u] = x2[r + u * stride]; y[u] = y2[r + u * stride]; }
+#pragma unroll
+            for (int u = 0; u < 8; u++) {
+                xlo = fmin(xlo, fmin(x[u].x, x[u].y)); xhi = fmax(xhi, fmax(x[u].x, x[u].y));
+                ylo = fmin(ylo, fmin(y[u].x, y[u].y)); yhi = fmax(yhi, fmax(y[u].x, y[u].y));
+            }
+        }
         for (; r + 3 * stride < n2; r += 4 * stride) {
             double2 x[4], y[4];
 #pragma unroll
