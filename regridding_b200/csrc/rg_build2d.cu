@@ -33,6 +33,7 @@
 #include "rg_geom.cuh"
 #include "rg_boundary.cuh"
 #include <mutex>
+#include <vector>
 
 // resident CTAs of 128 threads per SM the walk kernels are compiled for (8 -> 64 registers per thread)
 #ifndef RG_COUNT_MINB
@@ -2145,6 +2146,7 @@ __global__ void k_band_counts(int stage, const int64_t* __restrict__ total, int6
 namespace rg {
 struct BandSide {
     cudaStream_t stream;
+    cudaStream_t capture;   // one-walk builds are captured on this stream and replayed as CUDA graphs
     cudaEvent_t fork, join, emitted, verified;
 };
 static BandSide* band_side(int device)
@@ -2156,6 +2158,7 @@ static BandSide* band_side(int device)
     if (!table[device]) {
         BandSide* b = new BandSide();
         if (cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking) != cudaSuccess ||
+            cudaStreamCreateWithFlags(&b->capture, cudaStreamNonBlocking) != cudaSuccess ||
             cudaEventCreateWithFlags(&b->fork, cudaEventDisableTiming) != cudaSuccess ||
             cudaEventCreateWithFlags(&b->join, cudaEventDisableTiming) != cudaSuccess ||
             cudaEventCreateWithFlags(&b->emitted, cudaEventDisableTiming) != cudaSuccess ||
@@ -2166,6 +2169,30 @@ static BandSide* band_side(int device)
         table[device] = b;
     }
     return table[device];
+}
+}  // namespace rg
+
+namespace rg {
+struct BandGraphKey {
+    int device;
+    int64_t dims[4];
+    const void* ptrs[12];
+    int64_t nums[7];
+};
+struct BandGraphEntry {
+    BandGraphKey key;
+    cudaGraphExec_t exec;
+    uint64_t stamp;
+};
+static std::mutex& band_graph_mutex()
+{
+    static std::mutex m;
+    return m;
+}
+static std::vector<BandGraphEntry>& band_graph_cache()
+{
+    static std::vector<BandGraphEntry> c;
+    return c;
 }
 }  // namespace rg
 
@@ -2364,6 +2391,57 @@ extern "C" int rg_build2d_band_onewalk(int device, void* stream,
 {
     if (!frags_strided || bucket_capacity < 1 || bucket_capacity > 65535)
         return fail(RG_E_ARG, "rg_build2d_band_onewalk: bad bucket buffer");
+    // A one-walk build is a REPEAT build of its shape (the bucket capacity comes from an earlier one), so the whole
+    // enqueue -- ~30 operations on two streams, host-bound at its start -- is captured once per argument set and
+    // replayed as a CUDA graph (the caller's stream may be the legacy default stream, which cannot be captured: the
+    // capture runs on a library-owned stream, the graph is launched into the caller's).
+    BandGraphKey key;
+    memset(&key, 0, sizeof(key));
+    key.device = device;
+    key.dims[0] = nxi; key.dims[1] = nyi; key.dims[2] = nxo; key.dims[3] = nyo;
+    key.ptrs[0] = xin; key.ptrs[1] = yin; key.ptrs[2] = xout; key.ptrs[3] = yout; key.ptrs[4] = w_in;
+    key.ptrs[5] = workspace; key.ptrs[6] = frags; key.ptrs[7] = ii; key.ptrs[8] = io; key.ptrs[9] = v;
+    key.ptrs[10] = counts_dev; key.ptrs[11] = frags_strided;
+    key.nums[0] = row_lo; key.nums[1] = row_hi; key.nums[2] = (int64_t)workspace_bytes; key.nums[3] = frag_capacity;
+    key.nums[4] = nnz_capacity; key.nums[5] = bucket_capacity; key.nums[6] = getenv("RG_BAND_FORCE_MISMATCH") ? 1 : 0;
+    BandSide* side = getenv("RG_BAND_NO_GRAPH") ? nullptr : band_side(device);
+    if (side && cudaSetDevice(device) == cudaSuccess && sort_smem_opt_in(device) == RG_OK) {
+        std::lock_guard<std::mutex> lock(band_graph_mutex());
+        std::vector<BandGraphEntry>& cache = band_graph_cache();
+        static uint64_t clock = 0;
+        for (BandGraphEntry& e : cache)
+            if (memcmp(&e.key, &key, sizeof(key)) == 0) {
+                e.stamp = ++clock;
+                RG_CUDA(cudaGraphLaunch(e.exec, (cudaStream_t)stream));
+                return RG_OK;
+            }
+        cudaGraph_t graph = nullptr;
+        cudaGraphExec_t exec = nullptr;
+        if (cudaStreamBeginCapture(side->capture, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
+            const int rc = band_impl(device, side->capture, nxi, nyi, nxo, nyo, xin, yin, xout, yout, w_in, row_lo, row_hi, workspace,
+                                     workspace_bytes, frags, frag_capacity, ii, io, v, nnz_capacity, counts_dev, frags_strided,
+                                     bucket_capacity);
+            const cudaError_t ce = cudaStreamEndCapture(side->capture, &graph);
+            if (rc == RG_OK && ce == cudaSuccess && graph && cudaGraphInstantiate(&exec, graph, 0) == cudaSuccess) {
+                cudaGraphDestroy(graph);
+                if (cache.size() >= 16) {   // drop the least recently used argument set
+                    size_t old = 0;
+                    for (size_t q = 1; q < cache.size(); q++)
+                        if (cache[q].stamp < cache[old].stamp) old = q;
+                    cudaGraphExecDestroy(cache[old].exec);
+                    cache.erase(cache.begin() + (long)old);
+                }
+                cache.push_back(BandGraphEntry{ key, exec, ++clock });
+                RG_CUDA(cudaGraphLaunch(exec, (cudaStream_t)stream));
+                return RG_OK;
+            }
+            if (graph) cudaGraphDestroy(graph);
+            cudaGetLastError();   // the capture did not work out (an argument error, an unsupported call): plain launches
+            if (rc != RG_OK && rc < 0) return rc;   // argument errors are the caller's
+        } else {
+            cudaGetLastError();
+        }
+    }
     return band_impl(device, stream, nxi, nyi, nxo, nyo, xin, yin, xout, yout, w_in, row_lo, row_hi, workspace, workspace_bytes,
                      frags, frag_capacity, ii, io, v, nnz_capacity, counts_dev, frags_strided, bucket_capacity);
 }
