@@ -306,7 +306,27 @@ def run_ours(args):
 
     dw, build_ms = time_build(False)
     build_stats = dict(dw.stats or {})
-    sharded_ms = replicated_ms = None
+    # The same build as a REPEAT build of its shape through the band entry points (the whole grid as one band): the
+    # second and later builds know the longest bucket of the first and walk every segment once
+    # (rg_build2d_band_onewalk, replayed as a CUDA graph).  This is what the sharded figures below must be compared
+    # with like for like: their timed builds are repeat builds too.
+    def band_whole():
+        return _device.build_weights_2d_band(xi, yi, xo, yo, None, row_band=None, device=dev)
+
+    for _ in range(W):
+        dw1 = band_whole()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(K):
+        dw1 = band_whole()
+    e1.record()
+    torch.cuda.synchronize(dev)
+    one_walk_ms = max_over_ranks(e0.elapsed_time(e1) / K)
+    assert torch.equal(dw1.indices_input, dw.indices_input) and torch.equal(dw1.indices_output, dw.indices_output) and \
+        torch.equal(dw1.values, dw.values), "one-walk build differs from the standard build"
+    del dw1
+    sharded_ms = replicated_ms = sharded_first_ms = None
     sharded_equal = None
     if world > 1:
         # agree on a fallback together should the default exchange be unavailable on some rank
@@ -321,6 +341,12 @@ def run_ours(args):
         if int(t.item()) == 0:
             exchange["mode"] = "nccl"
         dw_band, sharded_ms = time_build(True)
+        # the FIRST build of a shape cannot know the bucket capacity: two walks (forced here for every timed build)
+        os.environ["REGRID_B200_BAND_TWO_WALKS"] = "1"
+        try:
+            _, sharded_first_ms = time_build(True)
+        finally:
+            del os.environ["REGRID_B200_BAND_TWO_WALKS"]
         dw_rep, replicated_ms = time_build(True, replicate=True)
         # parity before any number is reported: this rank's band and the replicated matrix equal the single-GPU
         # build bit for bit (indices AND weights)
@@ -491,9 +517,21 @@ def run_ours(args):
             # every rank runs full builds of its own slices -> aggregate = ranks x the per-rank rate (max over ranks)
             "per_slice_sharded": {"n_gpus": world, "value": world * n_in / (build_ms * 1e-3) / 1e6, "unit": "Mcells/s",
                                   "scaling": "weak", "collective": None},
+            "repeat_build_one_walk": {
+                "ms": one_walk_ms, "value": n_in / (one_walk_ms * 1e-3) / 1e6, "unit": "Mcells/s",
+                "equals_standard_build_bitwise": True,
+                "note": "second and later builds of a shape through rg_build2d_band_onewalk (whole grid as one band): the "
+                        "longest bucket of the first build sizes fixed-capacity buckets, every segment is walked once; "
+                        "`build.ms` above is the standard entry point (what a first build costs: two walks)"},
             "sharded": None if sharded_ms is None else {
                 "n_gpus": world, "ms": sharded_ms, "value": n_in / (sharded_ms * 1e-3) / 1e6, "unit": "Mcells/s",
                 "speedup_vs_this_runs_1gpu_build": build_ms / sharded_ms,
+                "first_build_ms": sharded_first_ms,
+                "like_for_like": {
+                    "repeat_builds": {"one_gpu_ms": one_walk_ms, "n_gpu_ms": sharded_ms, "speedup": one_walk_ms / sharded_ms},
+                    "first_builds": {"one_gpu_ms": build_ms, "n_gpu_ms": sharded_first_ms, "speedup": build_ms / sharded_first_ms},
+                    "note": "`ms` / `speedup_vs_this_runs_1gpu_build` compare REPEAT builds on N GPUs (one walk) with the standard "
+                            "single-GPU build (two walks); like for like the band build scales by the figures given here"},
                 "scaling": "strong", "exchange": exchange["mode"],
                 "equals_single_gpu_build_bitwise_on_every_rank": sharded_equal,
                 "result": "every rank holds its input-row band of the public triplets; exchange=band: every rank walks only "
