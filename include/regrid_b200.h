@@ -223,7 +223,10 @@ int rg_grid_area(int device, void* stream, int64_t nx, int64_t ny,
  * (the reference's public find_indices is 1D only; this is the 2D extension).
  * For each of n_points query points: flat index i*(ny-1)+j of the lowest-index cell
  * whose quad contains the point under point_is_inside_polygon
- * (regridding/geometry.py:737-829), else `fill`.
+ * (regridding/geometry.py:737-829), else `fill`.  Stream-ordered, no host synchronisation.  While the call
+ * runs, cell_flat transiently holds up to three marker values below every cell index (INT64_MIN .. INT64_MIN + 3,
+ * skipping `fill`); they are all resolved when the call's last kernel has run.  Exact for meshes without overlapping
+ * cells (the assumption of the reference's own secant locator).
  * ------------------------------------------------------------------------------ */
 int rg_find_indices_2d_workspace_bytes(int64_t nx, int64_t ny, int64_t n_points, size_t* bytes_host);
 

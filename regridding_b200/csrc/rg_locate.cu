@@ -8,12 +8,16 @@ namespace rg {
 
 // ---------------------------------------------------------------------------
 // 2D: lowest-index containing cell (index_of_point_brute semantics,
-// regridding/_weights/_weights_conservative_2d/_grids.py:223-279), found by a WALK: every thread locates a run of
-// consecutive points, each by a Newton iteration in index space seeded with its predecessor's solution (1-2
-// iterations on regular point sets) + the exact containment predicate / 3x3 lowest-index resolve (the role of
-// index_of_point_secant, _grids.py:356-463).  The grid stays L2-resident; the points stream through once.
-// A point the iteration cannot place in a cell is classified EXACTLY (see k_locate_walk); the rare leftovers go
-// to the exhaustive pass 2.
+// regridding/_weights/_weights_conservative_2d/_grids.py:223-279), found by a WALK.  Three passes, enqueued back to back
+// with no host round trip (the later ones read their work counts on the device):
+//   fast  (k_locate_fast)  one thread per point: seed cell predicted from the lane's previous points, cell walk by the
+//                          signs of the four edge cross products; points in no cell's bounding box (occupancy raster)
+//                          are answered at once; whatever the walk does not settle is MARKED (sentinel + queue);
+//   slow  (k_locate_slow)  one warp per marked point: boundary winding number for points whose walk left the grid,
+//                          Newton + the exact containment predicate / 3x3 lowest-index resolve for the others (the role
+//                          of index_of_point_secant, _grids.py:356-463);
+//   brute (k_locate_brute) exhaustive scan for points inside the boundary polygon that no cell was found for.
+// The grid stays L2-resident; the points stream through once.
 // ---------------------------------------------------------------------------
 constexpr int kLocRaster = 1024;   // occupancy raster over the grid's bounding box
 constexpr int kLocRun = 8;         // points per lane: a warp walks a strip of 32 x kLocRun consecutive points
