@@ -115,6 +115,7 @@ constexpr int kFlagUnknown = 2;    // number of vertices whose guess was "unknow
 constexpr int kFlagSeqOverflow = 3;  // piece index overflowed the 29-bit rank field
 constexpr int kFlagBandMismatch = 4; // band build: a walked segment did not start in the state its predecessor ended in
 constexpr int kFlagCapacity = 5;     // band build: the caller's fragment / triplet buffers are too small
+constexpr int kFlagMaxBucket = 6;    // standard build: fragments of the fullest input cell (sizes one-walk rebuilds)
 
 __device__ __forceinline__ int64_t vertex_of(const PassParams& P, int L, int k)
 {
@@ -1278,7 +1279,8 @@ extern "C" int rg_build2d_fill(int device, void* stream,
     rc = sort_smem_opt_in(device);
     if (rc) return rc;
     k_bucket_sort<<<(unsigned)ceil_div(l.Ci, kSortCells), kSortThreads, sizeof(SortSmem), st>>>(l.boff, l.Ci, (Frag*)frags,
-                                                                                           l.nuniq);
+                                                                                           l.nuniq, nullptr, nullptr, 0,
+                                                                                           l.flags + kFlagMaxBucket);
     RG_LAUNCH_CHECK("k_bucket_sort");
     rc = exclusive_scan_i32_i64(st, l.nuniq, l.colptr, l.Ci, l.scan_scratch);
     if (rc) return rc;
@@ -2409,15 +2411,19 @@ extern "C" int rg_build2d_band_onewalk(int device, void* stream,
         std::lock_guard<std::mutex> lock(band_graph_mutex());
         std::vector<BandGraphEntry>& cache = band_graph_cache();
         static uint64_t clock = 0;
-        for (BandGraphEntry& e : cache)
+        static int misses_in_a_row = 0;   // a caller whose argument sets never recur (e.g. it keeps every result alive)
+        for (BandGraphEntry& e : cache)   // must not pay for a capture (~1 ms) per build: after 4 misses, plain launches
             if (memcmp(&e.key, &key, sizeof(key)) == 0) {
                 e.stamp = ++clock;
+                misses_in_a_row = 0;
                 RG_CUDA(cudaGraphLaunch(e.exec, (cudaStream_t)stream));
                 return RG_OK;
             }
         cudaGraph_t graph = nullptr;
         cudaGraphExec_t exec = nullptr;
-        if (cudaStreamBeginCapture(side->capture, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
+        if (misses_in_a_row >= 4) {
+            // (fall through to the plain launches below)
+        } else if (++misses_in_a_row, cudaStreamBeginCapture(side->capture, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
             const int rc = band_impl(device, side->capture, nxi, nyi, nxo, nyo, xin, yin, xout, yout, w_in, row_lo, row_hi, workspace,
                                      workspace_bytes, frags, frag_capacity, ii, io, v, nnz_capacity, counts_dev, frags_strided,
                                      bucket_capacity);
