@@ -11,6 +11,7 @@ from __future__ import annotations
 import ctypes
 import dataclasses
 import os
+import threading
 import warnings
 
 import numpy as np
@@ -260,17 +261,24 @@ _band_onewalk_failed: set = set()   # shapes whose one-walk build overflowed its
 _band_scratch: dict = {}
 
 
-_pinned: dict = {}
+_pinned = threading.local()
 
 
 def _pinned_counts() -> torch.Tensor:
-    """pinned int64[8] the status counters of a band build are copied into (one per process: the copy is consumed
-    before the next build is finished)"""
-    t = _pinned.get("counts")
+    """pinned int64[8] the status counters of a band build are copied into (one per host thread: the copy is consumed
+    before the thread finishes its next build)"""
+    t = getattr(_pinned, "counts", None)
     if t is None:
         t = torch.empty(8, dtype=I64).pin_memory()
-        _pinned["counts"] = t
+        _pinned.counts = t
     return t
+
+
+def release_build_scratch() -> None:
+    """Drop the device buffers the band builds keep between calls (workspace, fragment buffer, the fixed-capacity buckets
+    of the one-walk builds: ~4 GB after a repeat build at 2048^2).  The learned sizes stay; the next build reallocates."""
+    _band_scratch.clear()
+    _band_buckets.clear()
 
 
 @dataclasses.dataclass
